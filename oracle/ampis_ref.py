@@ -1,0 +1,286 @@
+"""oracle/ampis_ref.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement of the AMPIS Python loops on the mask-evaluation hot path
+(SURVEY.md section 8a), written against ``oracle.cocomask`` the way the
+reference is written against ``pycocotools.mask``.  Loop structure is kept
+(per-GT loop over <=80-pred chunks, per-match merge+area, per-satellite x
+per-particle merge+area) because the same functions double as the CPU
+baseline timed by bench.py.  ``np.int``/``np.bool``/``np.float`` (removed from
+NumPy) are spelled ``np.int64``/``np.bool_``/``np.float64``.
+
+Inputs are plain containers (lists of RLE dicts, polygon coordinate lists,
+bool arrays); the type dispatch on InstanceSet/Instances/RLEMasks is host
+logic tested separately.
+
+PARITY STATUS: the reference itself cannot be imported here (pycocotools,
+detectron2, skimage, matplotlib absent; removed NumPy aliases), so parity is
+pinned by analyze.py:702-728's known-answer test and by cross-formulation
+checks only; everything else is "parity unpinned".
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+import numpy as np
+
+from . import cocomask as rle
+
+
+# ---- ampis/analyze.py -------------------------------------------------------
+
+def piecewise_iou(a, b, interval=80):
+    """analyze.py:54-112 -- len(a) x len(b) float64 IoU matrix in <=80x80 blocks."""
+    imax, jmax = len(a), len(b)
+    target = np.zeros((imax, jmax))
+    n_seg_a = imax // interval + int(bool(imax % interval))
+    n_seg_b = jmax // interval + int(bool(jmax % interval))
+    _is_crowd = np.zeros(interval, bool)
+    for i in range(n_seg_a):
+        i1 = interval * i
+        i2 = min(i1 + interval, imax)
+        a_masks = a[i1:i2]
+        is_crowd = _is_crowd[:i2 - i1]
+        for j in range(n_seg_b):
+            j1 = interval * j
+            j2 = min(j1 + interval, jmax)
+            b_masks = b[j1:j2]
+            target[i1:i2, j1:j2] = rle.iou(b_masks, a_masks, is_crowd).T
+    return target
+
+
+def piecewise_rle_match(gt, pred, iou_thresh=0.5, interval=80):
+    """analyze.py:115-181 -- per-GT arg-max matching (many-to-one allowed)."""
+    jmax = len(pred)
+    tp, fn, iou = [], [], []
+    pred_matched = np.zeros(len(pred), bool)
+    n_seg_pred = jmax // interval + int(jmax % interval > 0)
+    for gt_idx, gt_mask in enumerate(gt):
+        iou_max = 0.
+        iou_argmax = -1
+        for j in range(n_seg_pred):
+            j0 = interval * j
+            j1 = j0 + interval
+            pred_args = pred[j0:j1]
+            iou_scores_ = rle.iou(pred_args, [gt_mask], [False])[:, 0]
+            iou_amax_j = np.argmax(iou_scores_)
+            iou_max_j = iou_scores_[iou_amax_j]
+            if iou_max_j > iou_max:
+                iou_max = iou_max_j
+                iou_argmax = iou_amax_j + j0
+        if iou_max > iou_thresh:
+            tp.append([gt_idx, iou_argmax])
+            iou.append(iou_max)
+            pred_matched[iou_argmax] = True
+        else:
+            fn.append(gt_idx)
+    fp = np.array([x for x, matched in enumerate(pred_matched) if not matched], int)
+    return {'tp': np.asarray(tp, int),
+            'fn': np.asarray(fn, int),
+            'fp': np.asarray(fp, int),
+            'iou': np.asarray(iou)}
+
+
+def det_seg_scores(gtmasks, predmasks, iou_thresh=0.5):
+    """analyze.py:226-339 on RLE lists."""
+    detection_results_ = piecewise_rle_match(gtmasks, predmasks, iou_thresh)
+    matches_ = np.asarray(detection_results_['tp'])
+    TP_det_ = len(matches_)
+    FN_det_ = len(detection_results_['fn'])
+    FP_det_ = len(detection_results_['fp'])
+    det_precision = TP_det_ / (TP_det_ + FP_det_)
+    det_recall = TP_det_ / (TP_det_ + FN_det_)
+    gtmasks_tp = [gtmasks[i[0]] for i in matches_]
+    predmasks_tp = [predmasks[i[1]] for i in matches_]
+    seg_true_positive = np.array([rle.area(rle.merge([m1, m2], intersect=True))
+                                  for m1, m2 in zip(gtmasks_tp, predmasks_tp)], np.int64)
+    tp_gt_area = np.array([rle.area(m) for m in gtmasks_tp], np.int64)
+    tp_pred_area = np.array([rle.area(m) for m in predmasks_tp], np.int64)
+    seg_false_positive = tp_pred_area - seg_true_positive
+    seg_false_negative = tp_gt_area - seg_true_positive
+    with np.errstate(invalid='ignore', divide='ignore'):
+        seg_precision = seg_true_positive / (seg_true_positive + seg_false_positive)
+        seg_recall = seg_true_positive / (seg_true_positive + seg_false_negative)
+    return {'det_precision': det_precision,
+            'det_recall': det_recall,
+            'seg_precision': seg_precision,
+            'seg_recall': seg_recall,
+            'det_tp': matches_,
+            'det_fn': detection_results_['fn'],
+            'det_fp': detection_results_['fp'],
+            'seg_tp': seg_true_positive,
+            'seg_fn': seg_false_negative,
+            'seg_fp': seg_false_positive,
+            'det_tp_iou': detection_results_['iou']}
+
+
+# ---- ampis/applications/powder.py --------------------------------------------
+
+def rle_satellite_match(particles, satellites, match_thresh=0.5):
+    """powder.py:28-112 on RLE lists (no bbox pruning, merge+area per pair)."""
+    satellite_matches, intersection_scores, satellites_unmatched = [], [], []
+    particles_matched_bool = np.zeros(len(particles), dtype=np.bool_)
+    for satellite_idx, satellite_mask in enumerate(satellites):
+        with np.errstate(invalid='ignore', divide='ignore'):
+            intersects = np.array([rle.merge_area(satellite_mask, pmask, intersect=True)
+                                   for pmask in particles], np.uint32) / rle.area(satellite_mask)
+        iscore_amax = np.argmax(intersects)
+        iscore_max = intersects[iscore_amax]
+        if iscore_max > match_thresh:
+            satellite_matches.append([satellite_idx, iscore_amax])
+            particles_matched_bool[iscore_amax] = True
+            intersection_scores.append(iscore_max)
+        else:
+            satellites_unmatched.append(satellite_idx)
+    particles_unmatched = np.array([i for i, matched in enumerate(particles_matched_bool)
+                                    if not matched], np.int64)
+    satellite_matches = np.asarray(satellite_matches, np.int64)
+    satellites_unmatched = np.asarray(satellites_unmatched, np.int64)
+    intersection_scores = np.asarray(intersection_scores)
+    match_pairs = {x: [] for x in np.unique(satellite_matches[:, 1])}
+    for match in satellite_matches:
+        match_pairs[match[1]].append(match[0])
+    return {'satellite_matches': satellite_matches,
+            'satellites_unmatched': satellites_unmatched,
+            'particles_unmatched': particles_unmatched,
+            'intersection_scores': intersection_scores,
+            'match_pairs': match_pairs}
+
+
+def satellite_metrics(particles, n_satellites, matches):
+    """powder.py:221-273 on an RLE list of particles."""
+    matched_particle_idx = list(matches['match_pairs'])
+    mask_areas_all = rle.area(particles)
+    return {'n_satellites': n_satellites,
+            'n_particles_matched': len(matched_particle_idx),
+            'n_particles_all': len(particles),
+            'mask_areas_matched': mask_areas_all[matched_particle_idx],
+            'mask_areas_all': mask_areas_all}
+
+
+def satellite_measurements(matches, n_particles_per_image, n_satellites_per_image):
+    """powder.py:463-569 numerics on a list of per-image match dicts."""
+    n_images = len(matches)
+    n_particles_matched = sum([len(x['match_pairs'].keys()) for x in matches])
+    n_particles = n_particles_matched + sum([len(x['particles_unmatched']) for x in matches])
+    spp_list = []
+    for m in matches:
+        for v in m['match_pairs'].values():
+            spp_list.append(len(v))
+    spp_list = np.asarray(spp_list)
+    n_satellites_matched = sum(spp_list)
+    mspp = np.median(spp_list)
+    n_satellites_unmatched = sum([len(x['satellites_unmatched']) for x in matches])
+    sat_frac = n_particles_matched / n_particles
+    unique, counts = np.unique(spp_list, return_counts=True)
+    assert counts.sum() == n_particles_matched
+    assert n_particles == sum(n_particles_per_image)
+    assert n_satellites_matched + n_satellites_unmatched == sum(n_satellites_per_image)
+    counts = counts.cumsum() / counts.sum()
+    keys = ['n_images', 'n_particles', 'n_satellites', 'n_satellites_unmatched', 'n_satellited_particels',
+            'sat_frac', 'mspp', 'unique_satellites_per_particle', 'counts_satellites_per_particle']
+    values = [n_images, n_particles, n_satellites_matched, n_satellites_unmatched, n_particles_matched,
+              sat_frac, mspp, unique, counts]
+    return dict(zip(keys, values))
+
+
+def psd_from_areas(areas, xvals='d_eq', yvals='cvf'):
+    """powder.py:414-446 -- cumulative size distribution from a list of area arrays
+    (already scaled to length^2 if a pixel size applies)."""
+    if type(areas[0]) in (list, np.ndarray):
+        areas = np.concatenate(areas, axis=0)
+    unique, counts = np.unique(areas, return_counts=True)
+    if xvals.lower() == 'd_eq':
+        unique = 2 * np.sqrt(unique / np.pi)
+    elif xvals.lower() != 'area':
+        raise ValueError('xvals must be "d_eq" or "area"')
+    if yvals.lower() == 'cvf':
+        volumes = 4 / 3 * np.pi ** (-1 / 2) * unique ** (3 / 2)
+        counts = volumes * counts
+    elif yvals.lower() != 'counts':
+        raise ValueError('yvals must be "cvf" or "counts"')
+    counts = counts.cumsum()
+    counts = counts / counts[-1]
+    return {'x': unique, 'y': counts}
+
+
+# ---- ampis/structures.py ----------------------------------------------------------
+
+def mask_areas_rle(masks):
+    """structures.py:567-571 -- RLE.area(list) -> uint32[n]."""
+    return rle.area(masks)
+
+
+def shoelace_area(x, y):
+    """structures.py:586-610."""
+    return 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+
+
+def polygons_to_rle(polygons, size):
+    """structures.py:675-677 -- first polygon of each instance, frPyObjects."""
+    return [rle.frPyObjects(p, *size)[0] for p in polygons]
+
+
+def rle_to_bitmask_array(masks):
+    """structures.py:749-752 -- bool[n, r, c] from an RLE list."""
+    return rle.decode(masks).astype(np.bool_).transpose((2, 0, 1))
+
+
+def size_inliers(areas, min_thresh=100, max_thresh=100000):
+    """structures.py:407-416 -- strict min < area < max."""
+    inlier_min = np.ones(areas.shape, np.bool_) if min_thresh is None else areas > min_thresh
+    inlier_max = np.ones(areas.shape, np.bool_) if max_thresh is None else areas < max_thresh
+    return np.logical_and(inlier_min, inlier_max)
+
+
+def edge_inliers(masks, size, k=1):
+    """structures.py:460-468 -- masks that do not touch the k-pixel border frame."""
+    r, c = size
+    border = np.ones((r, c), dtype=np.bool_)
+    border[k:-k, k:-k] = 0
+    border = rle.encode(np.asfortranarray(border.astype(np.uint8)))
+    return rle.area([rle.merge([border, x], intersect=True) for x in masks]) == 0
+
+
+def rprops_basic(masks):
+    """structures.py:507-508 restricted to the in-scope keys:
+    area (int64), equivalent_diameter = sqrt(4*area/pi) (skimage 0.18.3
+    regionprops), bbox (min_row, min_col, max_row, max_col) half-open."""
+    out = {'area': [], 'equivalent_diameter': [], 'bbox': []}
+    for m in masks:
+        img = rle.decode(m).astype(np.int64)
+        a = int(img.sum())
+        out['area'].append(a)
+        out['equivalent_diameter'].append(np.sqrt(4 * a / np.pi))
+        rows = np.where(img.any(axis=1))[0]
+        cols = np.where(img.any(axis=0))[0]
+        if len(rows):
+            out['bbox'].append((rows[0], cols[0], rows[-1] + 1, cols[-1] + 1))
+        else:
+            out['bbox'].append((0, 0, 0, 0))
+    return out
+
+
+# ---- ampis/data_utils.py -----------------------------------------------------------
+
+def extract_boxes(masks, mask_mode='detectron2', box_mode='detectron2'):
+    """data_utils.py:180-252."""
+    if masks.ndim == 2:
+        masks = masks[np.newaxis, :, :]
+    else:
+        if mask_mode == 'matterport':
+            masks = masks.transpose((2, 0, 1))
+    dtype = np.float64 if box_mode == 'detectron2' else np.int64
+    boxes = np.zeros((masks.shape[0], 4), dtype=dtype)
+    for i, m in enumerate(masks):
+        horizontal_indicies = np.where(np.any(m, axis=0))[0]
+        vertical_indicies = np.where(np.any(m, axis=1))[0]
+        if horizontal_indicies.shape[0]:
+            x1, x2 = horizontal_indicies[[0, -1]]
+            y1, y2 = vertical_indicies[[0, -1]]
+        else:
+            x1, x2, y1, y2 = 0, 0, 0, 0
+        if box_mode == 'detectron2':
+            box = np.array([x1, y1, x2, y2], dtype=dtype)
+        else:
+            box = np.array([y1, y2 + 1, x1, x2 + 1], dtype=dtype)
+        boxes[i] = box
+    return boxes

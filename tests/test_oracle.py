@@ -1,0 +1,211 @@
+"""CPU tests that pin the oracle (oracle/maskapi_ref.c, oracle/cocomask.py,
+oracle/ampis_ref.py) -- SURVEY.md section 8c.  No GPU needed."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import ampis_ref as R
+from oracle import cocomask as rle
+from tests import _util as U
+
+
+def _enc(a):
+    return rle.encode(np.asfortranarray(np.array(a, np.uint8)))
+
+
+def test_reference_known_answer():
+    """The reference's only result-pinning test, analyze.py:702-728, verbatim values."""
+    m1 = _enc([[1, 1, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]])
+    m2 = _enc([[0, 0, 1, 1], [0, 0, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]])
+    m3 = _enc([[0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 0, 0], [1, 1, 0, 0]])
+    m4 = _enc([[0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 1, 1], [0, 0, 1, 1]])
+    gt = [m1, m2, m3, m4]
+    pred = [m3, m2, m4]
+    assert np.all(R.piecewise_iou(gt, pred) == np.array([[0, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1]]))
+    match = R.piecewise_rle_match(gt, pred)
+    assert np.all(match['tp'] == np.array([[1, 1], [2, 0], [3, 2]]))
+    assert np.all(match['fn'] == np.array([0]))
+    assert np.all(match['fp'] == np.array([]))
+    assert np.all(match['iou'] == np.ones(3))
+    # m1 encodes to counts [0,2,2,2,10]
+    assert list(rle.counts_from_string(m1['counts'])) == [0, 2, 2, 2, 10]
+
+
+def _all_golden_strings():
+    g = U.load('powder_match.npz')
+    for k in range(len(g['names'])):
+        _, gt, pr = U.powder_match_image(k)
+        yield from gt
+        yield from pr
+    s = U.load('powder_satellite.npz')
+    for k in range(len(s['names'])):
+        yield from U.powder_satellite_image(k)[2]
+    m = U.load('spheroidite_measure.npz')
+    for k in range(len(m['names'])):
+        yield from U.unpack_strings(m['%d_blob' % k], m['%d_off' % k], m['%d_size' % k])
+
+
+def test_codec_on_real_pycocotools_strings():
+    """The fixture strings were written by the real pycocotools.encode
+    (data_utils.py:275): they are golden vectors for rleFrString / rleToString."""
+    n = 0
+    for m in _all_golden_strings():
+        c = rle.counts_from_string(m['counts'])
+        h, w = m['size']
+        assert int(c.astype(np.int64).sum()) == h * w
+        assert (c[1:-1] > 0).all()            # canonical encode output has no interior zero runs
+        assert rle.string_from_counts(c) == m['counts']
+        n += 1
+    assert n > 3000
+
+
+def test_encode_canonical_form_matches_real_strings():
+    """decode -> encode must give back the exact bytes pycocotools wrote."""
+    _, gt, _ = U.powder_match_image(0)
+    for m in gt[:40]:
+        d = rle.decode(m)
+        assert rle.encode(np.asfortranarray(d))['counts'] == m['counts']
+        assert int(d.sum()) == int(rle.area(m))
+
+
+def test_runwalk_iou_equals_dense_formulation():
+    """Second, independent formulation: packed AND + popcount, IoU = I/(a+b-I)."""
+    g, gt, pr = U.powder_match_image(0)
+    hw = int(g['0_size'][0]) * int(g['0_size'][1])
+    pg = [U.counts_to_packed(rle.counts_from_string(m['counts']), hw) for m in gt]
+    pp = [U.counts_to_packed(rle.counts_from_string(m['counts']), hw) for m in pr]
+    ag = np.array([U.popcount(x) for x in pg])
+    ap = np.array([U.popcount(x) for x in pp])
+    assert (ag == g['0_gt_area']).all() and (ap == g['0_pr_area']).all()
+    iou = R.piecewise_iou(gt, pr)
+    nz = g['0_iou_nz_idx']
+    assert (np.argwhere(iou > 0) == nz).all()
+    rng = np.random.default_rng(0)
+    extra = np.stack([rng.integers(0, len(gt), 300), rng.integers(0, len(pr), 300)], 1)
+    for i, j in np.concatenate([nz, extra]):
+        inter = U.popcount(pg[i] & pp[j])
+        want = inter / (ag[i] + ap[j] - inter) if inter else 0.0
+        assert iou[i, j] == want
+        assert int(rle.merge_area(gt[i], pr[j])) == inter
+        assert int(rle.area(rle.merge([gt[i], pr[j]], intersect=True))) == inter
+        assert int(rle.area(rle.merge([gt[i], pr[j]], intersect=False))) == ag[i] + ap[j] - inter
+
+
+def test_golden_regression_match_and_scores():
+    for k in (0, 3):
+        g, gt, pr = U.powder_match_image(k)
+        res = R.det_seg_scores(gt, pr, 0.5)
+        for key in ('det_tp', 'det_fn', 'det_fp', 'seg_tp', 'seg_fn', 'seg_fp', 'det_tp_iou',
+                    'seg_precision', 'seg_recall'):
+            assert np.array_equal(np.asarray(res[key]), g['%d_%s' % (k, key)]), key
+        assert [res['det_precision'], res['det_recall']] == list(g['%d_det_pr' % k])
+
+
+def test_golden_regression_satellites():
+    s, part, sat = U.powder_satellite_image(1)
+    res = R.rle_satellite_match(part, sat, 0.5)
+    for key in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched', 'intersection_scores'):
+        assert np.array_equal(res[key], s['1_%s' % key])
+    # satellite score = popcount(AND)/area(sat)
+    hw = int(s['1_size'][0]) * int(s['1_size'][1])
+    for (si, pi), sc in list(zip(res['satellite_matches'], res['intersection_scores']))[:25]:
+        a = U.counts_to_packed(rle.counts_from_string(sat[si]['counts']), hw)
+        b = U.counts_to_packed(rle.counts_from_string(part[pi]['counts']), hw)
+        assert sc == U.popcount(a & b) / U.popcount(a)
+
+
+def test_polygon_rectangles_closed_form():
+    """Axis-aligned rectangles with half-integer corners cover exactly the pixels whose
+    centres lie inside (SURVEY A.7 sanity case), any vertex order / start."""
+    r = rle.frPyObjects([[2.5, 1.5, 6.5, 1.5, 6.5, 4.5, 2.5, 4.5]], 8, 10)[0]
+    assert list(rle.counts_from_string(r['counts'])) == [26, 3, 5, 3, 5, 3, 5, 3, 27]
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        h, w = rng.integers(4, 40, 2)
+        x0, x1 = sorted(rng.integers(0, w, 2)); y0, y1 = sorted(rng.integers(0, h, 2))
+        x1 += 1; y1 += 1
+        pts = [(x0 - .5, y0 - .5), (x1 - .5, y0 - .5), (x1 - .5, y1 - .5), (x0 - .5, y1 - .5)]
+        sh = rng.integers(0, 4)
+        pts = pts[sh:] + pts[:sh]
+        if rng.random() < .5:
+            pts = pts[::-1]
+        poly = [c + 0.5 for p in pts for c in p]          # pixel-edge coordinates x0..x1, y0..y1
+        m = rle.decode(rle.frPyObjects([poly], int(h), int(w))[0]).astype(bool)
+        want = np.zeros((h, w), bool)
+        want[y0:y1, x0:x1] = True
+        assert (m == want).all()
+
+
+def test_polygon_golden_vs_shoelace():
+    p = U.load('powder_polygons.npz')
+    xy, off, area = p['0_poly_xy'], p['0_poly_off'], p['0_area']
+    size = tuple(int(v) for v in p['0_size'])
+    rl = U.unpack_strings(p['0_rle_blob'], p['0_rle_off'], size)
+    rel = []
+    for i in range(len(off) - 1):
+        q = xy[off[i]:off[i + 1]]
+        sh = R.shoelace_area(q[::2], q[1::2])
+        rel.append((area[i] - sh) / sh)
+        if i < 25:   # regression of the frozen strings
+            assert rle.frPyObjects([q], *size)[0]['counts'] == rl[i]['counts']
+    rel = np.array(rel)
+    assert abs(np.median(rel)) < 0.005 and np.percentile(np.abs(rel), 90) < 0.05
+
+
+def test_measurements_regression():
+    m = U.load('spheroidite_measure.npz')
+    masks = U.unpack_strings(m['0_blob'], m['0_off'], m['0_size'])
+    bm = R.rle_to_bitmask_array(masks)
+    assert (bm.sum(axis=(1, 2)) == m['0_area']).all()
+    assert np.array_equal(R.extract_boxes(bm), m['0_boxes_d2'])
+    assert np.array_equal(R.extract_boxes(bm, box_mode='matterport'), m['0_boxes_mp'])
+    assert np.array_equal(R.edge_inliers(masks, tuple(m['0_size']), 1), m['0_edge_inliers'])
+    # rleToBbox contains the tight box
+    bb, t = m['0_rlebbox'], m['0_boxes_d2']
+    ne = m['0_area'] > 0
+    assert (bb[ne, 0] <= t[ne, 0]).all() and (bb[ne, 0] + bb[ne, 2] - 1 >= t[ne, 2]).all()
+    assert (bb[ne, 1] <= t[ne, 1]).all() and (bb[ne, 1] + bb[ne, 3] - 1 >= t[ne, 3]).all()
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 17), st.integers(1, 19), st.integers(0, 2 ** 31 - 1))
+def test_properties_random_masks(h, w, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.random((h, w)) < rng.random()
+    b = rng.random((h, w)) < rng.random()
+    ra, rb = _enc(a), _enc(b)
+    assert (rle.decode(ra).astype(bool) == a).all()                       # decode(encode) = id
+    assert int(rle.area(ra)) == int(a.sum())                              # area = popcount
+    assert int(rle.area(rle.merge([ra, rb], intersect=True))) == int((a & b).sum())
+    assert int(rle.area(rle.merge([ra, rb], intersect=False))) == int((a | b).sum())
+    i, u = int((a & b).sum()), int((a | b).sum())
+    assert rle.iou([ra], [rb], [False])[0, 0] == (i / u if i else 0.0)
+    c = rle.counts_from_string(ra['counts'])
+    assert rle.string_from_counts(c) == ra['counts']
+    if a.any():
+        bb = rle.to_bbox(ra)
+        ys, xs = np.where(a)
+        assert bb[0] <= xs.min() and bb[0] + bb[2] - 1 >= xs.max()
+        assert bb[1] <= ys.min() and bb[1] + bb[3] - 1 >= ys.max()
+
+
+def test_match_edge_cases():
+    z = _enc(np.zeros((6, 5)))
+    o = _enc(np.ones((6, 5)))
+    half = _enc(np.pad(np.ones((3, 5)), ((0, 3), (0, 0))))
+    # zero-area masks give IoU exactly 0.0, never NaN
+    assert (R.piecewise_iou([z, o], [z, half]) == np.array([[0, 0], [0, 0.5]])).all()
+    m = R.piecewise_rle_match([z, o, half], [half, half, z], 0.4)
+    assert m['tp'].tolist() == [[1, 0], [2, 0]] and m['fn'].tolist() == [0] and m['fp'].tolist() == [1, 2]
+    # strict '>' on the threshold
+    assert len(R.piecewise_rle_match([o], [half], 0.5)['tp']) == 0
+    # nothing matches: tp has shape (0,)
+    assert R.piecewise_rle_match([z], [z])['tp'].shape == (0,)
+    with pytest.raises(ZeroDivisionError):
+        R.det_seg_scores([], [], 0.5)
+    # satellites: zero-area satellite -> NaN row -> unmatched; no match at all -> IndexError
+    res = R.rle_satellite_match([half, o], [z, half], 0.5)
+    assert res['satellite_matches'].tolist() == [[1, 0]] and res['satellites_unmatched'].tolist() == [0]
+    assert res['particles_unmatched'].tolist() == [1] and res['match_pairs'] == {0: [1]}
+    with pytest.raises(IndexError):
+        R.rle_satellite_match([half], [z], 0.5)
