@@ -1,0 +1,74 @@
+"""ctypes binding of libampis_b200.so (the C ABI declared in include/ampis_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if a
+kernel entry point is called without a CUDA device the call raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+LAYOUT_SPAN, LAYOUT_FULL = 0, 1
+MODE_IOU, MODE_SAT = 0, 1
+ST_BAD_TOTAL = 1
+
+_p = C.c_void_p
+_i32, _i64, _u32, _u64, _f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+
+# name -> (restype, argtypes); must list every symbol of include/ampis_b200.h
+SIGNATURES = {
+    'ampis_version': (C.c_int, []),
+    'ampis_last_error': (C.c_char_p, []),
+    'ampis_sm_count': (C.c_int, []),
+    'ampis_rle_string_decode': (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
+    'ampis_rle_string_encode': (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p]),
+    'ampis_rle_measure': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'ampis_scan_tmp_bytes': (C.c_size_t, [_i64]),
+    'ampis_exclusive_scan_i64': (C.c_int, [_p, _p, _i64, _p, C.c_size_t, _p]),
+    'ampis_rle_decode_packed': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
+    'ampis_unpack_bool_nrc': (C.c_int, [_p, _p, _p, _p, _i32, _u32, _u32, _p, _p]),
+    'ampis_bool_area_bbox': (C.c_int, [_p, _i32, _u32, _u32, _p, _p, _p]),
+    'ampis_pack_bool_nrc': (C.c_int, [_p, _i32, _u32, _u32, _p, _p, _p]),
+    'ampis_intersect_rows': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p,
+                                       _p, _p]),
+    'ampis_iou_matrix_f64': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p]),
+    'ampis_match_counts': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p]),
+    'ampis_satellite_counts': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _p, _p, _i32, _p]),
+    'ampis_hist_u32': (C.c_int, [_p, _i64, _u32, _u32, _p, _i32, _p]),
+    'ampis_poly_to_rle': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    'ampis_synth_batch': (_i64, [_u64, _i32, _u32, _u32, _i32, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64,
+                                 _f64, _f64, _i32, _p, _i64, _p, _p]),
+}
+
+_lib = None
+
+
+class AmpisNativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building if necessary) libampis_b200.so."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()
+        l = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)     # AttributeError if the .so is stale / incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().ampis_last_error().decode('utf-8', 'replace')
+        raise AmpisNativeError('%s failed (%d): %s' % (what or 'libampis_b200 call', rc, msg))
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero code."""
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,142 @@
+"""Batch (many images per launch) evaluation on one GPU -- the form in which the hot path is
+benchmarked and sharded across GPUs.  Not part of the reference API: AMPIS evaluates one image
+per Python call (Colab cell 44); this module evaluates a whole shard of images with a handful
+of kernel launches and returns device tensors.
+
+Mask table layout of a batch: image by image, ``[rows of image g][columns of image g]`` where
+rows are ground-truth masks (or satellites) and columns are predictions (or particles).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import engine
+
+COCO_THRESHOLDS = np.arange(0.5, 1.0, 0.05)     # IoU 0.50:0.05:0.95
+
+#: synthetic workloads named after BASELINE.json's configs (DESIGN.md "Synthetic data")
+CONFIGS = {
+    # C1: one 1024x768 powder image, ~300 GT x ~300 predictions
+    'c1_powder_example': dict(h=768, w=1024, n_rows=300, n_cols=300, kind=0, median_diam=38.0, sigma_ln=0.45,
+                              max_aspect=1.3, sec_median_diam=0.0, mode=engine.MODE_IOU),
+    # C2 / C5: 1024x1024, 500 GT x 500 predictions per image
+    'c2_powder_batch': dict(h=1024, w=1024, n_rows=500, n_cols=500, kind=0, median_diam=34.0, sigma_ln=0.45,
+                            max_aspect=1.3, sec_median_diam=0.0, mode=engine.MODE_IOU),
+    # C3: 2048x2048, 200 satellites (rows) x 2000 particles (columns)
+    'c3_satellites': dict(h=2048, w=2048, n_rows=200, n_cols=2000, kind=1, median_diam=34.0, sigma_ln=0.45,
+                          max_aspect=1.3, sec_median_diam=17.0, mode=engine.MODE_SAT),
+    # C4: 2048x2048 spheroidite, 5000 x 5000 small elongated instances
+    'c4_spheroidite': dict(h=2048, w=2048, n_rows=5000, n_cols=5000, kind=0, median_diam=13.5, sigma_ln=0.6,
+                           max_aspect=3.0, sec_median_diam=0.0, mode=engine.MODE_IOU),
+}
+
+
+class HostCSR(object):
+    """Run counts of a batch on the host: cnt u32[], cnt_off i64[n], cnt_len i32[n]; every image
+    has n_rows + n_cols masks of size (h, w)."""
+
+    def __init__(self, cfg, n_images, cnt, cnt_off, cnt_len):
+        self.cfg, self.n_images = cfg, n_images
+        self.cnt, self.cnt_off, self.cnt_len = cnt, cnt_off, cnt_len
+        self.h, self.w = cfg['h'], cfg['w']
+        self.n_rows, self.n_cols = cfg['n_rows'], cfg['n_cols']
+        self.per_image = self.n_rows + self.n_cols
+        self.n_masks = n_images * self.per_image
+
+    def image_masks(self, g):
+        """(rows, cols) of image g as lists of uint32 count arrays."""
+        out = []
+        for k in range(g * self.per_image, (g + 1) * self.per_image):
+            out.append(self.cnt[self.cnt_off[k]:self.cnt_off[k] + self.cnt_len[k]])
+        return out[:self.n_rows], out[self.n_rows:]
+
+    def total_runs(self):
+        return int(self.cnt_len.sum())
+
+
+def synth(cfg, n_images, seed, jitter_px=2.0, scale_sigma=0.05, drop_frac=0.08, empty_frac=0.01, n_threads=None):
+    """Generate a synthetic batch on the host (csrc/synth.cpp).  In satellite configs the primaries
+    are the particles (columns) and the secondaries the satellites (rows); the generator emits
+    primaries first, so the masks are re-ordered to rows-first here."""
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    kind = cfg['kind']
+    n_gt, n_sec = (cfg['n_rows'], cfg['n_cols']) if kind == 0 else (cfg['n_cols'], cfg['n_rows'])
+    per = n_gt + n_sec
+    n = n_images * per
+    if n_threads is None:
+        n_threads = min(os.cpu_count() or 1, 32)
+    cap = max(n * (int(2.5 * cfg['median_diam']) + 8), 1024)
+    cnt_off = np.zeros(max(n, 1), np.int64)
+    cnt_len = np.zeros(max(n, 1), np.int32)
+    while True:
+        cnt = np.empty(cap, np.uint32)
+        r = N.lib().ampis_synth_batch(int(seed), n_images, cfg['h'], cfg['w'], n_gt, n_sec, kind,
+                                      float(cfg['median_diam']), float(cfg['sigma_ln']), float(cfg['max_aspect']),
+                                      float(cfg['sec_median_diam']), float(jitter_px), float(scale_sigma),
+                                      float(drop_frac), float(empty_frac), int(n_threads),
+                                      cnt.ctypes.data_as(C.c_void_p), cap, cnt_off.ctypes.data_as(C.c_void_p),
+                                      cnt_len.ctypes.data_as(C.c_void_p))
+        if r >= 0:
+            cnt = cnt[:r]
+            break
+        cap = -r
+    cnt_off, cnt_len = cnt_off[:n], cnt_len[:n]
+    if kind == 1:   # rows (satellites) first
+        idx = np.arange(n).reshape(n_images, per)
+        idx = np.concatenate([idx[:, n_gt:], idx[:, :n_gt]], axis=1).ravel()
+        cnt_off, cnt_len = cnt_off[idx], cnt_len[idx]
+    return HostCSR(cfg, n_images, cnt, cnt_off, cnt_len)
+
+
+class DeviceBatch(object):
+    """A HostCSR uploaded once (the "inputs resident in HBM" state of the benchmark)."""
+
+    def __init__(self, host, device=None, dense=False):
+        device = device or engine.require_cuda()
+        self.host, self.device = host, device
+        self.cnt = torch.from_numpy(host.cnt.view(np.int32)).to(device)
+        self.cnt_off = torch.from_numpy(host.cnt_off).to(device)
+        self.cnt_len = torch.from_numpy(host.cnt_len).to(device)
+        self.h = torch.full((max(host.n_masks, 1),), host.h, dtype=torch.int32, device=device)
+        self.w = torch.full((max(host.n_masks, 1),), host.w, dtype=torch.int32, device=device)
+        self.groups = engine.Groups.interleaved(device, [host.n_rows] * host.n_images,
+                                                [host.n_cols] * host.n_images, dense=dense)
+        self.mode = host.cfg['mode']
+
+
+class StepResult(object):
+    pass
+
+
+def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_out=None,
+              sat_thresh=0.5, check=False):
+    """One pass of the hot path over a device-resident batch: measure -> paint -> fused
+    intersect/arg-max rows -> per-image and total counts.  No host synchronisation when an
+    arena is supplied and check is False.  Returns device tensors."""
+    layout = engine.DEFAULT_LAYOUT if layout is None else layout
+    t = engine.MaskTable(batch.device, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
+                         batch.w, layout)
+    t.measure().paint(arena)
+    rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out)
+    r = StepResult()
+    r.table, r.rows = t, rows
+    if batch.mode == engine.MODE_IOU:
+        r.counts, r.totals = engine.match_counts(rows, batch.groups, thresholds)
+    else:
+        r.counts, r.spp_hist = engine.satellite_counts(t, rows, batch.groups, sat_thresh)
+    if check:
+        t.check()
+    return r
+
+
+def arena_chunks_needed(batch, layout):
+    """Number of uint4 chunks the packed-mask arena needs for a DeviceBatch: one measurement
+    pass on the GPU and a read-back (used to size the workspace before the timed region)."""
+    t = engine.MaskTable(batch.device, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
+                         batch.w, layout)
+    t.measure()
+    return int(t.bits_off[t.n].item())

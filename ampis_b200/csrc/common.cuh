@@ -1,0 +1,69 @@
+// Shared helpers for the sm_100a kernels of libampis_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ampis_b200.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+#define AMPIS_CHUNK_BITS 128u   // one uint4 = 128 pixels of the column-major bit vector
+
+void ampis_set_error(const char *fmt, ...);
+
+#define AMPIS_CHECK_LAUNCH(name)                                              \
+    do {                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) {                                             \
+            ampis_set_error("%s: %s", name, cudaGetErrorString(e__));         \
+            return AMPIS_ECUDA;                                               \
+        }                                                                     \
+    } while (0)
+
+#define AMPIS_REQUIRE(cond, msg)                                              \
+    do {                                                                      \
+        if (!(cond)) { ampis_set_error("%s: %s", __func__, msg); return AMPIS_EINVAL; } \
+    } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ u32 warp_sum(u32 v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ u32 warp_min(u32 v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+__device__ __forceinline__ u32 warp_max(u32 v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// streaming 128-bit store / load (data is written once and read by a later kernel)
+__device__ __forceinline__ void st_v4_stream(uint4 *p, uint4 v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_v4_nc(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 popc_and(uint4 a, uint4 b)
+{
+    return __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+}

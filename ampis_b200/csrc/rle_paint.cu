@@ -1,0 +1,229 @@
+// RLE -> bit-packed masks ("paint"), and conversions between packed masks and
+// bool[n][h][w] arrays.
+//
+// Layout: a mask is the h*w-bit vector of its pixels in COCO's column-major order
+// (bit k = pixel x*h+y), cut into 128-bit chunks (uint4).  Only the chunk region
+// [reg_lo,reg_hi) of a mask is stored (SPAN layout: first..last 1-pixel; FULL layout:
+// the whole frame).  Because every mask of an image uses the same linear index, the
+// intersection of two masks is AND+popc over the overlap of their regions with no shifts
+// and no transposes; only masks_to_bitmask_array needs the row-major view (unpack below).
+#include "common.cuh"
+
+// bits [lo,hi) of a 32-bit word, 0 <= lo <= hi <= 32
+__device__ __forceinline__ u32 bit_range(u32 lo, u32 hi)
+{
+    const u32 upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    const u32 upto_lo = lo >= 32 ? 0xffffffffu : ((1u << lo) - 1u);
+    return upto_hi & ~upto_lo;
+}
+
+// The 128 pixels [128c, 128c+128) of a mask whose run END positions are C[0..m).
+__device__ __forceinline__ uint4 paint_chunk(const u32 *__restrict__ C, int m, u32 c)
+{
+    const u64 b0 = (u64)c * AMPIS_CHUNK_BITS, b1 = b0 + AMPIS_CHUNK_BITS;
+    // first run r whose end lies beyond b0 -- the run that owns pixel b0
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((u64)__ldg(C + mid) > b0) hi = mid; else lo = mid + 1;
+    }
+    int r = lo;
+    u32 w[4] = {0u, 0u, 0u, 0u};
+    u64 pos = b0;
+    while (r < m && pos < b1) {
+        const u64 e = min((u64)__ldg(C + r), b1);
+        if (r & 1) {
+            const u32 s = (u32)(pos - b0), t = (u32)(e - b0);   // [s,t) within the chunk
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 ws = 32u * k;
+                const u32 a = s > ws ? s - ws : 0u;
+                const u32 b = t > ws ? min(t - ws, 32u) : 0u;
+                if (b > a) w[k] |= bit_range(a, b);
+            }
+        }
+        pos = e;
+        r++;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// One CTA per mask (grid-stride): threads stride over the mask's region so that a warp
+// stores 512 contiguous bytes per instruction.  Chunks outside the span are zeros and cost
+// no search; inside the span each chunk is located by a binary search over the run ends
+// (L1-resident: ~0.5 KB per mask).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+rle_paint_kernel(const u32 *__restrict__ cum, const i64 *__restrict__ cnt_off, const int *__restrict__ cnt_len,
+                 const uint2 *__restrict__ span, const uint2 *__restrict__ reg,
+                 const i64 *__restrict__ bits_off, int n, uint4 *__restrict__ bits, i64 capacity)
+{
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint2 rg = reg[i];
+        const i64 off = bits_off[i];
+        if (off + (i64)(rg.y - rg.x) > capacity) continue;
+        const uint2 sp = span[i];
+        const int m = cnt_len[i];
+        const u32 *C = cum + cnt_off[i];
+        uint4 *out = bits + off - rg.x;
+        for (u32 c = rg.x + threadIdx.x; c < rg.y; c += THREADS) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (c >= sp.x && c < sp.y) v = paint_chunk(C, m, c);
+            st_v4_stream(out + c, v);
+        }
+    }
+}
+
+extern "C" int ampis_rle_decode_packed(const uint32_t *d_cum, const int64_t *d_cnt_off,
+                                       const int32_t *d_cnt_len, const uint32_t *d_span, const uint32_t *d_reg,
+                                       const int64_t *d_bits_off, int32_t n, void *d_bits, int64_t bits_capacity,
+                                       void *stream)
+{
+    AMPIS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_cum && d_cnt_off && d_cnt_len && d_span && d_reg && d_bits_off && d_bits, "null pointer");
+    AMPIS_REQUIRE(((uintptr_t)d_bits & 15u) == 0, "bits arena must be 16-byte aligned");
+    const int grid = n < (1 << 20) ? n : (1 << 20);
+    rle_paint_kernel<256><<<grid, 256, 0, as_stream(stream)>>>(
+        d_cum, d_cnt_off, d_cnt_len, (const uint2 *)d_span, (const uint2 *)d_reg, d_bits_off, n, (uint4 *)d_bits,
+        bits_capacity);
+    AMPIS_CHECK_LAUNCH("rle_paint_kernel");
+    return AMPIS_OK;
+}
+
+// ---- packed -> bool[n][h][w] ------------------------------------------------------------
+// Output tile: 32 columns x 32 rows per warp step. Lane l loads the 32 pixels (x0+l, y0..y0+31)
+// as one funnel-shifted word; the warp transposes through shuffles-free ballot: for each row
+// yy the byte of column x0+l is bit yy of lane l's word, written as a 32-byte row segment.
+__device__ __forceinline__ u32 load_bits32(const u32 *__restrict__ words, const uint2 rg, u64 bit, u64 nbits)
+{
+    // 32 bits starting at linear pixel `bit` (zero outside the stored region / beyond nbits)
+    if (bit >= nbits) return 0u;
+    const u64 wlo = (u64)rg.x * 4, whi = (u64)rg.y * 4;   // region in 32-bit words
+    const u64 wi = bit >> 5;
+    const u32 sh = (u32)(bit & 31);
+    const u32 a = (wi >= wlo && wi < whi) ? words[wi - wlo] : 0u;
+    const u32 b = (wi + 1 >= wlo && wi + 1 < whi) ? words[wi + 1 - wlo] : 0u;
+    u32 v = __funnelshift_r(a, b, sh);
+    const u64 left = nbits - bit;
+    if (left < 32) v &= (1u << left) - 1u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+unpack_bool_nrc_kernel(const uint4 *__restrict__ bits, const i64 *__restrict__ bits_off,
+                       const uint2 *__restrict__ reg, const int *__restrict__ ids, u32 h, u32 w,
+                       uint8_t *__restrict__ out)
+{
+    const int k = blockIdx.z;
+    const int id = ids ? ids[k] : k;
+    const uint2 rg = reg[id];
+    const u32 *words = reinterpret_cast<const u32 *>(bits + bits_off[id]);
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const u32 x = blockIdx.x * 32 + lane;
+    const u32 y0 = (blockIdx.y * 8 + wid) * 32;
+    if (y0 >= h) return;
+    u32 v = 0;
+    if (x < w) v = load_bits32(words, rg, (u64)x * h + y0, (u64)(x + 1) * h);
+    uint8_t *o = out + (u64)k * h * w;
+    const u32 rows = min(32u, h - y0);
+    for (u32 yy = 0; yy < rows; yy++)
+        if (x < w) o[(u64)(y0 + yy) * w + x] = (uint8_t)((v >> yy) & 1u);
+}
+
+extern "C" int ampis_unpack_bool_nrc(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                                     const int32_t *d_mask_ids, int32_t n, uint32_t h, uint32_t w,
+                                     uint8_t *d_out, void *stream)
+{
+    AMPIS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0 || h == 0 || w == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_bits && d_bits_off && d_reg && d_out, "null pointer");
+    AMPIS_REQUIRE(n <= 65535, "at most 65535 masks per call");
+    dim3 grid((w + 31) / 32, (h + 255) / 256, n);
+    AMPIS_REQUIRE(grid.y <= 65535, "image too tall");
+    unpack_bool_nrc_kernel<<<grid, 256, 0, as_stream(stream)>>>((const uint4 *)d_bits, d_bits_off,
+                                                               (const uint2 *)d_reg, d_mask_ids, h, w, d_out);
+    AMPIS_CHECK_LAUNCH("unpack_bool_nrc_kernel");
+    return AMPIS_OK;
+}
+
+// ---- bool[n][h][w] -> packed (FULL layout) -------------------------------------------------
+// Thread per output 32-bit word: gathers 32 pixels of one or two columns.
+__global__ void __launch_bounds__(256)
+pack_bool_nrc_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, uint4 *__restrict__ bits,
+                     const i64 *__restrict__ bits_off)
+{
+    const int k = blockIdx.y;
+    const u64 hw = (u64)h * w;
+    const u64 nwords = ((hw + 127) / 128) * 4;
+    const u64 wi = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    const uint8_t *m = masks + (u64)k * hw;
+    u32 v = 0;
+    u64 p = wi * 32;
+    u32 x = (u32)(p / h), y = (u32)(p - (u64)x * h);
+#pragma unroll 4
+    for (int b = 0; b < 32; b++) {
+        if (p + b < hw && m[(u64)y * w + x]) v |= 1u << b;
+        if (++y == h) { y = 0; x++; }
+    }
+    reinterpret_cast<u32 *>(bits + bits_off[k])[wi] = v;
+}
+
+extern "C" int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w, void *d_bits,
+                                   const int64_t *d_bits_off, void *stream)
+{
+    AMPIS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0 || h == 0 || w == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_masks && d_bits && d_bits_off, "null pointer");
+    AMPIS_REQUIRE(n <= 65535, "at most 65535 masks per call");
+    const u64 nwords = (((u64)h * w + 127) / 128) * 4;
+    dim3 grid((unsigned)((nwords + 255) / 256), n);
+    pack_bool_nrc_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_masks, h, w, (uint4 *)d_bits, d_bits_off);
+    AMPIS_CHECK_LAUNCH("pack_bool_nrc_kernel");
+    return AMPIS_OK;
+}
+
+// ---- bool[n][h][w] -> area + tight bbox ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bool_area_bbox_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, u64 *__restrict__ area,
+                      int *__restrict__ bbox)
+{
+    const int k = blockIdx.x;
+    const u64 hw = (u64)h * w;
+    const uint8_t *m = masks + (u64)k * hw;
+    u32 a = 0, x0 = 0xffffffffu, y0 = 0xffffffffu, x1 = 0, y1 = 0;
+    for (u64 p = threadIdx.x; p < hw; p += blockDim.x) {
+        if (m[p]) {
+            const u32 y = (u32)(p / w), x = (u32)(p - (u64)y * w);
+            a++;
+            x0 = min(x0, x); x1 = max(x1, x + 1);
+            y0 = min(y0, y); y1 = max(y1, y + 1);
+        }
+    }
+    __shared__ u32 sa[8], sx0[8], sy0[8], sx1[8], sy1[8];
+    a = warp_sum(a); x0 = warp_min(x0); y0 = warp_min(y0); x1 = warp_max(x1); y1 = warp_max(y1);
+    const u32 wid = threadIdx.x >> 5;
+    if (lane_id() == 0) { sa[wid] = a; sx0[wid] = x0; sy0[wid] = y0; sx1[wid] = x1; sy1[wid] = y1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 A = 0;
+        for (int q = 0; q < 8; q++) {
+            A += sa[q]; x0 = min(x0, sx0[q]); y0 = min(y0, sy0[q]); x1 = max(x1, sx1[q]); y1 = max(y1, sy1[q]);
+        }
+        area[k] = A;
+        int4 bb = A ? make_int4((int)x0, (int)y0, (int)x1 - 1, (int)y1 - 1) : make_int4(0, 0, -1, -1);
+        reinterpret_cast<int4 *>(bbox)[k] = bb;
+    }
+}
+
+extern "C" int ampis_bool_area_bbox(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w,
+                                    uint64_t *d_area, int32_t *d_bbox, void *stream)
+{
+    AMPIS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_masks && d_area && d_bbox, "null pointer");
+    bool_area_bbox_kernel<<<n, 256, 0, as_stream(stream)>>>(d_masks, h, w, (u64 *)d_area, d_bbox);
+    AMPIS_CHECK_LAUNCH("bool_area_bbox_kernel");
+    return AMPIS_OK;
+}

@@ -1,0 +1,341 @@
+"""Device-side engine: marshals AMPIS mask containers into the GPU mask table and drives
+the kernels of libampis_b200.so.  PyTorch is used only for device memory, streams and
+(in ampis_b200.distributed) the NCCL plumbing; every computation on masks is one of the
+hand-written sm_100a kernels.  There is no CPU fallback anywhere in this module.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+LAYOUT_SPAN, LAYOUT_FULL = N.LAYOUT_SPAN, N.LAYOUT_FULL
+MODE_IOU, MODE_SAT = N.MODE_IOU, N.MODE_SAT
+DEFAULT_LAYOUT = LAYOUT_SPAN
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('ampis_b200 runs its mask arithmetic on a CUDA device (B200, sm_100a); '
+                           'no device is visible and there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _dev(a, dtype, device):
+    """numpy array -> device tensor of the given torch dtype (async copy from pinned memory)."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.numel() == 0:
+        return torch.empty(0, dtype=dtype, device=device)
+    if torch.device(device).type != 'cuda':
+        return t.clone()
+    return t.pin_memory().to(device, non_blocking=True)
+
+
+class MaskTable(object):
+    """Structure-of-arrays table of n masks on the GPU (see include/ampis_b200.h)."""
+
+    def __init__(self, device, n, cnt, cnt_off, cnt_len, h, w, layout):
+        self.device, self.n, self.layout = device, int(n), layout
+        self.cnt, self.cnt_off, self.cnt_len, self.h, self.w = cnt, cnt_off, cnt_len, h, w
+        i32, i64 = torch.int32, torch.int64
+        n1 = max(self.n, 1)
+        self.cum = torch.empty(max(cnt.numel(), 1), dtype=i32, device=device)
+        self.area = torch.empty(n1, dtype=i32, device=device)          # uint32 payload
+        self.bbox = torch.empty(4 * n1, dtype=i32, device=device)
+        self.span = torch.empty(2 * n1, dtype=i32, device=device)      # uint32 payload
+        self.reg = torch.empty(2 * n1, dtype=i32, device=device)       # uint32 payload
+        self.reg_chunks = torch.empty(n1, dtype=i64, device=device)
+        self.status = torch.zeros(n1, dtype=i32, device=device)
+        self.bits_off = torch.zeros(n1 + 1, dtype=i64, device=device)
+        self.bits = None
+        self.bits_capacity = 0
+
+    # -- construction steps ---------------------------------------------------------------
+    def measure(self):
+        N.call('ampis_rle_measure', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h), _p(self.w),
+               self.n, self.layout, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
+               _p(self.reg_chunks), _p(self.status), _stream())
+        tmp_bytes = N.lib().ampis_scan_tmp_bytes(self.n)
+        tmp = torch.empty(max(tmp_bytes // 8, 1), dtype=torch.int64, device=self.device)
+        N.call('ampis_exclusive_scan_i64', _p(self.reg_chunks), _p(self.bits_off), self.n, _p(tmp), tmp_bytes,
+               _stream())
+        return self
+
+    def paint(self, arena=None):
+        """RLE -> packed bits.  Without an arena the needed size is read back (one sync)."""
+        if arena is None:
+            total = int(self.bits_off[self.n].item()) if self.n else 0
+            arena = torch.empty(4 * max(total, 1), dtype=torch.int32, device=self.device)
+        self.bits = arena
+        self.bits_capacity = arena.numel() // 4
+        N.call('ampis_rle_decode_packed', _p(self.cum), _p(self.cnt_off), _p(self.cnt_len), _p(self.span),
+               _p(self.reg), _p(self.bits_off), self.n, _p(self.bits), self.bits_capacity, _stream())
+        return self
+
+    def check(self):
+        """Raise on malformed RLE (sum(counts) != h*w), where pycocotools would hang or mis-decode."""
+        if self.n and bool((self.status[:self.n] != 0).any().item()):
+            bad = torch.nonzero(self.status[:self.n]).flatten()[:8].tolist()
+            raise ValueError('malformed RLE: run counts do not sum to h*w for masks %s' % bad)
+        if self.bits is not None and self.n and int(self.bits_off[self.n].item()) > self.bits_capacity:
+            raise N.AmpisNativeError('packed-mask arena too small')
+        return self
+
+    # -- results ----------------------------------------------------------------------------
+    def areas_np(self):
+        return self.area[:self.n].cpu().numpy().view(np.uint32).copy()
+
+    def bbox_np(self):
+        return self.bbox[:4 * self.n].cpu().numpy().reshape(-1, 4).copy()
+
+
+def table_from_counts(cnt, cnt_off, cnt_len, h, w, layout=None, arena=None, check=True):
+    """Device-resident CSR run counts -> measured + painted MaskTable."""
+    layout = DEFAULT_LAYOUT if layout is None else layout
+    device = cnt.device
+    t = MaskTable(device, cnt_len.numel(), cnt, cnt_off, cnt_len, h, w, layout)
+    t.measure().paint(arena)
+    if check:
+        t.check()
+    return t
+
+
+def _rle_fields(masks):
+    """list of COCO RLE dicts -> (list of bytes, h array, w array); mirrors the input
+    handling of pycocotools' _frString (str counts are accepted and encoded)."""
+    strings, hs, ws = [], [], []
+    for m in masks:
+        c = m['counts']
+        if type(c) == str:
+            c = c.encode('ascii')
+        elif not isinstance(c, (bytes, bytearray)):
+            raise TypeError('RLE counts must be compressed bytes/str, got %s' % type(c))
+        strings.append(bytes(c))
+        hs.append(m['size'][0])
+        ws.append(m['size'][1])
+    return strings, hs, ws
+
+
+def table_from_rle(masks, layout=None, paint=True):
+    """Host list of compressed RLE dicts -> MaskTable (string decode happens on the GPU)."""
+    layout = DEFAULT_LAYOUT if layout is None else layout
+    device = require_cuda()
+    strings, hs, ws = _rle_fields(masks)
+    n = len(strings)
+    lens = np.fromiter((len(s) for s in strings), np.int64, n)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    blob = np.frombuffer(b''.join(strings), np.uint8).copy() if n else np.zeros(0, np.uint8)
+    d_chars = _dev(blob, torch.uint8, device)
+    d_off = _dev(off, torch.int64, device)
+    d_h = _dev(np.asarray(hs, np.int64), torch.int32, device)
+    d_w = _dev(np.asarray(ws, np.int64), torch.int32, device)
+    cnt = torch.empty(max(int(off[-1]), 1), dtype=torch.int32, device=device)
+    cnt_len = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+    N.call('ampis_rle_string_decode', _p(d_chars), _p(d_off), n, _p(cnt), _p(d_off), _p(cnt_len), _stream())
+    t = MaskTable(device, n, cnt, d_off, cnt_len, d_h, d_w, layout)
+    t.measure()
+    if paint:
+        t.paint()
+    t.check()
+    return t
+
+
+class Groups(object):
+    """Row/column bookkeeping of a batch: group g (an image) owns rows (ground truth or
+    satellites) and columns (predictions or particles); all are mask ids of one MaskTable."""
+
+    def __init__(self, device, row_mask, row_grp, grp_row_begin, grp_row_count, grp_col_begin, grp_col_count,
+                 dense=False):
+        self.device = device
+        self.n_rows = int(len(row_mask))
+        self.n_groups = int(len(grp_row_begin))
+        self.max_cols = int(max(grp_col_count)) if self.n_groups else 0
+        self.h_row_count = np.asarray(grp_row_count, np.int64)
+        self.h_col_count = np.asarray(grp_col_count, np.int64)
+        self.h_row_begin = np.asarray(grp_row_begin, np.int64)
+        i32 = torch.int32
+        self.row_mask = _dev(np.asarray(row_mask, np.int32), i32, device)
+        self.row_grp = _dev(np.asarray(row_grp, np.int32), i32, device)
+        self.grp_row_begin = _dev(np.asarray(grp_row_begin, np.int32), i32, device)
+        self.grp_row_count = _dev(np.asarray(grp_row_count, np.int32), i32, device)
+        self.grp_col_begin = _dev(np.asarray(grp_col_begin, np.int32), i32, device)
+        self.grp_col_count = _dev(np.asarray(grp_col_count, np.int32), i32, device)
+        self.imat_off = None
+        self.h_imat_off = None
+        self.imat_size = 0
+        if dense:
+            sizes = self.h_row_count * self.h_col_count
+            off = np.zeros(self.n_groups + 1, np.int64)
+            np.cumsum(sizes, out=off[1:])
+            self.h_imat_off = off
+            self.imat_size = int(off[-1])
+            self.imat_off = _dev(off[:-1], torch.int64, device)
+
+    @staticmethod
+    def interleaved(device, n_rows_per_group, n_cols_per_group, dense=False):
+        """Mask table laid out image by image as [rows of g][cols of g]."""
+        G = np.asarray(n_rows_per_group, np.int64)
+        P = np.asarray(n_cols_per_group, np.int64)
+        ng = len(G)
+        start = np.zeros(ng + 1, np.int64)
+        np.cumsum(G + P, out=start[1:])
+        row_begin = np.zeros(ng + 1, np.int64)
+        np.cumsum(G, out=row_begin[1:])
+        row_grp = np.repeat(np.arange(ng, dtype=np.int64), G)
+        row_mask = np.arange(int(row_begin[-1]), dtype=np.int64) - row_begin[row_grp] + start[row_grp]
+        return Groups(device, row_mask, row_grp, row_begin[:-1], G, start[:-1] + G, P, dense=dense)
+
+
+class RowResult(object):
+    def __init__(self, best_col, best_inter, best_score, imat):
+        self.best_col, self.best_inter, self.best_score, self.imat = best_col, best_inter, best_score, imat
+
+
+def intersect_rows(table, groups, mode, out=None):
+    """Run the fused row kernel.  Returns device tensors (no sync)."""
+    dev = table.device
+    nr = max(groups.n_rows, 1)
+    if out is None:
+        imat = torch.empty(max(groups.imat_size, 1), dtype=torch.int32, device=dev) \
+            if groups.imat_off is not None else None
+        out = RowResult(torch.empty(nr, dtype=torch.int32, device=dev),
+                        torch.empty(nr, dtype=torch.int32, device=dev),
+                        torch.empty(nr, dtype=torch.float64, device=dev), imat)
+    N.call('ampis_intersect_rows', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
+           _p(table.bbox), _p(table.area), _p(groups.row_mask), _p(groups.row_grp), groups.n_rows,
+           _p(groups.grp_row_begin), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off),
+           mode, _p(out.imat), _p(out.best_col), _p(out.best_inter), _p(out.best_score), _stream())
+    return out
+
+
+def match_counts(rows, groups, thresholds, totals=None):
+    """TP/FP/FN per group and threshold -> int32[n_groups, n_thresh, 3] (device), totals += ."""
+    dev = groups.device
+    th = _dev(np.asarray(thresholds, np.float64), torch.float64, dev)
+    nt = th.numel()
+    counts = torch.empty(max(groups.n_groups * nt * 3, 1), dtype=torch.int32, device=dev)
+    if totals is None:
+        totals = torch.zeros(max(nt * 3, 1), dtype=torch.int64, device=dev)
+    N.call('ampis_match_counts', _p(rows.best_col), _p(rows.best_score), _p(groups.grp_row_begin),
+           _p(groups.grp_row_count), _p(groups.grp_col_count), groups.n_groups, groups.max_cols, _p(th), nt,
+           _p(counts), _p(totals), _stream())
+    return counts[:groups.n_groups * nt * 3].view(groups.n_groups, nt, 3), totals[:nt * 3].view(nt, 3)
+
+
+def satellite_counts(table, rows, groups, thresh, n_bins=64, hist=None):
+    dev = groups.device
+    counts = torch.empty(max(groups.n_groups * 4, 1), dtype=torch.int32, device=dev)
+    if hist is None:
+        hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+    N.call('ampis_satellite_counts', _p(rows.best_col), _p(rows.best_inter), _p(table.area), _p(groups.row_mask),
+           _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_count), groups.n_groups,
+           groups.max_cols, float(thresh), _p(counts), _p(hist), n_bins, _stream())
+    return counts[:groups.n_groups * 4].view(groups.n_groups, 4), hist
+
+
+def iou_matrix(table, rows, groups, g=0):
+    """float64[G, P] IoU matrix of group g from the dense intersections."""
+    G, P = int(groups.h_row_count[g]), int(groups.h_col_count[g])
+    out = torch.empty(max(G * P, 1), dtype=torch.float64, device=table.device)
+    if G * P:
+        off = int(groups.h_imat_off[g])
+        imat = rows.imat[off:off + G * P]
+        r0 = int(groups.h_row_begin[g])
+        row_ids = groups.row_mask[r0:r0 + G].long()
+        c0 = int(groups.grp_col_begin[g].item())
+        ar = table.area[row_ids].contiguous()
+        ac = table.area[c0:c0 + P].contiguous()
+        N.call('ampis_iou_matrix_f64', _p(imat), _p(ar), _p(ac), G, P, _p(out), _stream())
+    return out[:G * P].view(G, P)
+
+
+def hist_u32(values, lo, bin_width, n_bins, hist=None):
+    if hist is None:
+        hist = torch.zeros(n_bins, dtype=torch.int64, device=values.device)
+    N.call('ampis_hist_u32', _p(values), values.numel(), int(lo), int(bin_width), _p(hist), n_bins, _stream())
+    return hist
+
+
+def unpack_bool(table, ids, h, w):
+    """Packed masks -> bool[n, h, w] device tensor (structures.masks_to_bitmask_array)."""
+    dev = table.device
+    n = len(ids)
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    d_ids = _dev(np.asarray(ids, np.int32), torch.int32, dev)
+    step = 32768
+    for s in range(0, n, step):
+        k = min(step, n - s)
+        N.call('ampis_unpack_bool_nrc', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(d_ids[s:]), k, h, w,
+               _p(out[s:]), _stream())
+    return out.view(torch.bool)
+
+
+def bool_area_bbox(masks_np):
+    """bool[n, h, w] host array -> (uint64 areas, int32 tight boxes x0,y0,x1,y1) on the host."""
+    dev = require_cuda()
+    m = np.ascontiguousarray(masks_np).view(np.uint8)
+    n, h, w = m.shape
+    d = _dev(m.reshape(-1), torch.uint8, dev)
+    area = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    bbox = torch.empty(4 * max(n, 1), dtype=torch.int32, device=dev)
+    N.call('ampis_bool_area_bbox', _p(d), n, h, w, _p(area), _p(bbox), _stream())
+    return area[:n].cpu().numpy().view(np.uint64), bbox[:4 * n].cpu().numpy().reshape(-1, 4)
+
+
+def polygons_to_counts(polys, h, w):
+    """list of flat [x0,y0,x1,y1,...] polygons -> (device cnt, cnt_off, cnt_len) via rleFrPoly on the GPU."""
+    dev = require_cuda()
+    n = len(polys)
+    lens = np.fromiter((len(p) for p in polys), np.int64, n)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    xy = np.concatenate([np.asarray(p, np.float64).ravel() for p in polys]) if n else np.zeros(0, np.float64)
+    cap = 2 * (int(w) + 2) + 8                      # typical: two crossings per column
+    d_xy = _dev(xy, torch.float64, dev)
+    d_off = _dev(off, torch.int64, dev)
+    d_h = torch.full((max(n, 1),), int(h), dtype=torch.int32, device=dev)
+    d_w = torch.full((max(n, 1),), int(w), dtype=torch.int32, device=dev)
+    while True:
+        coff = np.arange(n + 1, dtype=np.int64) * cap
+        d_coff = _dev(coff, torch.int64, dev)
+        cnt = torch.empty(max(n * cap, 1), dtype=torch.int32, device=dev)
+        clen = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        N.call('ampis_poly_to_rle', _p(d_xy), _p(d_off), _p(d_h), _p(d_w), n, _p(cnt), _p(d_coff), _p(clen),
+               _stream())
+        lens_out = clen[:n].cpu().numpy()
+        if n and lens_out.min() < 0:
+            raise ValueError('polygon %d is outside the GPU rasteriser limits (1..4096 vertices, '
+                             '<=8192 boundary crossings)' % int(np.argmin(lens_out)))
+        if n == 0 or lens_out.max() <= cap:
+            return cnt, d_coff, clen, d_h, d_w
+        cap = int(lens_out.max())
+
+
+def counts_to_strings(cnt, cnt_off, cnt_len, n):
+    """Device run counts -> list of compressed RLE byte strings (rleToString on the GPU)."""
+    if n == 0:
+        return []
+    dev = cnt.device
+    lens = cnt_len[:n].cpu().numpy().astype(np.int64)
+    choff = np.zeros(n + 1, np.int64)
+    np.cumsum(7 * lens, out=choff[1:])
+    d_choff = _dev(choff, torch.int64, dev)
+    chars = torch.empty(max(int(choff[-1]), 1), dtype=torch.uint8, device=dev)
+    chlen = torch.empty(n, dtype=torch.int32, device=dev)
+    N.call('ampis_rle_string_encode', _p(cnt), _p(cnt_off), _p(cnt_len), n, _p(chars), _p(d_choff), _p(chlen),
+           _stream())
+    buf = chars.cpu().numpy().tobytes()
+    ln = chlen.cpu().numpy()
+    return [buf[choff[i]:choff[i] + ln[i]] for i in range(n)]

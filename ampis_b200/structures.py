@@ -1,0 +1,345 @@
+"""Mask containers and converters -- drop-in for ``ampis.structures`` (reference
+ampis/structures.py) with the mask arithmetic running on the GPU.
+
+Same names, argument order, defaults, return dtypes and exceptions as the reference; the
+dispatch on ``type(x) ==`` (not isinstance) is deliberate, it is what the reference does
+(structures.py:57-81, 556-583, 663-690, 736-774).
+"""
+import colorsys
+import copy
+from pathlib import Path
+from typing import List, Union
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import engine
+from .containers import BitMasks, Boxes, Instances, PolygonMasks
+
+
+def random_colors(n, seed, bright=True):
+    """Seeded HSV colours (reference ampis/visualize.py:19-56; only used to fill the ``colors``
+    field the InstanceSet readers attach)."""
+    rs = np.random.RandomState(seed=seed)
+    brightness = 1.0 if bright else 0.7
+    hsv = [(i / n, 1, brightness) for i in range(n)]
+    colors = list(map(lambda c: colorsys.hsv_to_rgb(*c), hsv))
+    rs.shuffle(colors)
+    return np.asarray(colors)
+
+
+class RLEMasks(object):
+    """List of COCO RLE dicts with fancy indexing (reference structures.py:24-95)."""
+
+    def __init__(self, rle):
+        super().__init__()
+        self.rle = rle
+
+    def __getitem__(self, item: Union[int, slice, List[int], List[bool], torch.BoolTensor, np.ndarray]):
+        idx_list = False
+        if type(item) == int:
+            return RLEMasks(self.rle[item])          # wraps a dict, like the reference (quirk B.13)
+        elif type(item) == torch.BoolTensor or (type(item) == torch.Tensor and item.dtype == torch.bool):
+            return RLEMasks([mask for mask, bool_ in zip(self.rle, item) if bool_])
+        elif type(item) == np.ndarray:
+            if item.dtype == np.bool_:
+                assert item.shape[0] == len(self)
+                return RLEMasks([mask for mask, bool_ in zip(self.rle, item) if bool_])
+            else:
+                idx_list = True
+        elif type(item) == slice:
+            return RLEMasks(self.rle[item])
+        elif type(item) == list:
+            if type(item[0]) == bool:
+                assert len(item) == len(self)
+                return RLEMasks([mask for mask, bool_ in zip(self.rle, item) if bool_])
+            else:
+                idx_list = True
+        else:
+            idx_list = True
+        if idx_list:
+            return RLEMasks([self.rle[idx] for idx in item])
+
+    def __len__(self):
+        return len(self.rle)
+
+
+class InstanceSet(object):
+    """Instances of one image (reference structures.py:98-533)."""
+
+    def __init__(self, mask_format=None, bbox_mode=None, filepath=None, annotations=None, instances=None, img=None,
+                 dataset_class=None, pred_or_gt=None, HFW=None, HFW_units=None, randomstate=None):
+        super().__init__()
+        self.mask_format = mask_format
+        self.bbox_mode = bbox_mode
+        self.img = img
+        self.filepath = filepath
+        self.dataset_class = dataset_class
+        self.pred_or_gt = pred_or_gt
+        self.HFW = HFW
+        self.HFW_units = HFW_units
+        self.rprops = None
+        self.instances = instances
+        self.annotations = annotations
+        if randomstate is None:
+            randomstate = np.random.randint(2 ** 32 - 1)
+        self.randomstate = randomstate
+        self.colors = None
+
+    def read_from_ddict(self, ddict, inplace=True):
+        """Ground-truth data dict -> InstanceSet (reference structures.py:203-309)."""
+        self.pred_or_gt = 'gt'
+        self.filepath = Path(ddict['file_name'])
+        self.mask_format = ddict['mask_format']
+        image_size = (ddict['height'], ddict['width'])
+        class_idx = np.asarray([anno['category_id'] for anno in ddict['annotations']], np.int64)
+        bbox = np.stack([anno['bbox'] for anno in ddict['annotations']])
+        segs = [anno['segmentation'] for anno in ddict['annotations']]
+        segtype = type(segs[0])
+        if segtype == dict:
+            masks = RLEMasks(segs)
+        elif segtype == np.ndarray:
+            if segs[0].dtype == np.bool_:
+                masks = BitMasks(np.stack(segs))
+        else:
+            masks = PolygonMasks(segs)
+        instances = Instances(image_size, **{'masks': masks, 'boxes': bbox, 'class_idx': class_idx})
+        self.instances = instances
+        self.instances.colors = random_colors(len(instances), self.randomstate)
+        self.dataset_class = ddict.get('dataset_class', None)
+        HFW = ddict.get('HFW', None)
+        HFW_units = None
+        if HFW is not None:
+            try:
+                HFW = float(HFW)
+            except ValueError:
+                split = HFW.split(' ')
+                if len(split) == 2:
+                    HFW = float(split[0])
+                    HFW_units = split[1]
+        self.HFW = HFW
+        self.HFW_units = HFW_units
+        if not inplace:
+            return self
+        return
+
+    def read_from_model_out(self, outs, inplace=True):
+        """Formatted model output -> InstanceSet (reference structures.py:312-371)."""
+        self.pred_or_gt = 'pred'
+        self.mask_format = 'bitmask'
+        self.filepath = outs['file_name']
+        split = outs['dataset'].split('_')
+        if len(split) > 1:
+            self.dataset_class = outs['dataset'].split('_')[-1]
+        else:
+            self.dataset_class = outs['dataset']
+        instances_pred = outs['pred']['instances']
+        instances = Instances(instances_pred.image_size,
+                              **{'masks': RLEMasks(instances_pred.pred_masks),
+                                 'boxes': instances_pred.pred_boxes,
+                                 'class_idx': instances_pred.pred_classes,
+                                 'scores': instances_pred.scores})
+        self.instances = instances
+        self.instances.colors = random_colors(len(self.instances), self.randomstate)
+        if not inplace:
+            return self
+        return
+
+    def filter_mask_size(self, min_thresh=100, max_thresh=100000, to_rle=False):
+        """Instances with min_thresh < area < max_thresh, strict (reference structures.py:374-442)."""
+        masks = self.instances.masks
+        if to_rle:
+            masks = RLEMasks(masks_to_rle(masks, self.instances.image_size))
+        masktype = type(masks)
+        areas = mask_areas(masks)
+        if min_thresh is None:
+            inlier_min = np.ones(areas.shape, np.bool_)
+        else:
+            inlier_min = areas > min_thresh
+        if max_thresh is None:
+            inlier_max = np.ones(areas.shape, np.bool_)
+        else:
+            inlier_max = areas < max_thresh
+        inliers_bool = np.logical_and(inlier_min, inlier_max)
+        if masktype == PolygonMasks:
+            polygons = [p for p, b in zip(masks.polygons, inliers_bool) if b]
+            masks = PolygonMasks(polygons)
+        else:
+            masks = masks[inliers_bool]
+        new_instance_fields = {}
+        for key, value in self.instances._fields.items():
+            if key == 'masks':
+                new_instance_fields[key] = masks
+            else:
+                new_instance_fields[key] = value[inliers_bool]
+        return Instances(self.instances.image_size, **new_instance_fields)
+
+    def remove_edge_instances(self, k=1):
+        """Drop instances that touch the k-pixel image border, in place (reference
+        structures.py:445-469).  The reference intersects every mask with an RLE border frame
+        (``border[k:-k, k:-k] = 0``); a mask meets that frame iff its tight bounding box does,
+        so the GPU measurement pass answers it without any merge.  ``k=0`` keeps the reference
+        quirk: the slice is empty, the frame is the whole image and every non-empty mask goes."""
+        r, c = self.instances.image_size
+        rle = masks_to_rle(self.instances.masks, (r, c))
+        t = engine.table_from_rle(rle, paint=False)
+        bb, area = t.bbox_np(), t.areas_np()
+        # ``border[k:-k, k:-k] = 0`` zeroes nothing when the slice is empty
+        if k <= 0 or r - 2 * k <= 0 or c - 2 * k <= 0:
+            touches = area > 0
+        else:
+            # frame = complement of the zeroed interior [k, r-k) x [k, c-k)
+            touches = (area > 0) & ((bb[:, 0] < k) | (bb[:, 2] >= c - k) | (bb[:, 1] < k) | (bb[:, 3] >= r - k))
+        inlier_instances = ~touches
+        self.instances = self.instances[inlier_instances]
+
+    #: keys compute_rprops evaluates on the GPU; the remaining skimage keys are outside the
+    #: accelerated path
+    RPROPS_GPU_KEYS = ('area', 'equivalent_diameter', 'bbox')
+
+    def compute_rprops(self, keys=None, return_df=False):
+        """Region properties per mask (reference structures.py:474-514).  ``area``,
+        ``equivalent_diameter`` (= sqrt(4*area/pi), skimage 0.18.3) and ``bbox`` come from the GPU
+        measurement pass over the run counts; cells are 1-element arrays as regionprops_table
+        returns them.  Default keys are the in-scope subset of the reference default."""
+        if keys is None:
+            keys = ['area', 'equivalent_diameter']
+        unsupported = [k for k in keys if k not in self.RPROPS_GPU_KEYS]
+        if unsupported:
+            raise NotImplementedError('region properties %s are not part of the GPU path (supported: %s)'
+                                      % (unsupported, list(self.RPROPS_GPU_KEYS)))
+        rle = masks_to_rle(self.instances.masks, self.instances.image_size)
+        t = engine.table_from_rle(rle, paint=False)
+        area = t.areas_np().astype(np.int64)
+        bb = t.bbox_np()
+        rows = []
+        for i in range(len(rle)):
+            row = {}
+            for k in keys:
+                if k == 'area':
+                    row[k] = np.array([area[i]]) if area[i] else np.array([], np.int64)
+                elif k == 'equivalent_diameter':
+                    row[k] = np.sqrt(4 * np.array([area[i]]) / np.pi) if area[i] else np.array([])
+                else:
+                    b = [bb[i, 1], bb[i, 0], bb[i, 3] + 1, bb[i, 2] + 1]
+                    for j in range(4):
+                        row['bbox-%d' % j] = np.array([b[j]]) if area[i] else np.array([], np.int64)
+            rows.append(row)
+        df = pd.DataFrame(rows)
+        df['class_idx'] = self.instances.class_idx
+        self.rprops = df
+        if return_df:
+            return self.rprops
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+
+def mask_areas(masks):
+    """Area in pixels of each mask (reference structures.py:536-583): ndarray -> uint64 sums,
+    PolygonMasks -> shoelace float64, RLE -> uint32 pixel counts (GPU), containers recurse."""
+    masktype = type(masks)
+    if masktype == np.ndarray:
+        if masks.dtype == np.bool_ and masks.ndim == 3 and masks.size:
+            return engine.bool_area_bbox(masks)[0].astype(np.uint)
+        return masks.sum(axis=(1, 2), dtype=np.uint)
+    elif masktype == PolygonMasks:
+        return np.asarray([_shoelace_area(coords[0][::2], coords[0][1::2]) for coords in masks.polygons])
+    elif masktype == list and type(masks[0]) == dict:
+        return engine.table_from_rle(masks, paint=False).areas_np()
+    elif masktype == RLEMasks:
+        return engine.table_from_rle(masks.rle, paint=False).areas_np()
+    elif masktype == Instances:
+        return mask_areas(masks.masks)
+    elif masktype == InstanceSet:
+        return mask_areas(masks.instances)
+    elif masktype == list:
+        return [mask_areas(x) for x in masks]
+    else:
+        raise NotImplementedError('Not implemented for type {}'.format(masktype))
+
+
+def _shoelace_area(x, y):
+    """Polygon area from vertex coordinates (reference structures.py:586-610)."""
+    return 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+
+
+def boxes_to_array(boxes):
+    """Boxes / list / array -> n x 4 ndarray (reference structures.py:613-639)."""
+    dtype = type(boxes)
+    if dtype == np.ndarray:
+        return boxes
+    elif dtype == list:
+        assert len(boxes[0]) == 4
+        return np.asarray(boxes)
+    elif dtype == Boxes:
+        return boxes.tensor.to('cpu').numpy()
+
+
+def masks_to_rle(masks, size=None):
+    """Anything -> list of COCO RLE dicts (reference structures.py:643-690).  Polygons are
+    rasterised by the GPU restatement of rleFrPoly (first polygon of each instance only, as
+    ``RLE.frPyObjects(p, *size)[0]`` does) and compressed by the GPU string encoder."""
+    dtype = type(masks)
+    if dtype == list:
+        if type(masks[0]) == dict:
+            return masks
+        elif type(masks[0]) == list:
+            raise NotImplementedError('):')
+    if dtype == RLEMasks:
+        return masks.rle
+    elif dtype == PolygonMasks:
+        assert size is not None
+        h, w = int(size[0]), int(size[1])
+        polys = [np.asarray(p[0], np.float64) for p in masks.polygons]
+        cnt, cnt_off, cnt_len, _, _ = engine.polygons_to_counts(polys, h, w)
+        strings = engine.counts_to_strings(cnt, cnt_off, cnt_len, len(polys))
+        return [{'size': [h, w], 'counts': s} for s in strings]
+    elif dtype == InstanceSet:
+        return masks_to_rle(masks.instances.masks, masks.instances.image_size)
+    elif dtype == Instances:
+        return masks_to_rle(masks.masks, masks.image_size)
+    else:
+        raise NotImplementedError('cannot convert mask type {} to RLE'.format(masks))
+
+
+def _rle_to_bool(rle):
+    t = engine.table_from_rle(rle)
+    h, w = rle[0]['size']
+    for m in rle:
+        if list(m['size']) != [h, w]:
+            raise ValueError('all masks must share one image size')
+    return engine.unpack_bool(t, np.arange(len(rle)), int(h), int(w)).cpu().numpy()
+
+
+def masks_to_bitmask_array(masks, size=None):
+    """Anything -> bool[n_mask, r, c] (reference structures.py:717-774).  RLE input is decoded
+    and transposed on the GPU.  Polygon input is rasterised with the same rleFrPoly rule as
+    ``masks_to_rle`` -- the reference uses skimage.draw.polygon2mask here (structures.py:711),
+    a different rasteriser that is not available offline; see DESIGN.md."""
+    dtype = type(masks)
+    if dtype == np.ndarray:
+        assert masks.dtype == np.bool_
+        return masks
+    elif dtype == PolygonMasks:
+        assert size is not None
+        return _rle_to_bool(masks_to_rle(masks, size))
+    elif dtype == list:
+        if type(masks[0]) == dict:
+            return _rle_to_bool(masks)
+        elif type(masks[0]) == list or type(masks[0]) == np.ndarray:
+            assert size is not None
+            return _rle_to_bool(masks_to_rle(PolygonMasks([[p] for p in masks]), size))
+        else:
+            raise NotImplementedError
+    elif dtype == RLEMasks:
+        if type(masks.rle) == dict:      # RLEMasks[int] wraps one dict (quirk B.13)
+            return _rle_to_bool([masks.rle])
+        return _rle_to_bool(masks.rle)
+    elif dtype == InstanceSet:
+        return masks_to_bitmask_array(masks.instances.masks, masks.instances.image_size)
+    elif dtype == Instances:
+        return masks_to_bitmask_array(masks.masks, masks.image_size)
+    else:
+        raise NotImplementedError

@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the mask-evaluation hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--layout full|span] [--config NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU algorithm on the host cores
+
+A step is one pass of the hot path over one batch of synthetic images (BASELINE.json
+configs[1]: 1,000 images of 1024x1024 with 500 GT x 500 predicted masks each, per GPU):
+RLE run counts resident in HBM -> per-mask measurements -> bit-packed masks -> bbox-pruned
+intersections (dense int32 G x P matrix out) + per-GT arg-max IoU -> TP/FP/FN at IoU
+0.50:0.05:0.95 per image and in total (+ one NCCL all-reduce of the totals when N > 1).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'mask-pair IoUs/sec (GT x pred mask pairs matched and scored, IoU 0.50:0.95)'
+UNIT = 'pairs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='c2_powder_batch')
+    ap.add_argument('--images', type=int, default=1000, help='images per GPU per step')
+    ap.add_argument('--layout', default='full', choices=['full', 'span'],
+                    help='full = canonical full-frame packed masks (the roofline accounting of SURVEY 8d); '
+                         'span = culled storage (only first..last 1-pixel of each mask)')
+    ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-images', type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw'
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'note': 'nvidia-smi unavailable'}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'note': 'no samples'}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in rows)]
+        out = {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons, 'samples': len(rows)}
+        try:
+            out['power_w_max'] = max(float(r[6]) for r in rows)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_task(args):
+    gt, pr, th, mode = args
+    from oracle import ampis_ref as R
+    if mode == 0:
+        r = R.det_seg_scores(gt, pr, th)
+        return len(r['det_tp']), len(r['det_fp']), len(r['det_fn'])
+    r = R.rle_satellite_match(pr, gt, th)
+    return len(r['satellite_matches']), 0, len(r['satellites_unmatched'])
+
+
+def cpu_images(cfg_name, n_img, seed):
+    """n_img synthetic images as lists of compressed-RLE dicts (what the reference consumes)."""
+    from ampis_b200 import batch
+    from oracle import cocomask as rle
+    host = batch.synth(cfg_name, n_img, seed)
+    out = []
+    for g in range(n_img):
+        rows, cols = host.image_masks(g)
+        size = [host.h, host.w]
+        out.append(([{'size': size, 'counts': rle.string_from_counts(c)} for c in rows],
+                    [{'size': size, 'counts': rle.string_from_counts(c)} for c in cols]))
+    return host, out
+
+
+def cpu_run(pool, images, thresholds, mode):
+    tasks = [(gt, pr, float(t), mode) for gt, pr in images for t in thresholds]
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_task, tasks, chunksize=1)
+    return time.perf_counter() - t0, res
+
+
+def reference_arm(args):
+    """--impl reference: per step, `n_img` images of the same synthetic workload through the
+    reference's loops (analyze.py:149-172 + 315-327 restated in oracle/ampis_ref.py over the C
+    restatement of pycocotools), one det_seg_scores call per IoU threshold as a user of the
+    reference would do, on all host cores.  kind = "port": pycocotools itself is not installable
+    here."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from ampis_b200 import batch
+    from oracle import cocomask
+    cocomask.build()
+    cores = os.cpu_count() or 1
+    cfg = batch.CONFIGS[args.config]
+    thresholds = batch.COCO_THRESHOLDS if cfg['mode'] == 0 else [0.5]
+    per_task = 0.75 if cfg['mode'] == 0 else 2.5        # seconds per (image, threshold) on one core, measured
+    budget = min(8.0, 200.0 / max(args.steps + args.warmup, 1))
+    n_img = args.cpu_images or max(1, int(cores * budget / (per_task * len(thresholds))))
+    host, images = cpu_images(args.config, n_img, 777)
+    pairs = n_img * host.n_rows * host.n_cols
+    with mp.get_context('fork').Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_run(pool, images[:max(1, min(n_img, cores // len(thresholds)))], thresholds, cfg['mode'])
+        t = 0.0
+        for _ in range(args.steps):
+            dt, _ = cpu_run(pool, images, thresholds, cfg['mode'])
+            t += dt
+    value = pairs * args.steps / t
+    sample = '%d synthetic %s images per step, %d IoU thresholds each, oracle port of the reference loops, ' \
+             '%d processes' % (n_img, args.config, len(thresholds), cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
+        'images_per_s': n_img * args.steps / t,
+        'config': {'workload': workload_name(args, host), 'images_per_step': n_img},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_name(args, host):
+    return '%s: %dx%d px, %d x %d masks per image' % (args.config, host.w, host.h, host.n_rows, host.n_cols)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from ampis_b200 import batch, engine
+    from ampis_b200 import _native as N
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N.lib()
+
+    cfg = batch.CONFIGS[args.config]
+    layout = engine.LAYOUT_FULL if args.layout == 'full' else engine.LAYOUT_SPAN
+    n_img = args.images
+    chunks_per_mask = (cfg['h'] * cfg['w'] + 127) // 128
+    per_image = cfg['n_rows'] + cfg['n_cols']
+    if args.sub:
+        sub = args.sub
+    elif layout == engine.LAYOUT_FULL:
+        sub = max(1, min(n_img, int(12e9 // (per_image * chunks_per_mask * 16))))   # ~12 GB arena
+    else:
+        sub = min(n_img, 250)
+    thresholds = batch.COCO_THRESHOLDS
+
+    # ---- inputs: generated on the host, uploaded once (resident in HBM before the timed region)
+    t_gen = time.time()
+    subs = []
+    for s0 in range(0, n_img, sub):
+        k = min(sub, n_img - s0)
+        host = batch.synth(args.config, k, 1_000_003 * (rank + 1) + s0)
+        subs.append(batch.DeviceBatch(host, dev, dense=True))
+    t_gen = time.time() - t_gen
+    host0 = subs[0].host
+    total_runs = sum(b.host.total_runs() for b in subs)
+    arena_chunks = max(batch.arena_chunks_needed(b, layout) for b in subs)
+    arena = torch.empty(4 * arena_chunks, dtype=torch.int32, device=dev)
+    imat_elems = max(b.groups.imat_size for b in subs)
+    rows_out = [engine.RowResult(torch.empty(b.groups.n_rows, dtype=torch.int32, device=dev),
+                                 torch.empty(b.groups.n_rows, dtype=torch.int32, device=dev),
+                                 torch.empty(b.groups.n_rows, dtype=torch.float64, device=dev),
+                                 torch.empty(imat_elems, dtype=torch.int32, device=dev)) for b in subs[:1]]
+    span_chunks = sum(batch.arena_chunks_needed(b, engine.LAYOUT_SPAN) for b in subs)
+    totals = torch.zeros(len(thresholds) * 3, dtype=torch.int64, device=dev)
+    KERNELS = ['measure+scan', 'paint', 'rows', 'counts']
+
+    def step(record=None):
+        """one pass over the rank's batch; `record` collects (kernel, start_event, end_event)"""
+        totals.zero_()
+        for b in subs:
+            t = engine.MaskTable(dev, b.host.n_masks, b.cnt, b.cnt_off, b.cnt_len, b.h, b.w, layout)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record is not None else None
+            if ev: ev[0].record()
+            t.measure()
+            if ev: ev[1].record()
+            t.paint(arena)
+            if ev: ev[2].record()
+            rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out[0])
+            if ev: ev[3].record()
+            engine.match_counts(rows, b.groups, thresholds, totals=totals)
+            if ev:
+                ev[4].record()
+                record.append(ev)
+        if world > 1:
+            dist.all_reduce(totals)          # TP/FP/FN x thresholds: the only exchange on this path
+        return totals
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    record = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step(record)
+    e1.record()
+    sync()
+    wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    final_totals = totals.cpu().numpy().reshape(-1, 3)
+
+    kt = np.zeros(4)
+    for ev in record:
+        for i in range(4):
+            kt[i] += ev[i].elapsed_time(ev[i + 1])
+    n_launch_groups = len(record)
+
+    # ---- end to end through host buffers: compressed RLE strings in pinned memory -> H2D -> GPU string
+    # decode -> same pipeline -> D2H of per-image counts and per-GT matches
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, subs, dev, layout, arena, rows_out[0], thresholds, world, dist, sync)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pairs_per_step = world * n_img * cfg['n_rows'] * cfg['n_cols']
+    value = pairs_per_step * args.steps / (ms / 1e3)
+    peak, peak_src = peaks()
+    B_m = chunks_per_mask * 16
+    n_masks = n_img * per_image
+    bytes_decode = 4 * total_runs + (n_masks * B_m if layout == engine.LAYOUT_FULL else span_chunks * 16)
+    bytes_rows = n_masks * B_m + 4 * n_img * cfg['n_rows'] * cfg['n_cols']
+    canonical_img = (4 * total_runs / n_img + 2 * per_image * B_m + 4 * cfg['n_rows'] * cfg['n_cols']
+                     + 8 * per_image + 32 * cfg['n_rows'])
+    alg = {'paint': bytes_decode, 'rows': bytes_rows}
+    share = kt / kt.sum()
+    dom = 'paint' if kt[1] >= kt[2] else 'rows'
+    di = KERNELS.index(dom)
+    launches = len(subs)                                 # launches of the dominant kernel per step
+    dur_ms = kt[di] / (args.steps * launches)
+    achieved = alg[dom] / launches / (dur_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('%s/%s/%s' % (args.config, args.layout, dom))
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u32', 'data': 'synthetic',
+        'images_per_s': world * n_img * args.steps / (ms / 1e3),
+        'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': n_img, 'layout': args.layout,
+                   'images_per_launch': sub, 'thresholds': 'IoU 0.50:0.05:0.95',
+                   'runs_per_mask': total_runs / n_masks, 'l2': 'inputs (%.0f MB run counts) and the %.1f GB packed-'
+                   'mask arena are larger than L2; no explicit flush' % (4 * total_runs / 1e6, arena.numel() * 4 / 1e9),
+                   'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce per step' % world},
+        'roofline': {'bound': 'hbm', 'kernel': {'paint': 'rle_paint_kernel', 'rows': 'intersect_rows_kernel'}[dom],
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom] / launches,
+                     'launch_ms': dur_ms,
+                     'step_canonical': {'bytes_per_image': canonical_img,
+                                        'achieved': canonical_img * n_img * args.steps / (ms / 1e3) / 1e9 * 1.0,
+                                        'frac': canonical_img * n_img * args.steps / (ms / 1e3) / 1e9 / peak,
+                                        'note': 'whole step vs the two-pass full-frame accounting of SURVEY 8d '
+                                                '(per GPU); bbox culling lets the intersection read less than it'},
+                     'kernel_share': {k: float(s) for k, s in zip(KERNELS, share)}},
+        'gpu_launches': int(args.steps * len(subs) * 7),
+        'totals_tp_fp_fn_at_0.50': final_totals[0].tolist(),
+        'clocks': clocks, 'setup_s': {'synthesize': t_gen},
+    }
+    if e2e:
+        out['e2e'] = e2e
+    if not args.no_cpu:
+        out['cpu_baseline'] = cpu_baseline(args)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, sync):
+    """Same metric through host buffers: every step copies the compressed RLE strings (what the
+    reference API receives) from pinned host memory, decodes them on the GPU, runs the pipeline
+    and reads the per-image counts and per-GT matches back."""
+    import torch
+    from ampis_b200 import engine
+    from ampis_b200 import _native as N
+    _p, _s = engine._p, engine._stream
+    pinned = []
+    for b in subs:       # setup (untimed): strings produced by the GPU encoder, parked in pinned memory
+        n = b.host.n_masks
+        lens = b.cnt_len.cpu().numpy().astype(np.int64)
+        choff = np.zeros(n + 1, np.int64)
+        np.cumsum(7 * lens, out=choff[1:])
+        d_choff = torch.from_numpy(choff).to(dev)
+        chars = torch.empty(int(choff[-1]), dtype=torch.uint8, device=dev)
+        chlen = torch.empty(n, dtype=torch.int32, device=dev)
+        N.call('ampis_rle_string_encode', _p(b.cnt), _p(b.cnt_off), _p(b.cnt_len), n, _p(chars), _p(d_choff),
+               _p(chlen), _s())
+        ln = chlen.cpu().numpy().astype(np.int64)
+        buf = chars.cpu().numpy()
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum(ln, out=off[1:])
+        blob = np.concatenate([buf[choff[i]:choff[i] + ln[i]] for i in range(n)]) if n else np.zeros(0, np.uint8)
+        pinned.append((torch.from_numpy(blob).pin_memory(), torch.from_numpy(off).pin_memory(), b))
+    max_chars = max(p[0].numel() for p in pinned)
+    d_chars = torch.empty(max_chars, dtype=torch.uint8, device=dev)
+    d_cnt = torch.empty(max_chars, dtype=torch.int32, device=dev)
+    n_thr = len(thresholds)
+    h_out = []
+    for blob, off, b in pinned:
+        h_out.append((torch.empty((b.groups.n_groups, n_thr, 3), dtype=torch.int32).pin_memory(),
+                      torch.empty(b.groups.n_rows, dtype=torch.int32).pin_memory(),
+                      torch.empty(b.groups.n_rows, dtype=torch.float64).pin_memory()))
+    h2d = sum(p[0].numel() + p[1].numel() * 8 for p in pinned)
+    d2h = sum(o[0].numel() * 4 + o[1].numel() * 4 + o[2].numel() * 8 for o in h_out)
+    totals = torch.zeros(n_thr * 3, dtype=torch.int64, device=dev)
+
+    def step():
+        totals.zero_()
+        for (blob, off, b), (hc, hb, hs) in zip(pinned, h_out):
+            n = b.host.n_masks
+            dc = d_chars[:blob.numel()]
+            dc.copy_(blob, non_blocking=True)
+            d_off = off.to(dev, non_blocking=True)
+            cnt_len = torch.empty(n, dtype=torch.int32, device=dev)
+            N.call('ampis_rle_string_decode', _p(dc), _p(d_off), n, _p(d_cnt), _p(d_off), _p(cnt_len), _s())
+            t = engine.MaskTable(dev, n, d_cnt, d_off, cnt_len, b.h, b.w, layout)
+            t.measure().paint(arena)
+            rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out)
+            counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
+            hc.copy_(counts, non_blocking=True)
+            hb.copy_(rows.best_col[:b.groups.n_rows], non_blocking=True)
+            hs.copy_(rows.best_score[:b.groups.n_rows], non_blocking=True)
+        if world > 1:
+            dist.all_reduce(totals)
+        return totals.cpu()
+
+    for _ in range(2):
+        step()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    n_img = sum(b.host.n_images for b in subs)
+    pairs = world * n_img * subs[0].host.n_rows * subs[0].host.n_cols
+    return {'value': pairs * args.steps / (ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+            'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms / args.steps,
+            'input': 'COCO-compressed RLE strings in pinned host memory, decoded on the GPU'}
+
+
+def cpu_baseline(args):
+    """The reference's CPU algorithm (oracle port) on a bounded sample of the same workload, run in a
+    fresh process (no CUDA context is forked): one step of the --impl reference arm sized to ~15 s."""
+    cores = os.cpu_count() or 1
+    from ampis_b200 import batch
+    cfg = batch.CONFIGS[args.config]
+    n_thr = len(batch.COCO_THRESHOLDS) if cfg['mode'] == 0 else 1
+    per_task = 0.75 if cfg['mode'] == 0 else 2.5
+    n_img = args.cpu_images or max(1, int(cores * 15.0 / (per_task * n_thr)))
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1', CUDA_VISIBLE_DEVICES='')
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '0', '--config', args.config, '--cpu-images', str(n_img)],
+                       env=env, capture_output=True, text=True, timeout=900)
+    line = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    if r.returncode != 0 or not line:
+        return {'value': None, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': 'failed: ' + r.stderr[-300:]}
+    d = json.loads(line[-1])
+    cb = d['cpu_baseline']
+    cb['images_per_s'] = d['images_per_s']
+    return cb
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,198 @@
+/*
+ * ampis_b200.h -- C ABI of libampis_b200.so: the B200 (sm_100a) kernels behind
+ * AMPIS's mask-evaluation hot path.
+ *
+ * The reference (rccohn/AMPIS, pure Python) has no FFI of its own: every
+ * number on this path comes from pycocotools' C routines called through
+ * `pycocotools.mask`.  Each entry point below names the
+ * reference call site(s) it replaces.  All pointers prefixed d_ are DEVICE
+ * pointers owned by the caller (PyTorch allocates them); `stream` is a
+ * cudaStream_t passed as void*.  Nothing here allocates device memory, throws,
+ * or synchronises unless stated.  Return value: 0 on success, a negative
+ * AMPIS_E* code otherwise (ampis_last_error() gives the text).
+ *
+ * Device data model ("mask table", structure of arrays, n masks):
+ *   cnt      u32[]   run-length counts of all masks, COCO order: column-major pixels
+ *                    (index = x*h + y), first run counts zeros
+ *   cnt_off  i64[n]  first count of mask i inside cnt
+ *   cnt_len  i32[n]  number of runs of mask i
+ *   h, w     u32[n]  image size of mask i
+ *   cum      u32[]   inclusive prefix sums of cnt (same indexing) = run end positions
+ *   area     u32[n]  number of 1-pixels (rleArea)
+ *   bbox     i32[4n] tight box x0,y0,x1,y1 (inclusive); empty mask = 0,0,-1,-1
+ *   span     u32[2n] [lo,hi) in 128-bit chunks of the linear bit vector that holds all 1s
+ *   reg      u32[2n] [lo,hi) chunk region actually stored for mask i
+ *                    (layout SPAN: = span; layout FULL: 0..ceil(h*w/128))
+ *   bits_off i64[n+1] first uint4 of mask i's region inside the `bits` arena
+ *   bits     uint4[] packed masks: bit k of a mask = pixel k in column-major order,
+ *                    little-endian inside 32-bit words
+ */
+#ifndef AMPIS_B200_H
+#define AMPIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPIS_OK            0
+#define AMPIS_EINVAL       -1   /* bad argument */
+#define AMPIS_ECUDA        -2   /* CUDA runtime error (see ampis_last_error) */
+#define AMPIS_ENOSPC       -3   /* caller-provided buffer too small */
+
+#define AMPIS_LAYOUT_SPAN   0   /* store only [first 1, last 1] of each mask (culled) */
+#define AMPIS_LAYOUT_FULL   1   /* store the full h*w frame of each mask (canonical) */
+
+#define AMPIS_MODE_IOU      0   /* score = I / (a_row + a_col - I), analyze.py:158 */
+#define AMPIS_MODE_SAT      1   /* score = I / a_row,               powder.py:82-83 */
+
+/* bit flags written to status[i] by ampis_rle_measure */
+#define AMPIS_ST_BAD_TOTAL  1   /* sum(counts) != h*w (pycocotools would hang or mis-decode) */
+
+int         ampis_version(void);
+const char *ampis_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int         ampis_sm_count(void);
+
+/* ---- RLE string codec -------------------------------------------------------
+ * Replaces pycocotools rleFrString as invoked by every RLE.iou / merge / area /
+ * decode call in the reference (analyze.py:108,158,315-321; powder.py:82-83,264;
+ * structures.py:467,568,571,752,761).  d_chars holds the n compressed strings back
+ * to back, d_chr_off[n+1] their byte offsets.  Counts of mask i are written at
+ * d_cnt + d_cnt_off[i] (a string of L bytes yields at most L counts, so
+ * cnt_off = chr_off is always large enough); d_cnt_len[i] receives the run count. */
+int ampis_rle_string_decode(const uint8_t *d_chars, const int64_t *d_chr_off, int32_t n,
+                            uint32_t *d_cnt, const int64_t *d_cnt_off, int32_t *d_cnt_len,
+                            void *stream);
+
+/* Inverse (pycocotools rleToString; data_utils.py:275, structures.py:465 via RLE.encode).
+ * d_chars needs 7 bytes per count at d_chr_off[i] (= 7*cnt_off[i] is always enough);
+ * d_chr_len[i] receives the string length. */
+int ampis_rle_string_encode(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                            int32_t n, uint8_t *d_chars, const int64_t *d_chr_off, int32_t *d_chr_len,
+                            void *stream);
+
+/* ---- per-mask measurements ---------------------------------------------------
+ * One pass over the run counts: rleArea (structures.py:568,571; analyze.py:320-321;
+ * powder.py:264), the tight bounding box that extract_boxes (data_utils.py:180-252)
+ * reads off the decoded mask, the storage span/region, and the prefix sums the
+ * decoder needs.  d_reg_chunks[i] = reg_hi - reg_lo (input of the offset scan). */
+int ampis_rle_measure(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                      const uint32_t *d_h, const uint32_t *d_w, int32_t n, int32_t layout,
+                      uint32_t *d_cum, uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span,
+                      uint32_t *d_reg, int64_t *d_reg_chunks, int32_t *d_status, void *stream);
+
+/* Exclusive prefix sum of n int64 values into d_out[n+1] (d_out[n] = total).
+ * d_tmp needs ampis_scan_tmp_bytes(n) bytes. */
+size_t ampis_scan_tmp_bytes(int64_t n);
+int    ampis_exclusive_scan_i64(const int64_t *d_in, int64_t *d_out, int64_t n,
+                                void *d_tmp, size_t tmp_bytes, void *stream);
+
+/* ---- RLE -> bit-packed masks ---------------------------------------------------
+ * Replaces pycocotools rleDecode (structures.py:752,761; analyze.py:472-473) as the
+ * producer of the mask representation every later kernel reads.  Writes exactly the
+ * region [reg_lo,reg_hi) of every mask, 128 bits per store.  bits_capacity = number of
+ * uint4 in d_bits; masks that would not fit are skipped and AMPIS_ENOSPC is NOT
+ * detected here (the caller sized the arena from d_bits_off[n]). */
+int ampis_rle_decode_packed(const uint32_t *d_cum, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                            const uint32_t *d_span, const uint32_t *d_reg, const int64_t *d_bits_off,
+                            int32_t n, void *d_bits, int64_t bits_capacity, void *stream);
+
+/* bits -> bool[n][h][w] row-major bytes (RLE.decode(...).astype(bool).transpose(2,0,1),
+ * structures.py:752,765).  All n masks must share (h,w). d_mask_ids selects masks. */
+int ampis_unpack_bool_nrc(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                          const int32_t *d_mask_ids, int32_t n, uint32_t h, uint32_t w,
+                          uint8_t *d_out, void *stream);
+
+/* bool[n][h][w] -> area (u64) and tight bbox (mask_areas on ndarray, structures.py:558-560;
+ * extract_boxes, data_utils.py:229-239). */
+int ampis_bool_area_bbox(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w,
+                         uint64_t *d_area, int32_t *d_bbox, void *stream);
+
+/* bool[n][h][w] (row-major) -> packed FULL-layout bits (RLE.encode producer side,
+ * data_utils.py:275,423): region of mask i is chunk 0..ceil(h*w/128) at d_bits_off[i]. */
+int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w,
+                        void *d_bits, const int64_t *d_bits_off, void *stream);
+
+/* ---- intersection / IoU rows ----------------------------------------------------
+ * The fused hot kernel.  For every row mask r (a ground-truth mask, or a satellite) it
+ * visits the column masks of its group (the predictions, or the particles, of the same
+ * image), prunes by bounding box exactly as rleIou's bbIou pre-pass does, computes
+ * I = popcount(row AND col) over the overlap of the two spans, and keeps the first
+ * arg-max of the score.  Replaces the G x ceil(P/80) RLE.iou calls of
+ * analyze.py:149-164 and the S x N RLE.merge+RLE.area calls of powder.py:80-86.
+ *   row_mask[r], row_grp[r]        mask id and group id of row r
+ *   grp_row_begin[g]               first row of group g (rows of a group are contiguous)
+ *   grp_col_begin[g], grp_col_count[g]   column masks of group g (contiguous mask ids)
+ *   grp_imat_off[g]                offset (in int32) of group g's dense G x P intersection
+ *                                  matrix inside d_imat, or -1 / d_imat NULL for none
+ * Outputs per row: best_col (index inside the group, IOU mode: -1 if every IoU is 0;
+ * SAT mode: 0 if every intersection is 0), best_inter, best_score (double). */
+int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                         const uint32_t *d_span, const int32_t *d_bbox, const uint32_t *d_area,
+                         const int32_t *d_row_mask, const int32_t *d_row_grp, int32_t n_rows,
+                         const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
+                         const int32_t *d_grp_col_count, const int64_t *d_grp_imat_off,
+                         int32_t mode, int32_t *d_imat,
+                         int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
+                         void *stream);
+
+/* Full IoU matrix of one group as float64[G][P] from the dense intersections
+ * (analyze._piecewise_iou, analyze.py:54-112): I>0 ? I/(a_g+a_p-I) : 0.0 */
+int ampis_iou_matrix_f64(const int32_t *d_imat, const uint32_t *d_area_rows, const uint32_t *d_area_cols,
+                         int32_t G, int32_t P, double *d_out, void *stream);
+
+/* ---- matching / scoring ------------------------------------------------------------
+ * Per group (image): TP/FP/FN of AMPIS's per-GT arg-max matcher (analyze.py:166-174) at
+ * n_thresh IoU thresholds from ONE row pass (the arg-max does not depend on the threshold).
+ * d_grp_counts[g][t] = (tp, fp, fn) int32; d_totals[t] = (tp, fp, fn) int64, accumulated
+ * (+=) over groups: the all-reduce payload of a dataset evaluation. */
+int ampis_match_counts(const int32_t *d_best_col, const double *d_best_score,
+                       const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                       const int32_t *d_grp_col_count, int32_t n_groups, int32_t max_cols,
+                       const double *d_thresh, int32_t n_thresh,
+                       int32_t *d_grp_counts, int64_t *d_totals, void *stream);
+
+/* Satellite assignment summary (powder.py:88-96, 525-547): per group
+ * (n_sat_matched, n_sat_unmatched, n_particles_matched, n_particles) int32, and a global
+ * histogram (+=) of satellites per satellited particle, bins 0..n_bins-1 (last bin clamps). */
+int ampis_satellite_counts(const int32_t *d_best_col, const uint32_t *d_best_inter,
+                           const uint32_t *d_area, const int32_t *d_row_mask,
+                           const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                           const int32_t *d_grp_col_count, int32_t n_groups, int32_t max_cols,
+                           double thresh, int32_t *d_grp_counts, int64_t *d_spp_hist, int32_t n_bins,
+                           void *stream);
+
+/* Histogram (+=) of n uint32 values (mask areas) into n_bins uniform bins of `bin_width`
+ * starting at `lo`; values outside are clamped into the first/last bin (size
+ * distributions, powder.py:417 binned form used for multi-GPU reduction). */
+int ampis_hist_u32(const uint32_t *d_values, int64_t n, uint32_t lo, uint32_t bin_width,
+                   int64_t *d_hist, int32_t n_bins, void *stream);
+
+/* ---- polygon -> RLE (pycocotools rleFrPoly via RLE.frPyObjects, structures.py:677) -----
+ * d_xy: vertex coordinates x0,y0,x1,y1,... of all polygons, d_xy_off[n+1] offsets in doubles.
+ * Crossing positions (sorted, zero-length runs merged) are written as run counts at
+ * d_cnt + d_cnt_off[i]; capacity per polygon is d_cnt_off[i+1]-d_cnt_off[i], the number
+ * actually needed is returned in d_cnt_len[i] (> capacity means it did not fit). */
+int ampis_poly_to_rle(const double *d_xy, const int64_t *d_xy_off, const uint32_t *d_h,
+                      const uint32_t *d_w, int32_t n, uint32_t *d_cnt, const int64_t *d_cnt_off,
+                      int32_t *d_cnt_len, void *stream);
+
+/* ---- synthetic micrograph generator (bench / test data only; HOST code, host buffers) ----
+ * Deterministic powder-like images: per image n_gt primary blobs followed by n_sec secondary
+ * masks (kind 0: predictions of the primaries -- jitter, scale, drop_frac dropped and replaced
+ * by spurious blobs, shuffled; kind 1: satellites, 85 % on primary rims).  Writes the run
+ * counts of all n_images*(n_gt+n_sec) masks (image-major, primaries first) as CSR.
+ * Returns the number of counts written; if cnt_capacity is too small returns -(needed). */
+int64_t ampis_synth_batch(uint64_t seed, int32_t n_images, uint32_t h, uint32_t w, int32_t n_gt,
+                          int32_t n_sec, int32_t kind, double median_diam, double sigma_ln,
+                          double max_aspect, double sec_median_diam, double jitter_px,
+                          double scale_sigma, double drop_frac, double empty_frac, int32_t n_threads,
+                          uint32_t *cnt, int64_t cnt_capacity, int64_t *cnt_off, int32_t *cnt_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPIS_B200_H */

@@ -1,0 +1,404 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, called through the
+public drop-in API and the C ABI, against the CPU oracle and the frozen golden fixtures.
+Bit-exact for intersections, matches, counts, areas and boxes; float64 scores are compared
+for equality too (they are correctly-rounded divisions of exact integers),
+with 1e-6 relative as the stated tolerance for derived quantities (d_eq, psd)."""
+import numpy as np
+import pytest
+
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import torch
+    assert torch.cuda.is_available(), 'these tests need the B200'
+    from ampis_b200 import analyze, batch, data_utils, engine, structures
+    from ampis_b200.applications import powder
+    from oracle import ampis_ref as R
+    from oracle import cocomask as rle
+
+    class M:
+        pass
+    m = M()
+    m.torch, m.analyze, m.batch, m.data_utils, m.engine, m.structures = torch, analyze, batch, data_utils, engine, \
+        structures
+    m.powder, m.R, m.rle = powder, R, rle
+    return m
+
+
+def _enc(rle, a):
+    return rle.encode(np.asfortranarray(np.array(a, np.uint8)))
+
+
+def test_reference_known_answer(mods):
+    """analyze.py:702-728 through the GPU path."""
+    A, rle = mods.analyze, mods.rle
+    m1 = _enc(rle, [[1, 1, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]])
+    m2 = _enc(rle, [[0, 0, 1, 1], [0, 0, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]])
+    m3 = _enc(rle, [[0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 0, 0], [1, 1, 0, 0]])
+    m4 = _enc(rle, [[0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 1, 1], [0, 0, 1, 1]])
+    gt, pred = [m1, m2, m3, m4], [m3, m2, m4]
+    assert np.all(A._piecewise_iou(gt, pred) == np.array([[0, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1]]))
+    match = A._piecewise_rle_match(gt, pred)
+    assert np.all(match['tp'] == np.array([[1, 1], [2, 0], [3, 2]]))
+    assert np.all(match['fn'] == np.array([0]))
+    assert np.all(match['fp'] == np.array([]))
+    assert np.all(match['iou'] == np.ones(3))
+    assert match['tp'].dtype == np.int64 and match['iou'].dtype == np.float64
+
+
+def test_string_codec_and_measure_on_fixtures(mods):
+    E, rle, torch = mods.engine, mods.rle, mods.torch
+    m = U.load('spheroidite_measure.npz')
+    for k in range(len(m['names'])):
+        masks = U.unpack_strings(m['%d_blob' % k], m['%d_off' % k], m['%d_size' % k])
+        t = E.table_from_rle(masks)
+        # counts decoded on the GPU == oracle rleFrString
+        cnt = t.cnt.cpu().numpy().view(np.uint32)
+        off = t.cnt_off.cpu().numpy()
+        ln = t.cnt_len.cpu().numpy()
+        for i in range(0, len(masks), 7):
+            assert np.array_equal(cnt[off[i]:off[i] + ln[i]], rle.counts_from_string(masks[i]['counts']))
+        assert np.array_equal(t.areas_np(), m['%d_area' % k])
+        bb = t.bbox_np()
+        ne = m['%d_area' % k] > 0
+        assert np.array_equal(bb[ne].astype(np.float64), m['%d_boxes_d2' % k][ne])
+        assert (bb[~ne] == [0, 0, -1, -1]).all()
+        # GPU re-encode gives back the bytes pycocotools wrote
+        s = E.counts_to_strings(t.cnt, t.cnt_off, t.cnt_len, t.n)
+        assert s == [x['counts'] for x in masks]
+
+
+def test_structures_measurements(mods):
+    S, R = mods.structures, mods.R
+    from ampis_b200.containers import Instances
+    m = U.load('spheroidite_measure.npz')
+    masks = U.unpack_strings(m['0_blob'], m['0_off'], m['0_size'])
+    size = tuple(int(v) for v in m['0_size'])
+    areas = S.mask_areas(masks)
+    assert areas.dtype == np.uint32 and np.array_equal(areas, m['0_area'])
+    assert np.array_equal(S.mask_areas(S.RLEMasks(masks)), m['0_area'])
+    n = len(masks)
+    iset = S.InstanceSet(instances=Instances(size, masks=S.RLEMasks(masks), boxes=np.zeros((n, 4)),
+                                             class_idx=np.zeros(n, np.int64)))
+    filt = iset.filter_mask_size(100, 100000)
+    assert len(filt) == int(m['0_size_inliers'].sum())
+    assert filt.masks.rle == [x for x, b in zip(masks, m['0_size_inliers']) if b]
+    df = iset.compute_rprops(keys=['area', 'equivalent_diameter', 'bbox'], return_df=True)
+    ne = m['0_area'] > 0
+    got = np.array([v[0] for v in df['equivalent_diameter'][ne]])
+    assert np.allclose(got, m['0_deq'][ne], rtol=1e-6, atol=0)
+    assert [int(v[0]) for v in df['area'][ne]] == m['0_area'][ne].tolist()
+    for k in (1, 3):
+        i2 = iset.copy()
+        i2.remove_edge_instances(k)
+        want = R.edge_inliers(masks, size, k)
+        assert i2.instances.masks.rle == [x for x, b in zip(masks, want) if b]
+    i2 = iset.copy()
+    i2.remove_edge_instances(0)          # reference quirk: k=0 removes every non-empty mask
+    assert len(i2.instances) == int((m['0_area'] == 0).sum())
+
+
+def test_bitmask_array_and_extract_boxes(mods):
+    S, D, R = mods.structures, mods.data_utils, mods.R
+    m = U.load('spheroidite_measure.npz')
+    masks = U.unpack_strings(m['1_blob'], m['1_off'], m['1_size'])[:40]
+    bm = S.masks_to_bitmask_array(masks)
+    want = R.rle_to_bitmask_array(masks)
+    assert bm.dtype == np.bool_ and bm.shape == want.shape and (bm == want).all()
+    one = S.masks_to_bitmask_array(S.RLEMasks(masks)[3])
+    assert one.shape == (1,) + want.shape[1:] and (one[0] == want[3]).all()
+    assert np.array_equal(D.extract_boxes(bm), R.extract_boxes(want))
+    assert np.array_equal(D.extract_boxes(bm, box_mode='matterport'), R.extract_boxes(want, box_mode='matterport'))
+    mp = np.ascontiguousarray(want.transpose(1, 2, 0))
+    assert np.array_equal(D.extract_boxes(mp, mask_mode='matterport'), R.extract_boxes(mp, mask_mode='matterport'))
+    assert np.array_equal(D.extract_boxes(want[5]), R.extract_boxes(want[5]))
+    assert np.array_equal(S.mask_areas(want), want.sum(axis=(1, 2), dtype=np.uint))
+    # odd sizes: packed layout is exercised where h is not a multiple of 32
+    rng = np.random.default_rng(5)
+    for h, w in [(1, 1), (5, 3), (33, 7), (31, 129), (100, 64)]:
+        a = U.rand_masks(rng, 6, h, w)
+        enc = [mods.rle.encode(np.asfortranarray(x.astype(np.uint8))) for x in a]
+        assert (S.masks_to_bitmask_array(enc) == a).all()
+        assert np.array_equal(S.mask_areas(enc), a.sum(axis=(1, 2)).astype(np.uint32))
+        assert np.array_equal(D.extract_boxes(a), R.extract_boxes(a))
+
+
+@pytest.mark.parametrize('layout', ['span', 'full'])
+def test_golden_matching_all_images(mods, layout, monkeypatch):
+    A, E = mods.analyze, mods.engine
+    monkeypatch.setattr(E, 'DEFAULT_LAYOUT', E.LAYOUT_FULL if layout == 'full' else E.LAYOUT_SPAN)
+    g = U.load('powder_match.npz')
+    for k in range(len(g['names'])):
+        _, gt, pr = U.powder_match_image(k)
+        res = A.det_seg_scores(gt, pr, 0.5)
+        for key in ('det_tp', 'det_fn', 'det_fp', 'seg_tp', 'seg_fn', 'seg_fp', 'det_tp_iou', 'seg_precision',
+                    'seg_recall'):
+            want = g['%d_%s' % (k, key)]
+            assert np.asarray(res[key]).dtype == want.dtype, key
+            assert np.array_equal(np.asarray(res[key]), want), (k, key)
+        assert [res['det_precision'], res['det_recall']] == list(g['%d_det_pr' % k])
+        if k < 2:
+            iou = A._piecewise_iou(gt, pr)
+            nz = np.argwhere(iou > 0)
+            assert np.array_equal(nz, g['%d_iou_nz_idx' % k])
+            assert np.array_equal(iou[nz[:, 0], nz[:, 1]], g['%d_iou_nz_val' % k])
+        for t, want in zip(g['thresholds'][1::3], g['%d_thr_counts' % k][1::3]):
+            mt = A.rle_instance_matcher(gt, pr, t)
+            assert [len(mt['tp']), len(mt['fp']), len(mt['fn'])] == list(want)
+
+
+def test_golden_satellites(mods):
+    P, S = mods.powder, mods.structures
+    from ampis_b200.containers import Instances
+    s = U.load('powder_satellite.npz')
+    psis = []
+    for k in range(len(s['names'])):
+        _, part, sat = U.powder_satellite_image(k)
+        size = tuple(int(v) for v in s['%d_size' % k])
+        res = P._rle_satellite_match(part, sat, 0.5)
+        for key in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched', 'intersection_scores'):
+            assert np.array_equal(res[key], s['%d_%s' % (k, key)]), (k, key)
+            assert res[key].dtype == s['%d_%s' % (k, key)].dtype
+        mk = lambda ms: S.InstanceSet(instances=Instances(size, masks=S.RLEMasks(ms),
+                                                          boxes=np.zeros((len(ms), 4))))
+        psi = P.PowderSatelliteImage(mk(part), mk(sat))
+        psi.compute_matches()
+        assert psi.matches['match_pairs'] == res['match_pairs']
+        met = psi.compute_satellite_metrics()
+        assert np.array_equal(met['mask_areas_all'], mods.rle.area(part))
+        psis.append(psi)
+    got = P.satellite_measurements(psis, print_summary=False, output_dict=True)
+    want = mods.R.satellite_measurements([p.matches for p in psis], [len(p.particles.instances) for p in psis],
+                                         [len(p.satellites.instances) for p in psis])
+    for key in want:
+        assert np.array_equal(np.asarray(got[key]), np.asarray(want[key])), key
+    # size distribution: same numerics as the oracle on the same areas, within 1e-6
+    isets = [p.particles for p in psis]
+    for x in isets:
+        x.HFW, x.HFW_units = 103.6, 'um'
+    out = P.psd(isets, plot=False, return_results=True)
+    ref = mods.R.psd_from_areas([mods.rle.area(p.particles.instances.masks.rle) * (103.6 / 1536) ** 2 for p in psis])
+    assert np.allclose(out['x'], ref['x'], rtol=1e-6, atol=0) and np.allclose(out['y'], ref['y'], rtol=1e-6, atol=0)
+    assert out['x_label'] == 'Equivalent diameter, um'
+
+
+def test_golden_polygons(mods):
+    S = mods.structures
+    from ampis_b200.containers import PolygonMasks
+    p = U.load('powder_polygons.npz')
+    xy, off = p['0_poly_xy'], p['0_poly_off']
+    size = tuple(int(v) for v in p['0_size'])
+    polys = [[xy[off[i]:off[i + 1]]] for i in range(len(off) - 1)]
+    got = S.masks_to_rle(PolygonMasks(polys), size)
+    want = U.unpack_strings(p['0_rle_blob'], p['0_rle_off'], size)
+    assert [g['counts'] for g in got] == [w['counts'] for w in want]
+    assert np.array_equal(S.mask_areas(got), p['0_area'])
+
+
+def test_polygons_random_vs_oracle(mods):
+    S, rle = mods.structures, mods.rle
+    from ampis_b200.containers import PolygonMasks
+    rng = np.random.default_rng(11)
+    for h, w in [(37, 53), (128, 96), (300, 200)]:
+        polys = []
+        for _ in range(60):
+            k = int(rng.integers(3, 30))
+            if rng.random() < 0.3:     # integer / half-integer vertices provoke ties and duplicate crossings
+                pts = rng.integers(-3, max(h, w) + 3, (k, 2)).astype(np.float64) + rng.choice([0.0, 0.5])
+            else:
+                ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+                r = rng.uniform(0.2, 0.6) * min(h, w) * rng.uniform(0.5, 1.0, k)
+                pts = np.stack([w * rng.uniform(0.1, 0.9) + r * np.cos(ang), h * rng.uniform(0.1, 0.9) + r * np.sin(ang)], 1)
+            polys.append([pts.ravel()])
+        polys.append([np.array([0.0, 0.0, float(w), 0.0, float(w), float(h), 0.0, float(h)])])   # whole frame
+        polys.append([np.array([5.0, 5.0, 5.0, 5.0, 5.0, 5.0])])                                    # degenerate
+        got = S.masks_to_rle(PolygonMasks(polys), (h, w))
+        want = [rle.frPyObjects(q, h, w)[0] for q in polys]
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert a['counts'] == b['counts'], (h, w, i)
+
+
+def _counts_to_rle(rle, cnts, h, w):
+    return [{'size': [h, w], 'counts': rle.string_from_counts(c)} for c in cnts]
+
+
+def test_random_masks_match_oracle(mods):
+    """Ragged / empty / odd-sized inputs: GPU matcher and satellite assignment == oracle."""
+    A, P, R, rle = mods.analyze, mods.powder, mods.R, mods.rle
+    rng = np.random.default_rng(3)
+    for h, w, G, Pn in [(7, 9, 3, 4), (33, 31, 12, 9), (64, 100, 40, 70), (50, 37, 1, 90), (129, 65, 85, 2)]:
+        a = U.rand_masks(rng, G, h, w)
+        b = U.rand_masks(rng, Pn, h, w)
+        b[: min(G, Pn) // 2] = a[: min(G, Pn) // 2]          # exact duplicates -> IoU 1 and ties
+        ea = [rle.encode(np.asfortranarray(x.astype(np.uint8))) for x in a]
+        eb = [rle.encode(np.asfortranarray(x.astype(np.uint8))) for x in b]
+        assert np.array_equal(A._piecewise_iou(ea, eb), R.piecewise_iou(ea, eb))
+        for th in (0.0, 0.3, 0.5, 0.99):
+            got, want = A._piecewise_rle_match(ea, eb, th), R.piecewise_rle_match(ea, eb, th)
+            for key in want:
+                assert np.array_equal(got[key], want[key]) and got[key].shape == want[key].shape, (key, th)
+        try:
+            want = R.rle_satellite_match(eb, ea, 0.5)
+        except IndexError:
+            with pytest.raises(IndexError):
+                P._rle_satellite_match(eb, ea, 0.5)
+        else:
+            got = P._rle_satellite_match(eb, ea, 0.5)
+            for key in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched', 'intersection_scores'):
+                assert np.array_equal(got[key], want[key]), key
+            assert got['match_pairs'] == want['match_pairs']
+    with pytest.raises(ZeroDivisionError):
+        A.det_seg_scores(mods.structures.RLEMasks([]), mods.structures.RLEMasks([]), 0.5)
+    with pytest.raises(IndexError):          # masks_to_rle peeks at masks[0] (structures.py:665)
+        A.det_seg_scores([], [], 0.5)
+
+
+def test_empty_and_error_conventions(mods):
+    A, S, rle = mods.analyze, mods.structures, mods.rle
+    z = _enc(rle, np.zeros((6, 5)))
+    o = _enc(rle, np.ones((6, 5)))
+    assert A._piecewise_rle_match([z], [z])['tp'].shape == (0,)
+    m = A._piecewise_rle_match([o, z], [])
+    assert m['fn'].tolist() == [0, 1] and m['fp'].tolist() == [] and m['tp'].shape == (0,)
+    m = A._piecewise_rle_match([], [o, z])
+    assert m['fp'].tolist() == [0, 1] and m['fn'].tolist() == []
+    with pytest.raises(NotImplementedError):
+        S.masks_to_rle(np.zeros((2, 3, 3), bool))
+    with pytest.raises(NotImplementedError):
+        S.mask_areas('nope')
+    with pytest.raises(AssertionError):
+        from ampis_b200.containers import PolygonMasks
+        S.masks_to_rle(PolygonMasks([[np.array([1., 1, 5, 1, 5, 5])]]))
+    with pytest.raises(ValueError):
+        S.mask_areas([{'size': [6, 5], 'counts': rle.string_from_counts(np.array([3, 3], np.uint32))}])
+
+
+@pytest.mark.parametrize('cfg,n_img', [('c1_powder_example', 2), ('c2_powder_batch', 2)])
+@pytest.mark.parametrize('layout', ['span', 'full'])
+def test_batch_pipeline_vs_oracle(mods, cfg, n_img, layout):
+    """Synthetic images through the batch pipeline == oracle per image (matches, IoUs, counts at
+    the ten COCO thresholds, dense intersections)."""
+    B, E, R, rle = mods.batch, mods.engine, mods.R, mods.rle
+    host = B.synth(cfg, n_img, 1001)
+    dev = B.DeviceBatch(host, dense=True)
+    lay = E.LAYOUT_FULL if layout == 'full' else E.LAYOUT_SPAN
+    res = B.eval_step(dev, layout=lay, check=True)
+    G, Pn = host.n_rows, host.n_cols
+    best_col = res.rows.best_col.cpu().numpy().reshape(n_img, G)
+    best_iou = res.rows.best_score.cpu().numpy().reshape(n_img, G)
+    counts = res.counts.cpu().numpy()
+    imat = res.rows.imat.cpu().numpy().reshape(n_img, G, Pn)
+    tot = np.zeros((len(B.COCO_THRESHOLDS), 3), np.int64)
+    for g in range(n_img):
+        rows, cols = host.image_masks(g)
+        er, ec = _counts_to_rle(rle, rows, host.h, host.w), _counts_to_rle(rle, cols, host.h, host.w)
+        iou = R.piecewise_iou(er, ec)
+        ar, ac = rle.area(er).astype(np.int64), rle.area(ec).astype(np.int64)
+        # dense intersections: invert iou = I/(a+b-I) exactly where iou>0 via the oracle merge on a sample
+        nz = np.argwhere(iou > 0)
+        assert np.array_equal(np.argwhere(imat[g] > 0), nz)
+        for i, j in nz[:: max(1, len(nz) // 200)]:
+            assert imat[g, i, j] == int(rle.merge_area(er[i], ec[j]))
+        I = imat[g].astype(np.int64)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            mine = np.where(I > 0, I / (ar[:, None] + ac[None, :] - I), 0.0)
+        assert np.array_equal(mine, iou)
+        assert (np.diff(counts[g, :, 0]) <= 0).all()
+        for ti in (0, 5, 9):
+            th = B.COCO_THRESHOLDS[ti]
+            m = R.piecewise_rle_match(er, ec, th)
+            assert counts[g, ti].tolist() == [len(m['tp']), len(m['fp']), len(m['fn'])]
+            tot[ti] += counts[g, ti]
+            if ti == 0:
+                matched = best_iou[g] > th
+                assert np.array_equal(np.nonzero(matched)[0], m['tp'][:, 0])
+                assert np.array_equal(best_col[g][matched], m['tp'][:, 1])
+                assert np.array_equal(best_iou[g][matched], m['iou'])
+    assert np.array_equal(res.totals.cpu().numpy()[[0, 5, 9]], tot[[0, 5, 9]])
+    assert np.array_equal(res.totals.cpu().numpy(), counts.sum(axis=0))
+
+
+def test_batch_satellites_vs_oracle(mods):
+    B, E, R, rle = mods.batch, mods.engine, mods.R, mods.rle
+    cfg = dict(B.CONFIGS['c3_satellites'], h=512, w=512, n_rows=40, n_cols=300)
+    host = B.synth(cfg, 3, 3003)
+    dev = B.DeviceBatch(host)
+    res = B.eval_step(dev, check=True)
+    S, Np = host.n_rows, host.n_cols
+    best = res.rows.best_col.cpu().numpy().reshape(3, S)
+    score = res.rows.best_score.cpu().numpy().reshape(3, S)
+    counts = res.counts.cpu().numpy()
+    spp = np.zeros(64, np.int64)
+    for g in range(3):
+        rows, cols = host.image_masks(g)
+        er, ec = _counts_to_rle(rle, rows, host.h, host.w), _counts_to_rle(rle, cols, host.h, host.w)
+        want = R.rle_satellite_match(ec, er, 0.5)
+        with np.errstate(invalid='ignore'):
+            matched = score[g] > 0.5
+        assert np.array_equal(np.stack([np.nonzero(matched)[0], best[g][matched]], 1), want['satellite_matches'])
+        assert np.array_equal(score[g][matched], want['intersection_scores'])
+        assert counts[g].tolist() == [len(want['satellite_matches']), len(want['satellites_unmatched']),
+                                      len(want['match_pairs']), Np]
+        for v in want['match_pairs'].values():
+            spp[min(len(v), 63)] += 1
+    assert np.array_equal(res.spp_hist.cpu().numpy(), spp)
+
+
+def test_full_size_properties(mods):
+    """BASELINE config sizes (C2 image count reduced): size-independent properties --
+    span and full layouts agree bit for bit, I(gt,pred) == I(pred,gt)^T, area == popcount of the
+    unpacked mask, counts add up, self-match gives IoU 1 for every non-empty mask."""
+    B, E, torch = mods.batch, mods.engine, mods.torch
+    host = B.synth('c2_powder_batch', 6, 2002)
+    dev = B.DeviceBatch(host, dense=True)
+    a = B.eval_step(dev, layout=E.LAYOUT_SPAN, check=True)
+    b = B.eval_step(dev, layout=E.LAYOUT_FULL, check=True)
+    for x, y in [(a.rows.best_col, b.rows.best_col), (a.rows.best_inter, b.rows.best_inter),
+                 (a.rows.best_score, b.rows.best_score), (a.rows.imat, b.rows.imat), (a.counts, b.counts),
+                 (a.table.area, b.table.area), (a.table.bbox, b.table.bbox)]:
+        assert torch.equal(x, y)
+    G, P, n = host.n_rows, host.n_cols, host.n_images
+    c = a.counts.cpu().numpy()
+    assert (c[:, :, 0] + c[:, :, 2] == G).all() and (c[:, :, 1] <= P).all() and (c[:, :, 0] >= 0).all()
+    assert (np.diff(c[:, :, 0], axis=1) <= 0).all()          # TP is monotone in the threshold
+    # transpose property: swap the roles of rows and columns
+    per = G + P
+    idx = np.arange(n * per).reshape(n, per)
+    idx = np.concatenate([idx[:, G:], idx[:, :G]], 1).ravel()
+    host_t = B.HostCSR(dict(host.cfg, n_rows=P, n_cols=G), n, host.cnt, host.cnt_off[idx], host.cnt_len[idx])
+    t = B.eval_step(B.DeviceBatch(host_t, dense=True), check=True)
+    assert torch.equal(t.rows.imat.view(n, P, G).transpose(1, 2).contiguous(), a.rows.imat.view(n, G, P))
+    # area == popcount of unpacked bits (first image, rows)
+    ub = E.unpack_bool(b.table, np.arange(0, 64), host.h, host.w)
+    assert torch.equal(ub.sum(dim=(1, 2)).int(), b.table.area[:64])
+    # self match: rows vs rows
+    idx2 = np.arange(n * per).reshape(n, per)[:, :G]
+    idx2 = np.concatenate([idx2, idx2], 1).ravel()
+    host_s = B.HostCSR(dict(host.cfg, n_cols=G), n, host.cnt, host.cnt_off[idx2], host.cnt_len[idx2])
+    s = B.eval_step(B.DeviceBatch(host_s), check=True)
+    area = s.table.area.view(n, 2 * G)[:, :G].reshape(-1)
+    sc = s.rows.best_score
+    assert bool(((sc == 1.0) | (area == 0)).all())
+
+
+def test_hist_and_scan(mods):
+    E, torch = mods.engine, mods.torch
+    rng = np.random.default_rng(0)
+    v = rng.integers(0, 50000, 100003).astype(np.uint32)
+    d = torch.from_numpy(v.view(np.int32)).cuda()
+    hist = E.hist_u32(d, 100, 37, 512).cpu().numpy()
+    b = np.clip((v.astype(np.int64) - 100) // 37, 0, 511)
+    assert np.array_equal(hist, np.bincount(b, minlength=512))
+    from ampis_b200 import _native as N
+    for n in (1, 5, 2048, 2049, 300001):
+        x = torch.from_numpy(rng.integers(0, 1 << 33, n)).cuda()
+        out = torch.empty(n + 1, dtype=torch.int64, device='cuda')
+        nb = N.lib().ampis_scan_tmp_bytes(n)
+        tmp = torch.empty(nb // 8 + 1, dtype=torch.int64, device='cuda')
+        N.call('ampis_exclusive_scan_i64', E._p(x), E._p(out), n, E._p(tmp), nb, E._stream())
+        want = np.concatenate([[0], np.cumsum(x.cpu().numpy())])
+        assert np.array_equal(out.cpu().numpy(), want)

@@ -1,0 +1,133 @@
+"""CPU tests of the host side: the C ABI library loads and exports every declared symbol,
+containers behave like the reference's, group bookkeeping and the synthetic generator are
+consistent.  No kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ampis_b200 import _native
+    lib = _native.lib()
+    hdr = open(os.path.join(ROOT, 'include', 'ampis_b200.h')).read()
+    declared = set(re.findall(r'\b(ampis_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations found'
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ampis_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from ampis_b200 import analyze, engine
+    if torch.cuda.is_available():
+        pytest.skip('a device is present')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        engine.require_cuda()
+    m = {'size': [4, 4], 'counts': b'02208'}
+    with pytest.raises(RuntimeError):
+        analyze._piecewise_rle_match([m], [m])
+
+
+def test_product_never_imports_oracle():
+    import glob
+    for f in glob.glob(os.path.join(ROOT, 'ampis_b200', '**', '*.py'), recursive=True):
+        src = open(f).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f
+        assert 'oracle.' not in src and 'libmaskapi_ref' not in src, f
+
+
+def test_rlemasks_indexing():
+    import torch
+    from ampis_b200.structures import RLEMasks
+    r = RLEMasks([{'size': [2, 2], 'counts': bytes([48 + i])} for i in range(5)])
+    assert len(r) == 5
+    assert type(r[1].rle) == dict and len(r[1]) == 2               # quirk B.13: int wraps a dict
+    assert [m['counts'] for m in r[1:3].rle] == [b'1', b'2']
+    assert [m['counts'] for m in r[[4, 0]].rle] == [b'4', b'0']
+    assert [m['counts'] for m in r[np.array([3, 1])].rle] == [b'3', b'1']
+    mask = np.array([True, False, True, False, False])
+    assert [m['counts'] for m in r[mask].rle] == [b'0', b'2']
+    assert [m['counts'] for m in r[[bool(x) for x in mask]].rle] == [b'0', b'2']
+    assert [m['counts'] for m in r[torch.tensor(mask)].rle] == [b'0', b'2']
+    with pytest.raises(AssertionError):
+        r[np.array([True, False])]
+
+
+def test_instances_container_and_instance_set():
+    from ampis_b200.containers import Instances, PolygonMasks, load_pickle  # noqa: F401
+    from ampis_b200.structures import InstanceSet, RLEMasks
+    masks = RLEMasks([{'size': [4, 4], 'counts': b'02208'}] * 3)
+    inst = Instances((4, 4), masks=masks, boxes=np.zeros((3, 4)), class_idx=np.arange(3))
+    assert len(inst) == 3 and inst.image_size == (4, 4) and inst.has('boxes') and not inst.has('scores')
+    sub = inst[np.array([True, False, True])]
+    assert len(sub) == 2 and sub.class_idx.tolist() == [0, 2] and len(sub.masks) == 2
+    with pytest.raises(AssertionError):
+        inst.scores = np.zeros(2)
+    ddict = {'file_name': 'a/b.png', 'mask_format': 'polygon', 'height': 10, 'width': 12, 'HFW': '103.6 um',
+             'annotations': [{'category_id': 0, 'bbox': [1, 1, 5, 5],
+                              'segmentation': [[1.5, 1.5, 5.5, 1.5, 5.5, 5.5, 1.5, 5.5]]}]}
+    iset = InstanceSet().read_from_ddict(ddict, inplace=False)
+    assert iset.HFW == 103.6 and iset.HFW_units == 'um' and iset.pred_or_gt == 'gt'
+    assert type(iset.instances.masks) == PolygonMasks and iset.instances.colors.shape == (1, 3)
+    outs = {'file_name': 'x.png', 'dataset': 'powder_Training',
+            'pred': {'instances': Instances((4, 4), pred_masks=masks.rle, pred_boxes=np.zeros((3, 4)),
+                                            pred_classes=np.zeros(3, int), scores=np.ones(3))}}
+    pset = InstanceSet().read_from_model_out(outs, inplace=False)
+    assert pset.dataset_class == 'Training' and type(pset.instances.masks) == RLEMasks and len(pset.instances) == 3
+    c = pset.copy()
+    assert c is not pset and len(c.instances) == 3
+
+
+def test_align_and_merge_boxes_and_shoelace():
+    from ampis_b200 import analyze, structures
+
+    class F:
+        def __init__(self, p):
+            self.filepath = p
+    a = [F('x/1.png'), F('x/2.png'), F('x/3.png')]
+    b = [F('y/3.png'), F('y/1.png')]
+    ao, bo = analyze.align_instance_sets(a, b)
+    assert [i.filepath for i in ao] == ['x/1.png', 'x/3.png'] and [i.filepath for i in bo] == ['y/1.png', 'y/3.png']
+    assert analyze.merge_boxes([1, 5, 2, 6], [0, 4, 3, 9]).tolist() == [0, 5, 2, 9]
+    assert structures._shoelace_area(np.array([0., 4, 4, 0]), np.array([0., 0, 3, 3])) == 12.0
+    assert structures.boxes_to_array([[1, 2, 3, 4]]).shape == (1, 4)
+    assert analyze.fast_instance_match is analyze.rle_instance_matcher
+
+
+def test_group_bookkeeping_host_side():
+    import torch
+    from ampis_b200 import engine
+    g = engine.Groups.interleaved(torch.device('cpu'), [2, 0, 3], [4, 5, 1], dense=True)
+    assert g.row_mask.tolist() == [0, 1, 11, 12, 13] and g.row_grp.tolist() == [0, 0, 2, 2, 2]
+    assert g.grp_row_begin.tolist() == [0, 2, 2] and g.grp_col_begin.tolist() == [2, 6, 14]
+    assert g.grp_col_count.tolist() == [4, 5, 1] and g.max_cols == 5
+    assert g.h_imat_off.tolist() == [0, 8, 8, 11] and g.imat_size == 11
+
+
+def test_match_bookkeeping_from_rows():
+    from ampis_b200.analyze import _match_from_rows
+    r = _match_from_rows(np.array([2, -1, 0, 2]), np.array([0.9, 0.0, 0.5, 0.6]), 4, 0.5)
+    assert r['tp'].tolist() == [[0, 2], [3, 2]] and r['fn'].tolist() == [1, 2] and r['fp'].tolist() == [0, 1, 3]
+    assert r['iou'].tolist() == [0.9, 0.6]
+    r = _match_from_rows(np.array([-1]), np.array([0.0]), 2, 0.5)
+    assert r['tp'].shape == (0,) and r['fp'].tolist() == [0, 1]
+
+
+@pytest.mark.parametrize('name', ['c1_powder_example', 'c2_powder_batch', 'c3_satellites', 'c4_spheroidite'])
+def test_synthetic_generator_is_valid_and_deterministic(name):
+    from ampis_b200 import batch
+    h1 = batch.synth(name, 2, 99, n_threads=1)
+    h2 = batch.synth(name, 2, 99, n_threads=4)
+    assert np.array_equal(h1.cnt, h2.cnt) and np.array_equal(h1.cnt_off, h2.cnt_off)
+    hw = h1.h * h1.w
+    for k in range(h1.n_masks):
+        c = h1.cnt[h1.cnt_off[k]:h1.cnt_off[k] + h1.cnt_len[k]]
+        assert int(c.astype(np.int64).sum()) == hw
+        assert (c[1:] > 0).all()                         # canonical: no interior zero-length runs
+    assert h1.n_masks == 2 * (h1.n_rows + h1.n_cols)
