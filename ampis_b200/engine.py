@@ -56,8 +56,8 @@ class MaskTable(object):
         self.span = torch.empty(2 * n1, dtype=i32, device=device)      # uint32 payload
         self.reg = torch.empty(2 * n1, dtype=i32, device=device)       # uint32 payload
         self.reg_chunks = torch.empty(n1, dtype=i64, device=device)
-        self.status = torch.zeros(n1, dtype=i32, device=device)
-        self.bits_off = torch.zeros(n1 + 1, dtype=i64, device=device)
+        self.status = torch.empty(n1, dtype=i32, device=device)
+        self.bits_off = torch.empty(n1 + 1, dtype=i64, device=device)
         self.bits = None
         self.bits_capacity = 0
 

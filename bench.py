@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-span', action='store_true', help='skip the secondary span-layout measurement')
     ap.add_argument('--cpu-images', type=int, default=0)
     return ap.parse_args()
 
@@ -178,6 +179,112 @@ def workload_name(args, host):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+KERNELS = ['measure+scan', 'paint', 'rows', 'counts']
+
+
+class LayoutRun(object):
+    """Inputs of one rank resident in HBM + the workspace for one storage layout."""
+
+    def __init__(self, args, dev, rank, layout, sub):
+        import torch
+        from ampis_b200 import batch, engine
+        self.layout, self.sub, self.dev = layout, sub, dev
+        t0 = time.time()
+        self.subs = []
+        for s0 in range(0, args.images, sub):
+            k = min(sub, args.images - s0)
+            host = batch.synth(args.config, k, 1_000_003 * (rank + 1) + s0)
+            self.subs.append(batch.DeviceBatch(host, dev, dense=True))
+        self.t_gen = time.time() - t0
+        self.total_runs = sum(b.host.total_runs() for b in self.subs)
+        need = [batch.arena_chunks_needed(b, layout) for b in self.subs]
+        self.stored_chunks = sum(need)
+        self.arena = torch.empty(4 * max(need), dtype=torch.int32, device=dev)
+        n_rows = max(b.groups.n_rows for b in self.subs)
+        self.rows_out = engine.RowResult(torch.empty(n_rows, dtype=torch.int32, device=dev),
+                                         torch.empty(n_rows, dtype=torch.int32, device=dev),
+                                         torch.empty(n_rows, dtype=torch.float64, device=dev),
+                                         torch.empty(max(b.groups.imat_size for b in self.subs), dtype=torch.int32,
+                                                     device=dev))
+        self.thresholds = batch.COCO_THRESHOLDS
+        self.totals = torch.zeros(len(self.thresholds) * 3, dtype=torch.int64, device=dev)
+
+    def step(self, world, dist, record=None):
+        """one pass over the rank's batch; `record` collects the CUDA events around each kernel group"""
+        import torch
+        from ampis_b200 import engine
+        self.totals.zero_()
+        for b in self.subs:
+            t = engine.MaskTable(self.dev, b.host.n_masks, b.cnt, b.cnt_off, b.cnt_len, b.h, b.w, self.layout)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record is not None else None
+            if ev: ev[0].record()
+            t.measure()
+            if ev: ev[1].record()
+            t.paint(self.arena)
+            if ev: ev[2].record()
+            rows = engine.intersect_rows(t, b.groups, b.mode, out=self.rows_out)
+            if ev: ev[3].record()
+            engine.match_counts(rows, b.groups, self.thresholds, totals=self.totals)
+            if ev:
+                ev[4].record()
+                record.append(ev)
+        if world > 1:
+            dist.all_reduce(self.totals)      # TP/FP/FN x thresholds: the only exchange on this path
+        return self.totals
+
+    def timed(self, args, world, dist, sync):
+        import torch
+        for _ in range(max(args.warmup, 3)):
+            self.step(world, dist)
+        sync()
+        record = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            self.step(world, dist, record)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        kt = np.zeros(4)
+        for ev in record:
+            for i in range(4):
+                kt[i] += ev[i].elapsed_time(ev[i + 1])
+        return float(ms.item()), kt, self.totals.cpu().numpy().reshape(-1, 3)
+
+
+def roofline_of(args, cfg, run, ms, kt, world):
+    """Roofline of the dominant kernel + the whole step against the canonical accounting."""
+    from ampis_b200 import engine
+    peak, peak_src = peaks()
+    n_img = args.images
+    per_image = cfg['n_rows'] + cfg['n_cols']
+    B_m = ((cfg['h'] * cfg['w'] + 127) // 128) * 16
+    n_masks = n_img * per_image
+    pairs_img = cfg['n_rows'] * cfg['n_cols']
+    # SURVEY 8d per-kernel figures: decode = 4R + bytes stored; intersection = (G+P)*B_m + 4*G*P
+    alg = {'paint': 4 * run.total_runs + run.stored_chunks * 16, 'rows': n_masks * B_m + 4 * n_img * pairs_img}
+    canonical_img = 4 * run.total_runs / n_img + 2 * per_image * B_m + 4 * pairs_img + 8 * per_image + 32 * cfg['n_rows']
+    dom = 'paint' if kt[1] >= kt[2] else 'rows'
+    launches = len(run.subs)
+    dur_ms = kt[KERNELS.index(dom)] / (args.steps * launches)
+    achieved = alg[dom] / launches / (dur_ms / 1e3) / 1e9
+    lay = 'full' if run.layout == engine.LAYOUT_FULL else 'span'
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('%s/%s/%s' % (args.config, lay, dom))
+    step_gbs = canonical_img * n_img * args.steps / (ms / 1e3) / 1e9
+    return {'bound': 'hbm', 'kernel': {'paint': 'rle_paint_kernel', 'rows': 'intersect_rows_kernel'}[dom],
+            'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+            'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom] / launches, 'launch_ms': dur_ms,
+            'step_canonical': {'bytes_per_image': canonical_img, 'achieved': step_gbs, 'frac': step_gbs / peak,
+                               'note': 'whole step per GPU vs the two-pass full-frame accounting of SURVEY 8d; '
+                                       'bbox/span culling lets the step move fewer bytes than that'},
+            'kernel_share': {k: float(v) for k, v in zip(KERNELS, kt / kt.sum())}}
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -198,150 +305,79 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     N.lib()
 
-    cfg = batch.CONFIGS[args.config]
-    layout = engine.LAYOUT_FULL if args.layout == 'full' else engine.LAYOUT_SPAN
-    n_img = args.images
-    chunks_per_mask = (cfg['h'] * cfg['w'] + 127) // 128
-    per_image = cfg['n_rows'] + cfg['n_cols']
-    if args.sub:
-        sub = args.sub
-    elif layout == engine.LAYOUT_FULL:
-        sub = max(1, min(n_img, int(12e9 // (per_image * chunks_per_mask * 16))))   # ~12 GB arena
-    else:
-        sub = min(n_img, 250)
-    thresholds = batch.COCO_THRESHOLDS
-
-    # ---- inputs: generated on the host, uploaded once (resident in HBM before the timed region)
-    t_gen = time.time()
-    subs = []
-    for s0 in range(0, n_img, sub):
-        k = min(sub, n_img - s0)
-        host = batch.synth(args.config, k, 1_000_003 * (rank + 1) + s0)
-        subs.append(batch.DeviceBatch(host, dev, dense=True))
-    t_gen = time.time() - t_gen
-    host0 = subs[0].host
-    total_runs = sum(b.host.total_runs() for b in subs)
-    arena_chunks = max(batch.arena_chunks_needed(b, layout) for b in subs)
-    arena = torch.empty(4 * arena_chunks, dtype=torch.int32, device=dev)
-    imat_elems = max(b.groups.imat_size for b in subs)
-    rows_out = [engine.RowResult(torch.empty(b.groups.n_rows, dtype=torch.int32, device=dev),
-                                 torch.empty(b.groups.n_rows, dtype=torch.int32, device=dev),
-                                 torch.empty(b.groups.n_rows, dtype=torch.float64, device=dev),
-                                 torch.empty(imat_elems, dtype=torch.int32, device=dev)) for b in subs[:1]]
-    span_chunks = sum(batch.arena_chunks_needed(b, engine.LAYOUT_SPAN) for b in subs)
-    totals = torch.zeros(len(thresholds) * 3, dtype=torch.int64, device=dev)
-    KERNELS = ['measure+scan', 'paint', 'rows', 'counts']
-
-    def step(record=None):
-        """one pass over the rank's batch; `record` collects (kernel, start_event, end_event)"""
-        totals.zero_()
-        for b in subs:
-            t = engine.MaskTable(dev, b.host.n_masks, b.cnt, b.cnt_off, b.cnt_len, b.h, b.w, layout)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record is not None else None
-            if ev: ev[0].record()
-            t.measure()
-            if ev: ev[1].record()
-            t.paint(arena)
-            if ev: ev[2].record()
-            rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out[0])
-            if ev: ev[3].record()
-            engine.match_counts(rows, b.groups, thresholds, totals=totals)
-            if ev:
-                ev[4].record()
-                record.append(ev)
-        if world > 1:
-            dist.all_reduce(totals)          # TP/FP/FN x thresholds: the only exchange on this path
-        return totals
-
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync()
-    sampler = ClockSampler(local) if rank == 0 else None
-    record = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step(record)
-    e1.record()
-    sync()
-    wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(wall0, wall1) if sampler else None
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
-    final_totals = totals.cpu().numpy().reshape(-1, 3)
+    cfg = batch.CONFIGS[args.config]
+    layout = engine.LAYOUT_FULL if args.layout == 'full' else engine.LAYOUT_SPAN
+    per_image = cfg['n_rows'] + cfg['n_cols']
+    B_m = ((cfg['h'] * cfg['w'] + 127) // 128) * 16
 
-    kt = np.zeros(4)
-    for ev in record:
-        for i in range(4):
-            kt[i] += ev[i].elapsed_time(ev[i + 1])
-    n_launch_groups = len(record)
+    def auto_sub(lay):
+        if args.sub:
+            return args.sub
+        if lay == engine.LAYOUT_FULL:
+            return max(1, min(args.images, int(12e9 // (per_image * B_m))))       # ~12 GB arena
+        return min(args.images, 250)
+
+    sampler = ClockSampler(local) if rank == 0 else None       # samples cover warm-up + timed steps
+    wall0 = time.time()
+    run = LayoutRun(args, dev, rank, layout, auto_sub(layout))
+    ms, kt, final_totals = run.timed(args, world, dist, sync)
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
 
     # ---- end to end through host buffers: compressed RLE strings in pinned memory -> H2D -> GPU string
     # decode -> same pipeline -> D2H of per-image counts and per-GT matches
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, subs, dev, layout, arena, rows_out[0], thresholds, world, dist, sync)
+        e2e = run_e2e(args, run.subs, dev, layout, run.arena, run.rows_out, run.thresholds, world, dist, sync)
 
+    # ---- the culled storage layout (product default), measured beside the canonical one
+    span = None
+    if layout == engine.LAYOUT_FULL and not args.no_span:
+        del run.arena
+        srun = LayoutRun(args, dev, rank, engine.LAYOUT_SPAN, auto_sub(engine.LAYOUT_SPAN))
+        sms, skt, stot = srun.timed(args, world, dist, sync)
+        assert np.array_equal(stot, final_totals), 'span and full layouts disagree'
+        span = {'value': world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (sms / 1e3), 'unit': UNIT,
+                'images_per_s': world * args.images * args.steps / (sms / 1e3), 'ms_per_step': sms / args.steps,
+                'images_per_launch': srun.sub, 'roofline': roofline_of(args, cfg, srun, sms, skt, world),
+                'note': 'same inputs and bit-identical results; only first..last 1-pixel of each mask is stored'}
+        if not args.no_e2e:
+            span['e2e'] = run_e2e(args, srun.subs, dev, engine.LAYOUT_SPAN, srun.arena, srun.rows_out,
+                                  srun.thresholds, world, dist, sync)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pairs_per_step = world * n_img * cfg['n_rows'] * cfg['n_cols']
-    value = pairs_per_step * args.steps / (ms / 1e3)
-    peak, peak_src = peaks()
-    B_m = chunks_per_mask * 16
-    n_masks = n_img * per_image
-    bytes_decode = 4 * total_runs + (n_masks * B_m if layout == engine.LAYOUT_FULL else span_chunks * 16)
-    bytes_rows = n_masks * B_m + 4 * n_img * cfg['n_rows'] * cfg['n_cols']
-    canonical_img = (4 * total_runs / n_img + 2 * per_image * B_m + 4 * cfg['n_rows'] * cfg['n_cols']
-                     + 8 * per_image + 32 * cfg['n_rows'])
-    alg = {'paint': bytes_decode, 'rows': bytes_rows}
-    share = kt / kt.sum()
-    dom = 'paint' if kt[1] >= kt[2] else 'rows'
-    di = KERNELS.index(dom)
-    launches = len(subs)                                 # launches of the dominant kernel per step
-    dur_ms = kt[di] / (args.steps * launches)
-    achieved = alg[dom] / launches / (dur_ms / 1e3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get('%s/%s/%s' % (args.config, args.layout, dom))
+    host0 = run.subs[0].host
+    n_masks = args.images * per_image
+    value = world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (ms / 1e3)
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u32', 'data': 'synthetic',
-        'images_per_s': world * n_img * args.steps / (ms / 1e3),
-        'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': n_img, 'layout': args.layout,
-                   'images_per_launch': sub, 'thresholds': 'IoU 0.50:0.05:0.95',
-                   'runs_per_mask': total_runs / n_masks, 'l2': 'inputs (%.0f MB run counts) and the %.1f GB packed-'
-                   'mask arena are larger than L2; no explicit flush' % (4 * total_runs / 1e6, arena.numel() * 4 / 1e9),
-                   'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce per step' % world},
-        'roofline': {'bound': 'hbm', 'kernel': {'paint': 'rle_paint_kernel', 'rows': 'intersect_rows_kernel'}[dom],
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom] / launches,
-                     'launch_ms': dur_ms,
-                     'step_canonical': {'bytes_per_image': canonical_img,
-                                        'achieved': canonical_img * n_img * args.steps / (ms / 1e3) / 1e9 * 1.0,
-                                        'frac': canonical_img * n_img * args.steps / (ms / 1e3) / 1e9 / peak,
-                                        'note': 'whole step vs the two-pass full-frame accounting of SURVEY 8d '
-                                                '(per GPU); bbox culling lets the intersection read less than it'},
-                     'kernel_share': {k: float(s) for k, s in zip(KERNELS, share)}},
-        'gpu_launches': int(args.steps * len(subs) * 7),
+        'images_per_s': world * args.images * args.steps / (ms / 1e3),
+        'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
+                   'layout': args.layout, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95',
+                   'runs_per_mask': run.total_runs / n_masks,
+                   'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
+                         'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
+                                                                          run.stored_chunks * 16 / len(run.subs) / 1e9),
+                   'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN per step' % world},
+        'roofline': roofline_of(args, cfg, run, ms, kt, world),
+        'gpu_launches': int(args.steps * len(run.subs) * 7),
         'totals_tp_fp_fn_at_0.50': final_totals[0].tolist(),
-        'clocks': clocks, 'setup_s': {'synthesize': t_gen},
+        'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},
     }
     if e2e:
         out['e2e'] = e2e
+    if span:
+        out['span_layout'] = span
     if not args.no_cpu:
         out['cpu_baseline'] = cpu_baseline(args)
     print(json.dumps(out))
