@@ -29,8 +29,11 @@ SIGNATURES = {
     'ampis_unpack_bool_nrc': (C.c_int, [_p, _p, _p, _p, _i32, _u32, _u32, _p, _p]),
     'ampis_bool_area_bbox': (C.c_int, [_p, _i32, _u32, _u32, _p, _p, _p]),
     'ampis_pack_bool_nrc': (C.c_int, [_p, _i32, _u32, _u32, _p, _p, _p]),
-    'ampis_intersect_rows': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p,
-                                       _p, _p]),
+    'ampis_rows_per_block': (C.c_int, []),
+    'ampis_intersect_rows': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p,
+                                       _p, _p, _p]),
+    'ampis_rle_measure_paint': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
+                                          _p]),
     'ampis_iou_matrix_f64': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p]),
     'ampis_match_counts': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p]),
     'ampis_satellite_counts': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _p, _p, _i32, _p]),

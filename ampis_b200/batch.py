@@ -113,14 +113,19 @@ class StepResult(object):
 
 
 def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_out=None,
-              sat_thresh=0.5, check=False):
+              sat_thresh=0.5, check=False, fused=None):
     """One pass of the hot path over a device-resident batch: measure -> paint -> fused
     intersect/arg-max rows -> per-image and total counts.  No host synchronisation when an
     arena is supplied and check is False.  Returns device tensors."""
     layout = engine.DEFAULT_LAYOUT if layout is None else layout
     t = engine.MaskTable(batch.device, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
                          batch.w, layout)
-    t.measure().paint(arena)
+    if fused is None:
+        fused = arena is not None
+    if fused:
+        t.measure_paint(arena)       # one launch: measure + arena allocation + paint
+    else:
+        t.measure().paint(arena)     # five launches; sizes the arena exactly when none is given
     rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out)
     r = StepResult()
     r.table, r.rows = t, rows

@@ -8,12 +8,17 @@
 //   powder._rle_satellite_match   (powder.py:80-86)     for each satellite:
 //       area(merge(sat, particle, intersect)) / area(sat) against all particles, np.argmax.
 //
-// One warp owns one row mask.  Column masks are scanned 32 at a time (lane = column): a
-// tight-bbox + span overlap test yields the candidate set (pruning cannot change a result:
-// disjoint boxes => intersection 0 => score 0).  Candidates are then intersected one after
-// another by the whole warp: 128-bit loads of both packed masks over the overlap of their
-// spans, AND + popc, warp reduction.
+// A CTA owns up to 8 consecutive rows of ONE group (image); a warp owns one row.  The
+// column masks' metadata (tight box, span, area, biased data pointer) is staged once per CTA
+// into shared memory in tiles, so the 32-columns-at-a-time candidate scan of every warp runs
+// out of shared memory instead of paying a global round trip per step.  Candidates (boxes
+// overlap AND spans overlap; pruning cannot change a result: disjoint boxes => intersection 0
+// => score 0) are then intersected one after another by the whole warp: 128-bit loads of both
+// packed masks over the overlap of their spans, AND + popc, warp reduction.
 #include "common.cuh"
+
+#define ROWS_PER_CTA 8
+#define COL_TILE 512
 
 struct RowArgs {
     const uint4 *bits;
@@ -23,9 +28,10 @@ struct RowArgs {
     const int4 *bbox;
     const u32 *area;
     const int *row_mask;
-    const int *row_grp;
-    int n_rows;
+    const int *blk_grp;        // group of CTA b
+    const int *blk_row0;       // first row of CTA b
     const int *grp_row_begin;
+    const int *grp_row_count;
     const int *grp_col_begin;
     const int *grp_col_count;
     const i64 *grp_imat_off;
@@ -35,84 +41,109 @@ struct RowArgs {
     double *best_score;
 };
 
-// popcount(A & B) over chunks [lo,hi) of two masks; pointers are biased so that chunk c of a
-// mask is at base[c]. Whole-warp cooperative, 4 x 128-bit loads per operand in flight per lane.
+// popcount(A & B) over chunks [lo,hi); pointers are biased so that chunk c of a mask is at
+// base[c].  Whole-warp cooperative; up to 4 x 128-bit loads per operand in flight per lane,
+// predicated so that ranges up to 128 chunks (2 KB per operand) take ONE memory round trip.
 __device__ __forceinline__ u32 warp_intersect(const uint4 *__restrict__ A, const uint4 *__restrict__ B,
                                               u32 lo, u32 hi, u32 lane)
 {
     u32 acc = 0;
-    u32 c = lo + lane;
-    for (; c + 96 < hi; c += 128) {
-        const uint4 a0 = ld_v4_nc(A + c), a1 = ld_v4_nc(A + c + 32), a2 = ld_v4_nc(A + c + 64),
-                    a3 = ld_v4_nc(A + c + 96);
-        const uint4 b0 = ld_v4_nc(B + c), b1 = ld_v4_nc(B + c + 32), b2 = ld_v4_nc(B + c + 64),
-                    b3 = ld_v4_nc(B + c + 96);
-        acc += popc_and(a0, b0) + popc_and(a1, b1) + popc_and(a2, b2) + popc_and(a3, b3);
+    for (u32 c = lo + lane; c < hi; c += 128) {
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const u32 cc = c + 32u * k;
+            if (cc < hi) { a[k] = ld_v4_nc(A + cc); b[k] = ld_v4_nc(B + cc); }
+            else { a[k] = make_uint4(0u, 0u, 0u, 0u); b[k] = a[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += popc_and(a[k], b[k]);
     }
-    for (; c < hi; c += 32) acc += popc_and(ld_v4_nc(A + c), ld_v4_nc(B + c));
     return warp_sum(acc);
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
 intersect_rows_kernel(const RowArgs p)
 {
-    const int r = (int)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
-    if (r >= p.n_rows) return;
-    const u32 lane = lane_id();
-    const int rm = p.row_mask[r];
-    const int g = p.row_grp[r];
+    __shared__ int4 s_bbox[COL_TILE];
+    __shared__ uint2 s_span[COL_TILE];
+    __shared__ u32 s_area[COL_TILE];
+    __shared__ const uint4 *s_base[COL_TILE];
+
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const int g = p.blk_grp[blockIdx.x];
+    const int r = p.blk_row0[blockIdx.x] + (int)wid;
+    const bool valid = r < p.grp_row_begin[g] + p.grp_row_count[g];
     const int cb = p.grp_col_begin[g];
     const int P = p.grp_col_count[g];
     const i64 imat_off = (p.imat && p.grp_imat_off) ? p.grp_imat_off[g] : -1;
-    int *irow = imat_off >= 0 ? p.imat + imat_off + (i64)(r - p.grp_row_begin[g]) * P : nullptr;
+    int *irow = (valid && imat_off >= 0) ? p.imat + imat_off + (i64)(r - p.grp_row_begin[g]) * P : nullptr;
 
-    const int4 rb = p.bbox[rm];
-    const uint2 rs = p.span[rm];
-    const u32 ra = p.area[rm];
-    const uint4 *A = p.bits + p.bits_off[rm] - p.reg[rm].x;
+    int4 rb = make_int4(0, 0, -1, -1);
+    uint2 rs = make_uint2(0u, 0u);
+    u32 ra = 0;
+    const uint4 *A = nullptr;
+    if (valid) {
+        const int rm = p.row_mask[r];
+        rb = p.bbox[rm];
+        rs = p.span[rm];
+        ra = p.area[rm];
+        A = p.bits + p.bits_off[rm] - p.reg[rm].x;
+    }
 
     // lane-local running best over the columns this lane owns (increasing index => first max)
     double best_s = 0.0;
     u32 best_i = 0;
     int best_c = MODE == AMPIS_MODE_IOU ? -1 : (P > 0 ? 0 : -1);
 
-    for (int c0 = 0; c0 < P; c0 += 32) {
-        const int c = c0 + (int)lane;
-        bool cand = false;
-        uint2 cs = make_uint2(0u, 0u);
-        u32 ca = 0;
-        if (c < P && ra > 0) {
-            const int cm = cb + c;
-            const int4 b = p.bbox[cm];
-            cs = p.span[cm];
-            ca = p.area[cm];
-            cand = max(rb.x, b.x) <= min(rb.z, b.z) && max(rb.y, b.y) <= min(rb.w, b.w) &&
-                   max(rs.x, cs.x) < min(rs.y, cs.y);
+    for (int t0 = 0; t0 < P; t0 += COL_TILE) {
+        const int tn = min(COL_TILE, P - t0);
+        __syncthreads();   // previous tile fully consumed
+        for (int k = threadIdx.x; k < tn; k += blockDim.x) {
+            const int cm = cb + t0 + k;
+            s_bbox[k] = p.bbox[cm];
+            s_span[k] = p.span[cm];
+            s_area[k] = p.area[cm];
+            s_base[k] = p.bits + p.bits_off[cm] - p.reg[cm].x;
         }
-        u32 inter = 0;
-        u32 todo = __ballot_sync(0xffffffffu, cand);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int cm = cb + c0 + src;
-            const u32 slo = __shfl_sync(0xffffffffu, cs.x, src);
-            const u32 shi = __shfl_sync(0xffffffffu, cs.y, src);
-            const uint4 *B = p.bits + p.bits_off[cm] - p.reg[cm].x;
-            const u32 v = warp_intersect(A, B, max(rs.x, slo), min(rs.y, shi), lane);
-            if ((int)lane == src) inter = v;
-        }
-        if (c < P) {
-            if (irow) irow[c] = (int)inter;
-            if (MODE == AMPIS_MODE_IOU) {
-                // rleIou: u = a_r + a_c - i (the run walk's union); i == 0 => iou 0.0
-                const double s = inter ? (double)inter / (double)(ra + ca - inter) : 0.0;
-                if (s > best_s) { best_s = s; best_i = inter; best_c = c; }
-            } else {
-                if (inter > best_i) { best_i = inter; best_c = c; }
+        __syncthreads();
+        if (!valid) continue;
+        for (int c0 = 0; c0 < tn; c0 += 32) {
+            const int k = c0 + (int)lane;
+            bool cand = false;
+            uint2 cs = make_uint2(0u, 0u);
+            u32 ca = 0;
+            if (k < tn && ra > 0) {
+                const int4 b = s_bbox[k];
+                cs = s_span[k];
+                ca = s_area[k];
+                cand = max(rb.x, b.x) <= min(rb.z, b.z) && max(rb.y, b.y) <= min(rb.w, b.w) &&
+                       max(rs.x, cs.x) < min(rs.y, cs.y);
+            }
+            u32 inter = 0;
+            u32 todo = __ballot_sync(0xffffffffu, cand);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint2 ss = s_span[c0 + src];
+                const u32 v = warp_intersect(A, s_base[c0 + src], max(rs.x, ss.x), min(rs.y, ss.y), lane);
+                if ((int)lane == src) inter = v;
+            }
+            if (k < tn) {
+                const int c = t0 + k;
+                if (irow) irow[c] = (int)inter;
+                if (MODE == AMPIS_MODE_IOU) {
+                    // rleIou: u = a_r + a_c - i (the run walk's union); i == 0 => iou 0.0
+                    const double s = inter ? (double)inter / (double)(ra + ca - inter) : 0.0;
+                    if (s > best_s) { best_s = s; best_i = inter; best_c = c; }
+                } else {
+                    if (inter > best_i) { best_i = inter; best_c = c; }
+                }
             }
         }
     }
+    if (!valid) return;
     // warp arg-max: larger key wins, ties go to the smaller column index (np.argmax)
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -134,34 +165,37 @@ intersect_rows_kernel(const RowArgs p)
 
 extern "C" int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
                                     const uint32_t *d_span, const int32_t *d_bbox, const uint32_t *d_area,
-                                    const int32_t *d_row_mask, const int32_t *d_row_grp, int32_t n_rows,
-                                    const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
-                                    const int32_t *d_grp_col_count, const int64_t *d_grp_imat_off,
-                                    int32_t mode, int32_t *d_imat, int32_t *d_best_col,
-                                    uint32_t *d_best_inter, double *d_best_score, void *stream)
+                                    const int32_t *d_row_mask, const int32_t *d_blk_grp,
+                                    const int32_t *d_blk_row0, int32_t n_blocks,
+                                    const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                                    const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                                    const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
+                                    int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
+                                    void *stream)
 {
-    AMPIS_REQUIRE(n_rows >= 0, "n_rows < 0");
+    AMPIS_REQUIRE(n_blocks >= 0, "n_blocks < 0");
     AMPIS_REQUIRE(mode == AMPIS_MODE_IOU || mode == AMPIS_MODE_SAT, "bad mode");
-    if (n_rows == 0) return AMPIS_OK;
-    AMPIS_REQUIRE(d_bits_off && d_reg && d_span && d_bbox && d_area && d_row_mask && d_row_grp &&
-                      d_grp_row_begin && d_grp_col_begin && d_grp_col_count && d_best_col && d_best_inter &&
-                      d_best_score, "null pointer");
+    if (n_blocks == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_bits_off && d_reg && d_span && d_bbox && d_area && d_row_mask && d_blk_grp && d_blk_row0 &&
+                      d_grp_row_begin && d_grp_row_count && d_grp_col_begin && d_grp_col_count && d_best_col &&
+                      d_best_inter && d_best_score, "null pointer");
     RowArgs a;
     a.bits = (const uint4 *)d_bits; a.bits_off = d_bits_off; a.reg = (const uint2 *)d_reg;
     a.span = (const uint2 *)d_span; a.bbox = (const int4 *)d_bbox; a.area = d_area;
-    a.row_mask = d_row_mask; a.row_grp = d_row_grp; a.n_rows = n_rows;
-    a.grp_row_begin = d_grp_row_begin; a.grp_col_begin = d_grp_col_begin; a.grp_col_count = d_grp_col_count;
+    a.row_mask = d_row_mask; a.blk_grp = d_blk_grp; a.blk_row0 = d_blk_row0;
+    a.grp_row_begin = d_grp_row_begin; a.grp_row_count = d_grp_row_count;
+    a.grp_col_begin = d_grp_col_begin; a.grp_col_count = d_grp_col_count;
     a.grp_imat_off = d_grp_imat_off; a.imat = d_imat;
     a.best_col = d_best_col; a.best_inter = d_best_inter; a.best_score = d_best_score;
-    const int warps = 8;
-    const unsigned blocks = (unsigned)((n_rows + warps - 1) / warps);
     if (mode == AMPIS_MODE_IOU)
-        intersect_rows_kernel<AMPIS_MODE_IOU><<<blocks, warps * 32, 0, as_stream(stream)>>>(a);
+        intersect_rows_kernel<AMPIS_MODE_IOU><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
     else
-        intersect_rows_kernel<AMPIS_MODE_SAT><<<blocks, warps * 32, 0, as_stream(stream)>>>(a);
+        intersect_rows_kernel<AMPIS_MODE_SAT><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
     AMPIS_CHECK_LAUNCH("intersect_rows_kernel");
     return AMPIS_OK;
 }
+
+extern "C" int ampis_rows_per_block(void) { return ROWS_PER_CTA; }
 
 // float64 IoU matrix from dense intersections (analyze._piecewise_iou, analyze.py:54-112)
 __global__ void __launch_bounds__(256)

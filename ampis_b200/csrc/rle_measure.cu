@@ -6,6 +6,7 @@
 // decoded mask -- without decoding: a 1-run [s,e) in column-major order lies in column s/h
 // if it does not wrap; if it wraps it touches rows 0 and h-1.
 #include "common.cuh"
+#include "rle_measure.cuh"
 
 __global__ void __launch_bounds__(256)
 rle_measure_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
@@ -16,61 +17,14 @@ rle_measure_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
 {
     const int i = (int)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
     if (i >= n) return;
-    const u32 lane = lane_id();
-    const int m = cnt_len[i];
     const i64 base = cnt_off[i];
     const u32 H = hh[i];
     const u64 HW = (u64)H * ww[i];
-
-    u64 carry = 0;           // end position of the previous run
-    u32 a = 0;               // area
-    u32 first = 0xffffffffu; // first 1-pixel
-    u32 last = 0;            // one past the last 1-pixel
-    u32 ymin = 0xffffffffu, ymax = 0;
-    for (int j0 = 0; j0 < m; j0 += 32) {
-        const int j = j0 + (int)lane;
-        const u32 c = j < m ? cnt[base + j] : 0u;
-        u64 incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u64 t = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((int)lane >= d) incl += t;
-        }
-        const u64 end64 = carry + incl;
-        const u32 end = (u32)min(end64, (u64)0xffffffffu);
-        if (j < m) cum[base + j] = end;
-        if ((j & 1) && c > 0 && j < m && end64 <= HW) {
-            const u32 start = end - c;
-            a += c;
-            first = min(first, start);
-            last = max(last, end);
-            const u32 xs = start / H, xe = (end - 1) / H;
-            if (xs != xe) { ymin = 0; ymax = H - 1; }
-            else { ymin = min(ymin, start - xs * H); ymax = max(ymax, end - 1 - xe * H); }
-        }
-        carry = __shfl_sync(0xffffffffu, end64, 31);
-    }
-    a = warp_sum(a);
-    first = warp_min(first);
-    last = warp_max(last);
-    ymin = warp_min(ymin);
-    ymax = warp_max(ymax);
-    if (lane == 0) {
-        const u32 nchunks = (u32)((HW + AMPIS_CHUNK_BITS - 1) / AMPIS_CHUNK_BITS);
-        u32 slo = 0, shi = 0;
-        int4 bb = make_int4(0, 0, -1, -1);
-        if (a > 0) {
-            slo = first / AMPIS_CHUNK_BITS;
-            shi = min((last + AMPIS_CHUNK_BITS - 1) / AMPIS_CHUNK_BITS, nchunks);
-            bb = make_int4((int)(first / H), (int)ymin, (int)((last - 1) / H), (int)ymax);
-        }
-        area[i] = a;
-        reinterpret_cast<int4 *>(bbox)[i] = bb;
-        reinterpret_cast<uint2 *>(span)[i] = make_uint2(slo, shi);
-        const uint2 r = layout == AMPIS_LAYOUT_FULL ? make_uint2(0u, nchunks) : make_uint2(slo, shi);
-        reinterpret_cast<uint2 *>(reg)[i] = r;
-        reg_chunks[i] = (i64)(r.y - r.x);
-        status[i] = carry == HW ? 0 : AMPIS_ST_BAD_TOTAL;
+    const MaskMeasure ms = warp_measure(cnt + base, cnt_len[i], H, HW, nullptr, 0, cum + base);
+    if (lane_id() == 0) {
+        uint2 sp, rg;
+        store_measure(ms, H, HW, layout, i, area, bbox, span, reg, status, &sp, &rg);
+        reg_chunks[i] = (i64)(rg.y - rg.x);
     }
 }
 

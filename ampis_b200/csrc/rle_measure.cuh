@@ -1,0 +1,81 @@
+// Warp-level measurement of one RLE mask, shared by rle_measure_kernel and the fused
+// measure+paint kernel.
+#pragma once
+#include "common.cuh"
+
+struct MaskMeasure {
+    u32 area;     // number of 1-pixels (rleArea)
+    u32 first;    // first 1-pixel (column-major index), 0xffffffff if none
+    u32 last;     // one past the last 1-pixel
+    u32 ymin, ymax;
+    u64 total;    // sum of all run counts
+};
+
+// One warp walks the m run counts of a mask 32 at a time (inclusive warp scan with carry).
+// Run end positions are written to cum_s[j] for j < cum_s_cap (shared memory, may be null)
+// and to cum_g[j] (global memory, may be null).  Result valid in all lanes.
+__device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt, int m, u32 H, u64 HW,
+                                                    u32 *cum_s, int cum_s_cap, u32 *cum_g)
+{
+    const u32 lane = lane_id();
+    u64 carry = 0;
+    u32 a = 0, first = 0xffffffffu, last = 0, ymin = 0xffffffffu, ymax = 0;
+    for (int j0 = 0; j0 < m; j0 += 32) {
+        const int j = j0 + (int)lane;
+        const u32 c = j < m ? __ldg(cnt + j) : 0u;
+        u64 incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        const u64 end64 = carry + incl;
+        const u32 end = (u32)min(end64, (u64)0xffffffffu);
+        if (j < m) {
+            if (cum_s && j < cum_s_cap) cum_s[j] = end;
+            if (cum_g) cum_g[j] = end;
+        }
+        if ((j & 1) && c > 0 && j < m && end64 <= HW) {
+            const u32 start = end - c;
+            a += c;
+            first = min(first, start);
+            last = max(last, end);
+            const u32 xs = start / H, xe = (end - 1) / H;
+            if (xs != xe) { ymin = 0; ymax = H - 1; }
+            else { ymin = min(ymin, start - xs * H); ymax = max(ymax, end - 1 - xe * H); }
+        }
+        carry = __shfl_sync(0xffffffffu, end64, 31);
+    }
+    MaskMeasure r;
+    r.area = warp_sum(a);
+    r.first = warp_min(first);
+    r.last = warp_max(last);
+    r.ymin = warp_min(ymin);
+    r.ymax = warp_max(ymax);
+    r.total = carry;
+    return r;
+}
+
+// Derived per-mask records written by lane 0.
+__device__ __forceinline__ void store_measure(const MaskMeasure &ms, u32 H, u64 HW, int layout, int i,
+                                              u32 *area, int *bbox, u32 *span, u32 *reg, int *status,
+                                              uint2 *span_out, uint2 *reg_out)
+{
+    const u32 nchunks = (u32)((HW + AMPIS_CHUNK_BITS - 1) / AMPIS_CHUNK_BITS);
+    u32 slo = 0, shi = 0;
+    int4 bb = make_int4(0, 0, -1, -1);
+    if (ms.area > 0) {
+        slo = ms.first / AMPIS_CHUNK_BITS;
+        shi = min((ms.last + AMPIS_CHUNK_BITS - 1) / AMPIS_CHUNK_BITS, nchunks);
+        bb = make_int4((int)(ms.first / H), (int)ms.ymin, (int)((ms.last - 1) / H), (int)ms.ymax);
+    }
+    const uint2 sp = make_uint2(slo, shi);
+    const uint2 rg = layout == AMPIS_LAYOUT_FULL ? make_uint2(0u, nchunks) : sp;
+    area[i] = ms.area;
+    reinterpret_cast<int4 *>(bbox)[i] = bb;
+    reinterpret_cast<uint2 *>(span)[i] = sp;
+    reinterpret_cast<uint2 *>(reg)[i] = rg;
+    status[i] = ms.total == HW ? 0 : AMPIS_ST_BAD_TOTAL;
+    *span_out = sp;
+    *reg_out = rg;
+}

@@ -8,6 +8,7 @@
 // intersection of two masks is AND+popc over the overlap of their regions with no shifts
 // and no transposes; only masks_to_bitmask_array needs the row-major view (unpack below).
 #include "common.cuh"
+#include "rle_measure.cuh"
 
 // bits [lo,hi) of a 32-bit word, 0 <= lo <= hi <= 32
 __device__ __forceinline__ u32 bit_range(u32 lo, u32 hi)
@@ -18,20 +19,23 @@ __device__ __forceinline__ u32 bit_range(u32 lo, u32 hi)
 }
 
 // The 128 pixels [128c, 128c+128) of a mask whose run END positions are C[0..m).
-__device__ __forceinline__ uint4 paint_chunk(const u32 *__restrict__ C, int m, u32 c)
+// LDG: C is read-only global memory written by an earlier kernel (non-coherent loads allowed);
+// otherwise C is shared memory or global memory written earlier in this kernel.
+template <bool LDG>
+__device__ __forceinline__ uint4 paint_chunk(const u32 *C, int m, u32 c)
 {
     const u64 b0 = (u64)c * AMPIS_CHUNK_BITS, b1 = b0 + AMPIS_CHUNK_BITS;
     // first run r whose end lies beyond b0 -- the run that owns pixel b0
     int lo = 0, hi = m;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if ((u64)__ldg(C + mid) > b0) hi = mid; else lo = mid + 1;
+        if ((u64)(LDG ? __ldg(C + mid) : C[mid]) > b0) hi = mid; else lo = mid + 1;
     }
     int r = lo;
     u32 w[4] = {0u, 0u, 0u, 0u};
     u64 pos = b0;
     while (r < m && pos < b1) {
-        const u64 e = min((u64)__ldg(C + r), b1);
+        const u64 e = min((u64)(LDG ? __ldg(C + r) : C[r]), b1);
         if (r & 1) {
             const u32 s = (u32)(pos - b0), t = (u32)(e - b0);   // [s,t) within the chunk
 #pragma unroll
@@ -68,7 +72,7 @@ rle_paint_kernel(const u32 *__restrict__ cum, const i64 *__restrict__ cnt_off, c
         uint4 *out = bits + off - rg.x;
         for (u32 c = rg.x + threadIdx.x; c < rg.y; c += THREADS) {
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (c >= sp.x && c < sp.y) v = paint_chunk(C, m, c);
+            if (c >= sp.x && c < sp.y) v = paint_chunk<true>(C, m, c);
             st_v4_stream(out + c, v);
         }
     }
@@ -88,6 +92,97 @@ extern "C" int ampis_rle_decode_packed(const uint32_t *d_cum, const int64_t *d_c
         d_cum, d_cnt_off, d_cnt_len, (const uint2 *)d_span, (const uint2 *)d_reg, d_bits_off, n, (uint4 *)d_bits,
         bits_capacity);
     AMPIS_CHECK_LAUNCH("rle_paint_kernel");
+    return AMPIS_OK;
+}
+
+// ---- fused measure + paint ---------------------------------------------------------------------
+// One launch instead of five (measure, 3 x scan, paint): a team of TEAM_WARPS warps owns one
+// mask.  The team's first warp measures the mask (area, box, span) and leaves the run end
+// positions in shared memory; the CTA then reserves arena space for all its masks with ONE
+// atomicAdd on a global cursor (arena order is therefore arbitrary, which nothing depends on) and
+// every team paints its region.  SPAN layout: TEAM_WARPS = 1 (8 masks per CTA, regions are a few
+// KB); FULL layout: TEAM_WARPS = 8 (one mask per CTA, regions are 100s of KB).
+#define MP_WARPS 8
+#define MP_CUM_WORDS 4096      // shared run-end words per CTA, split evenly between its masks
+
+template <int TEAM_WARPS>
+__global__ void __launch_bounds__(MP_WARPS * 32)
+rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
+                         const int *__restrict__ cnt_len, const u32 *__restrict__ hh,
+                         const u32 *__restrict__ ww, int n, int layout, u32 *cum_g, u32 *__restrict__ area,
+                         int *__restrict__ bbox, u32 *__restrict__ span, u32 *__restrict__ reg,
+                         i64 *__restrict__ bits_off, int *__restrict__ status, uint4 *__restrict__ bits,
+                         i64 capacity, unsigned long long *__restrict__ cursor)
+{
+    constexpr int MASKS = MP_WARPS / TEAM_WARPS;
+    constexpr int CUM_CAP = MP_CUM_WORDS / MASKS;
+    __shared__ u32 s_cum[MP_CUM_WORDS];
+    __shared__ uint2 s_span[MASKS], s_reg[MASKS];
+    __shared__ i64 s_off[MASKS];
+    __shared__ i64 s_base;
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const int team = (int)wid / TEAM_WARPS, tw = (int)wid % TEAM_WARPS;
+    const int i = blockIdx.x * MASKS + team;
+    const bool valid = i < n;
+    int m = 0;
+    i64 base = 0;
+    if (valid) { m = cnt_len[i]; base = cnt_off[i]; }
+    if (tw == 0) {
+        uint2 sp = make_uint2(0u, 0u), rg = sp;
+        if (valid) {
+            const u32 H = hh[i];
+            const u64 HW = (u64)H * ww[i];
+            const MaskMeasure ms = warp_measure(cnt + base, m, H, HW, s_cum + team * CUM_CAP, CUM_CAP,
+                                                m > CUM_CAP ? cum_g + base : nullptr);
+            if (lane == 0) store_measure(ms, H, HW, layout, i, area, bbox, span, reg, status, &sp, &rg);
+        }
+        if (lane == 0) { s_span[team] = sp; s_reg[team] = rg; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        i64 tot = 0;
+        for (int k = 0; k < MASKS; k++) { s_off[k] = tot; tot += (i64)(s_reg[k].y - s_reg[k].x); }
+        s_base = tot ? (i64)atomicAdd(cursor, (unsigned long long)tot) : 0;
+    }
+    __syncthreads();
+    if (!valid) return;
+    const uint2 rg = s_reg[team], sp = s_span[team];
+    const i64 off = s_base + s_off[team];
+    if (tw == 0 && lane == 0) bits_off[i] = off;
+    if (off + (i64)(rg.y - rg.x) > capacity) return;     // caller checks *cursor against capacity
+    const u32 *C = m > CUM_CAP ? cum_g + base : s_cum + team * CUM_CAP;
+    uint4 *out = bits + off - rg.x;
+    for (u32 c = rg.x + tw * 32 + lane; c < rg.y; c += TEAM_WARPS * 32) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c >= sp.x && c < sp.y) v = paint_chunk<false>(C, m, c);
+        st_v4_stream(out + c, v);
+    }
+}
+
+extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off,
+                                       const int32_t *d_cnt_len, const uint32_t *d_h, const uint32_t *d_w,
+                                       int32_t n, int32_t layout, uint32_t *d_cum, uint32_t *d_area,
+                                       int32_t *d_bbox, uint32_t *d_span, uint32_t *d_reg, int64_t *d_bits_off,
+                                       int32_t *d_status, void *d_bits, int64_t bits_capacity,
+                                       uint64_t *d_cursor, void *stream)
+{
+    AMPIS_REQUIRE(n >= 0, "n < 0");
+    AMPIS_REQUIRE(layout == AMPIS_LAYOUT_SPAN || layout == AMPIS_LAYOUT_FULL, "bad layout");
+    if (n == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_cnt && d_cnt_off && d_cnt_len && d_h && d_w && d_cum && d_area && d_bbox && d_span &&
+                      d_reg && d_bits_off && d_status && d_bits && d_cursor, "null pointer");
+    AMPIS_REQUIRE(((uintptr_t)d_bits & 15u) == 0, "bits arena must be 16-byte aligned");
+    cudaError_t e = cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), as_stream(stream));
+    if (e != cudaSuccess) { ampis_set_error("cursor memset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+    if (layout == AMPIS_LAYOUT_FULL)
+        rle_measure_paint_kernel<MP_WARPS><<<n, MP_WARPS * 32, 0, as_stream(stream)>>>(
+            d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
+            d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
+    else
+        rle_measure_paint_kernel<1><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
+            d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
+            d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
+    AMPIS_CHECK_LAUNCH("rle_measure_paint_kernel");
     return AMPIS_OK;
 }
 

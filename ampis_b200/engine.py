@@ -58,6 +58,7 @@ class MaskTable(object):
         self.reg_chunks = torch.empty(n1, dtype=i64, device=device)
         self.status = torch.empty(n1, dtype=i32, device=device)
         self.bits_off = torch.empty(n1 + 1, dtype=i64, device=device)
+        self.cursor = None      # set by measure_paint(): chunks the arena needed (device int64[1])
         self.bits = None
         self.bits_capacity = 0
 
@@ -83,13 +84,28 @@ class MaskTable(object):
                _p(self.reg), _p(self.bits_off), self.n, _p(self.bits), self.bits_capacity, _stream())
         return self
 
+    def measure_paint(self, arena):
+        """Fused single-launch form of measure() + paint(arena): arena space is handed out by an
+        atomic cursor, so the arena must be supplied (size it with a previous measure() or
+        generously) and overflow is detected afterwards by check()."""
+        self.bits = arena
+        self.bits_capacity = arena.numel() // 4
+        self.cursor = torch.empty(1, dtype=torch.int64, device=self.device)
+        N.call('ampis_rle_measure_paint', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h), _p(self.w),
+               self.n, self.layout, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
+               _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor), _stream())
+        return self
+
     def check(self):
         """Raise on malformed RLE (sum(counts) != h*w), where pycocotools would hang or mis-decode."""
         if self.n and bool((self.status[:self.n] != 0).any().item()):
             bad = torch.nonzero(self.status[:self.n]).flatten()[:8].tolist()
             raise ValueError('malformed RLE: run counts do not sum to h*w for masks %s' % bad)
-        if self.bits is not None and self.n and int(self.bits_off[self.n].item()) > self.bits_capacity:
-            raise N.AmpisNativeError('packed-mask arena too small')
+        if self.bits is not None and self.n:
+            need = int((self.cursor if self.cursor is not None else self.bits_off[self.n]).item())
+            if need > self.bits_capacity:
+                raise N.AmpisNativeError('packed-mask arena too small: %d chunks needed, %d available'
+                                         % (need, self.bits_capacity))
         return self
 
     # -- results ----------------------------------------------------------------------------
@@ -168,6 +184,15 @@ class Groups(object):
         i32 = torch.int32
         self.row_mask = _dev(np.asarray(row_mask, np.int32), i32, device)
         self.row_grp = _dev(np.asarray(row_grp, np.int32), i32, device)
+        rpb = N.lib().ampis_rows_per_block()
+        nb = (self.h_row_count + rpb - 1) // rpb                    # CTAs per group
+        blk_grp = np.repeat(np.arange(self.n_groups, dtype=np.int64), nb)
+        first = np.zeros(self.n_groups + 1, np.int64)
+        np.cumsum(nb, out=first[1:])
+        blk_row0 = self.h_row_begin[blk_grp] + rpb * (np.arange(int(first[-1]), dtype=np.int64) - first[blk_grp])
+        self.n_blocks = int(first[-1])
+        self.blk_grp = _dev(blk_grp.astype(np.int32), i32, device)
+        self.blk_row0 = _dev(blk_row0.astype(np.int32), i32, device)
         self.grp_row_begin = _dev(np.asarray(grp_row_begin, np.int32), i32, device)
         self.grp_row_count = _dev(np.asarray(grp_row_count, np.int32), i32, device)
         self.grp_col_begin = _dev(np.asarray(grp_col_begin, np.int32), i32, device)
@@ -214,9 +239,10 @@ def intersect_rows(table, groups, mode, out=None):
                         torch.empty(nr, dtype=torch.int32, device=dev),
                         torch.empty(nr, dtype=torch.float64, device=dev), imat)
     N.call('ampis_intersect_rows', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
-           _p(table.bbox), _p(table.area), _p(groups.row_mask), _p(groups.row_grp), groups.n_rows,
-           _p(groups.grp_row_begin), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off),
-           mode, _p(out.imat), _p(out.best_col), _p(out.best_inter), _p(out.best_score), _stream())
+           _p(table.bbox), _p(table.area), _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0),
+           groups.n_blocks, _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),
+           _p(groups.grp_col_count), _p(groups.imat_off), mode, _p(out.imat), _p(out.best_col),
+           _p(out.best_inter), _p(out.best_score), _stream())
     return out
 
 

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--unfused', action='store_true', help='separate measure / scan / paint launches')
     ap.add_argument('--no-span', action='store_true', help='skip the secondary span-layout measurement')
     ap.add_argument('--cpu-images', type=int, default=0)
     return ap.parse_args()
@@ -189,6 +190,8 @@ class LayoutRun(object):
         import torch
         from ampis_b200 import batch, engine
         self.layout, self.sub, self.dev = layout, sub, dev
+        self.fused = not args.unfused
+        self.last_table = None
         t0 = time.time()
         self.subs = []
         for s0 in range(0, args.images, sub):
@@ -218,13 +221,18 @@ class LayoutRun(object):
             t = engine.MaskTable(self.dev, b.host.n_masks, b.cnt, b.cnt_off, b.cnt_len, b.h, b.w, self.layout)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record is not None else None
             if ev: ev[0].record()
-            t.measure()
-            if ev: ev[1].record()
-            t.paint(self.arena)
+            if self.fused:
+                if ev: ev[1].record()
+                t.measure_paint(self.arena)       # measure + arena allocation + paint in one launch
+            else:
+                t.measure()
+                if ev: ev[1].record()
+                t.paint(self.arena)
             if ev: ev[2].record()
             rows = engine.intersect_rows(t, b.groups, b.mode, out=self.rows_out)
             if ev: ev[3].record()
             engine.match_counts(rows, b.groups, self.thresholds, totals=self.totals)
+            self.last_table = t
             if ev:
                 ev[4].record()
                 record.append(ev)
@@ -251,6 +259,7 @@ class LayoutRun(object):
         for ev in record:
             for i in range(4):
                 kt[i] += ev[i].elapsed_time(ev[i + 1])
+        self.last_table.check()      # arena large enough, RLE well-formed (after the timed region)
         return float(ms.item()), kt, self.totals.cpu().numpy().reshape(-1, 3)
 
 
@@ -276,7 +285,8 @@ def roofline_of(args, cfg, run, ms, kt, world):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get('%s/%s/%s' % (args.config, lay, dom))
     step_gbs = canonical_img * n_img * args.steps / (ms / 1e3) / 1e9
-    return {'bound': 'hbm', 'kernel': {'paint': 'rle_paint_kernel', 'rows': 'intersect_rows_kernel'}[dom],
+    pk = 'rle_paint_kernel' if args.unfused else 'rle_measure_paint_kernel'
+    return {'bound': 'hbm', 'kernel': {'paint': pk, 'rows': 'intersect_rows_kernel'}[dom],
             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
             'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom] / launches, 'launch_ms': dur_ms,
             'step_canonical': {'bytes_per_image': canonical_img, 'achieved': step_gbs, 'frac': step_gbs / peak,
@@ -370,7 +380,7 @@ def main():
                                                                           run.stored_chunks * 16 / len(run.subs) / 1e9),
                    'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN per step' % world},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
-        'gpu_launches': int(args.steps * len(run.subs) * 7),
+        'gpu_launches': int(args.steps * len(run.subs) * (7 if args.unfused else 3)),
         'totals_tp_fp_fn_at_0.50': final_totals[0].tolist(),
         'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},
     }
@@ -433,7 +443,10 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
             cnt_len = torch.empty(n, dtype=torch.int32, device=dev)
             N.call('ampis_rle_string_decode', _p(dc), _p(d_off), n, _p(d_cnt), _p(d_off), _p(cnt_len), _s())
             t = engine.MaskTable(dev, n, d_cnt, d_off, cnt_len, b.h, b.w, layout)
-            t.measure().paint(arena)
+            if args.unfused:
+                t.measure().paint(arena)
+            else:
+                t.measure_paint(arena)
             rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out)
             counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
             hc.copy_(counts, non_blocking=True)

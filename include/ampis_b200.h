@@ -100,6 +100,18 @@ int ampis_rle_decode_packed(const uint32_t *d_cum, const int64_t *d_cnt_off, con
                             const uint32_t *d_span, const uint32_t *d_reg, const int64_t *d_bits_off,
                             int32_t n, void *d_bits, int64_t bits_capacity, void *stream);
 
+/* Fused form of ampis_rle_measure + scan + ampis_rle_decode_packed in ONE launch: every CTA
+ * measures its masks, reserves arena space with one atomicAdd on *d_cursor (zeroed by this call)
+ * and paints.  Arena order is arbitrary (d_bits_off[i] is still written per mask; there is no
+ * d_bits_off[n]).  After the stream has completed, *d_cursor = uint4 chunks needed; if it exceeds
+ * bits_capacity some masks were not painted and the caller must retry with a larger arena.
+ * d_cum is only touched for masks with more runs than fit in shared memory. */
+int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                            const uint32_t *d_h, const uint32_t *d_w, int32_t n, int32_t layout,
+                            uint32_t *d_cum, uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span,
+                            uint32_t *d_reg, int64_t *d_bits_off, int32_t *d_status, void *d_bits,
+                            int64_t bits_capacity, uint64_t *d_cursor, void *stream);
+
 /* bits -> bool[n][h][w] row-major bytes (RLE.decode(...).astype(bool).transpose(2,0,1),
  * structures.py:752,765).  All n masks must share (h,w). d_mask_ids selects masks. */
 int ampis_unpack_bool_nrc(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
@@ -123,19 +135,22 @@ int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t 
  * I = popcount(row AND col) over the overlap of the two spans, and keeps the first
  * arg-max of the score.  Replaces the G x ceil(P/80) RLE.iou calls of
  * analyze.py:149-164 and the S x N RLE.merge+RLE.area calls of powder.py:80-86.
- *   row_mask[r], row_grp[r]        mask id and group id of row r
- *   grp_row_begin[g]               first row of group g (rows of a group are contiguous)
+ *   row_mask[r]                    mask id of row r (rows of a group are contiguous)
+ *   blk_grp[b], blk_row0[b]        CTA b handles rows blk_row0[b] .. +ampis_rows_per_block()-1
+ *                                  (clipped to the group) of group blk_grp[b]
+ *   grp_row_begin[g], grp_row_count[g]   rows of group g
  *   grp_col_begin[g], grp_col_count[g]   column masks of group g (contiguous mask ids)
  *   grp_imat_off[g]                offset (in int32) of group g's dense G x P intersection
  *                                  matrix inside d_imat, or -1 / d_imat NULL for none
  * Outputs per row: best_col (index inside the group, IOU mode: -1 if every IoU is 0;
  * SAT mode: 0 if every intersection is 0), best_inter, best_score (double). */
+int ampis_rows_per_block(void);
 int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
                          const uint32_t *d_span, const int32_t *d_bbox, const uint32_t *d_area,
-                         const int32_t *d_row_mask, const int32_t *d_row_grp, int32_t n_rows,
-                         const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
-                         const int32_t *d_grp_col_count, const int64_t *d_grp_imat_off,
-                         int32_t mode, int32_t *d_imat,
+                         const int32_t *d_row_mask, const int32_t *d_blk_grp, const int32_t *d_blk_row0,
+                         int32_t n_blocks, const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                         const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                         const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
                          int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                          void *stream);
 

@@ -278,15 +278,18 @@ def test_empty_and_error_conventions(mods):
 
 
 @pytest.mark.parametrize('cfg,n_img', [('c1_powder_example', 2), ('c2_powder_batch', 2)])
-@pytest.mark.parametrize('layout', ['span', 'full'])
-def test_batch_pipeline_vs_oracle(mods, cfg, n_img, layout):
+@pytest.mark.parametrize('layout,fused', [('span', False), ('full', False), ('span', True), ('full', True)])
+def test_batch_pipeline_vs_oracle(mods, cfg, n_img, layout, fused):
     """Synthetic images through the batch pipeline == oracle per image (matches, IoUs, counts at
     the ten COCO thresholds, dense intersections)."""
     B, E, R, rle = mods.batch, mods.engine, mods.R, mods.rle
     host = B.synth(cfg, n_img, 1001)
     dev = B.DeviceBatch(host, dense=True)
     lay = E.LAYOUT_FULL if layout == 'full' else E.LAYOUT_SPAN
-    res = B.eval_step(dev, layout=lay, check=True)
+    arena = None
+    if fused:
+        arena = mods.torch.empty(4 * B.arena_chunks_needed(dev, lay), dtype=mods.torch.int32, device='cuda')
+    res = B.eval_step(dev, layout=lay, check=True, arena=arena)
     G, Pn = host.n_rows, host.n_cols
     best_col = res.rows.best_col.cpu().numpy().reshape(n_img, G)
     best_iou = res.rows.best_score.cpu().numpy().reshape(n_img, G)
@@ -357,6 +360,15 @@ def test_full_size_properties(mods):
     dev = B.DeviceBatch(host, dense=True)
     a = B.eval_step(dev, layout=E.LAYOUT_SPAN, check=True)
     b = B.eval_step(dev, layout=E.LAYOUT_FULL, check=True)
+    arena = torch.empty(4 * B.arena_chunks_needed(dev, E.LAYOUT_SPAN), dtype=torch.int32, device='cuda')
+    f = B.eval_step(dev, layout=E.LAYOUT_SPAN, check=True, arena=arena)          # fused measure+paint
+    for x, y in [(a.rows.best_col, f.rows.best_col), (a.rows.best_score, f.rows.best_score),
+                 (a.rows.imat, f.rows.imat), (a.counts, f.counts), (a.table.area, f.table.area),
+                 (a.table.bbox, f.table.bbox), (a.table.span, f.table.span)]:
+        assert torch.equal(x, y)
+    small = torch.empty(4 * 1000, dtype=torch.int32, device='cuda')             # arena overflow is detected
+    with pytest.raises(Exception, match='arena too small'):
+        B.eval_step(dev, layout=E.LAYOUT_SPAN, check=True, arena=small)
     for x, y in [(a.rows.best_col, b.rows.best_col), (a.rows.best_inter, b.rows.best_inter),
                  (a.rows.best_score, b.rows.best_score), (a.rows.imat, b.rows.imat), (a.counts, b.counts),
                  (a.table.area, b.table.area), (a.table.bbox, b.table.bbox)]:
