@@ -138,6 +138,55 @@ def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_o
     return r
 
 
+class Pipeline(object):
+    """The per-batch launch sequence with every buffer allocated up front, so that a step is
+    nothing but kernel launches (and can be captured in a CUDA graph):
+    fused measure+paint -> intersect rows -> counts."""
+
+    def __init__(self, batch, layout, arena, rows_out=None, thresholds=COCO_THRESHOLDS, totals=None,
+                 sat_thresh=0.5, fused=True):
+        dev = batch.device
+        self.batch, self.layout, self.arena, self.fused = batch, layout, arena, fused
+        self.table = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
+                                      batch.w, layout)
+        g = batch.groups
+        nr = max(g.n_rows, 1)
+        self.rows = rows_out or engine.RowResult(
+            torch.empty(nr, dtype=torch.int32, device=dev), torch.empty(nr, dtype=torch.int32, device=dev),
+            torch.empty(nr, dtype=torch.float64, device=dev),
+            torch.empty(max(g.imat_size, 1), dtype=torch.int32, device=dev) if g.imat_off is not None else None)
+        self.th = torch.from_numpy(np.asarray(thresholds, np.float64)).to(dev)
+        self.sat_thresh = sat_thresh
+        if batch.mode == engine.MODE_IOU:
+            self.counts = torch.empty(max(g.n_groups * self.th.numel() * 3, 1), dtype=torch.int32, device=dev)
+            self.totals = totals if totals is not None else torch.zeros(self.th.numel() * 3, dtype=torch.int64,
+                                                                       device=dev)
+        else:
+            self.counts = None
+            self.spp_hist = torch.zeros(64, dtype=torch.int64, device=dev)
+
+    def launch(self, mark=None):
+        """Enqueue the kernels on the current stream; `mark(i)` is called between kernel groups."""
+        t = self.table
+        if mark: mark(0)
+        if self.fused:
+            if mark: mark(1)
+            t.measure_paint(self.arena)
+        else:
+            t.measure()
+            if mark: mark(1)
+            t.paint(self.arena)
+        if mark: mark(2)
+        engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows)
+        if mark: mark(3)
+        if self.batch.mode == engine.MODE_IOU:
+            engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)
+        else:
+            self.counts, _ = engine.satellite_counts(t, self.rows, self.batch.groups, self.sat_thresh,
+                                                     hist=self.spp_hist)
+        if mark: mark(4)
+
+
 def arena_chunks_needed(batch, layout):
     """Number of uint4 chunks the packed-mask arena needs for a DeviceBatch: one measurement
     pass on the GPU and a read-back (used to size the workspace before the timed region)."""

@@ -63,7 +63,7 @@ __device__ __forceinline__ u32 warp_intersect(const uint4 *__restrict__ A, const
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32, 6)
 intersect_rows_kernel(const RowArgs p)
 {
     __shared__ int4 s_bbox[COL_TILE];

@@ -20,31 +20,44 @@ __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt,
     const u32 lane = lane_id();
     u64 carry = 0;
     u32 a = 0, first = 0xffffffffu, last = 0, ymin = 0xffffffffu, ymax = 0;
-    for (int j0 = 0; j0 < m; j0 += 32) {
-        const int j = j0 + (int)lane;
-        const u32 c = j < m ? __ldg(cnt + j) : 0u;
-        u64 incl = c;
+    // 128 runs per outer step: the four loads are independent, so a typical mask (~75 runs)
+    // costs ONE global round trip before the scans start
+    for (int jb = 0; jb < m; jb += 128) {
+        u32 cc[4];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u64 t = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((int)lane >= d) incl += t;
+        for (int k = 0; k < 4; k++) {
+            const int j = jb + 32 * k + (int)lane;
+            cc[k] = j < m ? __ldg(cnt + j) : 0u;
         }
-        const u64 end64 = carry + incl;
-        const u32 end = (u32)min(end64, (u64)0xffffffffu);
-        if (j < m) {
-            if (cum_s && j < cum_s_cap) cum_s[j] = end;
-            if (cum_g) cum_g[j] = end;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int j0 = jb + 32 * k;
+            if (j0 >= m) break;
+            const int j = j0 + (int)lane;
+            const u32 c = cc[k];
+            u64 incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            const u64 end64 = carry + incl;
+            const u32 end = (u32)min(end64, (u64)0xffffffffu);
+            if (j < m) {
+                if (cum_s && j < cum_s_cap) cum_s[j] = end;
+                if (cum_g) cum_g[j] = end;
+            }
+            if ((j & 1) && c > 0 && j < m && end64 <= HW) {
+                const u32 start = end - c;
+                a += c;
+                first = min(first, start);
+                last = max(last, end);
+                const u32 xs = start / H, xe = (end - 1) / H;
+                if (xs != xe) { ymin = 0; ymax = H - 1; }
+                else { ymin = min(ymin, start - xs * H); ymax = max(ymax, end - 1 - xe * H); }
+            }
+            carry = __shfl_sync(0xffffffffu, end64, 31);
         }
-        if ((j & 1) && c > 0 && j < m && end64 <= HW) {
-            const u32 start = end - c;
-            a += c;
-            first = min(first, start);
-            last = max(last, end);
-            const u32 xs = start / H, xe = (end - 1) / H;
-            if (xs != xe) { ymin = 0; ymax = H - 1; }
-            else { ymin = min(ymin, start - xs * H); ymax = max(ymax, end - 1 - xe * H); }
-        }
-        carry = __shfl_sync(0xffffffffu, end64, 31);
     }
     MaskMeasure r;
     r.area = warp_sum(a);

@@ -103,10 +103,89 @@ extern "C" int ampis_rle_decode_packed(const uint32_t *d_cum, const int64_t *d_c
 // every team paints its region.  SPAN layout: TEAM_WARPS = 1 (8 masks per CTA, regions are a few
 // KB); FULL layout: TEAM_WARPS = 8 (one mask per CTA, regions are 100s of KB).
 #define MP_WARPS 8
-#define MP_CUM_WORDS 4096      // shared run-end words per CTA, split evenly between its masks
+#define MP_CUM_WORDS 2048      // shared run-end words per CTA, split evenly between its masks
+#define MP_TILE 128            // chunks (2 KB) of packed mask a warp assembles in shared memory at a time
 
-template <int TEAM_WARPS>
-__global__ void __launch_bounds__(MP_WARPS * 32)
+// first index r in [0,m) with C[r] > b (C ascending); m if none
+__device__ __forceinline__ int upper_bound_u32(const u32 *C, int m, u64 b)
+{
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((u64)C[mid] > b) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// One warp assembles chunks [t0,t1) (at most MP_TILE) of a mask in its shared tile and streams
+// them out.  Run driven: the tile is zeroed, then every lane takes 1-runs that intersect the
+// tile and sets their bits (whole words by plain stores, the two boundary words by shared
+// atomicOr since neighbouring runs may share a word).  A typical particle has ~40 1-runs, i.e.
+// about one per lane -- far less work than locating each chunk by binary search.
+__device__ __forceinline__ void warp_paint_tile(const u32 *C, int m, u32 t0, u32 t1, u32 *tile, uint4 *out,
+                                                u32 lane)
+{
+    const u32 nch = t1 - t0;
+    uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+    for (u32 k = lane; k < nch; k += 32) tile4[k] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    const u64 b0 = (u64)t0 * AMPIS_CHUNK_BITS, b1 = (u64)t1 * AMPIS_CHUNK_BITS;
+    const int r0 = upper_bound_u32(C, m, b0);          // run that owns bit b0
+    const int r1 = upper_bound_u32(C, m, b1 - 1);      // run that owns bit b1-1 (m if beyond the runs)
+    for (int r = (r0 | 1) + 2 * (int)lane; r <= r1 && r < m; r += 64) {   // odd runs are the 1-runs
+        const u64 rs = (u64)C[r - 1], re = (u64)C[r];
+        const u64 s64 = rs > b0 ? rs : b0, e64 = re < b1 ? re : b1;
+        if (e64 <= s64) continue;
+        const u32 s = (u32)(s64 - b0), e = (u32)(e64 - b0);      // bit range inside the tile
+        const u32 w0 = s >> 5, w1 = (e - 1) >> 5;
+        if (w0 == w1) {
+            atomicOr(&tile[w0], bit_range(s & 31u, ((e - 1) & 31u) + 1u));
+        } else {
+            atomicOr(&tile[w0], bit_range(s & 31u, 32u));
+            for (u32 w = w0 + 1; w < w1; w++) tile[w] = 0xffffffffu;
+            atomicOr(&tile[w1], bit_range(0u, ((e - 1) & 31u) + 1u));
+        }
+    }
+    __syncwarp();
+    for (u32 k = lane; k < nch; k += 32) st_v4_stream(out + t0 + k, tile4[k]);
+    __syncwarp();
+}
+
+// Same, for a mask whose run ends all sit in shared memory (m <= cap): no search at all -- every
+// lane walks the 1-runs it owns (r = 1 + 2*lane, +64, ...) and clips them to the tile.
+__device__ __forceinline__ void warp_paint_tile_smem(const u32 *sC, int m, u32 t0, u32 t1, u32 *tile, uint4 *out,
+                                                     u32 lane)
+{
+    const u32 nch = t1 - t0;
+    uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+    for (u32 k = lane; k < nch; k += 32) tile4[k] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    const u64 b0 = (u64)t0 * AMPIS_CHUNK_BITS, b1 = (u64)t1 * AMPIS_CHUNK_BITS;
+    for (int r = 1 + 2 * (int)lane; r < m; r += 64) {
+        const u64 rs = (u64)sC[r - 1], re = (u64)sC[r];
+        if (rs >= b1) break;
+        const u64 s64 = rs > b0 ? rs : b0, e64 = re < b1 ? re : b1;
+        if (e64 <= s64) continue;
+        const u32 s = (u32)(s64 - b0), e = (u32)(e64 - b0);
+        const u32 w0 = s >> 5, w1 = (e - 1) >> 5;
+        if (w0 == w1) {
+            atomicOr(&tile[w0], bit_range(s & 31u, ((e - 1) & 31u) + 1u));
+        } else {
+            atomicOr(&tile[w0], bit_range(s & 31u, 32u));
+            for (u32 w = w0 + 1; w < w1; w++) tile[w] = 0xffffffffu;
+            atomicOr(&tile[w1], bit_range(0u, ((e - 1) & 31u) + 1u));
+        }
+    }
+    __syncwarp();
+    for (u32 k = lane; k < nch; k += 32) st_v4_stream(out + t0 + k, tile4[k]);
+    __syncwarp();
+}
+
+// TILED: the span is assembled run-driven in shared-memory tiles (SPAN layout, where the span is
+// the whole job); otherwise in-span chunks are located by binary search (FULL layout, where 97 %
+// of the stores are zeros outside the span and occupancy of the store stream matters most).
+template <int TEAM_WARPS, bool TILED>
+__global__ void __launch_bounds__(MP_WARPS * 32, TILED ? 5 : 8)
 rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
                          const int *__restrict__ cnt_len, const u32 *__restrict__ hh,
                          const u32 *__restrict__ ww, int n, int layout, u32 *cum_g, u32 *__restrict__ area,
@@ -117,6 +196,7 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
     constexpr int MASKS = MP_WARPS / TEAM_WARPS;
     constexpr int CUM_CAP = MP_CUM_WORDS / MASKS;
     __shared__ u32 s_cum[MP_CUM_WORDS];
+    __shared__ __align__(16) u32 s_tile[TILED ? MP_WARPS : 1][TILED ? MP_TILE * 4 : 4];
     __shared__ uint2 s_span[MASKS], s_reg[MASKS];
     __shared__ i64 s_off[MASKS];
     __shared__ i64 s_base;
@@ -148,14 +228,36 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
     if (!valid) return;
     const uint2 rg = s_reg[team], sp = s_span[team];
     const i64 off = s_base + s_off[team];
+    if (off + (i64)(rg.y - rg.x) > capacity) {
+        // arena exhausted: leave the mask empty so later kernels stay inside the arena; the
+        // caller sees *cursor > capacity and retries (ampis_rle_measure_paint contract)
+        if (tw == 0 && lane == 0) {
+            bits_off[i] = 0;
+            reinterpret_cast<uint2 *>(span)[i] = make_uint2(0u, 0u);
+            reinterpret_cast<uint2 *>(reg)[i] = make_uint2(0u, 0u);
+        }
+        return;
+    }
     if (tw == 0 && lane == 0) bits_off[i] = off;
-    if (off + (i64)(rg.y - rg.x) > capacity) return;     // caller checks *cursor against capacity
     const u32 *C = m > CUM_CAP ? cum_g + base : s_cum + team * CUM_CAP;
     uint4 *out = bits + off - rg.x;
-    for (u32 c = rg.x + tw * 32 + lane; c < rg.y; c += TEAM_WARPS * 32) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (c >= sp.x && c < sp.y) v = paint_chunk<false>(C, m, c);
-        st_v4_stream(out + c, v);
+    // zeros outside the span (FULL layout only; in SPAN layout region == span)
+    for (u32 c = rg.x + tw * 32 + lane; c < sp.x; c += TEAM_WARPS * 32) st_v4_stream(out + c, make_uint4(0u, 0u, 0u, 0u));
+    for (u32 c = max(sp.y, rg.x) + tw * 32 + lane; c < rg.y; c += TEAM_WARPS * 32)
+        st_v4_stream(out + c, make_uint4(0u, 0u, 0u, 0u));
+    if (TILED) {
+        // the span itself, one tile per warp at a time
+        if (m <= CUM_CAP) {
+            for (u32 t0 = sp.x + (u32)tw * MP_TILE; t0 < sp.y; t0 += TEAM_WARPS * MP_TILE)
+                warp_paint_tile_smem(s_cum + team * CUM_CAP, m, t0, min(t0 + MP_TILE, sp.y),
+                                     s_tile[TILED ? wid : 0], out, lane);
+        } else {
+            for (u32 t0 = sp.x + (u32)tw * MP_TILE; t0 < sp.y; t0 += TEAM_WARPS * MP_TILE)
+                warp_paint_tile(C, m, t0, min(t0 + MP_TILE, sp.y), s_tile[TILED ? wid : 0], out, lane);
+        }
+    } else {
+        for (u32 c = sp.x + tw * 32 + lane; c < sp.y; c += TEAM_WARPS * 32)
+            st_v4_stream(out + c, paint_chunk<false>(C, m, c));
     }
 }
 
@@ -175,11 +277,11 @@ extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_c
     cudaError_t e = cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), as_stream(stream));
     if (e != cudaSuccess) { ampis_set_error("cursor memset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     if (layout == AMPIS_LAYOUT_FULL)
-        rle_measure_paint_kernel<MP_WARPS><<<n, MP_WARPS * 32, 0, as_stream(stream)>>>(
+        rle_measure_paint_kernel<MP_WARPS, false><<<n, MP_WARPS * 32, 0, as_stream(stream)>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
             d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
     else
-        rle_measure_paint_kernel<1><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
+        rle_measure_paint_kernel<1, true><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
             d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
     AMPIS_CHECK_LAUNCH("rle_measure_paint_kernel");

@@ -58,7 +58,8 @@ class MaskTable(object):
         self.reg_chunks = torch.empty(n1, dtype=i64, device=device)
         self.status = torch.empty(n1, dtype=i32, device=device)
         self.bits_off = torch.empty(n1 + 1, dtype=i64, device=device)
-        self.cursor = None      # set by measure_paint(): chunks the arena needed (device int64[1])
+        self.cursor = torch.empty(1, dtype=i64, device=device)   # chunks the arena needed (fused path)
+        self.fused = False
         self.bits = None
         self.bits_capacity = 0
 
@@ -90,7 +91,7 @@ class MaskTable(object):
         generously) and overflow is detected afterwards by check()."""
         self.bits = arena
         self.bits_capacity = arena.numel() // 4
-        self.cursor = torch.empty(1, dtype=torch.int64, device=self.device)
+        self.fused = True
         N.call('ampis_rle_measure_paint', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h), _p(self.w),
                self.n, self.layout, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
                _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor), _stream())
@@ -102,7 +103,7 @@ class MaskTable(object):
             bad = torch.nonzero(self.status[:self.n]).flatten()[:8].tolist()
             raise ValueError('malformed RLE: run counts do not sum to h*w for masks %s' % bad)
         if self.bits is not None and self.n:
-            need = int((self.cursor if self.cursor is not None else self.bits_off[self.n]).item())
+            need = int((self.cursor[0] if self.fused else self.bits_off[self.n]).item())
             if need > self.bits_capacity:
                 raise N.AmpisNativeError('packed-mask arena too small: %d chunks needed, %d available'
                                          % (need, self.bits_capacity))
@@ -246,12 +247,15 @@ def intersect_rows(table, groups, mode, out=None):
     return out
 
 
-def match_counts(rows, groups, thresholds, totals=None):
-    """TP/FP/FN per group and threshold -> int32[n_groups, n_thresh, 3] (device), totals += ."""
+def match_counts(rows, groups, thresholds, totals=None, counts=None):
+    """TP/FP/FN per group and threshold -> int32[n_groups, n_thresh, 3] (device), totals += .
+    `thresholds` may be a host sequence or a float64 device tensor (no copy then)."""
     dev = groups.device
-    th = _dev(np.asarray(thresholds, np.float64), torch.float64, dev)
+    th = thresholds if isinstance(thresholds, torch.Tensor) else \
+        _dev(np.asarray(thresholds, np.float64), torch.float64, dev)
     nt = th.numel()
-    counts = torch.empty(max(groups.n_groups * nt * 3, 1), dtype=torch.int32, device=dev)
+    if counts is None:
+        counts = torch.empty(max(groups.n_groups * nt * 3, 1), dtype=torch.int32, device=dev)
     if totals is None:
         totals = torch.zeros(max(nt * 3, 1), dtype=torch.int64, device=dev)
     N.call('ampis_match_counts', _p(rows.best_col), _p(rows.best_score), _p(groups.grp_row_begin),

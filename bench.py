@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='replay each step from a CUDA graph')
+    ap.add_argument('--span-sub', type=int, default=0, help='images per launch group of the span run')
     ap.add_argument('--unfused', action='store_true', help='separate measure / scan / paint launches')
     ap.add_argument('--no-span', action='store_true', help='skip the secondary span-layout measurement')
     ap.add_argument('--cpu-images', type=int, default=0)
@@ -211,31 +213,40 @@ class LayoutRun(object):
                                                      device=dev))
         self.thresholds = batch.COCO_THRESHOLDS
         self.totals = torch.zeros(len(self.thresholds) * 3, dtype=torch.int64, device=dev)
+        self.pipes = [batch.Pipeline(b, layout, self.arena, self.rows_out, self.thresholds, self.totals,
+                                     fused=self.fused) for b in self.subs]
+        self.graph = None
+
+    def launch_all(self, record=None):
+        import torch
+        self.totals.zero_()
+        for p in self.pipes:
+            if record is None:
+                p.launch()
+            else:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                p.launch(lambda i, ev=ev: ev[i].record())
+                record.append(ev)
+
+    def capture(self):
+        """Capture one step's launch sequence in a CUDA graph (launch-bound for small launch groups)."""
+        import torch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.launch_all()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.launch_all()
 
     def step(self, world, dist, record=None):
         """one pass over the rank's batch; `record` collects the CUDA events around each kernel group"""
-        import torch
-        from ampis_b200 import engine
-        self.totals.zero_()
-        for b in self.subs:
-            t = engine.MaskTable(self.dev, b.host.n_masks, b.cnt, b.cnt_off, b.cnt_len, b.h, b.w, self.layout)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record is not None else None
-            if ev: ev[0].record()
-            if self.fused:
-                if ev: ev[1].record()
-                t.measure_paint(self.arena)       # measure + arena allocation + paint in one launch
-            else:
-                t.measure()
-                if ev: ev[1].record()
-                t.paint(self.arena)
-            if ev: ev[2].record()
-            rows = engine.intersect_rows(t, b.groups, b.mode, out=self.rows_out)
-            if ev: ev[3].record()
-            engine.match_counts(rows, b.groups, self.thresholds, totals=self.totals)
-            self.last_table = t
-            if ev:
-                ev[4].record()
-                record.append(ev)
+        if self.graph is not None and record is None:
+            self.graph.replay()
+        else:
+            self.launch_all(record)
         if world > 1:
             dist.all_reduce(self.totals)      # TP/FP/FN x thresholds: the only exchange on this path
         return self.totals
@@ -246,10 +257,15 @@ class LayoutRun(object):
             self.step(world, dist)
         sync()
         record = []
+        use_graph = self.graph is not None
+        if use_graph:     # per-kernel shares come from an instrumented pass outside the timed region
+            for _ in range(2):
+                self.launch_all(record)
+            sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            self.step(world, dist, record)
+            self.step(world, dist, None if use_graph else record)
         e1.record()
         sync()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
@@ -259,7 +275,7 @@ class LayoutRun(object):
         for ev in record:
             for i in range(4):
                 kt[i] += ev[i].elapsed_time(ev[i + 1])
-        self.last_table.check()      # arena large enough, RLE well-formed (after the timed region)
+        self.pipes[-1].table.check()      # arena large enough, RLE well-formed (after the timed region)
         return float(ms.item()), kt, self.totals.cpu().numpy().reshape(-1, 3)
 
 
@@ -277,7 +293,7 @@ def roofline_of(args, cfg, run, ms, kt, world):
     canonical_img = 4 * run.total_runs / n_img + 2 * per_image * B_m + 4 * pairs_img + 8 * per_image + 32 * cfg['n_rows']
     dom = 'paint' if kt[1] >= kt[2] else 'rows'
     launches = len(run.subs)
-    dur_ms = kt[KERNELS.index(dom)] / (args.steps * launches)
+    dur_ms = kt[KERNELS.index(dom)] / ((2 if run.graph is not None else args.steps) * launches)
     achieved = alg[dom] / launches / (dur_ms / 1e3) / 1e9
     lay = 'full' if run.layout == engine.LAYOUT_FULL else 'span'
     traffic = None
@@ -335,6 +351,8 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None       # samples cover warm-up + timed steps
     wall0 = time.time()
     run = LayoutRun(args, dev, rank, layout, auto_sub(layout))
+    if args.graph:
+        run.capture()
     ms, kt, final_totals = run.timed(args, world, dist, sync)
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if sampler else None
@@ -349,7 +367,9 @@ def main():
     span = None
     if layout == engine.LAYOUT_FULL and not args.no_span:
         del run.arena
-        srun = LayoutRun(args, dev, rank, engine.LAYOUT_SPAN, auto_sub(engine.LAYOUT_SPAN))
+        srun = LayoutRun(args, dev, rank, engine.LAYOUT_SPAN, args.span_sub or auto_sub(engine.LAYOUT_SPAN))
+        if args.graph:
+            srun.capture()
         sms, skt, stot = srun.timed(args, world, dist, sync)
         assert np.array_equal(stot, final_totals), 'span and full layouts disagree'
         span = {'value': world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (sms / 1e3), 'unit': UNIT,
