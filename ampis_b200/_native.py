@@ -34,6 +34,10 @@ SIGNATURES = {
                                        _p, _p, _p]),
     'ampis_rle_measure_paint': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
                                           _p]),
+    'ampis_mma_tile_rows': (C.c_int, []),
+    'ampis_mma_tile_cols': (C.c_int, []),
+    'ampis_intersect_tcgen05': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    'ampis_rows_from_imat': (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p]),
     'ampis_iou_matrix_f64': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p]),
     'ampis_match_counts': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p]),
     'ampis_satellite_counts': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _p, _p, _i32, _p]),

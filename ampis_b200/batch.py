@@ -31,6 +31,11 @@ CONFIGS = {
     # C4: 2048x2048 spheroidite, 5000 x 5000 small elongated instances
     'c4_spheroidite': dict(h=2048, w=2048, n_rows=5000, n_cols=5000, kind=0, median_diam=13.5, sigma_ln=0.6,
                            max_aspect=3.0, sec_median_diam=0.0, mode=engine.MODE_IOU),
+    # crowded frame: 512 x 512 large overlapping instances in 256x256 px (about a quarter of all pairs have
+    # overlapping boxes) -- the regime of the tensor-core contraction (engine.intersect_mma), not a
+    # BASELINE.json config
+    'dense_overlap': dict(h=256, w=256, n_rows=512, n_cols=512, kind=0, median_diam=64.0, sigma_ln=0.3,
+                          max_aspect=1.5, sec_median_diam=0.0, mode=engine.MODE_IOU),
 }
 
 

@@ -1,0 +1,450 @@
+// Dense intersection matrices on the 5th-generation tensor cores (tcgen05, sm_100a only).
+//
+// For images whose instances overlap heavily (candidate density of tens of percent) the
+// bbox-culled AND+popc walk of intersect.cu re-reads every mask once per overlapping partner.
+// There the whole G x P matrix of an image is cheaper as ONE integer contraction
+//
+//        I[r][c] = sum_k A[r][k] * B[c][k]          k = pixel index, A, B in {0,1}
+//
+// i.e. exactly the quantity pycocotools' rleIou run walk accumulates for every pair
+// (analyze.py:108,158 via RLE.iou; powder.py:82 via RLE.merge(intersect=True) + RLE.area), with
+// no pruning at all.  int32 accumulation makes it bit-exact.
+//
+// One CTA computes one 128 x 256 tile of one image's matrix:
+//   warp 0      producer: 1-D TMA bulk copies (cp.async.bulk) of the PACKED bits of the 384 masks
+//               of the tile, 4 slabs (4 x 128 pixels) per mask per stage, mbarrier complete_tx
+//   warps 2..9  expanders: packed bits -> u8 operand tiles in shared memory, K-major with the
+//               128-byte swizzle tcgen05 expects (one 128-pixel slab = one 128-byte row)
+//   warp 1      one thread issues tcgen05.mma.kind::i8 (M128 N256 K32, 4 per slab) with the
+//               accumulator in TMEM (256 columns), tcgen05.commit releases operand stages
+//   warps 2..9  epilogue: tcgen05.ld of the accumulator, >> 7, int32 stores
+//
+// Bit expansion without shifts: a byte of packed bits is replicated by one PRMT and masked, so
+// pixel j of an A row becomes the value 2^(j%8) (bit kept in place) and pixel j of a B row
+// becomes 2^(7-j%8) (bit kept in place of the bit-reversed word).  Every product of two set
+// pixels is then exactly 128, every other product 0, and I = accumulator >> 7.  u8 x u8 -> s32
+// wraps only above 2^32/128 = 33.5 M pixels per mask (5792 x 5792).
+#include "common.cuh"
+
+#define MMA_TM 128
+#define MMA_TN 256
+#define MMA_SLOTS (MMA_TM + MMA_TN)         // mask slots of a tile: 128 rows then 256 columns
+#define MMA_SUPER 4                          // slabs (128-bit chunks) per packed-bit stage
+#define MMA_NB 2                             // packed-bit stages
+#define MMA_NO 3                             // expanded operand stages
+#define MMA_PITCH 80                         // bytes per slot in a packed-bit stage (64 + 16: conflict-free LDS)
+#define MMA_A_BYTES (MMA_TM * 128)
+#define MMA_B_BYTES (MMA_TN * 128)
+#define MMA_OP_BYTES (MMA_A_BYTES + MMA_B_BYTES)
+#define MMA_BITS_BYTES (MMA_SLOTS * MMA_PITCH)
+#define MMA_EXP_WARPS 8
+#define MMA_THREADS ((2 + MMA_EXP_WARPS) * 32)
+#define MMA_TMEM_COLS 256
+#define MMA_WAIT_CYCLES (4ll << 30)            // ~2 s: a wait this long is a protocol bug
+
+// dynamic shared memory map (base aligned to 1024 by hand)
+#define MMA_OFF_OPS 0
+#define MMA_OFF_BITS (MMA_NO * MMA_OP_BYTES)
+#define MMA_OFF_SRC (MMA_OFF_BITS + MMA_NB * MMA_BITS_BYTES)
+#define MMA_OFF_LO (MMA_OFF_SRC + MMA_SLOTS * 8)
+#define MMA_OFF_HI (MMA_OFF_LO + MMA_SLOTS * 4)
+#define MMA_OFF_BAR (MMA_OFF_HI + MMA_SLOTS * 4)
+#define MMA_N_BARS (2 * MMA_NB + 2 * MMA_NO + 1)
+#define MMA_OFF_MISC (MMA_OFF_BAR + MMA_N_BARS * 8)
+#define MMA_SMEM_BYTES (MMA_OFF_MISC + 64 + 1024)
+
+struct MmaArgs {
+    const uint4 *bits;
+    const i64 *bits_off;
+    const uint2 *reg;
+    const uint2 *span;
+    const int *row_mask;
+    const int *tile_grp, *tile_m0, *tile_n0;
+    const int *grp_row_begin, *grp_row_count, *grp_col_begin, *grp_col_count;
+    const i64 *grp_imat_off;
+    int *imat;
+};
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(u32 bar, u32 tx)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(u32 bar, u32 parity)
+{
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
+{
+    long long t0 = 0;
+    for (u32 spin = 0; !mbar_try(bar, parity); ++spin) {
+        if (spin == 0) t0 = clock64();
+        else if ((spin & 0x3ffu) == 0 && clock64() - t0 > MMA_WAIT_CYCLES) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u32 bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, M128 N256 K32
+__device__ __forceinline__ void tc_mma_i8(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ u64 smem_desc_sw128(u32 addr)
+{
+    return (u64)((addr >> 4) & 0x3fffu) | (1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: C = s32, A = B = u8, both K-major, N = 256, M = 128
+#define MMA_IDESC ((2u << 4) | (0u << 7) | (0u << 10) | ((u32)(MMA_TN >> 3) << 17) | ((u32)(MMA_TM >> 4) << 24))
+
+__device__ __forceinline__ void tc_ld32(u32 taddr, u32 (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 packed pixels -> 32 operand bytes (two 16-byte chunks)
+template <bool IS_B>
+__device__ __forceinline__ void expand_word(u32 x, uint4 &o0, uint4 &o1)
+{
+    if (IS_B) x = __brev(x);
+    const u32 v0 = __byte_perm(x, 0u, IS_B ? 0x3333u : 0x0000u);    // packed byte 0 in all four lanes
+    const u32 v1 = __byte_perm(x, 0u, IS_B ? 0x2222u : 0x1111u);
+    const u32 v2 = __byte_perm(x, 0u, IS_B ? 0x1111u : 0x2222u);
+    const u32 v3 = __byte_perm(x, 0u, IS_B ? 0x0000u : 0x3333u);
+    const u32 mlo = IS_B ? 0x10204080u : 0x08040201u;               // pixels 0..3 of the byte
+    const u32 mhi = IS_B ? 0x01020408u : 0x80402010u;               // pixels 4..7 of the byte
+    o0 = make_uint4(v0 & mlo, v0 & mhi, v1 & mlo, v1 & mhi);
+    o1 = make_uint4(v2 & mlo, v2 & mhi, v3 & mlo, v3 & mhi);
+}
+
+__device__ __forceinline__ void sts_v4(u32 addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ u32 lds_u32(u32 addr)
+{
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+intersect_mma_kernel(const MmaArgs p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const u32 base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));            // generic pointer to the same place
+    const uint4 **s_src = reinterpret_cast<const uint4 **>(gen + MMA_OFF_SRC);
+    u32 *s_lo = reinterpret_cast<u32 *>(gen + MMA_OFF_LO);
+    u32 *s_hi = reinterpret_cast<u32 *>(gen + MMA_OFF_HI);
+    u32 *s_misc = reinterpret_cast<u32 *>(gen + MMA_OFF_MISC);        // [0] tmem base, [1..4] k-range reduction
+    const u32 bar0 = base + MMA_OFF_BAR;
+    // barrier ids
+    auto bar_bits_full = [&](u32 s) { return bar0 + 8u * s; };
+    auto bar_bits_empty = [&](u32 s) { return bar0 + 8u * (MMA_NB + s); };
+    auto bar_op_full = [&](u32 s) { return bar0 + 8u * (2 * MMA_NB + s); };
+    auto bar_op_empty = [&](u32 s) { return bar0 + 8u * (2 * MMA_NB + MMA_NO + s); };
+    const u32 bar_acc = bar0 + 8u * (2 * MMA_NB + 2 * MMA_NO);
+
+    const u32 tid = threadIdx.x, wid = tid >> 5, lane = tid & 31u;
+    const int g = p.tile_grp[blockIdx.x], m0 = p.tile_m0[blockIdx.x], n0 = p.tile_n0[blockIdx.x];
+    const int G = p.grp_row_count[g], P = p.grp_col_count[g];
+    const int rb = p.grp_row_begin[g], cb = p.grp_col_begin[g];
+
+    if (tid == 0) {
+        for (u32 s = 0; s < MMA_NB; s++) { mbar_init(bar_bits_full(s), 1); mbar_init(bar_bits_empty(s), MMA_EXP_WARPS); }
+        for (u32 s = 0; s < MMA_NO; s++) { mbar_init(bar_op_full(s), MMA_EXP_WARPS); mbar_init(bar_op_empty(s), 1); }
+        mbar_init(bar_acc, 1);
+        s_misc[1] = 0xffffffffu; s_misc[2] = 0u;      // rows: min lo, max hi
+        s_misc[3] = 0xffffffffu; s_misc[4] = 0u;      // cols: min lo, max hi
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(base + MMA_OFF_MISC), "r"((u32)MMA_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    // slot table: where each mask's packed bits live and which slabs hold its 1-pixels
+    for (u32 s = tid; s < MMA_SLOTS; s += MMA_THREADS) {
+        int mask = -1;
+        if (s < MMA_TM) { if (m0 + (int)s < G) mask = p.row_mask[rb + m0 + (int)s]; }
+        else if (n0 + (int)(s - MMA_TM) < P) mask = cb + n0 + (int)(s - MMA_TM);
+        u32 lo = 0, hi = 0;
+        const uint4 *src = nullptr;
+        if (mask >= 0) {
+            const uint2 sp = p.span[mask];
+            lo = sp.x; hi = sp.y;
+            src = p.bits + p.bits_off[mask] - p.reg[mask].x;
+            if (hi > lo) {
+                atomicMin(&s_misc[s < MMA_TM ? 1 : 3], lo);
+                atomicMax(&s_misc[s < MMA_TM ? 2 : 4], hi);
+            }
+        }
+        s_src[s] = src; s_lo[s] = lo; s_hi[s] = hi;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem = s_misc[0];
+    const u32 klo = max(s_misc[1], s_misc[3]), khi = min(s_misc[2], s_misc[4]);
+    const u32 nslab = khi > klo ? khi - klo : 0u;                   // slabs in which a row AND a column have pixels
+    const u32 nsuper = (nslab + MMA_SUPER - 1) / MMA_SUPER;
+
+    if (wid == 0) {
+        // ---------------- producer: packed bits of every slot, MMA_SUPER slabs per stage -------------
+        for (u32 S = 0; S < nsuper; S++) {
+            const u32 b = S % MMA_NB;
+            mbar_wait(bar_bits_empty(b), ((S / MMA_NB) & 1u) ^ 1u);
+            const u32 k0 = klo + S * MMA_SUPER, k1 = min(k0 + MMA_SUPER, khi);
+            const u32 stage = base + MMA_OFF_BITS + b * MMA_BITS_BYTES;
+            u32 bytes = 0;
+            for (u32 s = lane; s < MMA_SLOTS; s += 32) {
+                const u32 lo = max(k0, s_lo[s]), hi = min(k1, s_hi[s]);
+                if (hi > lo) {
+                    const u32 nb = (hi - lo) * 16u;
+                    bulk_g2s(stage + s * MMA_PITCH + (lo - k0) * 16u, s_src[s] + lo, nb, bar_bits_full(b));
+                    bytes += nb;
+                }
+            }
+            bytes = warp_sum(bytes);
+            if (lane == 0) mbar_arrive_tx(bar_bits_full(b), bytes);
+        }
+    } else if (wid == 1) {
+        // ---------------- MMA issuer: one thread ------------------------------------------------------
+        if (lane == 0) {
+            for (u32 i = 0; i < nslab; i++) {
+                const u32 o = i % MMA_NO;
+                mbar_wait(bar_op_full(o), (i / MMA_NO) & 1u);
+                tc_fence_after();
+                const u32 a_addr = base + MMA_OFF_OPS + o * MMA_OP_BYTES, b_addr = a_addr + MMA_A_BYTES;
+                const u64 ad = smem_desc_sw128(a_addr), bd = smem_desc_sw128(b_addr);
+#pragma unroll
+                for (u32 k = 0; k < 4; k++)        // 4 x K32 inside the 128-byte swizzle atom: +32 bytes each
+                    tc_mma_i8(tmem, ad + 2u * k, bd + 2u * k, MMA_IDESC, (i | k) ? 1u : 0u);
+                tc_commit(bar_op_empty(o));        // implies tcgen05.fence::before_thread_sync
+            }
+            if (nslab) tc_commit(bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- expanders: bits -> u8 operand rows -----------------------------------------
+        const u32 e = wid - 2u, sub = lane >> 2, j = lane & 3u;
+        u32 lo_[6], hi_[6], src_[6], dst_[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const u32 slot = (u32)q * 64u + e * 8u + sub;
+            lo_[q] = s_lo[slot]; hi_[q] = s_hi[slot];
+            src_[q] = slot * MMA_PITCH + j * 4u;
+            const u32 r = slot < MMA_TM ? slot : slot - MMA_TM;
+            dst_[q] = (slot < MMA_TM ? 0u : (u32)MMA_A_BYTES) + (r >> 3) * 1024u + (r & 7u) * 128u +
+                      (((2u * j) ^ (r & 7u)) << 4);
+        }
+        for (u32 i = 0; i < nslab; i++) {
+            const u32 S = i / MMA_SUPER, si = i % MMA_SUPER, b = S % MMA_NB, o = i % MMA_NO;
+            if (si == 0) mbar_wait(bar_bits_full(b), (S / MMA_NB) & 1u);
+            mbar_wait(bar_op_empty(o), ((i / MMA_NO) & 1u) ^ 1u);
+            const u32 k = klo + i;
+            const u32 bsrc = base + MMA_OFF_BITS + b * MMA_BITS_BYTES + si * 16u;
+            const u32 odst = base + MMA_OFF_OPS + o * MMA_OP_BYTES;
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                u32 x = lds_u32(bsrc + src_[q]);
+                if (k < lo_[q] || k >= hi_[q]) x = 0u;          // outside the mask's span the stage holds stale data
+                uint4 o0, o1;
+                if (q < 2) expand_word<false>(x, o0, o1); else expand_word<true>(x, o0, o1);
+                sts_v4(odst + dst_[q], o0);
+                sts_v4(odst + (dst_[q] ^ 16u), o1);
+            }
+            fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_op_full(o));
+                if (si == MMA_SUPER - 1 || i + 1 == nslab) mbar_arrive(bar_bits_empty(b));
+            }
+        }
+        // ---------------- epilogue: TMEM -> int32 matrix ---------------------------------------------
+        const i64 off = p.grp_imat_off[g];
+        const u32 quarter = wid & 3u, half = e >> 2;            // TMEM lanes 32*quarter.., columns 128*half..
+        const int row = m0 + (int)(32u * quarter + lane);
+        if (nslab) {
+            mbar_wait(bar_acc, 0u);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (u32 cbk = 0; cbk < 4; cbk++) {
+            u32 v[32];
+            const u32 col0 = half * 128u + cbk * 32u;
+            if (nslab) {
+                tc_ld32(tmem + ((32u * quarter) << 16) + col0, v);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 32; t++) v[t] = 0u;
+            }
+            if (row < G) {
+                int *orow = p.imat + off + (i64)row * P;
+#pragma unroll
+                for (int t = 0; t < 32; t++) {
+                    const int c = n0 + (int)col0 + t;
+                    if (c < P) orow[c] = (int)(v[t] >> 7);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (wid == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)MMA_TMEM_COLS) : "memory");
+    }
+}
+
+extern "C" int ampis_mma_tile_rows(void) { return MMA_TM; }
+extern "C" int ampis_mma_tile_cols(void) { return MMA_TN; }
+
+extern "C" int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                                       const uint32_t *d_span, const int32_t *d_row_mask,
+                                       const int32_t *d_tile_grp, const int32_t *d_tile_m0,
+                                       const int32_t *d_tile_n0, int32_t n_tiles,
+                                       const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                                       const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                                       const int64_t *d_grp_imat_off, int32_t *d_imat, void *stream)
+{
+    AMPIS_REQUIRE(n_tiles >= 0, "n_tiles < 0");
+    if (n_tiles == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_bits && d_bits_off && d_reg && d_span && d_row_mask && d_tile_grp && d_tile_m0 && d_tile_n0 &&
+                      d_grp_row_begin && d_grp_row_count && d_grp_col_begin && d_grp_col_count && d_grp_imat_off &&
+                      d_imat, "null pointer");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(intersect_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             MMA_SMEM_BYTES);
+        if (e != cudaSuccess) { ampis_set_error("intersect_mma_kernel smem: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+        configured = true;
+    }
+    MmaArgs a;
+    a.bits = (const uint4 *)d_bits; a.bits_off = d_bits_off; a.reg = (const uint2 *)d_reg;
+    a.span = (const uint2 *)d_span; a.row_mask = d_row_mask;
+    a.tile_grp = d_tile_grp; a.tile_m0 = d_tile_m0; a.tile_n0 = d_tile_n0;
+    a.grp_row_begin = d_grp_row_begin; a.grp_row_count = d_grp_row_count;
+    a.grp_col_begin = d_grp_col_begin; a.grp_col_count = d_grp_col_count;
+    a.grp_imat_off = d_grp_imat_off; a.imat = d_imat;
+    intersect_mma_kernel<<<n_tiles, MMA_THREADS, MMA_SMEM_BYTES, as_stream(stream)>>>(a);
+    AMPIS_CHECK_LAUNCH("intersect_mma_kernel");
+    return AMPIS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row results from a dense intersection matrix: score, first arg-max (same rules as
+// intersect_rows_kernel; analyze.py:158-164, powder.py:82-86).  Warp per row.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+rows_from_imat_kernel(const int *__restrict__ imat, const i64 *__restrict__ grp_imat_off,
+                      const u32 *__restrict__ area, const int *__restrict__ row_mask,
+                      const int *__restrict__ row_grp, int n_rows, const int *__restrict__ grp_row_begin,
+                      const int *__restrict__ grp_col_begin, const int *__restrict__ grp_col_count,
+                      int *__restrict__ best_col, u32 *__restrict__ best_inter, double *__restrict__ best_score)
+{
+    const int r = (int)((blockIdx.x * (u32)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_rows) return;
+    const u32 lane = lane_id();
+    const int g = row_grp[r];
+    const int P = grp_col_count[g], cb = grp_col_begin[g];
+    const int *irow = imat + grp_imat_off[g] + (i64)(r - grp_row_begin[g]) * P;
+    const u32 ra = area[row_mask[r]];
+    double best_s = 0.0;
+    u32 best_i = 0;
+    int best_c = MODE == AMPIS_MODE_IOU ? -1 : (P > 0 ? 0 : -1);
+    for (int c = (int)lane; c < P; c += 32) {
+        const u32 inter = (u32)irow[c];
+        if (MODE == AMPIS_MODE_IOU) {
+            const double s = inter ? (double)inter / (double)(ra + area[cb + c] - inter) : 0.0;
+            if (s > best_s) { best_s = s; best_i = inter; best_c = c; }
+        } else {
+            if (inter > best_i) { best_i = inter; best_c = c; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, best_s, d);
+        const u32 oi = __shfl_xor_sync(0xffffffffu, best_i, d);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, d);
+        bool take;
+        if (MODE == AMPIS_MODE_IOU) take = os > best_s || (os == best_s && (unsigned)oc < (unsigned)best_c);
+        else take = oi > best_i || (oi == best_i && (unsigned)oc < (unsigned)best_c);
+        if (take) { best_s = os; best_i = oi; best_c = oc; }
+    }
+    if (lane == 0) {
+        if (MODE == AMPIS_MODE_SAT) best_s = (double)best_i / (double)ra;
+        best_col[r] = best_c;
+        best_inter[r] = best_i;
+        best_score[r] = best_s;
+    }
+}
+
+extern "C" int ampis_rows_from_imat(const int32_t *d_imat, const int64_t *d_grp_imat_off, const uint32_t *d_area,
+                                    const int32_t *d_row_mask, const int32_t *d_row_grp, int32_t n_rows,
+                                    const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
+                                    const int32_t *d_grp_col_count, int32_t mode, int32_t *d_best_col,
+                                    uint32_t *d_best_inter, double *d_best_score, void *stream)
+{
+    AMPIS_REQUIRE(n_rows >= 0, "n_rows < 0");
+    AMPIS_REQUIRE(mode == AMPIS_MODE_IOU || mode == AMPIS_MODE_SAT, "bad mode");
+    if (n_rows == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_imat && d_grp_imat_off && d_area && d_row_mask && d_row_grp && d_grp_row_begin &&
+                      d_grp_col_begin && d_grp_col_count && d_best_col && d_best_inter && d_best_score,
+                  "null pointer");
+    const unsigned blocks = (unsigned)(((i64)n_rows * 32 + 255) / 256);
+    if (mode == AMPIS_MODE_IOU)
+        rows_from_imat_kernel<AMPIS_MODE_IOU><<<blocks, 256, 0, as_stream(stream)>>>(
+            d_imat, d_grp_imat_off, d_area, d_row_mask, d_row_grp, n_rows, d_grp_row_begin, d_grp_col_begin,
+            d_grp_col_count, d_best_col, d_best_inter, d_best_score);
+    else
+        rows_from_imat_kernel<AMPIS_MODE_SAT><<<blocks, 256, 0, as_stream(stream)>>>(
+            d_imat, d_grp_imat_off, d_area, d_row_mask, d_row_grp, n_rows, d_grp_row_begin, d_grp_col_begin,
+            d_grp_col_count, d_best_col, d_best_inter, d_best_score);
+    AMPIS_CHECK_LAUNCH("rows_from_imat_kernel");
+    return AMPIS_OK;
+}

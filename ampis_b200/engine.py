@@ -209,6 +209,26 @@ class Groups(object):
             self.imat_size = int(off[-1])
             self.imat_off = _dev(off[:-1], torch.int64, device)
 
+    def mma_tiles(self):
+        """Tile list of the tensor-core contraction (ampis_intersect_tcgen05): every group's dense
+        matrix cut into ampis_mma_tile_rows() x ampis_mma_tile_cols() tiles; built once, cached."""
+        if getattr(self, '_mma', None) is None:
+            assert self.imat_off is not None, 'the tensor-core path writes dense matrices: Groups(dense=True)'
+            tm, tn = N.lib().ampis_mma_tile_rows(), N.lib().ampis_mma_tile_cols()
+            grp, m0, n0 = [], [], []
+            for g in range(self.n_groups):
+                G, P = int(self.h_row_count[g]), int(self.h_col_count[g])
+                if G == 0 or P == 0:
+                    continue
+                mm, nn = np.meshgrid(np.arange(0, G, tm), np.arange(0, P, tn), indexing='ij')
+                grp.append(np.full(mm.size, g, np.int32))
+                m0.append(mm.ravel().astype(np.int32))
+                n0.append(nn.ravel().astype(np.int32))
+            cat = lambda v: np.concatenate(v) if v else np.zeros(0, np.int32)
+            self._mma = (len(cat(grp)), _dev(cat(grp), torch.int32, self.device),
+                         _dev(cat(m0), torch.int32, self.device), _dev(cat(n0), torch.int32, self.device))
+        return self._mma
+
     @staticmethod
     def interleaved(device, n_rows_per_group, n_cols_per_group, dense=False):
         """Mask table laid out image by image as [rows of g][cols of g]."""
@@ -244,6 +264,29 @@ def intersect_rows(table, groups, mode, out=None):
            groups.n_blocks, _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),
            _p(groups.grp_col_count), _p(groups.imat_off), mode, _p(out.imat), _p(out.best_col),
            _p(out.best_inter), _p(out.best_score), _stream())
+    return out
+
+
+def intersect_mma(table, groups, mode, out=None):
+    """Dense intersection matrices by the int8 tcgen05 contraction (no pruning), then the per-row
+    arg-max from the matrices.  Same RowResult as intersect_rows(), bit for bit; the choice
+    between the two is a cost decision."""
+    dev = table.device
+    nr = max(groups.n_rows, 1)
+    n_tiles, tile_grp, tile_m0, tile_n0 = groups.mma_tiles()
+    if out is None:
+        out = RowResult(torch.empty(nr, dtype=torch.int32, device=dev),
+                        torch.empty(nr, dtype=torch.int32, device=dev),
+                        torch.empty(nr, dtype=torch.float64, device=dev),
+                        torch.empty(max(groups.imat_size, 1), dtype=torch.int32, device=dev))
+    assert out.imat is not None
+    N.call('ampis_intersect_tcgen05', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
+           _p(groups.row_mask), _p(tile_grp), _p(tile_m0), _p(tile_n0), n_tiles, _p(groups.grp_row_begin),
+           _p(groups.grp_row_count), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off),
+           _p(out.imat), _stream())
+    N.call('ampis_rows_from_imat', _p(out.imat), _p(groups.imat_off), _p(table.area), _p(groups.row_mask),
+           _p(groups.row_grp), groups.n_rows, _p(groups.grp_row_begin), _p(groups.grp_col_begin),
+           _p(groups.grp_col_count), mode, _p(out.best_col), _p(out.best_inter), _p(out.best_score), _stream())
     return out
 
 

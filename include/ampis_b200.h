@@ -154,6 +154,33 @@ int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_off, const ui
                          int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                          void *stream);
 
+/* ---- dense intersection matrices on the tensor cores (tcgen05, int8 contraction) -----------
+ * Same quantity as the dense output of ampis_intersect_rows -- I[r][c] = popcount(row AND col),
+ * what rleIou's run walk accumulates per pair (analyze.py:108,158; powder.py:82) -- computed for
+ * EVERY pair of a group as I = A * B^T over pixels with u8 operands expanded from the packed
+ * bits in shared memory and an int32 accumulator in tensor memory.  No pruning: cost grows with
+ * G*P*(pixel range), so this is the path for images with heavily overlapping instances; the
+ * culled AND+popc kernel is the one for sparse images ("choice of intersection kernel").
+ * A tile is ampis_mma_tile_rows() x ampis_mma_tile_cols() cells of one group's matrix:
+ *   tile_grp[t], tile_m0[t], tile_n0[t]   group and first row / first column of tile t
+ * Every group with at least one tile must have a dense matrix (grp_imat_off[g] >= 0). */
+int ampis_mma_tile_rows(void);
+int ampis_mma_tile_cols(void);
+int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                            const uint32_t *d_span, const int32_t *d_row_mask,
+                            const int32_t *d_tile_grp, const int32_t *d_tile_m0, const int32_t *d_tile_n0,
+                            int32_t n_tiles, const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                            const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                            const int64_t *d_grp_imat_off, int32_t *d_imat, void *stream);
+
+/* Per-row results (same outputs and tie rules as ampis_intersect_rows) from dense matrices:
+ * row_grp[r] = group of row r. */
+int ampis_rows_from_imat(const int32_t *d_imat, const int64_t *d_grp_imat_off, const uint32_t *d_area,
+                         const int32_t *d_row_mask, const int32_t *d_row_grp, int32_t n_rows,
+                         const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
+                         const int32_t *d_grp_col_count, int32_t mode, int32_t *d_best_col,
+                         uint32_t *d_best_inter, double *d_best_score, void *stream);
+
 /* Full IoU matrix of one group as float64[G][P] from the dense intersections
  * (analyze._piecewise_iou, analyze.py:54-112): I>0 ? I/(a_g+a_p-I) : 0.0 */
 int ampis_iou_matrix_f64(const int32_t *d_imat, const uint32_t *d_area_rows, const uint32_t *d_area_cols,

@@ -397,6 +397,39 @@ def test_full_size_properties(mods):
     assert bool(((sc == 1.0) | (area == 0)).all())
 
 
+@pytest.mark.parametrize('cfg,over,n_img', [
+    ('c2_powder_batch', dict(h=256, w=256, n_rows=150, n_cols=300, median_diam=14.0), 3),   # ragged single tiles
+    ('dense_overlap', dict(n_rows=300, n_cols=520), 2),                                     # 3 x 3 tiles, ragged
+    ('c3_satellites', dict(h=512, w=512, n_rows=40, n_cols=300), 2),                         # satellite scores
+])
+@pytest.mark.parametrize('layout', ['span', 'full'])
+def test_tensor_core_contraction_equals_culled_popc(mods, cfg, over, n_img, layout):
+    """ampis_intersect_tcgen05 (dense int8 contraction, no pruning) == ampis_intersect_rows (bbox-culled
+    AND+popc): dense intersections, arg-max, scores and counts bit for bit; first image also against
+    the oracle's run-walk intersections."""
+    B, E, R, rle, torch = mods.batch, mods.engine, mods.R, mods.rle, mods.torch
+    c = dict(B.CONFIGS[cfg], **over)
+    host = B.synth(c, n_img, 4242)
+    dev = B.DeviceBatch(host, dense=True)
+    lay = E.LAYOUT_FULL if layout == 'full' else E.LAYOUT_SPAN
+    t = E.MaskTable(dev.device, host.n_masks, dev.cnt, dev.cnt_off, dev.cnt_len, dev.h, dev.w, lay)
+    t.measure().paint().check()
+    a = E.intersect_rows(t, dev.groups, dev.mode)
+    m = E.intersect_mma(t, dev.groups, dev.mode)
+    torch.cuda.synchronize()
+    assert torch.equal(a.imat, m.imat)
+    assert torch.equal(a.best_col, m.best_col) and torch.equal(a.best_inter, m.best_inter)
+    sa, sm = a.best_score.cpu().numpy(), m.best_score.cpu().numpy()
+    assert np.array_equal(sa, sm, equal_nan=True)
+    rows, cols = host.image_masks(0)
+    er, ec = _counts_to_rle(rle, rows, host.h, host.w), _counts_to_rle(rle, cols, host.h, host.w)
+    imat = m.imat.cpu().numpy()[:host.n_rows * host.n_cols].reshape(host.n_rows, host.n_cols)
+    rng = np.random.default_rng(5)
+    for i, j in zip(rng.integers(0, host.n_rows, 300), rng.integers(0, host.n_cols, 300)):
+        assert imat[i, j] == int(rle.merge_area(er[i], ec[j]))
+    assert imat.max() > 0
+
+
 def test_hist_and_scan(mods):
     E, torch = mods.engine, mods.torch
     rng = np.random.default_rng(0)
