@@ -118,7 +118,7 @@ class StepResult(object):
 
 
 def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_out=None,
-              sat_thresh=0.5, check=False, fused=None):
+              sat_thresh=0.5, check=False, fused=None, kernel='rows'):
     """One pass of the hot path over a device-resident batch: measure -> paint -> fused
     intersect/arg-max rows -> per-image and total counts.  No host synchronisation when an
     arena is supplied and check is False.  Returns device tensors."""
@@ -131,7 +131,10 @@ def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_o
         t.measure_paint(arena)       # one launch: measure + arena allocation + paint
     else:
         t.measure().paint(arena)     # five launches; sizes the arena exactly when none is given
-    rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out)
+    if kernel == 'mma':
+        rows = engine.intersect_mma(t, batch.groups, batch.mode, out=rows_out)
+    else:
+        rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out)
     r = StepResult()
     r.table, r.rows = t, rows
     if batch.mode == engine.MODE_IOU:
@@ -149,9 +152,13 @@ class Pipeline(object):
     fused measure+paint -> intersect rows -> counts."""
 
     def __init__(self, batch, layout, arena, rows_out=None, thresholds=COCO_THRESHOLDS, totals=None,
-                 sat_thresh=0.5, fused=True):
+                 sat_thresh=0.5, fused=True, kernel='rows'):
         dev = batch.device
         self.batch, self.layout, self.arena, self.fused = batch, layout, arena, fused
+        assert kernel in ('rows', 'mma')
+        self.kernel = kernel        # 'rows': bbox-culled AND+popc; 'mma': dense int8 tcgen05 contraction
+        if kernel == 'mma':
+            batch.groups.mma_tiles()
         self.table = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
                                       batch.w, layout)
         g = batch.groups
@@ -182,7 +189,10 @@ class Pipeline(object):
             if mark: mark(1)
             t.paint(self.arena)
         if mark: mark(2)
-        engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows)
+        if self.kernel == 'mma':
+            engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows)
+        else:
+            engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows)
         if mark: mark(3)
         if self.batch.mode == engine.MODE_IOU:
             engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)

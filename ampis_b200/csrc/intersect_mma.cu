@@ -11,13 +11,14 @@
 // no pruning at all.  int32 accumulation makes it bit-exact.
 //
 // One CTA computes one 128 x 256 tile of one image's matrix:
-//   warp 0      producer: 1-D TMA bulk copies (cp.async.bulk) of the PACKED bits of the 384 masks
-//               of the tile, 4 slabs (4 x 128 pixels) per mask per stage, mbarrier complete_tx
-//   warps 2..9  expanders: packed bits -> u8 operand tiles in shared memory, K-major with the
-//               128-byte swizzle tcgen05 expects (one 128-pixel slab = one 128-byte row)
-//   warp 1      one thread issues tcgen05.mma.kind::i8 (M128 N256 K32, 4 per slab) with the
-//               accumulator in TMEM (256 columns), tcgen05.commit releases operand stages
-//   warps 2..9  epilogue: tcgen05.ld of the accumulator, >> 7, int32 stores
+//   warps 1..12  expanders, one THREAD per mask of the tile (128 rows + 256 columns): the thread
+//                streams its mask's packed bits from HBM/L2 (two 128-bit chunks = one 32-byte sector
+//                per iteration, prefetched two iterations ahead in registers) and expands them to a
+//                u8 operand row in shared memory, K-major with the 128-byte swizzle tcgen05 expects
+//                (one 128-pixel slab = one 128-byte row; a stage holds two slabs)
+//   warp 0       one thread issues tcgen05.mma.kind::i8 (M128 N256 K32, 8 per stage) with the
+//                accumulator in tensor memory (256 columns); tcgen05.commit hands stages back
+//   warps 1..8   epilogue: tcgen05.ld of the accumulator, >> 7, int32 stores
 //
 // Bit expansion without shifts: a byte of packed bits is replicated by one PRMT and masked, so
 // pixel j of an A row becomes the value 2^(j%8) (bit kept in place) and pixel j of a B row
@@ -29,27 +30,22 @@
 #define MMA_TM 128
 #define MMA_TN 256
 #define MMA_SLOTS (MMA_TM + MMA_TN)         // mask slots of a tile: 128 rows then 256 columns
-#define MMA_SUPER 4                          // slabs (128-bit chunks) per packed-bit stage
-#define MMA_NB 2                             // packed-bit stages
-#define MMA_NO 3                             // expanded operand stages
-#define MMA_PITCH 80                         // bytes per slot in a packed-bit stage (64 + 16: conflict-free LDS)
+#define MMA_SLABS 2                          // 128-pixel slabs per operand stage
+#define MMA_NO 2                             // operand stages
+#define MMA_PF 2                             // iterations of packed bits prefetched in registers
 #define MMA_A_BYTES (MMA_TM * 128)
 #define MMA_B_BYTES (MMA_TN * 128)
-#define MMA_OP_BYTES (MMA_A_BYTES + MMA_B_BYTES)
-#define MMA_BITS_BYTES (MMA_SLOTS * MMA_PITCH)
-#define MMA_EXP_WARPS 8
-#define MMA_THREADS ((2 + MMA_EXP_WARPS) * 32)
+#define MMA_SLAB_BYTES (MMA_A_BYTES + MMA_B_BYTES)
+#define MMA_OP_BYTES (MMA_SLABS * MMA_SLAB_BYTES)
+#define MMA_EXP_WARPS (MMA_SLOTS / 32)
+#define MMA_THREADS ((1 + MMA_EXP_WARPS) * 32)
 #define MMA_TMEM_COLS 256
 #define MMA_WAIT_CYCLES (4ll << 30)            // ~2 s: a wait this long is a protocol bug
 
 // dynamic shared memory map (base aligned to 1024 by hand)
 #define MMA_OFF_OPS 0
-#define MMA_OFF_BITS (MMA_NO * MMA_OP_BYTES)
-#define MMA_OFF_SRC (MMA_OFF_BITS + MMA_NB * MMA_BITS_BYTES)
-#define MMA_OFF_LO (MMA_OFF_SRC + MMA_SLOTS * 8)
-#define MMA_OFF_HI (MMA_OFF_LO + MMA_SLOTS * 4)
-#define MMA_OFF_BAR (MMA_OFF_HI + MMA_SLOTS * 4)
-#define MMA_N_BARS (2 * MMA_NB + 2 * MMA_NO + 1)
+#define MMA_OFF_BAR (MMA_NO * MMA_OP_BYTES)
+#define MMA_N_BARS (2 * MMA_NO + 1)
 #define MMA_OFF_MISC (MMA_OFF_BAR + MMA_N_BARS * 8)
 #define MMA_SMEM_BYTES (MMA_OFF_MISC + 64 + 1024)
 
@@ -169,23 +165,40 @@ __device__ __forceinline__ u32 lds_u32(u32 addr)
     return v;
 }
 
+__device__ __forceinline__ uint4 ldg_v4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// one 128-pixel chunk -> one 128-byte operand row (8 swizzled 16-byte stores)
+template <bool IS_B>
+__device__ __forceinline__ void expand_chunk(uint4 c, u32 row_addr, u32 r7)
+{
+    uint4 o0, o1;
+    expand_word<IS_B>(c.x, o0, o1);
+    sts_v4(row_addr + ((0u ^ r7) << 4), o0); sts_v4(row_addr + ((1u ^ r7) << 4), o1);
+    expand_word<IS_B>(c.y, o0, o1);
+    sts_v4(row_addr + ((2u ^ r7) << 4), o0); sts_v4(row_addr + ((3u ^ r7) << 4), o1);
+    expand_word<IS_B>(c.z, o0, o1);
+    sts_v4(row_addr + ((4u ^ r7) << 4), o0); sts_v4(row_addr + ((5u ^ r7) << 4), o1);
+    expand_word<IS_B>(c.w, o0, o1);
+    sts_v4(row_addr + ((6u ^ r7) << 4), o0); sts_v4(row_addr + ((7u ^ r7) << 4), o1);
+}
+
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 intersect_mma_kernel(const MmaArgs p)
 {
     extern __shared__ uint8_t smem_raw[];
     const u32 base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));            // generic pointer to the same place
-    const uint4 **s_src = reinterpret_cast<const uint4 **>(gen + MMA_OFF_SRC);
-    u32 *s_lo = reinterpret_cast<u32 *>(gen + MMA_OFF_LO);
-    u32 *s_hi = reinterpret_cast<u32 *>(gen + MMA_OFF_HI);
     u32 *s_misc = reinterpret_cast<u32 *>(gen + MMA_OFF_MISC);        // [0] tmem base, [1..4] k-range reduction
     const u32 bar0 = base + MMA_OFF_BAR;
-    // barrier ids
-    auto bar_bits_full = [&](u32 s) { return bar0 + 8u * s; };
-    auto bar_bits_empty = [&](u32 s) { return bar0 + 8u * (MMA_NB + s); };
-    auto bar_op_full = [&](u32 s) { return bar0 + 8u * (2 * MMA_NB + s); };
-    auto bar_op_empty = [&](u32 s) { return bar0 + 8u * (2 * MMA_NB + MMA_NO + s); };
-    const u32 bar_acc = bar0 + 8u * (2 * MMA_NB + 2 * MMA_NO);
+    auto bar_op_full = [&](u32 s) { return bar0 + 8u * s; };
+    auto bar_op_empty = [&](u32 s) { return bar0 + 8u * (MMA_NO + s); };
+    const u32 bar_acc = bar0 + 8u * (2 * MMA_NO);
 
     const u32 tid = threadIdx.x, wid = tid >> 5, lane = tid & 31u;
     const int g = p.tile_grp[blockIdx.x], m0 = p.tile_m0[blockIdx.x], n0 = p.tile_n0[blockIdx.x];
@@ -193,148 +206,137 @@ intersect_mma_kernel(const MmaArgs p)
     const int rb = p.grp_row_begin[g], cb = p.grp_col_begin[g];
 
     if (tid == 0) {
-        for (u32 s = 0; s < MMA_NB; s++) { mbar_init(bar_bits_full(s), 1); mbar_init(bar_bits_empty(s), MMA_EXP_WARPS); }
         for (u32 s = 0; s < MMA_NO; s++) { mbar_init(bar_op_full(s), MMA_EXP_WARPS); mbar_init(bar_op_empty(s), 1); }
         mbar_init(bar_acc, 1);
         s_misc[1] = 0xffffffffu; s_misc[2] = 0u;      // rows: min lo, max hi
         s_misc[3] = 0xffffffffu; s_misc[4] = 0u;      // cols: min lo, max hi
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (wid == 1) {
+    if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(base + MMA_OFF_MISC), "r"((u32)MMA_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     __syncthreads();
-    // slot table: where each mask's packed bits live and which slabs hold its 1-pixels
-    for (u32 s = tid; s < MMA_SLOTS; s += MMA_THREADS) {
+    // this thread's mask (expander threads): where its packed bits live, which slabs hold 1-pixels
+    const u32 slot = tid - 32u;                      // 0..383 for warps 1..12
+    const bool is_b = slot >= MMA_TM;
+    u32 lo = 0, hi = 0;
+    const uint4 *src = nullptr;
+    if (wid > 0) {
         int mask = -1;
-        if (s < MMA_TM) { if (m0 + (int)s < G) mask = p.row_mask[rb + m0 + (int)s]; }
-        else if (n0 + (int)(s - MMA_TM) < P) mask = cb + n0 + (int)(s - MMA_TM);
-        u32 lo = 0, hi = 0;
-        const uint4 *src = nullptr;
+        if (!is_b) { if (m0 + (int)slot < G) mask = p.row_mask[rb + m0 + (int)slot]; }
+        else if (n0 + (int)(slot - MMA_TM) < P) mask = cb + n0 + (int)(slot - MMA_TM);
         if (mask >= 0) {
             const uint2 sp = p.span[mask];
             lo = sp.x; hi = sp.y;
-            src = p.bits + p.bits_off[mask] - p.reg[mask].x;
-            if (hi > lo) {
-                atomicMin(&s_misc[s < MMA_TM ? 1 : 3], lo);
-                atomicMax(&s_misc[s < MMA_TM ? 2 : 4], hi);
-            }
+            src = p.bits + p.bits_off[mask] - p.reg[mask].x;        // chunk k of the mask is src[k]
         }
-        s_src[s] = src; s_lo[s] = lo; s_hi[s] = hi;
+        // warp-level then CTA-level range of occupied slabs, rows and columns separately
+        const u32 wlo = warp_min(hi > lo ? lo : 0xffffffffu), whi = warp_max(hi > lo ? hi : 0u);
+        if (lane == 0 && whi > 0) {
+            atomicMin(&s_misc[is_b ? 3 : 1], wlo);
+            atomicMax(&s_misc[is_b ? 4 : 2], whi);
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const u32 tmem = s_misc[0];
-    const u32 klo = max(s_misc[1], s_misc[3]), khi = min(s_misc[2], s_misc[4]);
-    const u32 nslab = khi > klo ? khi - klo : 0u;                   // slabs in which a row AND a column have pixels
-    const u32 nsuper = (nslab + MMA_SUPER - 1) / MMA_SUPER;
+    // slabs in which a row AND a column have pixels; start on an even chunk (32-byte sectors)
+    const u32 klo = max(s_misc[1], s_misc[3]) & ~1u, khi = min(s_misc[2], s_misc[4]);
+    const u32 nslab = khi > klo ? khi - klo : 0u;
+    const u32 niter = (nslab + MMA_SLABS - 1) / MMA_SLABS;
 
     if (wid == 0) {
-        // ---------------- producer: packed bits of every slot, MMA_SUPER slabs per stage -------------
-        for (u32 S = 0; S < nsuper; S++) {
-            const u32 b = S % MMA_NB;
-            mbar_wait(bar_bits_empty(b), ((S / MMA_NB) & 1u) ^ 1u);
-            const u32 k0 = klo + S * MMA_SUPER, k1 = min(k0 + MMA_SUPER, khi);
-            const u32 stage = base + MMA_OFF_BITS + b * MMA_BITS_BYTES;
-            u32 bytes = 0;
-            for (u32 s = lane; s < MMA_SLOTS; s += 32) {
-                const u32 lo = max(k0, s_lo[s]), hi = min(k1, s_hi[s]);
-                if (hi > lo) {
-                    const u32 nb = (hi - lo) * 16u;
-                    bulk_g2s(stage + s * MMA_PITCH + (lo - k0) * 16u, s_src[s] + lo, nb, bar_bits_full(b));
-                    bytes += nb;
-                }
-            }
-            bytes = warp_sum(bytes);
-            if (lane == 0) mbar_arrive_tx(bar_bits_full(b), bytes);
-        }
-    } else if (wid == 1) {
         // ---------------- MMA issuer: one thread ------------------------------------------------------
         if (lane == 0) {
-            for (u32 i = 0; i < nslab; i++) {
-                const u32 o = i % MMA_NO;
-                mbar_wait(bar_op_full(o), (i / MMA_NO) & 1u);
+            for (u32 it = 0; it < niter; it++) {
+                const u32 o = it % MMA_NO;
+                mbar_wait(bar_op_full(o), (it / MMA_NO) & 1u);
                 tc_fence_after();
-                const u32 a_addr = base + MMA_OFF_OPS + o * MMA_OP_BYTES, b_addr = a_addr + MMA_A_BYTES;
-                const u64 ad = smem_desc_sw128(a_addr), bd = smem_desc_sw128(b_addr);
 #pragma unroll
-                for (u32 k = 0; k < 4; k++)        // 4 x K32 inside the 128-byte swizzle atom: +32 bytes each
-                    tc_mma_i8(tmem, ad + 2u * k, bd + 2u * k, MMA_IDESC, (i | k) ? 1u : 0u);
+                for (u32 sl = 0; sl < MMA_SLABS; sl++) {
+                    const u32 a_addr = base + MMA_OFF_OPS + o * MMA_OP_BYTES + sl * MMA_SLAB_BYTES;
+                    const u64 ad = smem_desc_sw128(a_addr), bd = smem_desc_sw128(a_addr + MMA_A_BYTES);
+#pragma unroll
+                    for (u32 k = 0; k < 4; k++)    // 4 x K32 inside the 128-byte swizzle atom: +32 bytes each
+                        tc_mma_i8(tmem, ad + 2u * k, bd + 2u * k, MMA_IDESC, (it | sl | k) ? 1u : 0u);
+                }
                 tc_commit(bar_op_empty(o));        // implies tcgen05.fence::before_thread_sync
             }
-            if (nslab) tc_commit(bar_acc);
+            if (niter) tc_commit(bar_acc);
         }
         __syncwarp();
     } else {
         // ---------------- expanders: bits -> u8 operand rows -----------------------------------------
-        const u32 e = wid - 2u, sub = lane >> 2, j = lane & 3u;
-        u32 lo_[6], hi_[6], src_[6], dst_[6];
+        const u32 r = is_b ? slot - MMA_TM : slot, r7 = r & 7u;
+        const u32 row_off = (is_b ? (u32)MMA_A_BYTES : 0u) + (r >> 3) * 1024u + r7 * 128u;
+        uint4 buf[MMA_PF + 1][MMA_SLABS];
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        auto fetch = [&](u32 it, uint4 (&d)[MMA_SLABS]) {
 #pragma unroll
-        for (int q = 0; q < 6; q++) {
-            const u32 slot = (u32)q * 64u + e * 8u + sub;
-            lo_[q] = s_lo[slot]; hi_[q] = s_hi[slot];
-            src_[q] = slot * MMA_PITCH + j * 4u;
-            const u32 r = slot < MMA_TM ? slot : slot - MMA_TM;
-            dst_[q] = (slot < MMA_TM ? 0u : (u32)MMA_A_BYTES) + (r >> 3) * 1024u + (r & 7u) * 128u +
-                      (((2u * j) ^ (r & 7u)) << 4);
+            for (u32 sl = 0; sl < MMA_SLABS; sl++) {
+                const u32 k = klo + it * MMA_SLABS + sl;
+                d[sl] = (k >= lo && k < hi) ? ldg_v4(src + k) : zero4;
+            }
+        };
+#pragma unroll
+        for (u32 f = 0; f < MMA_PF; f++) {
+            if (f < niter) fetch(f, buf[f]);
         }
-        for (u32 i = 0; i < nslab; i++) {
-            const u32 S = i / MMA_SUPER, si = i % MMA_SUPER, b = S % MMA_NB, o = i % MMA_NO;
-            if (si == 0) mbar_wait(bar_bits_full(b), (S / MMA_NB) & 1u);
-            mbar_wait(bar_op_empty(o), ((i / MMA_NO) & 1u) ^ 1u);
-            const u32 k = klo + i;
-            const u32 bsrc = base + MMA_OFF_BITS + b * MMA_BITS_BYTES + si * 16u;
-            const u32 odst = base + MMA_OFF_OPS + o * MMA_OP_BYTES;
+        for (u32 it = 0; it < niter; it++) {
+            if (it + MMA_PF < niter) fetch(it + MMA_PF, buf[MMA_PF]);
+            const u32 o = it % MMA_NO;
+            mbar_wait(bar_op_empty(o), ((it / MMA_NO) & 1u) ^ 1u);
+            const u32 stage = base + MMA_OFF_OPS + o * MMA_OP_BYTES + row_off;
 #pragma unroll
-            for (int q = 0; q < 6; q++) {
-                u32 x = lds_u32(bsrc + src_[q]);
-                if (k < lo_[q] || k >= hi_[q]) x = 0u;          // outside the mask's span the stage holds stale data
-                uint4 o0, o1;
-                if (q < 2) expand_word<false>(x, o0, o1); else expand_word<true>(x, o0, o1);
-                sts_v4(odst + dst_[q], o0);
-                sts_v4(odst + (dst_[q] ^ 16u), o1);
+            for (u32 sl = 0; sl < MMA_SLABS; sl++) {
+                if (is_b) expand_chunk<true>(buf[0][sl], stage + sl * MMA_SLAB_BYTES, r7);
+                else expand_chunk<false>(buf[0][sl], stage + sl * MMA_SLAB_BYTES, r7);
             }
             fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_op_full(o));
-                if (si == MMA_SUPER - 1 || i + 1 == nslab) mbar_arrive(bar_bits_empty(b));
+            if (lane == 0) mbar_arrive(bar_op_full(o));
+#pragma unroll
+            for (u32 f = 0; f < MMA_PF; f++) {
+#pragma unroll
+                for (u32 sl = 0; sl < MMA_SLABS; sl++) buf[f][sl] = buf[f + 1][sl];
             }
         }
-        // ---------------- epilogue: TMEM -> int32 matrix ---------------------------------------------
-        const i64 off = p.grp_imat_off[g];
-        const u32 quarter = wid & 3u, half = e >> 2;            // TMEM lanes 32*quarter.., columns 128*half..
-        const int row = m0 + (int)(32u * quarter + lane);
-        if (nslab) {
-            mbar_wait(bar_acc, 0u);
-            tc_fence_after();
-        }
+        // ---------------- epilogue: TMEM -> int32 matrix (warps 1..8) --------------------------------
+        if (wid <= 8) {
+            const i64 off = p.grp_imat_off[g];
+            const u32 quarter = wid & 3u, half = (wid - 1u) >> 2;   // TMEM lanes 32*quarter.., columns 128*half..
+            const int row = m0 + (int)(32u * quarter + lane);
+            if (niter) {
+                mbar_wait(bar_acc, 0u);
+                tc_fence_after();
+            }
 #pragma unroll 1
-        for (u32 cbk = 0; cbk < 4; cbk++) {
-            u32 v[32];
-            const u32 col0 = half * 128u + cbk * 32u;
-            if (nslab) {
-                tc_ld32(tmem + ((32u * quarter) << 16) + col0, v);
-            } else {
+            for (u32 cbk = 0; cbk < 4; cbk++) {
+                u32 v[32];
+                const u32 col0 = half * 128u + cbk * 32u;
+                if (niter) {
+                    tc_ld32(tmem + ((32u * quarter) << 16) + col0, v);
+                } else {
 #pragma unroll
-                for (int t = 0; t < 32; t++) v[t] = 0u;
-            }
-            if (row < G) {
-                int *orow = p.imat + off + (i64)row * P;
+                    for (int t = 0; t < 32; t++) v[t] = 0u;
+                }
+                if (row < G) {
+                    int *orow = p.imat + off + (i64)row * P;
 #pragma unroll
-                for (int t = 0; t < 32; t++) {
-                    const int c = n0 + (int)col0 + t;
-                    if (c < P) orow[c] = (int)(v[t] >> 7);
+                    for (int t = 0; t < 32; t++) {
+                        const int c = n0 + (int)col0 + t;
+                        if (c < P) orow[c] = (int)(v[t] >> 7);
+                    }
                 }
             }
+            tc_fence_before();
         }
-        tc_fence_before();
     }
     __syncthreads();
-    if (wid == 1) {
+    if (wid == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((u32)MMA_TMEM_COLS) : "memory");
     }

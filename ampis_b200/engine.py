@@ -290,6 +290,37 @@ def intersect_mma(table, groups, mode, out=None):
     return out
 
 
+#: operand fill above which the dense tensor-core contraction beats the culled AND+popc walk
+#: (measured crossover, profiles/crossover_r01.md)
+MMA_FILL_THRESHOLD = 0.30
+
+
+def operand_fill(table, groups=None):
+    """Fraction of the dense operand volume (masks x 128-pixel slabs of the frame) that lies inside
+    the masks' spans -- a device reduction and one 8-byte read-back."""
+    n = table.n
+    if n == 0:
+        return 0.0
+    sp = table.span[:2 * n].view(n, 2).to(torch.int64)
+    slabs = (table.h[:n].to(torch.int64) * table.w[:n].to(torch.int64) + 127) // 128
+    return float(((sp[:, 1] - sp[:, 0]).sum().double() / slabs.sum().double().clamp(min=1)).item())
+
+
+def choose_kernel(table, groups):
+    """'mma' (dense int8 tcgen05 contraction) for crowded images, 'rows' (bbox-culled AND+popc)
+    otherwise.  Both give identical results; this is only a cost decision."""
+    if groups.imat_off is None or groups.n_rows == 0:
+        return 'rows'
+    return 'mma' if operand_fill(table, groups) >= MMA_FILL_THRESHOLD else 'rows'
+
+
+def intersect(table, groups, mode, out=None, kernel='auto'):
+    """Intersection rows by the kernel named (or chosen by choose_kernel for 'auto')."""
+    if kernel == 'auto':
+        kernel = choose_kernel(table, groups)
+    return (intersect_mma if kernel == 'mma' else intersect_rows)(table, groups, mode, out=out)
+
+
 def match_counts(rows, groups, thresholds, totals=None, counts=None):
     """TP/FP/FN per group and threshold -> int32[n_groups, n_thresh, 3] (device), totals += .
     `thresholds` may be a host sequence or a float64 device tensor (no copy then)."""

@@ -42,6 +42,9 @@ def parse():
                     help='full = canonical full-frame packed masks (the roofline accounting of SURVEY 8d); '
                          'span = culled storage (only first..last 1-pixel of each mask)')
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
+    ap.add_argument('--kernel', default='rows', choices=['rows', 'mma'],
+                    help='intersection kernel: rows = bbox-culled AND+popc (default); mma = dense int8 tcgen05 '
+                         'contraction (for crowded images, e.g. --config dense_overlap)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--graph', action='store_true', help='replay each step from a CUDA graph')
@@ -58,6 +61,17 @@ def peaks():
         d = json.load(open(p))
         return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def tensor_peak_tops():
+    """int8 tensor peak in TOP/s: twice the measured dense bf16 rate (the i8 pipe is 2x bf16 on sm_100;
+    nominal 4.5 POP/s).  Burst figure: the contraction draws ~230 W and holds 1965 MHz, it never
+    reaches the power cap that defines the sustained bf16 number."""
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return 2.0 * float(d['bf16_tflops']), '2 x measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)'
+    return 2.0 * 1590.0, '2 x fallback bf16 burst (B200_PROFILING.md)'
 
 
 class ClockSampler(object):
@@ -213,8 +227,9 @@ class LayoutRun(object):
                                                      device=dev))
         self.thresholds = batch.COCO_THRESHOLDS
         self.totals = torch.zeros(len(self.thresholds) * 3, dtype=torch.int64, device=dev)
+        self.kernel = args.kernel
         self.pipes = [batch.Pipeline(b, layout, self.arena, self.rows_out, self.thresholds, self.totals,
-                                     fused=self.fused) for b in self.subs]
+                                     fused=self.fused, kernel=args.kernel) for b in self.subs]
         self.graph = None
 
     def launch_all(self, record=None):
@@ -301,6 +316,16 @@ def roofline_of(args, cfg, run, ms, kt, world):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get('%s/%s/%s' % (args.config, lay, dom))
     step_gbs = canonical_img * n_img * args.steps / (ms / 1e3) / 1e9
+    if run.kernel == 'mma' and dom == 'rows':
+        # dense contraction: 2*G*P*H*W integer ops per image, tensor-pipe bound
+        tpeak, tsrc = tensor_peak_tops()
+        ops = 2.0 * pairs_img * cfg['h'] * cfg['w'] * n_img / launches
+        ach = ops / (dur_ms / 1e3) / 1e12
+        return {'bound': 'tensor', 'kernel': 'intersect_mma_kernel (+ rows_from_imat_kernel)', 'achieved': ach,
+                'peak': tpeak, 'unit': 'TOP/s', 'frac': ach / tpeak, 'traffic': None, 'peak_source': tsrc,
+                'algorithmic_ops_per_launch': ops, 'launch_ms': dur_ms,
+                'step_canonical': {'bytes_per_image': canonical_img, 'achieved': step_gbs, 'frac': step_gbs / peak},
+                'kernel_share': {k: float(v) for k, v in zip(KERNELS, kt / kt.sum())}}
     pk = 'rle_paint_kernel' if args.unfused else 'rle_measure_paint_kernel'
     return {'bound': 'hbm', 'kernel': {'paint': pk, 'rows': 'intersect_rows_kernel'}[dom],
             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
@@ -393,14 +418,14 @@ def main():
         'dtype': 'u32', 'data': 'synthetic',
         'images_per_s': world * args.images * args.steps / (ms / 1e3),
         'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
-                   'layout': args.layout, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95',
+                   'layout': args.layout, 'intersection_kernel': args.kernel, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95',
                    'runs_per_mask': run.total_runs / n_masks,
                    'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
                          'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
                                                                           run.stored_chunks * 16 / len(run.subs) / 1e9),
                    'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN per step' % world},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
-        'gpu_launches': int(args.steps * len(run.subs) * (7 if args.unfused else 3)),
+        'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel == 'mma' else 0))),
         'totals_tp_fp_fn_at_0.50': final_totals[0].tolist(),
         'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},
     }
@@ -467,7 +492,8 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
                 t.measure().paint(arena)
             else:
                 t.measure_paint(arena)
-            rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out)
+            rows = (engine.intersect_mma if args.kernel == 'mma' else engine.intersect_rows)(
+                t, b.groups, b.mode, out=rows_out)
             counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
             hc.copy_(counts, non_blocking=True)
             hb.copy_(rows.best_col[:b.groups.n_rows], non_blocking=True)
