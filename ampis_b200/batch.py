@@ -174,6 +174,7 @@ class Pipeline(object):
             self.totals = totals if totals is not None else torch.zeros(self.th.numel() * 3, dtype=torch.int64,
                                                                        device=dev)
         else:
+            self.counts_buf = torch.empty(max(g.n_groups * 4, 1), dtype=torch.int32, device=dev)
             self.counts = None
             self.spp_hist = torch.zeros(64, dtype=torch.int64, device=dev)
 
@@ -198,7 +199,7 @@ class Pipeline(object):
             engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)
         else:
             self.counts, _ = engine.satellite_counts(t, self.rows, self.batch.groups, self.sat_thresh,
-                                                     hist=self.spp_hist)
+                                                     hist=self.spp_hist, counts=self.counts_buf)
         if mark: mark(4)
 
 

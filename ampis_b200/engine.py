@@ -338,9 +338,10 @@ def match_counts(rows, groups, thresholds, totals=None, counts=None):
     return counts[:groups.n_groups * nt * 3].view(groups.n_groups, nt, 3), totals[:nt * 3].view(nt, 3)
 
 
-def satellite_counts(table, rows, groups, thresh, n_bins=64, hist=None):
+def satellite_counts(table, rows, groups, thresh, n_bins=64, hist=None, counts=None):
     dev = groups.device
-    counts = torch.empty(max(groups.n_groups * 4, 1), dtype=torch.int32, device=dev)
+    if counts is None:
+        counts = torch.empty(max(groups.n_groups * 4, 1), dtype=torch.int32, device=dev)
     if hist is None:
         hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
     N.call('ampis_satellite_counts', _p(rows.best_col), _p(rows.best_inter), _p(table.area), _p(groups.row_mask),

@@ -228,13 +228,19 @@ class LayoutRun(object):
         self.thresholds = batch.COCO_THRESHOLDS
         self.totals = torch.zeros(len(self.thresholds) * 3, dtype=torch.int64, device=dev)
         self.kernel = args.kernel
+        self.mode = batch.CONFIGS[args.config]['mode']
         self.pipes = [batch.Pipeline(b, layout, self.arena, self.rows_out, self.thresholds, self.totals,
                                      fused=self.fused, kernel=args.kernel) for b in self.subs]
+        if self.mode != 0:
+            for p in self.pipes[1:]:
+                p.spp_hist = self.pipes[0].spp_hist
         self.graph = None
 
     def launch_all(self, record=None):
         import torch
         self.totals.zero_()
+        if self.mode != 0:
+            self.pipes[0].spp_hist.zero_()
         for p in self.pipes:
             if record is None:
                 p.launch()
@@ -262,8 +268,8 @@ class LayoutRun(object):
             self.graph.replay()
         else:
             self.launch_all(record)
-        if world > 1:
-            dist.all_reduce(self.totals)      # TP/FP/FN x thresholds: the only exchange on this path
+        if world > 1:       # TP/FP/FN x thresholds (or the satellites-per-particle histogram): the only exchange
+            dist.all_reduce(self.totals if self.mode == 0 else self.pipes[0].spp_hist)
         return self.totals
 
     def timed(self, args, world, dist, sync):
@@ -291,6 +297,9 @@ class LayoutRun(object):
             for i in range(4):
                 kt[i] += ev[i].elapsed_time(ev[i + 1])
         self.pipes[-1].table.check()      # arena large enough, RLE well-formed (after the timed region)
+        if self.mode != 0:      # satellites: per-image counts summed over the batch + the global histogram
+            c = sum(p.counts.cpu().numpy().sum(axis=0) for p in self.pipes)
+            return float(ms.item()), kt, np.concatenate([c, self.pipes[0].spp_hist.cpu().numpy()[:8]]).reshape(1, -1)
         return float(ms.item()), kt, self.totals.cpu().numpy().reshape(-1, 3)
 
 
@@ -418,7 +427,7 @@ def main():
         'dtype': 'u32', 'data': 'synthetic',
         'images_per_s': world * args.images * args.steps / (ms / 1e3),
         'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
-                   'layout': args.layout, 'intersection_kernel': args.kernel, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95',
+                   'layout': args.layout, 'intersection_kernel': args.kernel, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
                    'runs_per_mask': run.total_runs / n_masks,
                    'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
                          'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
@@ -426,7 +435,7 @@ def main():
                    'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN per step' % world},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
         'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel == 'mma' else 0))),
-        'totals_tp_fp_fn_at_0.50': final_totals[0].tolist(),
+        ('totals_tp_fp_fn_at_0.50' if cfg['mode'] == 0 else 'sat_matched_unmatched_satellited_particles+spp_hist'): final_totals[0].tolist(),
         'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},
     }
     if e2e:
@@ -471,15 +480,18 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
     n_thr = len(thresholds)
     h_out = []
     for blob, off, b in pinned:
-        h_out.append((torch.empty((b.groups.n_groups, n_thr, 3), dtype=torch.int32).pin_memory(),
+        shape = (b.groups.n_groups, n_thr, 3) if b.mode == engine.MODE_IOU else (b.groups.n_groups, 4)
+        h_out.append((torch.empty(shape, dtype=torch.int32).pin_memory(),
                       torch.empty(b.groups.n_rows, dtype=torch.int32).pin_memory(),
                       torch.empty(b.groups.n_rows, dtype=torch.float64).pin_memory()))
     h2d = sum(p[0].numel() + p[1].numel() * 8 for p in pinned)
     d2h = sum(o[0].numel() * 4 + o[1].numel() * 4 + o[2].numel() * 8 for o in h_out)
     totals = torch.zeros(n_thr * 3, dtype=torch.int64, device=dev)
+    spp_hist = torch.zeros(64, dtype=torch.int64, device=dev)
 
     def step():
         totals.zero_()
+        spp_hist.zero_()
         for (blob, off, b), (hc, hb, hs) in zip(pinned, h_out):
             n = b.host.n_masks
             dc = d_chars[:blob.numel()]
@@ -494,13 +506,17 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
                 t.measure_paint(arena)
             rows = (engine.intersect_mma if args.kernel == 'mma' else engine.intersect_rows)(
                 t, b.groups, b.mode, out=rows_out)
-            counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
+            if b.mode == engine.MODE_IOU:
+                counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
+            else:       # satellites: per-image (matched, unmatched, satellited particles, particles) + global histogram
+                counts, _ = engine.satellite_counts(t, rows, b.groups, 0.5, hist=spp_hist)
             hc.copy_(counts, non_blocking=True)
             hb.copy_(rows.best_col[:b.groups.n_rows], non_blocking=True)
             hs.copy_(rows.best_score[:b.groups.n_rows], non_blocking=True)
+        red = totals if subs[0].mode == engine.MODE_IOU else spp_hist
         if world > 1:
-            dist.all_reduce(totals)
-        return totals.cpu()
+            dist.all_reduce(red)
+        return red.cpu()
 
     for _ in range(2):
         step()
