@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-LAYOUT_SPAN, LAYOUT_FULL = 0, 1
+LAYOUT_SPAN, LAYOUT_FULL, LAYOUT_CROP = 0, 1, 2
 MODE_IOU, MODE_SAT = 0, 1
 ST_BAD_TOTAL = 1
 
@@ -34,6 +34,9 @@ SIGNATURES = {
                                        _p, _p, _p]),
     'ampis_rle_measure_paint': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
                                           _p]),
+    'ampis_intersect_rows_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p,
+                                            _p, _p]),
+    'ampis_rle_decode_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     'ampis_mma_tile_rows': (C.c_int, []),
     'ampis_mma_tile_cols': (C.c_int, []),
     'ampis_intersect_tcgen05': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),

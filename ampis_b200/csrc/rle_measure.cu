@@ -34,7 +34,8 @@ extern "C" int ampis_rle_measure(const uint32_t *d_cnt, const int64_t *d_cnt_off
                                  uint32_t *d_reg, int64_t *d_reg_chunks, int32_t *d_status, void *stream)
 {
     AMPIS_REQUIRE(n >= 0, "n < 0");
-    AMPIS_REQUIRE(layout == AMPIS_LAYOUT_SPAN || layout == AMPIS_LAYOUT_FULL, "bad layout");
+    AMPIS_REQUIRE(layout == AMPIS_LAYOUT_SPAN || layout == AMPIS_LAYOUT_FULL || layout == AMPIS_LAYOUT_CROP,
+                  "bad layout");
     if (n == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_cnt && d_cnt_off && d_cnt_len && d_h && d_w && d_cum && d_area && d_bbox && d_span &&
                       d_reg && d_reg_chunks && d_status, "null pointer");

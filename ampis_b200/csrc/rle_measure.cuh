@@ -69,10 +69,18 @@ __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt,
     return r;
 }
 
+// AMPIS_LAYOUT_CROP window of a mask with tight box bb: columns bb.x..bb.z, and for each column
+// the absolute 32-row bands (bb.y >> 5)..(bb.w >> 5).  Number of 32-bit words stored.
+__device__ __forceinline__ u32 crop_words(const int4 bb)
+{
+    if (bb.z < bb.x) return 0u;
+    return (u32)(bb.z - bb.x + 1) * (u32)((bb.w >> 5) - (bb.y >> 5) + 1);
+}
+
 // Derived per-mask records written by lane 0.
 __device__ __forceinline__ void store_measure(const MaskMeasure &ms, u32 H, u64 HW, int layout, int i,
                                               u32 *area, int *bbox, u32 *span, u32 *reg, int *status,
-                                              uint2 *span_out, uint2 *reg_out)
+                                              uint2 *span_out, uint2 *reg_out, int4 *bbox_out = nullptr)
 {
     const u32 nchunks = (u32)((HW + AMPIS_CHUNK_BITS - 1) / AMPIS_CHUNK_BITS);
     u32 slo = 0, shi = 0;
@@ -83,7 +91,8 @@ __device__ __forceinline__ void store_measure(const MaskMeasure &ms, u32 H, u64 
         bb = make_int4((int)(ms.first / H), (int)ms.ymin, (int)((ms.last - 1) / H), (int)ms.ymax);
     }
     const uint2 sp = make_uint2(slo, shi);
-    const uint2 rg = layout == AMPIS_LAYOUT_FULL ? make_uint2(0u, nchunks) : sp;
+    uint2 rg = layout == AMPIS_LAYOUT_FULL ? make_uint2(0u, nchunks) : sp;
+    if (layout == AMPIS_LAYOUT_CROP) rg = make_uint2(0u, (crop_words(bb) + 3u) / 4u);
     area[i] = ms.area;
     reinterpret_cast<int4 *>(bbox)[i] = bb;
     reinterpret_cast<uint2 *>(span)[i] = sp;
@@ -91,4 +100,5 @@ __device__ __forceinline__ void store_measure(const MaskMeasure &ms, u32 H, u64 
     status[i] = ms.total == HW ? 0 : AMPIS_ST_BAD_TOTAL;
     *span_out = sp;
     *reg_out = rg;
+    if (bbox_out) *bbox_out = bb;
 }

@@ -181,11 +181,64 @@ __device__ __forceinline__ void warp_paint_tile_smem(const u32 *sC, int m, u32 t
     __syncwarp();
 }
 
-// TILED: the span is assembled run-driven in shared-memory tiles (SPAN layout, where the span is
-// the whole job); otherwise in-span chunks are located by binary search (FULL layout, where 97 %
-// of the stores are zeros outside the span and occupancy of the store stream matters most).
-template <int TEAM_WARPS, bool TILED>
-__global__ void __launch_bounds__(MP_WARPS * 32, TILED ? 5 : 8)
+// AMPIS_LAYOUT_CROP: one warp assembles the bounding-box window of a mask (columns bb.x..bb.z, for
+// each column the absolute 32-row bands (bb.y>>5)..(bb.w>>5)) in shared-memory tiles of whole
+// columns and writes the words out, coalesced.  Run driven like warp_paint_tile: each lane takes
+// 1-runs, cuts them at column boundaries (a run that reaches the bottom of a column continues at
+// the top of the next) and sets the bits of every piece.  `searched` = false when all runs are
+// known to fall in one tile (small masks: no binary search at all).
+__device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, const int4 bb, u32 *tile,
+                                                u32 tile_words, u32 *out, u32 lane)
+{
+    if (bb.z < bb.x) return;
+    const u32 wy0 = (u32)bb.y >> 5, nwy = ((u32)bb.w >> 5) - wy0 + 1u;
+    const u32 x_end = (u32)bb.z + 1u;
+    const u32 cols_per_tile = max(1u, tile_words / nwy);
+    const bool one_tile = (x_end - (u32)bb.x) <= cols_per_tile;
+    for (u32 xa = (u32)bb.x; xa < x_end; xa += cols_per_tile) {
+        const u32 xb = min(xa + cols_per_tile, x_end);
+        const u32 tw = (xb - xa) * nwy;
+        for (u32 k = lane; k < tw; k += 32) tile[k] = 0u;
+        __syncwarp();
+        const u64 b0 = (u64)xa * H, b1 = (u64)xb * H;
+        int r0 = 0, r1 = m - 1;
+        if (!one_tile) {
+            r0 = upper_bound_u32(C, m, b0);          // run that owns bit b0
+            r1 = upper_bound_u32(C, m, b1 - 1);      // run that owns bit b1-1 (m if beyond the runs)
+        }
+        for (int r = (r0 | 1) + 2 * (int)lane; r <= r1 && r < m; r += 64) {   // odd runs are the 1-runs
+            const u64 rs = (u64)C[r - 1], re = (u64)C[r];
+            u64 s = rs > b0 ? rs : b0;
+            const u64 e = re < b1 ? re : b1;
+            while (s < e) {
+                const u32 x = (u32)(s / H);
+                const u64 cs = (u64)x * H;
+                const u32 ys = (u32)(s - cs), ye = (u32)(min(e, cs + H) - cs);      // rows [ys,ye) of column x
+                u32 *col = tile + (x - xa) * nwy - wy0;
+                const u32 w0 = ys >> 5, w1 = (ye - 1) >> 5;
+                if (w0 == w1) {
+                    atomicOr(&col[w0], bit_range(ys & 31u, ((ye - 1) & 31u) + 1u));
+                } else {
+                    atomicOr(&col[w0], bit_range(ys & 31u, 32u));
+                    for (u32 w = w0 + 1; w < w1; w++) col[w] = 0xffffffffu;
+                    atomicOr(&col[w1], bit_range(0u, ((ye - 1) & 31u) + 1u));
+                }
+                s = cs + H;
+            }
+        }
+        __syncwarp();
+        u32 *o = out + (xa - (u32)bb.x) * nwy;
+        for (u32 k = lane; k < tw; k += 32) o[k] = tile[k];
+        __syncwarp();
+    }
+}
+
+// KIND 0: in-span chunks located by binary search (FULL layout, where 97 % of the stores are zeros
+// outside the span and occupancy of the store stream matters most); KIND 1: the span is assembled
+// run-driven in shared-memory tiles (SPAN layout, where the span is the whole job); KIND 2: the
+// bounding-box window is assembled the same way (CROP layout).
+template <int TEAM_WARPS, int KIND>
+__global__ void __launch_bounds__(MP_WARPS * 32, KIND ? 5 : 8)
 rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
                          const int *__restrict__ cnt_len, const u32 *__restrict__ hh,
                          const u32 *__restrict__ ww, int n, int layout, u32 *cum_g, u32 *__restrict__ area,
@@ -196,8 +249,10 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
     constexpr int MASKS = MP_WARPS / TEAM_WARPS;
     constexpr int CUM_CAP = MP_CUM_WORDS / MASKS;
     __shared__ u32 s_cum[MP_CUM_WORDS];
-    __shared__ __align__(16) u32 s_tile[TILED ? MP_WARPS : 1][TILED ? MP_TILE * 4 : 4];
+    constexpr bool TILED = KIND == 1;
+    __shared__ __align__(16) u32 s_tile[KIND ? MP_WARPS : 1][KIND ? MP_TILE * 4 : 4];
     __shared__ uint2 s_span[MASKS], s_reg[MASKS];
+    __shared__ int4 s_bbox[MASKS];
     __shared__ i64 s_off[MASKS];
     __shared__ i64 s_base;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
@@ -214,7 +269,7 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
             const u64 HW = (u64)H * ww[i];
             const MaskMeasure ms = warp_measure(cnt + base, m, H, HW, s_cum + team * CUM_CAP, CUM_CAP,
                                                 m > CUM_CAP ? cum_g + base : nullptr);
-            if (lane == 0) store_measure(ms, H, HW, layout, i, area, bbox, span, reg, status, &sp, &rg);
+            if (lane == 0) store_measure(ms, H, HW, layout, i, area, bbox, span, reg, status, &sp, &rg, &s_bbox[team]);
         }
         if (lane == 0) { s_span[team] = sp; s_reg[team] = rg; }
     }
@@ -240,6 +295,12 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
     }
     if (tw == 0 && lane == 0) bits_off[i] = off;
     const u32 *C = m > CUM_CAP ? cum_g + base : s_cum + team * CUM_CAP;
+    if (KIND == 2) {
+        // bounding-box window, one warp per mask
+        warp_paint_crop(C, m, hh[i], s_bbox[team], s_tile[KIND ? wid : 0], MP_TILE * 4,
+                        reinterpret_cast<u32 *>(bits + off), lane);
+        return;
+    }
     uint4 *out = bits + off - rg.x;
     // zeros outside the span (FULL layout only; in SPAN layout region == span)
     for (u32 c = rg.x + tw * 32 + lane; c < sp.x; c += TEAM_WARPS * 32) st_v4_stream(out + c, make_uint4(0u, 0u, 0u, 0u));
@@ -261,6 +322,39 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
     }
 }
 
+// CROP layout painter for tables measured by ampis_rle_measure (offsets from the scan): one warp
+// per mask, run ends read from global memory.
+__global__ void __launch_bounds__(256)
+rle_paint_crop_kernel(const u32 *__restrict__ cum, const i64 *__restrict__ cnt_off,
+                      const int *__restrict__ cnt_len, const int4 *__restrict__ bbox,
+                      const u32 *__restrict__ hh, const i64 *__restrict__ bits_off, int n,
+                      uint4 *__restrict__ bits, i64 capacity)
+{
+    __shared__ u32 s_tile[8][MP_TILE * 4];
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * 8 + (int)wid;
+    if (i >= n) return;
+    const int4 bb = bbox[i];
+    const i64 off = bits_off[i];
+    if (off + (i64)((crop_words(bb) + 3u) / 4u) > capacity) return;
+    warp_paint_crop(cum + cnt_off[i], cnt_len[i], hh[i], bb, s_tile[wid], MP_TILE * 4,
+                    reinterpret_cast<u32 *>(bits + off), lane);
+}
+
+extern "C" int ampis_rle_decode_crop(const uint32_t *d_cum, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                                     const int32_t *d_bbox, const uint32_t *d_h, const int64_t *d_bits_off,
+                                     int32_t n, void *d_bits, int64_t bits_capacity, void *stream)
+{
+    AMPIS_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return AMPIS_OK;
+    AMPIS_REQUIRE(d_cum && d_cnt_off && d_cnt_len && d_bbox && d_h && d_bits_off && d_bits, "null pointer");
+    AMPIS_REQUIRE(((uintptr_t)d_bits & 15u) == 0, "bits arena must be 16-byte aligned");
+    rle_paint_crop_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(
+        d_cum, d_cnt_off, d_cnt_len, (const int4 *)d_bbox, d_h, d_bits_off, n, (uint4 *)d_bits, bits_capacity);
+    AMPIS_CHECK_LAUNCH("rle_paint_crop_kernel");
+    return AMPIS_OK;
+}
+
 extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off,
                                        const int32_t *d_cnt_len, const uint32_t *d_h, const uint32_t *d_w,
                                        int32_t n, int32_t layout, uint32_t *d_cum, uint32_t *d_area,
@@ -269,7 +363,8 @@ extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_c
                                        uint64_t *d_cursor, void *stream)
 {
     AMPIS_REQUIRE(n >= 0, "n < 0");
-    AMPIS_REQUIRE(layout == AMPIS_LAYOUT_SPAN || layout == AMPIS_LAYOUT_FULL, "bad layout");
+    AMPIS_REQUIRE(layout == AMPIS_LAYOUT_SPAN || layout == AMPIS_LAYOUT_FULL || layout == AMPIS_LAYOUT_CROP,
+                  "bad layout");
     if (n == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_cnt && d_cnt_off && d_cnt_len && d_h && d_w && d_cum && d_area && d_bbox && d_span &&
                       d_reg && d_bits_off && d_status && d_bits && d_cursor, "null pointer");
@@ -277,11 +372,15 @@ extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_c
     cudaError_t e = cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), as_stream(stream));
     if (e != cudaSuccess) { ampis_set_error("cursor memset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     if (layout == AMPIS_LAYOUT_FULL)
-        rle_measure_paint_kernel<MP_WARPS, false><<<n, MP_WARPS * 32, 0, as_stream(stream)>>>(
+        rle_measure_paint_kernel<MP_WARPS, 0><<<n, MP_WARPS * 32, 0, as_stream(stream)>>>(
+            d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
+            d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
+    else if (layout == AMPIS_LAYOUT_CROP)
+        rle_measure_paint_kernel<1, 2><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
             d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
     else
-        rle_measure_paint_kernel<1, true><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
+        rle_measure_paint_kernel<1, 1><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
             d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
     AMPIS_CHECK_LAUNCH("rle_measure_paint_kernel");

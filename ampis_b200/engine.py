@@ -10,7 +10,7 @@ import torch
 
 from . import _native as N
 
-LAYOUT_SPAN, LAYOUT_FULL = N.LAYOUT_SPAN, N.LAYOUT_FULL
+LAYOUT_SPAN, LAYOUT_FULL, LAYOUT_CROP = N.LAYOUT_SPAN, N.LAYOUT_FULL, N.LAYOUT_CROP
 MODE_IOU, MODE_SAT = N.MODE_IOU, N.MODE_SAT
 DEFAULT_LAYOUT = LAYOUT_SPAN
 
@@ -81,8 +81,12 @@ class MaskTable(object):
             arena = torch.empty(4 * max(total, 1), dtype=torch.int32, device=self.device)
         self.bits = arena
         self.bits_capacity = arena.numel() // 4
-        N.call('ampis_rle_decode_packed', _p(self.cum), _p(self.cnt_off), _p(self.cnt_len), _p(self.span),
-               _p(self.reg), _p(self.bits_off), self.n, _p(self.bits), self.bits_capacity, _stream())
+        if self.layout == LAYOUT_CROP:
+            N.call('ampis_rle_decode_crop', _p(self.cum), _p(self.cnt_off), _p(self.cnt_len), _p(self.bbox),
+                   _p(self.h), _p(self.bits_off), self.n, _p(self.bits), self.bits_capacity, _stream())
+        else:
+            N.call('ampis_rle_decode_packed', _p(self.cum), _p(self.cnt_off), _p(self.cnt_len), _p(self.span),
+                   _p(self.reg), _p(self.bits_off), self.n, _p(self.bits), self.bits_capacity, _stream())
         return self
 
     def measure_paint(self, arena):
@@ -259,6 +263,13 @@ def intersect_rows(table, groups, mode, out=None):
         out = RowResult(torch.empty(nr, dtype=torch.int32, device=dev),
                         torch.empty(nr, dtype=torch.int32, device=dev),
                         torch.empty(nr, dtype=torch.float64, device=dev), imat)
+    if table.layout == LAYOUT_CROP:
+        N.call('ampis_intersect_rows_crop', _p(table.bits), _p(table.bits_off), _p(table.bbox), _p(table.area),
+               _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0), groups.n_blocks,
+               _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),
+               _p(groups.grp_col_count), _p(groups.imat_off), mode, _p(out.imat), _p(out.best_col),
+               _p(out.best_inter), _p(out.best_score), _stream())
+        return out
     N.call('ampis_intersect_rows', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
            _p(table.bbox), _p(table.area), _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0),
            groups.n_blocks, _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),
@@ -272,6 +283,7 @@ def intersect_mma(table, groups, mode, out=None):
     arg-max from the matrices.  Same RowResult as intersect_rows(), bit for bit; the choice
     between the two is a cost decision."""
     dev = table.device
+    assert table.layout != LAYOUT_CROP, 'the contraction reads linear packed masks (span or full layout)'
     nr = max(groups.n_rows, 1)
     n_tiles, tile_grp, tile_m0, tile_n0 = groups.mma_tiles()
     if out is None:
@@ -309,7 +321,7 @@ def operand_fill(table, groups=None):
 def choose_kernel(table, groups):
     """'mma' (dense int8 tcgen05 contraction) for crowded images, 'rows' (bbox-culled AND+popc)
     otherwise.  Both give identical results; this is only a cost decision."""
-    if groups.imat_off is None or groups.n_rows == 0:
+    if groups.imat_off is None or groups.n_rows == 0 or table.layout == LAYOUT_CROP:
         return 'rows'
     return 'mma' if operand_fill(table, groups) >= MMA_FILL_THRESHOLD else 'rows'
 
@@ -376,6 +388,8 @@ def hist_u32(values, lo, bin_width, n_bins, hist=None):
 def unpack_bool(table, ids, h, w):
     """Packed masks -> bool[n, h, w] device tensor (structures.masks_to_bitmask_array)."""
     dev = table.device
+    assert table.layout != LAYOUT_CROP, 'unpack reads linear packed masks (span or full layout)'
+    
     n = len(ids)
     out = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     d_ids = _dev(np.asarray(ids, np.int32), torch.int32, dev)

@@ -38,9 +38,10 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2_powder_batch')
     ap.add_argument('--images', type=int, default=1000, help='images per GPU per step')
-    ap.add_argument('--layout', default='full', choices=['full', 'span'],
+    ap.add_argument('--layout', default='full', choices=['full', 'span', 'crop'],
                     help='full = canonical full-frame packed masks (the roofline accounting of SURVEY 8d); '
-                         'span = culled storage (only first..last 1-pixel of each mask)')
+                         'span = culled storage (only first..last 1-pixel of each mask); '
+                         'crop = bounding-box windows (the cropped accounting of SURVEY 8d)')
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
     ap.add_argument('--kernel', default='rows', choices=['rows', 'mma'],
                     help='intersection kernel: rows = bbox-culled AND+popc (default); mma = dense int8 tcgen05 '
@@ -319,7 +320,7 @@ def roofline_of(args, cfg, run, ms, kt, world):
     launches = len(run.subs)
     dur_ms = kt[KERNELS.index(dom)] / ((2 if run.graph is not None else args.steps) * launches)
     achieved = alg[dom] / launches / (dur_ms / 1e3) / 1e9
-    lay = 'full' if run.layout == engine.LAYOUT_FULL else 'span'
+    lay = {engine.LAYOUT_FULL: 'full', engine.LAYOUT_SPAN: 'span', engine.LAYOUT_CROP: 'crop'}[run.layout]
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
@@ -371,7 +372,7 @@ def main():
         torch.cuda.synchronize()
 
     cfg = batch.CONFIGS[args.config]
-    layout = engine.LAYOUT_FULL if args.layout == 'full' else engine.LAYOUT_SPAN
+    layout = {'full': engine.LAYOUT_FULL, 'span': engine.LAYOUT_SPAN, 'crop': engine.LAYOUT_CROP}[args.layout]
     per_image = cfg['n_rows'] + cfg['n_cols']
     B_m = ((cfg['h'] * cfg['w'] + 127) // 128) * 16
 
@@ -379,8 +380,10 @@ def main():
         if args.sub:
             return args.sub
         if lay == engine.LAYOUT_FULL:
-            return max(1, min(args.images, int(12e9 // (per_image * B_m))))       # ~12 GB arena
-        return min(args.images, 250)
+            by_imat = max(1, int(4e9 // (4 * cfg['n_rows'] * cfg['n_cols'])))
+            return max(1, min(args.images, int(12e9 // (per_image * B_m)), by_imat))       # ~12 GB arena
+        by_imat = max(1, int(4e9 // (4 * cfg['n_rows'] * cfg['n_cols'])))          # dense matrices <= 4 GB per launch
+        return min(args.images, 250, by_imat)
 
     sampler = ClockSampler(local) if rank == 0 else None       # samples cover warm-up + timed steps
     wall0 = time.time()
@@ -413,6 +416,24 @@ def main():
         if not args.no_e2e:
             span['e2e'] = run_e2e(args, srun.subs, dev, engine.LAYOUT_SPAN, srun.arena, srun.rows_out,
                                   srun.thresholds, world, dist, sync)
+    # ---- bounding-box windows: the smallest storage, same results
+    crop = None
+    if layout == engine.LAYOUT_FULL and not args.no_span and args.kernel == 'rows':
+        del srun.arena
+        crun = LayoutRun(args, dev, rank, engine.LAYOUT_CROP, args.span_sub or auto_sub(engine.LAYOUT_CROP))
+        if args.graph:
+            crun.capture()
+        cms, ckt, ctot = crun.timed(args, world, dist, sync)
+        assert np.array_equal(ctot, final_totals), 'crop and full layouts disagree'
+        crop = {'value': world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (cms / 1e3), 'unit': UNIT,
+                'images_per_s': world * args.images * args.steps / (cms / 1e3), 'ms_per_step': cms / args.steps,
+                'images_per_launch': crun.sub, 'roofline': roofline_of(args, cfg, crun, cms, ckt, world),
+                'stored_bytes_per_image': crun.stored_chunks * 16 / args.images,
+                'note': 'same inputs and bit-identical results; only the bounding-box window of each mask is '
+                        'stored (32-row bands of the box columns)'}
+        if not args.no_e2e:
+            crop['e2e'] = run_e2e(args, crun.subs, dev, engine.LAYOUT_CROP, crun.arena, crun.rows_out,
+                                  crun.thresholds, world, dist, sync)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -442,6 +463,8 @@ def main():
         out['e2e'] = e2e
     if span:
         out['span_layout'] = span
+    if crop:
+        out['crop_layout'] = crop
     if not args.no_cpu:
         out['cpu_baseline'] = cpu_baseline(args)
     print(json.dumps(out))

@@ -44,6 +44,9 @@ extern "C" {
 
 #define AMPIS_LAYOUT_SPAN   0   /* store only [first 1, last 1] of each mask (culled) */
 #define AMPIS_LAYOUT_FULL   1   /* store the full h*w frame of each mask (canonical) */
+#define AMPIS_LAYOUT_CROP   2   /* store only the bounding-box window of each mask: for every column
+                                   x0..x1 the 32-row words (y0>>5)..(y1>>5) of that column, column after
+                                   column (SURVEY 8d "cropped accounting"); reg = [0, ceil(words/4)) */
 
 #define AMPIS_MODE_IOU      0   /* score = I / (a_row + a_col - I), analyze.py:158 */
 #define AMPIS_MODE_SAT      1   /* score = I / a_row,               powder.py:82-83 */
@@ -100,6 +103,11 @@ int ampis_rle_decode_packed(const uint32_t *d_cum, const int64_t *d_cnt_off, con
                             const uint32_t *d_span, const uint32_t *d_reg, const int64_t *d_bits_off,
                             int32_t n, void *d_bits, int64_t bits_capacity, void *stream);
 
+/* Same for AMPIS_LAYOUT_CROP tables (needs the tight boxes and image heights of the masks). */
+int ampis_rle_decode_crop(const uint32_t *d_cum, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                          const int32_t *d_bbox, const uint32_t *d_h, const int64_t *d_bits_off, int32_t n,
+                          void *d_bits, int64_t bits_capacity, void *stream);
+
 /* Fused form of ampis_rle_measure + scan + ampis_rle_decode_packed in ONE launch: every CTA
  * measures its masks, reserves arena space with one atomicAdd on *d_cursor (zeroed by this call)
  * and paints.  Arena order is arbitrary (d_bits_off[i] is still written per mask; there is no
@@ -153,6 +161,17 @@ int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_off, const ui
                          const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
                          int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                          void *stream);
+
+/* The same kernel over AMPIS_LAYOUT_CROP tables: AND+popc only over the overlap of the two
+ * bounding-box windows (words of the same column and the same 32-row band line up without
+ * shifts because bands are absolute).  Same outputs, bit for bit. */
+int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
+                              const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_blk_grp,
+                              const int32_t *d_blk_row0, int32_t n_blocks, const int32_t *d_grp_row_begin,
+                              const int32_t *d_grp_row_count, const int32_t *d_grp_col_begin,
+                              const int32_t *d_grp_col_count, const int64_t *d_grp_imat_off, int32_t mode,
+                              int32_t *d_imat, int32_t *d_best_col, uint32_t *d_best_inter,
+                              double *d_best_score, void *stream);
 
 /* ---- dense intersection matrices on the tensor cores (tcgen05, int8 contraction) -----------
  * Same quantity as the dense output of ampis_intersect_rows -- I[r][c] = popcount(row AND col),

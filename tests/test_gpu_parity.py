@@ -278,14 +278,15 @@ def test_empty_and_error_conventions(mods):
 
 
 @pytest.mark.parametrize('cfg,n_img', [('c1_powder_example', 2), ('c2_powder_batch', 2)])
-@pytest.mark.parametrize('layout,fused', [('span', False), ('full', False), ('span', True), ('full', True)])
+@pytest.mark.parametrize('layout,fused', [('span', False), ('full', False), ('span', True), ('full', True),
+                                          ('crop', False), ('crop', True)])
 def test_batch_pipeline_vs_oracle(mods, cfg, n_img, layout, fused):
     """Synthetic images through the batch pipeline == oracle per image (matches, IoUs, counts at
     the ten COCO thresholds, dense intersections)."""
     B, E, R, rle = mods.batch, mods.engine, mods.R, mods.rle
     host = B.synth(cfg, n_img, 1001)
     dev = B.DeviceBatch(host, dense=True)
-    lay = E.LAYOUT_FULL if layout == 'full' else E.LAYOUT_SPAN
+    lay = {'full': E.LAYOUT_FULL, 'span': E.LAYOUT_SPAN, 'crop': E.LAYOUT_CROP}[layout]
     arena = None
     if fused:
         arena = mods.torch.empty(4 * B.arena_chunks_needed(dev, lay), dtype=mods.torch.int32, device='cuda')
@@ -349,6 +350,33 @@ def test_batch_satellites_vs_oracle(mods):
         for v in want['match_pairs'].values():
             spp[min(len(v), 63)] += 1
     assert np.array_equal(res.spp_hist.cpu().numpy(), spp)
+
+
+@pytest.mark.parametrize('cfg,over,n_img', [
+    ('c2_powder_batch', {}, 3),
+    ('c4_spheroidite', dict(n_rows=1500, n_cols=1500, h=1024, w=1024), 2),
+    ('dense_overlap', {}, 1),
+    ('c3_satellites', dict(n_cols=600, h=1024, w=1024), 2),
+    ('c2_powder_batch', dict(h=70, w=45, n_rows=9, n_cols=11, median_diam=30.0), 4),      # windows wider than the frame
+])
+def test_crop_layout_equals_span_layout(mods, cfg, over, n_img):
+    """AMPIS_LAYOUT_CROP (bounding-box windows) == AMPIS_LAYOUT_SPAN bit for bit: measurements, dense
+    intersections, arg-max, scores, counts -- fused and unfused construction."""
+    B, E, torch = mods.batch, mods.engine, mods.torch
+    host = B.synth(dict(B.CONFIGS[cfg], **over), n_img, 777)
+    dev = B.DeviceBatch(host, dense=True)
+    a = B.eval_step(dev, layout=E.LAYOUT_SPAN, check=True)
+    b = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True)                       # measure, scan, crop painter
+    arena = torch.empty(4 * B.arena_chunks_needed(dev, E.LAYOUT_CROP), dtype=torch.int32, device='cuda')
+    c = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, arena=arena)          # fused measure+paint
+    assert B.arena_chunks_needed(dev, E.LAYOUT_CROP) <= B.arena_chunks_needed(dev, E.LAYOUT_SPAN) or host.h < 128
+    for o in (b, c):
+        assert torch.equal(a.rows.imat, o.rows.imat)
+        assert torch.equal(a.rows.best_col, o.rows.best_col) and torch.equal(a.rows.best_inter, o.rows.best_inter)
+        assert np.array_equal(a.rows.best_score.cpu().numpy(), o.rows.best_score.cpu().numpy(), equal_nan=True)
+        assert torch.equal(a.counts, o.counts)
+        assert torch.equal(a.table.area, o.table.area) and torch.equal(a.table.bbox, o.table.bbox)
+    assert int(a.rows.imat.max()) > 0
 
 
 def test_full_size_properties(mods):
