@@ -45,6 +45,12 @@ SIGNATURES = {
     'ampis_match_counts': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p]),
     'ampis_satellite_counts': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _f64, _p, _p, _i32, _p]),
     'ampis_hist_u32': (C.c_int, [_p, _i64, _u32, _u32, _p, _i32, _p]),
+    'ampis_bits_to_rle_count': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p]),
+    'ampis_bits_to_rle_emit': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    'ampis_project_pairs': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    'ampis_edge_count': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    'ampis_edge_distances': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                       _p, _p]),
     'ampis_poly_to_rle': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p]),
     'ampis_synth_batch': (_i64, [_u64, _i32, _u32, _u32, _i32, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64,
                                  _f64, _f64, _i32, _p, _i64, _p, _p]),

@@ -11,8 +11,10 @@ compatibility; it never affected results.
 from pathlib import Path
 
 import numpy as np
+import torch
 
 from . import engine
+from .containers import Instances
 from .structures import InstanceSet, RLEMasks, masks_to_rle, masks_to_bitmask_array  # noqa: F401
 
 
@@ -150,3 +152,129 @@ def merge_boxes(box1, box2):
     r11, r12, c11, c12 = box1
     r21, r22, c21, c22 = box2
     return np.array([min(r11, r21), max(r12, r22), min(c11, c21), max(c12, c22)])
+
+
+def _min_euclid(a, b):
+    """Minimum Euclidean distance from each row of *a* (n x 2) to the rows of *b* (m x 2), float64
+    tensor (analyze.py:379-413).  Tensor plumbing on whatever device the inputs live on; the
+    mask-level path (mask_edge_distance) uses the dedicated kernel instead of an n x m table."""
+    a = a.unsqueeze(1)
+    square_diffs = torch.pow(a.double() - b.double(), 2)
+    distances = torch.sqrt(square_diffs.sum(axis=2))
+    return distances.min(axis=1)[0]
+
+
+def mask_edge_distance(gt_mask, pred_mask, gt_box, pred_box, matches, device='auto'):
+    """Distances from false-positive pixels to the nearest ground-truth pixel and from
+    false-negative pixels to the nearest predicted pixel, per matched pair, inside the merged
+    box of the pair (analyze.py:416-499).  Boxes are index boxes [r1, r2, c1, c2].
+
+    Returns two lists of float64 tensors in the reference's order (np.where / torch.where order
+    of the cropped window).  device='cuda' returns CUDA tensors, anything else CPU tensors --
+    the arithmetic always runs on the GPU (csrc/edge.cu); the reference's n x m distance table
+    is replaced by a search over boundary pixels, which gives the same minima."""
+    if type(gt_mask) == RLEMasks:
+        gt_mask = gt_mask.rle
+    if type(pred_mask) == RLEMasks:
+        pred_mask = pred_mask.rle
+    matches = np.asarray(matches).reshape(-1, 2)
+    n = len(matches)
+    if n == 0:
+        return [], []
+    _check_same_size(gt_mask, pred_mask)
+    h, w = int(gt_mask[0]['size'][0]), int(gt_mask[0]['size'][1])
+    gi, pi = matches[:, 0].astype(np.int64), matches[:, 1].astype(np.int64)
+    ug, inv_g = np.unique(gi, return_inverse=True)
+    up, inv_p = np.unique(pi, return_inverse=True)
+    table = engine.table_from_rle([gt_mask[i] for i in ug] + [pred_mask[i] for i in up])
+    win = np.zeros((n, 4), np.int64)
+    for k in range(n):
+        box = merge_boxes(gt_box[gi[k]], pred_box[pi[k]])
+        if (np.asarray(box) < 0).any():
+            raise ValueError('negative box indices are not supported')
+        r1, r2, c1, c2 = [int(v) for v in box]
+        win[k] = (min(r1, h), min(r2, h), min(c1, w), min(c2, w))     # numpy slicing clips at the frame
+    if (win[:, 1] - win[:, 0]).max() > 32767 or (win[:, 3] - win[:, 2]).max() > 32767:
+        raise ValueError('merged boxes larger than 32767 pixels a side are not supported')
+    counts, d_fp, d_fn, off_fp, off_fn = engine.edge_distances(table, inv_g, len(ug) + inv_p, win)
+    on_gpu = str(device).lower() == 'cuda'
+    if not on_gpu:
+        d_fp, d_fn = d_fp.cpu(), d_fn.cpu()
+    FP = [d_fp[off_fp[k]:off_fp[k + 1]].clone() for k in range(n)]
+    FN = [d_fn[off_fn[k]:off_fn[k + 1]].clone() for k in range(n)]
+    return FP, FN
+
+
+def det_perf_iset(gt, pred, match_results=None, colormap=None, tp_gt=False):
+    """Detection TP / FP / FN instances gathered in one InstanceSet for display
+    (analyze.py:502-586).  Host bookkeeping over the matcher's output."""
+    if match_results is None:
+        match_results = rle_instance_matcher(gt, pred)
+    return_colormap = colormap is None
+    size = gt.instances.image_size
+    gt_masks = masks_to_rle(gt.instances.masks, size)
+    pred_masks = masks_to_rle(pred.instances.masks, size)
+    gt_bbox = gt.instances.boxes if type(gt.instances.boxes) == np.ndarray else gt.instances.boxes.tensor.numpy()
+    pred_bbox = pred.instances.boxes if type(pred.instances.boxes) == np.ndarray \
+        else pred.instances.boxes.tensor.numpy()
+    if colormap is None:
+        colormap = {'TP': np.asarray([0.5, 0., 1.], np.float64),
+                    'FP': np.asarray([0., 1., 1.], np.float64),
+                    'FN': np.asarray([1., 0., 0.], np.float64)}
+    if tp_gt:
+        tp_idx = match_results['tp'][:, 0]
+        tp_masks = [gt_masks[i] for i in tp_idx]
+        tp_bbox = gt_bbox[tp_idx]
+    else:
+        tp_idx = match_results['tp'][:, 1]
+        tp_masks = [pred_masks[i] for i in tp_idx]
+        tp_bbox = pred_bbox[tp_idx]
+    tp_colors = np.tile(colormap['TP'], (len(tp_masks), 1))
+    fp_idx = match_results['fp']
+    fp_masks = [pred_masks[i] for i in fp_idx]
+    fp_bbox = pred_bbox[fp_idx]
+    fp_colors = np.tile(colormap['FP'], (len(fp_masks), 1))
+    fn_idx = match_results['fn']
+    fn_masks = [gt_masks[i] for i in fn_idx]
+    fn_bbox = gt_bbox[fn_idx]
+    fn_colors = np.tile(colormap['FN'], (len(fn_masks), 1))
+    masks = RLEMasks(tp_masks + fp_masks + fn_masks)
+    bbox = np.concatenate((tp_bbox, fp_bbox, fn_bbox), axis=0)
+    colors = np.concatenate((tp_colors, fp_colors, fn_colors), axis=0)
+    iset = InstanceSet()
+    iset.instances = Instances(image_size=masks.rle[0]['size'], **{'masks': masks, 'boxes': bbox, 'colors': colors})
+    if return_colormap:
+        return iset, colormap
+    return iset
+
+
+_SEG_COLORS_ALL = np.array([[0., 0., 0.], [0.153, 0.153, 0.000], [0.286, 1., 0.], [1., 0.857, 0.], [1., 0., 0.],
+                            [0., 0.571, 1.], [0., 1., 0.571], [0.285, 0., 1.]])
+_SEG_COLORS_REDUCED = np.array([[0.5, 0., 1.], [1., 0., 0.], [0., 1., 1.], [1., 1., 0.]])
+
+
+def seg_perf_iset(gt_masks, pred_masks, match_results=None, mode='reduced'):
+    """Pixel-level TP / FN / FP classes of the matched pairs as an InstanceSet of class masks
+    (analyze.py:589-699).  The reference decodes every mask to a full frame, forms the three
+    boolean stacks, OR-reduces them and re-encodes; here the projection, the class logic and the
+    RLE encoding all run on packed bits on the GPU (csrc/rle_encode.cu), nothing is decoded."""
+    if match_results is None:
+        match_results = rle_instance_matcher(gt_masks, pred_masks)
+    g_rle, p_rle = masks_to_rle(gt_masks), masks_to_rle(pred_masks)
+    _check_same_size(g_rle, p_rle)
+    h, w = int(g_rle[0]['size'][0]), int(g_rle[0]['size'][1])
+    tp_idx = np.asarray(match_results['tp']).reshape(-1, 2)
+    gi, pi = tp_idx[:, 0].astype(np.int64), tp_idx[:, 1].astype(np.int64)
+    ug, inv_g = np.unique(gi, return_inverse=True)
+    up, inv_p = np.unique(pi, return_inverse=True)
+    table = engine.table_from_rle([g_rle[i] for i in ug] + [p_rle[i] for i in up])
+    rles = engine.project_pairs(table, inv_g, len(ug) + inv_p, h, w, 'all' if mode == 'all' else 'reduced')
+    if mode == 'all':
+        colors = [_SEG_COLORS_ALL[1:], ['Other', 'TP', 'FN', 'TP+FN', 'FP', 'TP+FP', 'FN+FP', 'TP+FN+FP']]
+    else:
+        colors = [_SEG_COLORS_REDUCED, ['TP', 'FN', 'FP', 'other']]
+    masks = RLEMasks(rles)
+    i = InstanceSet()
+    i.instances = Instances(image_size=masks.rle[0]['size'], **{'masks': masks, 'colors': colors[0],
+                                                                'boxes': np.zeros((len(masks), 4))})
+    return i, colors

@@ -378,6 +378,37 @@ def iou_matrix(table, rows, groups, g=0):
     return out[:G * P].view(G, P)
 
 
+def edge_distances(table, gt_ids, pred_ids, windows):
+    """Boundary disagreement of matched pairs (analyze.mask_edge_distance): for pair i the masks
+    gt_ids[i], pred_ids[i] of `table` inside windows[i] = (r1, r2, c1, c2).  Returns
+    (counts int64[n, 4], fp_dist float64 device tensor, fn_dist float64 device tensor, off_fp, off_fn)."""
+    assert table.layout != LAYOUT_CROP
+    dev = table.device
+    n = len(gt_ids)
+    d_g = _dev(np.asarray(gt_ids, np.int32), torch.int32, dev)
+    d_p = _dev(np.asarray(pred_ids, np.int32), torch.int32, dev)
+    d_w = _dev(np.asarray(windows, np.int32).reshape(-1), torch.int32, dev)
+    counts = torch.empty(max(4 * n, 1), dtype=torch.int32, device=dev)
+    N.call('ampis_edge_count', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span), _p(table.h),
+           _p(d_g), _p(d_p), _p(d_w), n, _p(counts), _stream())
+    c = counts[:4 * n].cpu().numpy().reshape(n, 4).astype(np.int64)
+    off = np.zeros((4, n + 1), np.int64)
+    np.cumsum(c.T, axis=1, out=off[:, 1:])
+    d_off = [_dev(off[k, :n], torch.int64, dev) for k in range(4)]
+    lists = [torch.empty(max(int(off[k, n]), 1), dtype=torch.int32, device=dev) for k in range(4)]
+    d_fp = torch.empty(max(int(off[0, n]), 1), dtype=torch.float64, device=dev)
+    d_fn = torch.empty(max(int(off[1, n]), 1), dtype=torch.float64, device=dev)
+    status = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    N.call('ampis_edge_distances', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span), _p(table.h),
+           _p(d_g), _p(d_p), _p(d_w), n, _p(d_off[0]), _p(d_off[1]), _p(d_off[2]), _p(d_off[3]), _p(lists[0]),
+           _p(lists[1]), _p(lists[2]), _p(lists[3]), _p(d_fp), _p(d_fn), _p(status), _stream())
+    if n and bool(status[:n].any().item()):
+        bad = int(torch.nonzero(status[:n]).flatten()[0].item())
+        raise RuntimeError('mask_edge_distance: pair %d has disagreement pixels but no pixel of the other mask '
+                           'inside the merged box (min over an empty set)' % bad)
+    return c, d_fp[:int(off[0, n])], d_fn[:int(off[1, n])], off[0], off[1]
+
+
 def hist_u32(values, lo, bin_width, n_bins, hist=None):
     if hist is None:
         hist = torch.zeros(n_bins, dtype=torch.int64, device=values.device)
@@ -458,3 +489,69 @@ def counts_to_strings(cnt, cnt_off, cnt_len, n):
     buf = chars.cpu().numpy().tobytes()
     ln = chlen.cpu().numpy()
     return [buf[choff[i]:choff[i] + ln[i]] for i in range(n)]
+
+
+def exclusive_scan(values_i64):
+    """Exclusive prefix sum on the device: int64[n] -> int64[n + 1] (last = total)."""
+    n = values_i64.numel()
+    out = torch.empty(n + 1, dtype=torch.int64, device=values_i64.device)
+    tmp_bytes = N.lib().ampis_scan_tmp_bytes(n)
+    tmp = torch.empty(max(tmp_bytes // 8, 1), dtype=torch.int64, device=values_i64.device)
+    N.call('ampis_exclusive_scan_i64', _p(values_i64), _p(out), n, _p(tmp), tmp_bytes, _stream())
+    return out
+
+
+def frames_to_rle(bits, n, h, w):
+    """n consecutive FULL-layout frames of (h, w) in `bits` (int32 device tensor) -> list of COCO RLE
+    dicts: rleEncode + rleToString on the GPU (the reference's RLE.encode)."""
+    if n == 0:
+        return []
+    dev = bits.device
+    chunks = (int(h) * int(w) + 127) // 128
+    d_off = torch.arange(n, dtype=torch.int64, device=dev) * chunks
+    d_h = torch.full((n,), int(h), dtype=torch.int32, device=dev)
+    d_w = torch.full((n,), int(w), dtype=torch.int32, device=dev)
+    n_runs = torch.empty(n, dtype=torch.int64, device=dev)
+    N.call('ampis_bits_to_rle_count', _p(bits), _p(d_off), _p(d_h), _p(d_w), n, _p(n_runs), _stream())
+    cnt_off = exclusive_scan(n_runs)
+    total = int(cnt_off[n].item())
+    cnt = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    cnt_len = torch.empty(n, dtype=torch.int32, device=dev)
+    N.call('ampis_bits_to_rle_emit', _p(bits), _p(d_off), _p(d_h), _p(d_w), n, _p(cnt_off), _p(cnt), _p(cnt_len),
+           _stream())
+    strings = counts_to_strings(cnt, cnt_off, cnt_len, n)
+    return [{'size': [int(h), int(w)], 'counts': s} for s in strings]
+
+
+def encode_bool(masks_np):
+    """bool/uint8 [n, h, w] host array -> list of COCO RLE dicts (RLE.encode of the Fortran-ordered
+    h x w x n stack, data_utils.py:275,423): pack, run-length encode and string-encode on the GPU."""
+    dev = require_cuda()
+    m = np.ascontiguousarray(masks_np)
+    if m.dtype == np.bool_:
+        m = m.view(np.uint8)
+    assert m.ndim == 3 and m.dtype == np.uint8
+    n, h, w = m.shape
+    if n == 0:
+        return []
+    chunks = (h * w + 127) // 128
+    d = _dev(m.reshape(-1), torch.uint8, dev)
+    bits = torch.empty(4 * n * chunks, dtype=torch.int32, device=dev)
+    d_off = torch.arange(n, dtype=torch.int64, device=dev) * chunks
+    N.call('ampis_pack_bool_nrc', _p(d), n, h, w, _p(bits), _p(d_off), _stream())
+    return frames_to_rle(bits, n, h, w)
+
+
+def project_pairs(table, gt_ids, pred_ids, h, w, mode):
+    """Pixel-class frames of analyze.seg_perf_iset as RLE dicts: mode 'reduced' -> 4, 'all' -> 7."""
+    assert table.layout != LAYOUT_CROP
+    dev = table.device
+    chunks = (int(h) * int(w) + 127) // 128
+    n_out = 4 if mode == 'reduced' else 7
+    d_g = _dev(np.asarray(gt_ids, np.int32), torch.int32, dev)
+    d_p = _dev(np.asarray(pred_ids, np.int32), torch.int32, dev)
+    tmp = torch.empty(4 * 3 * chunks, dtype=torch.int32, device=dev)
+    out = torch.empty(4 * n_out * chunks, dtype=torch.int32, device=dev)
+    N.call('ampis_project_pairs', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span), _p(d_g),
+           _p(d_p), len(gt_ids), chunks, 0 if mode == 'reduced' else 1, _p(tmp), _p(out), _stream())
+    return frames_to_rle(out, n_out, h, w)

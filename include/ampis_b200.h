@@ -232,6 +232,50 @@ int ampis_satellite_counts(const int32_t *d_best_col, const uint32_t *d_best_int
 int ampis_hist_u32(const uint32_t *d_values, int64_t n, uint32_t lo, uint32_t bin_width,
                    int64_t *d_hist, int32_t n_bins, void *stream);
 
+/* ---- packed masks -> RLE (pycocotools rleEncode; RLE.encode at analyze.py:692, data_utils.py:275,423,
+ * structures.py:465, powder.py:209).  Masks are FULL-layout frames (ceil(h*w/128) chunks at
+ * d_bits_off[i], bits beyond h*w zero).  ampis_bits_to_rle_count gives the number of runs of each
+ * mask; after an exclusive scan of those (ampis_exclusive_scan_i64 -> d_cnt_off),
+ * ampis_bits_to_rle_emit writes the counts (first run counts zeros and may be 0) and d_cnt_len. */
+int ampis_bits_to_rle_count(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_h,
+                            const uint32_t *d_w, int32_t n, int64_t *d_n_runs, void *stream);
+int ampis_bits_to_rle_emit(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_h,
+                           const uint32_t *d_w, int32_t n, const int64_t *d_cnt_off, uint32_t *d_cnt,
+                           int32_t *d_cnt_len, void *stream);
+
+/* Pixel classes of matched pairs projected onto the frame (analyze.seg_perf_iset, analyze.py:637-690):
+ * TP = OR(g & p), FN = OR(g & ~p), FP = OR(~g & p) over the pairs, then class bitmaps written as
+ * consecutive FULL-layout frames into d_out_bits: mode 0 ('reduced') 4 frames [TP only, FN only,
+ * FP only, two or more]; mode 1 ('all') 7 frames for codes 1..7 of TP + 2 FN + 4 FP.
+ * d_tmp3 = scratch of 3 frames (zeroed here). */
+int ampis_project_pairs(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                        const uint32_t *d_span, const int32_t *d_pair_gt, const int32_t *d_pair_pr,
+                        int32_t n_pairs, int64_t frame_chunks, int32_t mode, void *d_tmp3, void *d_out_bits,
+                        void *stream);
+
+/* ---- boundary disagreement of matched pairs (analyze.mask_edge_distance, analyze.py:416-499) ------
+ * For pair i: masks pair_gt[i], pair_pr[i] (SPAN or FULL layout table) and the window
+ * win[i] = (r1, r2, c1, c2), half open, inside the frame (the merged box of analyze.py:466).
+ * ampis_edge_count   -> counts[i] = (#false-positive px, #false-negative px, #gt boundary px,
+ *                       #pred boundary px) inside the window.
+ * ampis_edge_distances, given exclusive offsets of those counts (off_*[i], int64) and scratch
+ * lists of matching sizes, writes for every false-positive pixel (row-major order inside the
+ * window, np.where order) the distance to the nearest gt pixel, and for every false-negative
+ * pixel the distance to the nearest predicted pixel, as float64 = sqrt(exact integer);
+ * status[i] = 1 when a pair has false-positive (negative) pixels but no gt (pred) pixel in the
+ * window (the reference's torch.min raises there). Window sides must be <= 32767. */
+int ampis_edge_count(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                     const uint32_t *d_span, const uint32_t *d_h, const int32_t *d_pair_gt,
+                     const int32_t *d_pair_pr, const int32_t *d_win, int32_t n_pairs, int32_t *d_counts,
+                     void *stream);
+int ampis_edge_distances(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                         const uint32_t *d_span, const uint32_t *d_h, const int32_t *d_pair_gt,
+                         const int32_t *d_pair_pr, const int32_t *d_win, int32_t n_pairs,
+                         const int64_t *d_off_fp, const int64_t *d_off_fn, const int64_t *d_off_gb,
+                         const int64_t *d_off_pb, uint32_t *d_list_fp, uint32_t *d_list_fn,
+                         uint32_t *d_list_gb, uint32_t *d_list_pb, double *d_dist_fp, double *d_dist_fn,
+                         int32_t *d_status, void *stream);
+
 /* ---- polygon -> RLE (pycocotools rleFrPoly via RLE.frPyObjects, structures.py:677) -----
  * d_xy: vertex coordinates x0,y0,x1,y1,... of all polygons, d_xy_off[n+1] offsets in doubles.
  * Crossing positions (sorted, zero-length runs merged) are written as run counts at

@@ -284,3 +284,66 @@ def extract_boxes(masks, mask_mode='detectron2', box_mode='detectron2'):
             box = np.array([y1, y2 + 1, x1, x2 + 1], dtype=dtype)
         boxes[i] = box
     return boxes
+
+
+# ---- ampis/analyze.py: boundary disagreement and pixel-class maps ----------------------------
+
+def merge_boxes(box1, box2):
+    """analyze.py:342-376 -- smallest [r1, r2, c1, c2] box enclosing both."""
+    r11, r12, c11, c12 = box1
+    r21, r22, c21, c22 = box2
+    return np.array([min(r11, r21), max(r12, r22), min(c11, c21), max(c12, c22)])
+
+
+def min_euclid(a, b):
+    """analyze.py:379-413 -- for every row of a (n x 2) the smallest Euclidean distance to a row
+    of b (m x 2), float64; blocked so the n x m table never materialises."""
+    a = np.asarray(a, np.float64).reshape(-1, 2)
+    b = np.asarray(b, np.float64).reshape(-1, 2)
+    if b.shape[0] == 0:
+        raise RuntimeError('min over an empty set of pixels (torch raises here too)')
+    out = np.empty(a.shape[0], np.float64)
+    step = max(1, (1 << 22) // max(b.shape[0], 1))
+    for i in range(0, a.shape[0], step):
+        d = a[i:i + step, None, :] - b[None, :, :]
+        out[i:i + step] = np.sqrt((d * d).sum(axis=2)).min(axis=1)
+    return out
+
+
+def mask_edge_distance(gt_mask, pred_mask, gt_box, pred_box, matches):
+    """analyze.py:416-499 -- per matched pair: distances from false-positive pixels to the nearest
+    ground-truth pixel and from false-negative pixels to the nearest predicted pixel, inside the
+    merged box [r1:r2, c1:c2]; pixel order is np.where's (row-major)."""
+    fp_all, fn_all = [], []
+    for gi, pi in np.asarray(matches).reshape(-1, 2):
+        r1, r2, c1, c2 = merge_boxes(gt_box[gi], pred_box[pi])
+        gm = rle.decode(gt_mask[gi])[r1:r2, c1:c2].astype(bool)
+        pm = rle.decode(pred_mask[pi])[r1:r2, c1:c2].astype(bool)
+        gt_where = np.stack(np.where(gm), axis=1)
+        pred_where = np.stack(np.where(pm), axis=1)
+        fp_where = np.stack(np.where(pm & ~gm), axis=1)
+        fn_where = np.stack(np.where(gm & ~pm), axis=1)
+        fp_all.append(min_euclid(fp_where, gt_where) if fp_where.size else np.zeros(0, np.float64))
+        fn_all.append(min_euclid(fn_where, pred_where) if fn_where.size else np.zeros(0, np.float64))
+    return fp_all, fn_all
+
+
+def seg_perf_masks(gt_masks, pred_masks, tp_idx, mode='reduced'):
+    """analyze.py:637-692 -- pixel classes of the matched pairs projected onto the frame and
+    encoded: 'reduced' -> [TP, FN, FP, other], 'all' -> codes 1..7 of TP + 2 FN + 4 FP."""
+    g = rle_to_bitmask_array(gt_masks)[tp_idx[:, 0]]
+    p = rle_to_bitmask_array(pred_masks)[tp_idx[:, 1]]
+    tp = np.logical_or.reduce(g & p, axis=0).astype(np.uint64)
+    fn = np.logical_or.reduce(g & ~p, axis=0).astype(np.uint64) * 2
+    fp = np.logical_or.reduce(~g & p, axis=0).astype(np.uint64) * 4
+    pixel_map = tp + fn + fp
+    if mode == 'all':
+        masks = np.zeros((*pixel_map.shape[:2], 7), bool)
+        for i in range(1, 8):
+            masks[:, :, i - 1] = pixel_map == i
+    else:
+        masks = np.zeros((*pixel_map.shape[:2], 4), bool)
+        for i, idx in enumerate([1, 2, 4]):
+            masks[:, :, i] = pixel_map == idx
+        masks[:, :, 3] = np.logical_or.reduce([pixel_map == i for i in [3, 5, 6, 7]], axis=0)
+    return rle.encode(np.asfortranarray(masks.astype(np.uint8)))

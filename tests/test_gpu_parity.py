@@ -475,3 +475,100 @@ def test_hist_and_scan(mods):
         N.call('ampis_exclusive_scan_i64', E._p(x), E._p(out), n, E._p(tmp), nb, E._stream())
         want = np.concatenate([[0], np.cumsum(x.cpu().numpy())])
         assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_encode_on_gpu_equals_pycocotools_strings(mods):
+    """engine.encode_bool (pack + rleEncode + rleToString on the GPU) reproduces, byte for byte, the
+    strings the real pycocotools.encode wrote into the shipped prediction pickles (decode -> encode
+    round trip), and the oracle's encode on random masks incl. first-pixel-set and all-ones."""
+    E, S, rle = mods.engine, mods.structures, mods.rle
+    _, gt, pr = U.powder_match_image(0)
+    sample = pr[:60]
+    dense = S.masks_to_bitmask_array(sample)
+    got = E.encode_bool(dense)
+    assert [g['counts'] for g in got] == [m['counts'] for m in sample]
+    assert got[0]['size'] == list(sample[0]['size'])
+    rng = np.random.default_rng(11)
+    for h, w in [(1, 1), (7, 5), (64, 2), (33, 129), (128, 128)]:
+        a = U.rand_masks(rng, 9, h, w)
+        a[0] = True
+        a[1] = False
+        a[2, 0, 0] = True
+        a[3, -1, -1] = True
+        want = rle.encode(np.asfortranarray(a.transpose(1, 2, 0).astype(np.uint8)))
+        got = E.encode_bool(a)
+        assert [g['counts'] for g in got] == [m['counts'] for m in want], (h, w)
+
+
+def test_mask_edge_distance_vs_oracle(mods):
+    """analyze.mask_edge_distance == reference algorithm (decode, crop, n x m distances), bit for bit,
+    on matched pairs of a shipped image and on random blobs with loose / clipped boxes."""
+    A, R, D, S, rle = mods.analyze, mods.R, mods.data_utils, mods.structures, mods.rle
+    _, gt, pr = U.powder_match_image(1)
+    m = A.rle_instance_matcher(gt, pr, 0.5)
+    matches = m['tp'][:40]
+    gb = D.extract_boxes(S.masks_to_bitmask_array(gt), box_mode='matterport')
+    pb = D.extract_boxes(S.masks_to_bitmask_array(pr), box_mode='matterport')
+    fp, fn = A.mask_edge_distance(gt, pr, gb, pb, matches)
+    wfp, wfn = R.mask_edge_distance(gt, pr, gb, pb, matches)
+    assert len(fp) == len(matches)
+    for a, b in zip(fp + fn, wfp + wfn):
+        assert a.dtype == mods.torch.float64 and np.array_equal(a.numpy(), b)
+    assert sum(len(x) for x in fp) > 100 and sum(len(x) for x in fn) > 100
+    # RLEMasks input, CUDA output, loose boxes that stick out of the frame
+    rng = np.random.default_rng(3)
+    h, w = 61, 47
+    g = U.rand_masks(rng, 6, h, w, p_empty=0)
+    p = g.copy()
+    p[:, 1:] |= g[:, :-1]
+    p[:, :, :3] = False
+    ge = rle.encode(np.asfortranarray(g.transpose(1, 2, 0).astype(np.uint8)))
+    pe = rle.encode(np.asfortranarray(p.transpose(1, 2, 0).astype(np.uint8)))
+    boxes = np.tile(np.array([0, h + 5, 0, w + 9]), (6, 1))
+    mt = np.stack([np.arange(6), np.arange(6)[::-1]], 1)
+    fp, fn = A.mask_edge_distance(S.RLEMasks(ge), S.RLEMasks(pe), boxes, boxes, mt, device='cuda')
+    wfp, wfn = R.mask_edge_distance(ge, pe, boxes, boxes, mt)
+    for a, b in zip(fp + fn, wfp + wfn):
+        assert a.is_cuda and np.array_equal(a.cpu().numpy(), b)
+    assert A.mask_edge_distance(ge, pe, boxes, boxes, np.zeros((0, 2), int)) == ([], [])
+    # the reference's torch.min raises when the other mask has no pixel in the window
+    tiny = np.tile(np.array([0, 2, 0, 2]), (6, 1))
+    e = np.zeros((1, h, w), np.uint8)
+    f = np.zeros((1, h, w), np.uint8)
+    f[0, 0, 0] = 1
+    ee = rle.encode(np.asfortranarray(e.transpose(1, 2, 0)))
+    fe = rle.encode(np.asfortranarray(f.transpose(1, 2, 0)))
+    with pytest.raises(RuntimeError):
+        A.mask_edge_distance(ee, fe, tiny, tiny, np.array([[0, 0]]))
+    a = mods.torch.tensor([[0, 0], [3, 4]])
+    assert A._min_euclid(a, mods.torch.tensor([[0, 1], [3, 0]])).tolist() == [1.0, 4.0]
+
+
+@pytest.mark.parametrize('mode', ['reduced', 'all'])
+def test_seg_and_det_perf_isets_vs_oracle(mods, mode):
+    A, R, S, rle = mods.analyze, mods.R, mods.structures, mods.rle
+    from ampis_b200.containers import Instances
+    _, gt, pr = U.powder_match_image(2)
+    m = A.rle_instance_matcher(gt, pr, 0.5)
+    iset, colors = A.seg_perf_iset(gt, pr, m, mode=mode)
+    want = R.seg_perf_masks(gt, pr, m['tp'], mode)
+    got = iset.instances.masks.rle
+    assert [x['counts'] for x in got] == [x['counts'] for x in want]
+    assert len(colors[0]) == len(got) == (4 if mode == 'reduced' else 7)
+    assert len(colors[1]) == (4 if mode == 'reduced' else 8)      # the reference lists 8 names for 7 masks
+    assert iset.instances.boxes.shape == (len(got), 4)
+    iset2, _ = A.seg_perf_iset(S.RLEMasks(gt), S.RLEMasks(pr), None, mode=mode)       # matcher called inside
+    assert [x['counts'] for x in iset2.instances.masks.rle] == [x['counts'] for x in want]
+    # det_perf_iset: bookkeeping over the matcher's output
+    size = tuple(gt[0]['size'])
+    mk = lambda ms: S.InstanceSet(instances=Instances(size, masks=S.RLEMasks(ms),
+                                                      boxes=np.arange(4 * len(ms), dtype=float).reshape(-1, 4)))
+    G, P = mk(gt), mk(pr)
+    d, cmap = A.det_perf_iset(G, P)
+    n_tp, n_fp, n_fn = len(m['tp']), len(m['fp']), len(m['fn'])
+    assert len(d.instances) == n_tp + n_fp + n_fn and set(cmap) == {'TP', 'FP', 'FN'}
+    assert [x['counts'] for x in d.instances.masks.rle[:n_tp]] == [pr[i]['counts'] for i in m['tp'][:, 1]]
+    assert np.array_equal(d.instances.boxes[n_tp:n_tp + n_fp], P.instances.boxes[m['fp']])
+    assert np.array_equal(d.instances.colors[-1], cmap['FN'])
+    d2 = A.det_perf_iset(G, P, m, colormap=cmap, tp_gt=True)
+    assert [x['counts'] for x in d2.instances.masks.rle[:n_tp]] == [gt[i]['counts'] for i in m['tp'][:, 0]]
