@@ -555,3 +555,59 @@ def project_pairs(table, gt_ids, pred_ids, h, w, mode):
     N.call('ampis_project_pairs', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span), _p(d_g),
            _p(d_p), len(gt_ids), chunks, 0 if mode == 'reduced' else 1, _p(tmp), _p(out), _stream())
     return frames_to_rle(out, n_out, h, w)
+
+
+MAX_LABEL_VALUE = 1 << 24     # 'label' annotation images: values are ranked through a flag table of this size
+
+
+def label_image_to_instances(ann, binary):
+    """Annotation image (H x W host array) -> (list of RLE dicts, int32 tight boxes x0,y0,x1,y1), one
+    per instance in the reference's order (data_utils.py:408-424): `binary` -> connected components
+    (8-connectivity, raster order), otherwise ascending label value with a leading 0 skipped."""
+    dev = require_cuda()
+    a = np.asarray(ann)
+    if a.ndim != 2:
+        raise ValueError('annotation images must be 2-D, got shape %s' % (a.shape,))
+    h, w = a.shape
+    n = h * w
+    dense_t = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    if binary:
+        img = _dev(np.ascontiguousarray(a.astype(np.bool_)).view(np.uint8).reshape(-1), torch.uint8, dev)
+        work = torch.empty(n, dtype=torch.int32, device=dev)
+        flags = torch.empty(n, dtype=torch.int64, device=dev)
+        rank = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        tmp_bytes = N.lib().ampis_scan_tmp_bytes(n)
+        tmp = torch.empty(max(tmp_bytes // 8, 1), dtype=torch.int64, device=dev)
+        N.call('ampis_ccl_label', _p(img), h, w, _p(work), _p(flags), _p(rank), _p(tmp), tmp_bytes, _p(dense_t),
+               _stream())
+        n_labels = int(rank[n].item())
+    else:
+        if not np.issubdtype(a.dtype, np.integer) and not a.dtype == np.bool_:
+            raise ValueError('label images must hold integers, got %s' % a.dtype)
+        lo, hi = (int(a.min()), int(a.max())) if n else (0, 0)
+        if lo < 0 or hi >= MAX_LABEL_VALUE:
+            raise ValueError('label values must lie in [0, %d)' % MAX_LABEL_VALUE)
+        n_values = hi + 1                                       # size of the flag table
+        d_ann = _dev(np.ascontiguousarray(a).astype(np.int64).reshape(-1), torch.int32, dev)
+        present = torch.zeros(n_values, dtype=torch.int64, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        N.call('ampis_label_values_present', _p(d_ann), n, _p(present), n_values, _p(bad), _stream())
+        rank = exclusive_scan(present)
+        zero_present = int(present[0].item())
+        n_labels = int(rank[n_values].item()) - zero_present
+        N.call('ampis_label_dense', _p(d_ann), _p(rank), zero_present, h, w, _p(dense_t), _stream())
+    if n_labels == 0:
+        return [], np.zeros((0, 4), np.int32)
+    big = np.iinfo(np.int32).max
+    bbox = torch.tensor([big, big, -1, -1], dtype=torch.int32, device=dev).repeat(n_labels).contiguous()
+    N.call('ampis_label_bbox', _p(dense_t), h, w, n_labels, _p(bbox), _stream())
+    n_runs = torch.empty(n_labels, dtype=torch.int64, device=dev)
+    N.call('ampis_label_rle_count', _p(dense_t), h, w, n_labels, _p(bbox), _p(n_runs), _stream())
+    cnt_off = exclusive_scan(n_runs)
+    cnt = torch.empty(max(int(cnt_off[n_labels].item()), 1), dtype=torch.int32, device=dev)
+    cnt_len = torch.empty(n_labels, dtype=torch.int32, device=dev)
+    N.call('ampis_label_rle_emit', _p(dense_t), h, w, n_labels, _p(bbox), _p(cnt_off), _p(cnt), _p(cnt_len),
+           _stream())
+    strings = counts_to_strings(cnt, cnt_off, cnt_len, n_labels)
+    rles = [{'size': [int(h), int(w)], 'counts': s} for s in strings]
+    return rles, bbox.cpu().numpy().reshape(-1, 4)

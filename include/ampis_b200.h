@@ -253,6 +253,30 @@ int ampis_project_pairs(const void *d_bits, const int64_t *d_bits_off, const uin
                         int32_t n_pairs, int64_t frame_chunks, int32_t mode, void *d_tmp3, void *d_out_bits,
                         void *stream);
 
+/* ---- annotation images -> instances (data_utils.get_ddicts 'binary' / 'label', data_utils.py:394-433) ----
+ * ampis_ccl_label: skimage.measure.label of a binary image (row-major u8[h][w], non-zero = foreground,
+ *   full 8-connectivity, labels 1..n in raster order of each component's first pixel).  d_work i32[h*w],
+ *   d_flags i64[h*w], d_rank i64[h*w+1] (d_rank[h*w] = number of labels afterwards), scan scratch as for
+ *   ampis_exclusive_scan_i64.  Output d_dense_t: labels in COLUMN-major order (index x*h + y).
+ * ampis_label_values_present / ampis_label_dense: the 'label' format -- arbitrary non-negative label
+ *   values < n_values are ranked in ascending order (np.unique), 0 = background when present.
+ * ampis_label_bbox: tight box of every label 1..n_labels (d_bbox pre-filled with INT_MAX,INT_MAX,-1,-1).
+ * ampis_label_rle_count / _emit: RLE.encode(ann == u) for every label, from the label's box window
+ *   only; counts at d_cnt + d_cnt_off[u-1]. */
+int ampis_ccl_label(const uint8_t *d_img, int32_t h, int32_t w, int32_t *d_work, int64_t *d_flags,
+                    int64_t *d_rank, void *d_scan_tmp, size_t scan_tmp_bytes, int32_t *d_dense_t, void *stream);
+int ampis_label_values_present(const int32_t *d_ann, int64_t n, int64_t *d_present, int32_t n_values,
+                               int32_t *d_bad, void *stream);
+int ampis_label_dense(const int32_t *d_ann, const int64_t *d_rank, int32_t zero_present, int32_t h, int32_t w,
+                      int32_t *d_dense_t, void *stream);
+int ampis_label_bbox(const int32_t *d_dense_t, int32_t h, int32_t w, int32_t n_labels, int32_t *d_bbox,
+                     void *stream);
+int ampis_label_rle_count(const int32_t *d_dense_t, int32_t h, int32_t w, int32_t n_labels,
+                          const int32_t *d_bbox, int64_t *d_n_runs, void *stream);
+int ampis_label_rle_emit(const int32_t *d_dense_t, int32_t h, int32_t w, int32_t n_labels,
+                         const int32_t *d_bbox, const int64_t *d_cnt_off, uint32_t *d_cnt, int32_t *d_cnt_len,
+                         void *stream);
+
 /* ---- boundary disagreement of matched pairs (analyze.mask_edge_distance, analyze.py:416-499) ------
  * For pair i: masks pair_gt[i], pair_pr[i] (SPAN or FULL layout table) and the window
  * win[i] = (r1, r2, c1, c2), half open, inside the frame (the merged box of analyze.py:466).

@@ -347,3 +347,30 @@ def seg_perf_masks(gt_masks, pred_masks, tp_idx, mode='reduced'):
             masks[:, :, i] = pixel_map == idx
         masks[:, :, 3] = np.logical_or.reduce([pixel_map == i for i in [3, 5, 6, 7]], axis=0)
     return rle.encode(np.asfortranarray(masks.astype(np.uint8)))
+
+
+# ---- ampis/data_utils.py: annotation images -> instances ---------------------------------------
+
+def label_binary(ann):
+    """skimage.measure.label(ann.astype(bool)) as called at data_utils.py:410: 2-D, default
+    connectivity = ndim (8-connected), labels 1..n in raster order.  skimage is absent offline;
+    scipy.ndimage.label with a full 3x3 structure is the same labelling with the same numbering."""
+    import scipy.ndimage as ndi
+    lab, _ = ndi.label(np.asarray(ann).astype(bool), structure=np.ones((3, 3), int))
+    return lab
+
+
+def annotations_from_label_image(ann, binary):
+    """data_utils.py:409-424 -- per instance: box (extract_boxes, detectron2 mode) and RLE.encode(mask)."""
+    ann = np.asarray(ann)
+    if binary:
+        ann = label_binary(ann)
+    unique = np.unique(ann)
+    if unique[0] == 0:
+        unique = unique[1:]
+    out = []
+    for u in unique:
+        mask = ann == u
+        bbox = extract_boxes(mask)[0]
+        out.append((bbox, rle.encode(np.asfortranarray(mask.astype(np.uint8)))))
+    return out

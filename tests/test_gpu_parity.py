@@ -3,6 +3,8 @@ public drop-in API and the C ABI, against the CPU oracle and the frozen golden f
 Bit-exact for intersections, matches, counts, areas and boxes; float64 scores are compared
 for equality too (they are correctly-rounded divisions of exact integers),
 with 1e-6 relative as the stated tolerance for derived quantities (d_eq, psd)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -572,3 +574,83 @@ def test_seg_and_det_perf_isets_vs_oracle(mods, mode):
     assert np.array_equal(d.instances.colors[-1], cmap['FN'])
     d2 = A.det_perf_iset(G, P, m, colormap=cmap, tp_gt=True)
     assert [x['counts'] for x in d2.instances.masks.rle[:n_tp]] == [gt[i]['counts'] for i in m['tp'][:, 0]]
+
+
+def _write_png(path, arr):
+    from PIL import Image
+    Image.fromarray(arr).save(str(path))
+
+
+def test_get_ddicts_binary_and_label_images(mods, tmp_path, monkeypatch):
+    """data_utils.get_ddicts('binary' / 'label'): connected components, boxes and RLE of the
+    reference's own annotation images == oracle (committed fixture), plus random label images
+    with gaps in the label values, touching components and frame-filling instances."""
+    D, R, E = mods.data_utils, mods.R, mods.engine
+    g = U.load('spheroidite_annotations.npz')
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / 'im').mkdir()
+    (tmp_path / 'ann').mkdir()
+    for k, name in enumerate(g['names']):
+        shape = tuple(int(v) for v in g['%d_shape' % k])
+        a = np.unpackbits(g['%d_bits' % k])[:shape[0] * shape[1]].reshape(shape).astype(np.uint8) * 255
+        _write_png(tmp_path / 'im' / str(name), a)
+        _write_png(tmp_path / 'ann' / str(name), a)
+    dd = D.get_ddicts('binary', 'im', 'ann', dataset_class='Training')
+    assert len(dd) == 2
+    by_name = {os.path.basename(d['file_name']): d for d in dd}
+    for k, name in enumerate(g['names']):
+        d = by_name[str(name)]
+        shape = tuple(int(v) for v in g['%d_shape' % k])
+        want = U.unpack_strings(g['%d_blob' % k], g['%d_off' % k], shape)
+        assert (d['height'], d['width']) == shape and d['mask_format'] == 'bitmask'
+        assert d['num_instances'] == len(want) == len(d['annotations']) and d['dataset_class'] == 'Training'
+        assert [x['segmentation']['counts'] for x in d['annotations']] == [m['counts'] for m in want]
+        assert np.array_equal(np.stack([x['bbox'] for x in d['annotations']]), g['%d_boxes' % k])
+        assert d['annotations'][0]['bbox'].dtype == np.float64 and d['annotations'][0]['category_id'] == 0
+    # label images (.npy) with arbitrary values; engine level against the oracle
+    rng = np.random.default_rng(8)
+    for h, w in [(5, 7), (64, 33), (97, 130)]:
+        lab = rng.choice(np.array([0, 0, 0, 3, 4, 9, 500, 70000]), size=(h, w))
+        lab[:, 0] = 9                      # a column-filling instance whose runs cross column ends
+        for binary in (False, True):
+            rles, bb = E.label_image_to_instances(lab, binary=binary)
+            want = R.annotations_from_label_image(lab, binary=binary)
+            assert len(rles) == len(want)
+            assert [m['counts'] for m in rles] == [m['counts'] for _, m in want]
+            assert np.array_equal(bb.astype(np.float64), np.stack([b for b, _ in want]))
+    full = np.ones((33, 65), np.int64)
+    rles, bb = E.label_image_to_instances(full, binary=True)
+    assert len(rles) == 1 and bb.tolist() == [[0, 0, 64, 32]]
+    assert rles[0]['counts'] == mods.rle.encode(np.asfortranarray(full.astype(np.uint8)))['counts']
+    assert E.label_image_to_instances(np.zeros((4, 4), np.uint8), binary=True)[0] == []
+    np.save(str(tmp_path / 'ann2.npy'), lab)
+    with pytest.raises(ValueError):
+        E.label_image_to_instances(-lab, binary=False)
+
+
+def test_get_ddicts_rle_json_and_compress_pred(mods, tmp_path, monkeypatch):
+    import json
+    D, R, S, rle = mods.data_utils, mods.R, mods.structures, mods.rle
+    _, gt, pr = U.powder_match_image(0)
+    sample = pr[:25]
+    monkeypatch.chdir(tmp_path)
+    data = [{'file_name': 'images/a.png',
+             'segmentations': [{'size': list(m['size']), 'counts': m['counts'].decode('utf-8')} for m in sample]}]
+    json.dump(data, open('ann.json', 'w'))
+    dd = D.get_ddicts('rle', 'ann.json')
+    assert len(dd) == 1 and dd[0]['num_instances'] == 25 and dd[0]['file_name'] == 'images/a.png'
+    dense = S.masks_to_bitmask_array(sample)
+    assert np.array_equal(np.stack([a['bbox'] for a in dd[0]['annotations']]), R.extract_boxes(dense))
+    assert [a['segmentation']['counts'] for a in dd[0]['annotations']] == [m['counts'] for m in sample]
+
+    class Pred(object):
+        pass
+    p = Pred()
+    p.pred_masks = mods.torch.from_numpy(dense).cuda()
+    p.pred_boxes = mods.torch.arange(100, dtype=mods.torch.float32).reshape(25, 4)
+    p.scores = mods.torch.linspace(0, 1, 25)
+    p.pred_classes = mods.torch.zeros(25, dtype=mods.torch.int64)
+    out = D.format_outputs('a.png', 'Validation', {'instances': p})
+    assert out['dataset'] == 'Validation' and out['pred']['instances'] is p
+    assert [m['counts'] for m in p.pred_masks] == [m['counts'] for m in sample]
+    assert isinstance(p.scores, np.ndarray) and p.pred_boxes.shape == (25, 4) and p.pred_classes.dtype == np.int64

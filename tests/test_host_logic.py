@@ -131,3 +131,31 @@ def test_synthetic_generator_is_valid_and_deterministic(name):
         assert int(c.astype(np.int64).sum()) == hw
         assert (c[1:] > 0).all()                         # canonical: no interior zero-length runs
     assert h1.n_masks == 2 * (h1.n_rows + h1.n_cols)
+
+
+def test_get_ddicts_via2_json(tmp_path, monkeypatch):
+    """data_utils.get_ddicts('via2') is host logic: VIA 2 JSON -> polygon data dicts (data_utils.py:436-480)."""
+    import json
+    from ampis_b200 import data_utils as D
+    from ampis_b200.containers import BoxMode
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / 'via').mkdir()
+    via = {'_via_settings': {'core': {'default_filepath': '../images/'}},
+           '_via_img_metadata': {
+               'a.png123': {'filename': 'a.png', 'file_attributes': {'Size (width, height)': '1536, 1024', 'HFW': '103.6 um'},
+                            'regions': [{'shape_attributes': {'name': 'polygon', 'all_points_x': [10, 20, 15],
+                                                              'all_points_y': [5, 5, 30]}, 'region_attributes': {}},
+                                        {'shape_attributes': {'name': 'polygon', 'all_points_x': [0, 4, 4, 0],
+                                                              'all_points_y': [0, 0, 4, 4]}, 'region_attributes': {}}]},
+               'b.png77': {'filename': 'b.png', 'file_attributes': {'Size (width, height)': '64, 32'}, 'regions': []}}}
+    json.dump(via, open('via/anns.json', 'w'))
+    dd = D.get_ddicts('via2', 'via/anns.json', dataset_class='Validation')
+    assert [d['image_id'] for d in dd] == [0, 1] and dd[0]['file_name'] == 'via/../images/a.png'
+    assert (dd[0]['height'], dd[0]['width'], dd[0]['HFW'], dd[0]['mask_format']) == (1024, 1536, '103.6 um', 'polygon')
+    assert dd[0]['annotation_file'] == 'anns.json' and dd[0]['dataset_class'] == 'Validation'
+    a = dd[0]['annotations']
+    assert dd[0]['num_instances'] == 2 and a[0]['segmentation'] == [[10.5, 5.5, 20.5, 5.5, 15.5, 30.5]]
+    assert a[0]['bbox'].tolist() == [10, 5, 20, 30] and a[0]['bbox_mode'] == BoxMode.XYXY_ABS and a[0]['category_id'] == 0
+    assert dd[1]['num_instances'] == 0 and dd[1]['HFW'] is None and (dd[1]['height'], dd[1]['width']) == (32, 64)
+    with pytest.raises(ValueError):
+        D.get_ddicts('coco', 'via/anns.json')
