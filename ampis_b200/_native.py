@@ -48,6 +48,9 @@ SIGNATURES = {
     'ampis_bits_to_rle_count': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p]),
     'ampis_bits_to_rle_emit': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p]),
     'ampis_project_pairs': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    'ampis_rle_moments': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p]),
+    'ampis_crop_perimeter': (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),
+    'ampis_crop_convex_area': (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p]),
     'ampis_ccl_label': (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, C.c_size_t, _p, _p]),
     'ampis_label_values_present': (C.c_int, [_p, _i64, _p, _i32, _p, _p]),
     'ampis_label_dense': (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),

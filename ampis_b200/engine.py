@@ -611,3 +611,28 @@ def label_image_to_instances(ann, binary):
     strings = counts_to_strings(cnt, cnt_off, cnt_len, n_labels)
     rles = [{'size': [int(h), int(w)], 'counts': s} for s in strings]
     return rles, bbox.cpu().numpy().reshape(-1, 4)
+
+
+def region_measurements(masks):
+    """Per-mask raw measurements behind compute_rprops, all exact integers: dict of numpy arrays
+    area[n], bbox[n,4] (x0,y0,x1,y1), moments[n,6] (N, Sx, Sy, Sxx, Syy, Sxy as Python-int-safe uint64),
+    perimeter_hist[n,10], convex_area[n].  One CROP-layout table, four small launches."""
+    t = table_from_rle(masks, layout=LAYOUT_CROP)
+    dev, n = t.device, t.n
+    mom = torch.empty(max(6 * n, 1), dtype=torch.int64, device=dev)
+    N.call('ampis_rle_moments', _p(t.cum), _p(t.cnt_off), _p(t.cnt_len), _p(t.h), n, _p(mom), _stream())
+    border = torch.empty_like(t.bits)
+    hist = torch.empty(max(10 * n, 1), dtype=torch.int32, device=dev)
+    N.call('ampis_crop_perimeter', _p(t.bits), _p(t.bits_off), _p(t.bbox), n, _p(border), _p(hist), _stream())
+    bb = t.bbox_np()
+    bw = np.maximum(bb[:, 2] - bb[:, 0] + 1, 0).astype(np.int64)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(10 * bw + 4, out=off[1:])
+    scratch = torch.empty(max(int(off[n]), 1), dtype=torch.int32, device=dev)
+    convex = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    N.call('ampis_crop_convex_area', _p(t.bits), _p(t.bits_off), _p(t.bbox), n, _p(_dev(off[:n], torch.int64, dev)),
+           _p(scratch), _p(convex), _stream())
+    return {'area': t.areas_np().astype(np.int64), 'bbox': bb,
+            'moments': mom[:6 * n].cpu().numpy().view(np.uint64).reshape(n, 6),
+            'perimeter_hist': hist[:10 * n].cpu().numpy().reshape(n, 10).astype(np.int64),
+            'convex_area': convex[:n].cpu().numpy().astype(np.int64)}

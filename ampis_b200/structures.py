@@ -194,37 +194,48 @@ class InstanceSet(object):
         inlier_instances = ~touches
         self.instances = self.instances[inlier_instances]
 
-    #: keys compute_rprops evaluates on the GPU; the remaining skimage keys are outside the
-    #: accelerated path
-    RPROPS_GPU_KEYS = ('area', 'equivalent_diameter', 'bbox')
+    #: region properties compute_rprops derives from the GPU measurements (skimage names)
+    RPROPS_GPU_KEYS = ('area', 'bbox', 'bbox_area', 'centroid', 'local_centroid', 'convex_area', 'eccentricity',
+                       'equivalent_diameter', 'extent', 'label', 'major_axis_length', 'minor_axis_length',
+                       'orientation', 'perimeter', 'solidity')
 
     def compute_rprops(self, keys=None, return_df=False):
-        """Region properties per mask (reference structures.py:474-514).  ``area``,
-        ``equivalent_diameter`` (= sqrt(4*area/pi), skimage 0.18.3) and ``bbox`` come from the GPU
-        measurement pass over the run counts; cells are 1-element arrays as regionprops_table
-        returns them.  Default keys are the in-scope subset of the reference default."""
+        """Region properties per mask (reference structures.py:474-514, which decodes every mask to a
+        full int64 frame and runs skimage.measure.regionprops_table on it).  Here the GPU delivers
+        exact integer measurements from the run table and the packed bounding-box windows
+        (csrc/rprops.cu: raw moments, perimeter histogram, convex-hull pixel count) and the
+        properties are formed on the host with skimage 0.18.3's formulas.  Default keys are the
+        reference's; cells are 1-element arrays (empty for an empty mask) as regionprops_table
+        returns them; tuple-valued properties become ``key-0``, ``key-1`` ... columns."""
         if keys is None:
-            keys = ['area', 'equivalent_diameter']
+            keys = ['area', 'equivalent_diameter', 'major_axis_length', 'perimeter', 'solidity', 'orientation']
         unsupported = [k for k in keys if k not in self.RPROPS_GPU_KEYS]
         if unsupported:
             raise NotImplementedError('region properties %s are not part of the GPU path (supported: %s)'
                                       % (unsupported, list(self.RPROPS_GPU_KEYS)))
         rle = masks_to_rle(self.instances.masks, self.instances.image_size)
-        t = engine.table_from_rle(rle, paint=False)
-        area = t.areas_np().astype(np.int64)
-        bb = t.bbox_np()
+        if type(rle) == dict:
+            rle = [rle]
+        props = region_properties(rle)
         rows = []
-        for i in range(len(rle)):
+        for p in props:
             row = {}
             for k in keys:
-                if k == 'area':
-                    row[k] = np.array([area[i]]) if area[i] else np.array([], np.int64)
-                elif k == 'equivalent_diameter':
-                    row[k] = np.sqrt(4 * np.array([area[i]]) / np.pi) if area[i] else np.array([])
+                v = p.get(k)
+                if isinstance(v, tuple):
+                    for j, x in enumerate(v):
+                        row['%s-%d' % (k, j)] = np.array([x])
+                elif v is None:            # empty mask: regionprops finds no region
+                    width = {'bbox': 4, 'centroid': 2, 'local_centroid': 2}.get(k, 0)
+                    empty = np.array([], np.int64 if k in ('area', 'bbox', 'bbox_area', 'convex_area', 'label')
+                                     else np.float64)
+                    if width:
+                        for j in range(width):
+                            row['%s-%d' % (k, j)] = empty
+                    else:
+                        row[k] = empty
                 else:
-                    b = [bb[i, 1], bb[i, 0], bb[i, 3] + 1, bb[i, 2] + 1]
-                    for j in range(4):
-                        row['bbox-%d' % j] = np.array([b[j]]) if area[i] else np.array([], np.int64)
+                    row[k] = np.array([v])
             rows.append(row)
         df = pd.DataFrame(rows)
         df['class_idx'] = self.instances.class_idx
@@ -343,3 +354,48 @@ def masks_to_bitmask_array(masks, size=None):
         return masks_to_bitmask_array(masks.masks, masks.image_size)
     else:
         raise NotImplementedError
+
+
+_PERIMETER_CODES = [5, 7, 15, 17, 25, 27, 21, 33, 13, 23]
+
+
+def region_properties(rle):
+    """skimage 0.18.3 region properties of every mask of an RLE list (one region per mask, as
+    ``regionprops_table(mask.astype(int))`` sees it) from the exact GPU measurements.  Returns one
+    dict per mask ({} for an empty mask)."""
+    m = engine.region_measurements(rle)
+    weights = np.zeros(50, dtype=np.double)
+    weights[[5, 7, 15, 17, 25, 27]] = 1
+    weights[[21, 33]] = np.sqrt(2)
+    weights[[13, 23]] = (1 + np.sqrt(2)) / 2
+    out = []
+    for i in range(len(rle)):
+        n = int(m['area'][i])
+        if n == 0:
+            out.append({})
+            continue
+        x0, y0, x1, y1 = (int(v) for v in m['bbox'][i])
+        N, Sx, Sy, Sxx, Syy, Sxy = (int(v) for v in m['moments'][i])
+        # central second moments times N, exact integers: N*mu20 = N*Syy - Sy^2, ...
+        n_rr, n_cc, n_rc = N * Syy - Sy * Sy, N * Sxx - Sx * Sx, N * Sxy - Sx * Sy
+        a, c, b = n_cc / (N * N), n_rr / (N * N), -(n_rc / (N * N))    # inertia tensor [[a, b], [b, c]]; -0.0 kept
+        half_tr, half_diff = (a + c) / 2, (a - c) / 2
+        l1 = half_tr + np.sqrt(half_diff * half_diff + b * b)
+        det = (n_cc * n_rr - n_rc * n_rc) / (N ** 4)                    # exact numerator: no cancellation
+        l2 = max(det / l1, 0.0) if l1 > 0 else 0.0
+        if n_cc == n_rr:
+            orientation = -np.pi / 4. if b < 0 else np.pi / 4.
+        else:
+            orientation = 0.5 * np.arctan2(-2 * b, c - a)
+        hist = np.zeros(50, np.int64)
+        hist[_PERIMETER_CODES] = m['perimeter_hist'][i]
+        convex_area = int(m['convex_area'][i])
+        bbox_area = (y1 - y0 + 1) * (x1 - x0 + 1)
+        out.append({'area': n, 'bbox': (y0, x0, y1 + 1, x1 + 1), 'bbox_area': bbox_area,
+                    'centroid': (Sy / N, Sx / N), 'local_centroid': ((Sy - N * y0) / N, (Sx - N * x0) / N),
+                    'convex_area': convex_area, 'eccentricity': 0. if l1 == 0 else float(np.sqrt(1 - l2 / l1)),
+                    'equivalent_diameter': float(np.sqrt(4 * n / np.pi)), 'extent': n / bbox_area,
+                    'major_axis_length': float(4 * np.sqrt(l1)), 'minor_axis_length': float(4 * np.sqrt(l2)),
+                    'orientation': float(orientation), 'perimeter': float(hist @ weights),
+                    'solidity': n / convex_area, 'label': 1})
+    return out

@@ -253,6 +253,24 @@ int ampis_project_pairs(const void *d_bits, const int64_t *d_bits_off, const uin
                         int32_t n_pairs, int64_t frame_chunks, int32_t mode, void *d_tmp3, void *d_out_bits,
                         void *stream);
 
+/* ---- region properties (InstanceSet.compute_rprops -> skimage.measure.regionprops_table,
+ * structures.py:505-508) -------------------------------------------------------------------------
+ * ampis_rle_moments: exact raw moments of every mask from its run table (d_cum = run end positions
+ *   from ampis_rle_measure): d_out[i] = { N, sum x, sum y, sum x^2, sum y^2, sum x*y } (x column, y row).
+ * ampis_crop_perimeter (AMPIS_LAYOUT_CROP table): skimage.measure.perimeter(neighbourhood=4) as the
+ *   ten weighted bins of its 50-bin histogram, order 5,7,15,17,25,27 (weight 1), 21,33 (sqrt 2),
+ *   13,23 ((1+sqrt 2)/2); d_border_scratch has the size of the bits arena.
+ * ampis_crop_convex_area: number of pixels of skimage's convex_hull_image (hull of the pixel-edge
+ *   midpoints, crossing-number test of the pixel centres); scratch of 10*box_width+4 ints per mask
+ *   at d_scratch_off[i]. */
+int ampis_rle_moments(const uint32_t *d_cum, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                      const uint32_t *d_h, int32_t n, uint64_t *d_out, void *stream);
+int ampis_crop_perimeter(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox, int32_t n,
+                         void *d_border_scratch, uint32_t *d_hist10, void *stream);
+int ampis_crop_convex_area(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox, int32_t n,
+                           const int64_t *d_scratch_off, int32_t *d_scratch, uint64_t *d_convex_area,
+                           void *stream);
+
 /* ---- annotation images -> instances (data_utils.get_ddicts 'binary' / 'label', data_utils.py:394-433) ----
  * ampis_ccl_label: skimage.measure.label of a binary image (row-major u8[h][w], non-zero = foreground,
  *   full 8-connectivity, labels 1..n in raster order of each component's first pixel).  d_work i32[h*w],

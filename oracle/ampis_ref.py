@@ -374,3 +374,106 @@ def annotations_from_label_image(ann, binary):
         bbox = extract_boxes(mask)[0]
         out.append((bbox, rle.encode(np.asfortranarray(mask.astype(np.uint8)))))
     return out
+
+
+# ---- skimage.measure.regionprops_table as called by compute_rprops (structures.py:505-508) ------
+# scikit-image 0.18.3 (docker/env.yml:16) is not installable offline; the functions below restate
+# its algorithms (measure/_moments.py, measure/_regionprops.py, measure/_regionprops_utils.perimeter,
+# morphology/convex_hull.py, measure/_pnpoly.pxd) with numpy / scipy.  PARITY UNPINNED against a
+# real skimage.
+
+def _moments_central(image, center, order):
+    calc = image.astype(float)
+    for dim, dim_length in enumerate(image.shape):
+        delta = np.arange(dim_length, dtype=float) - center[dim]
+        powers_of_delta = delta[:, np.newaxis] ** np.arange(order + 1)
+        calc = np.rollaxis(calc, dim, image.ndim)
+        calc = np.dot(calc, powers_of_delta)
+        calc = np.rollaxis(calc, -1, dim)
+    return calc
+
+
+def _perimeter4(image):
+    import scipy.ndimage as ndi
+    strel = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], np.uint8)
+    image = image.astype(np.uint8)
+    eroded = ndi.binary_erosion(image, strel, border_value=0)
+    border = image - eroded
+    weights = np.zeros(50, dtype=np.double)
+    weights[[5, 7, 15, 17, 25, 27]] = 1
+    weights[[21, 33]] = np.sqrt(2)
+    weights[[13, 23]] = (1 + np.sqrt(2)) / 2
+    pim = ndi.convolve(border, np.array([[10, 2, 10], [2, 1, 2], [10, 2, 10]]), mode='constant', cval=0)
+    hist = np.bincount(pim.ravel(), minlength=50)
+    return hist @ weights
+
+
+def _pnpoly_grid(shape, verts):
+    """grid_points_in_poly of skimage 0.18 (crossing-number test of _pnpoly.pxd, x = row, y = col)."""
+    xp, yp = verts[:, 0], verts[:, 1]
+    m, n = np.mgrid[0:shape[0], 0:shape[1]]
+    x, y = m.astype(float), n.astype(float)
+    c = np.zeros(shape, bool)
+    j = len(xp) - 1
+    for i in range(len(xp)):
+        cond = ((yp[i] <= y) & (y < yp[j])) | ((yp[j] <= y) & (y < yp[i]))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            xi = (xp[j] - xp[i]) * (y - yp[i]) / (yp[j] - yp[i]) + xp[i]
+        c ^= cond & (x < xi)
+        j = i
+    return c
+
+
+def _convex_hull_image(image):
+    from scipy.spatial import ConvexHull
+    if not image.any():
+        return np.zeros(image.shape, bool)
+    rows, cols = np.nonzero(image)
+    coords = []
+    for r in np.unique(rows):                    # possible_hull: first / last pixel of every row and column
+        cc = cols[rows == r]
+        coords += [(r, cc.min()), (r, cc.max())]
+    for c in np.unique(cols):
+        rr = rows[cols == c]
+        coords += [(rr.min(), c), (rr.max(), c)]
+    coords = np.array(coords, float)
+    offsets = np.array([[-0.5, 0], [0.5, 0], [0, -0.5], [0, 0.5]])
+    coords = (coords[:, None, :] + offsets).reshape(-1, 2)
+    coords = np.unique(coords, axis=0)
+    hull = ConvexHull(coords)
+    verts = hull.points[hull.vertices]
+    return _pnpoly_grid(image.shape, verts)
+
+
+def regionprops_one(mask):
+    """Properties of the single region `mask.astype(int)` defines (label 1), as regionprops_table
+    would report them; {} for an empty mask."""
+    mask = np.asarray(mask, bool)
+    if not mask.any():
+        return {}
+    rows, cols = np.nonzero(mask)
+    r0, r1, c0, c1 = rows.min(), rows.max() + 1, cols.min(), cols.max() + 1
+    img = mask[r0:r1, c0:c1]
+    area = int(img.sum())
+    M = _moments_central(img.astype(np.uint8), (0, 0), 3)
+    local_centroid = (M[1, 0] / M[0, 0], M[0, 1] / M[0, 0])
+    mu = _moments_central(img.astype(np.uint8), local_centroid, 3)
+    mu0 = mu[0, 0]
+    T = np.array([[mu[0, 2] / mu0, -mu[1, 1] / mu0], [-mu[1, 1] / mu0, mu[2, 0] / mu0]])
+    ev = np.linalg.eigvalsh(T)
+    ev = np.clip(ev, 0, None, out=ev)
+    l1, l2 = sorted(ev, reverse=True)
+    a, b, b, c = T.flat
+    if a - c == 0:
+        orientation = -np.pi / 4. if b < 0 else np.pi / 4.
+    else:
+        orientation = 0.5 * np.arctan2(-2 * b, c - a)
+    convex_area = int(_convex_hull_image(img).sum())
+    return {'area': area, 'bbox': (int(r0), int(c0), int(r1), int(c1)), 'bbox_area': int(img.size),
+            'centroid': (float(rows.mean()), float(cols.mean())),
+            'local_centroid': (float(local_centroid[0]), float(local_centroid[1])),
+            'convex_area': convex_area, 'eccentricity': 0. if l1 == 0 else float(np.sqrt(1 - l2 / l1)),
+            'equivalent_diameter': float(np.sqrt(4 * area / np.pi)), 'extent': area / img.size,
+            'major_axis_length': float(4 * np.sqrt(l1)), 'minor_axis_length': float(4 * np.sqrt(l2)),
+            'orientation': float(orientation), 'perimeter': float(_perimeter4(img)),
+            'solidity': area / convex_area, 'label': 1}

@@ -654,3 +654,66 @@ def test_get_ddicts_rle_json_and_compress_pred(mods, tmp_path, monkeypatch):
     assert out['dataset'] == 'Validation' and out['pred']['instances'] is p
     assert [m['counts'] for m in p.pred_masks] == [m['counts'] for m in sample]
     assert isinstance(p.scores, np.ndarray) and p.pred_boxes.shape == (25, 4) and p.pred_classes.dtype == np.int64
+
+
+RPROP_KEYS = ['area', 'bbox', 'bbox_area', 'centroid', 'local_centroid', 'convex_area', 'eccentricity',
+              'equivalent_diameter', 'extent', 'label', 'major_axis_length', 'minor_axis_length', 'orientation',
+              'perimeter', 'solidity']
+
+
+def _check_rprops(got, want):
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert set(g) == set(w), i
+        for k in w:
+            if k in ('area', 'bbox', 'bbox_area', 'convex_area', 'label'):
+                assert g[k] == w[k], (i, k, g[k], w[k])             # integers: exact
+            else:                                                   # derived floats: 1e-6 (north_star)
+                assert np.allclose(g[k], w[k], rtol=1e-6, atol=1e-6), (i, k, g[k], w[k])
+
+
+def test_region_properties_vs_skimage_restatement(mods):
+    """compute_rprops keys from exact GPU measurements == oracle restatement of skimage 0.18.3
+    (moments, inertia eigenvalues, orientation, 4-neighbourhood perimeter, convex hull image) on
+    shipped spheroidite predictions, powder predictions and random / degenerate masks."""
+    S, R, rle = mods.structures, mods.R, mods.rle
+    from ampis_b200.containers import Instances
+    m = U.load('spheroidite_measure.npz')
+    masks = U.unpack_strings(m['1_blob'], m['1_off'], m['1_size'])[:60]
+    _, gt, pr = U.powder_match_image(3)
+    for ms in (masks, pr[:25]):
+        dense = rle.decode(ms).transpose(2, 0, 1).astype(bool)
+        _check_rprops(S.region_properties(ms), [R.regionprops_one(d) for d in dense])
+    rng = np.random.default_rng(21)
+    for h, w in [(1, 1), (3, 40), (40, 3), (37, 53), (70, 70)]:
+        a = U.rand_masks(rng, 12, h, w)
+        a[0] = True                                  # whole frame
+        a[1] = False
+        a[1, h // 2, w // 2] = True                  # single pixel
+        a[2] = np.eye(h, w, dtype=bool)              # diagonal line
+        a[3] = False
+        a[3, 0, :] = True                            # one-pixel-wide line along the frame edge
+        a[3, -1, -1] = True                          # + a detached pixel (one region, two components)
+        enc = rle.encode(np.asfortranarray(a.transpose(1, 2, 0).astype(np.uint8)))
+        _check_rprops(S.region_properties(enc), [R.regionprops_one(d) for d in a])
+    # through InstanceSet.compute_rprops: reference default keys, 1-element cells, tuple keys split
+    n = len(masks)
+    size = tuple(int(v) for v in m['1_size'])
+    iset = S.InstanceSet(instances=Instances(size, masks=S.RLEMasks(masks), boxes=np.zeros((n, 4)),
+                                             class_idx=np.arange(n)))
+    iset.compute_rprops()
+    assert list(iset.rprops.columns) == ['area', 'equivalent_diameter', 'major_axis_length', 'perimeter', 'solidity',
+                                         'orientation', 'class_idx']
+    dense = rle.decode(masks).transpose(2, 0, 1).astype(bool)
+    want = [R.regionprops_one(d) for d in dense]
+    for i in range(n):
+        for k in ('major_axis_length', 'perimeter', 'solidity', 'orientation'):
+            cell = iset.rprops[k][i]
+            if want[i]:
+                assert cell.shape == (1,) and np.allclose(cell[0], want[i][k], rtol=1e-6, atol=1e-6)
+            else:
+                assert cell.shape == (0,)
+    df = iset.compute_rprops(keys=['centroid', 'bbox'], return_df=True)
+    assert list(df.columns) == ['centroid-0', 'centroid-1', 'bbox-0', 'bbox-1', 'bbox-2', 'bbox-3', 'class_idx']
+    with pytest.raises(NotImplementedError):
+        iset.compute_rprops(keys=['euler_number'])
