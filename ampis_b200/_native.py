@@ -61,6 +61,7 @@ SIGNATURES = {
     'ampis_edge_distances': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                        _p, _p]),
     'ampis_poly_to_rle': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    'ampis_polygon2mask': (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     'ampis_synth_batch': (_i64, [_u64, _i32, _u32, _u32, _i32, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64,
                                  _f64, _f64, _i32, _p, _i64, _p, _p]),
 }

@@ -630,9 +630,27 @@ def region_measurements(masks):
     np.cumsum(10 * bw + 4, out=off[1:])
     scratch = torch.empty(max(int(off[n]), 1), dtype=torch.int32, device=dev)
     convex = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
-    N.call('ampis_crop_convex_area', _p(t.bits), _p(t.bits_off), _p(t.bbox), n, _p(_dev(off[:n], torch.int64, dev)),
-           _p(scratch), _p(convex), _stream())
+    d_off = _dev(off[:n], torch.int64, dev)          # named: a temporary would be recycled before the launch
+    N.call('ampis_crop_convex_area', _p(t.bits), _p(t.bits_off), _p(t.bbox), n, _p(d_off), _p(scratch), _p(convex),
+           _stream())
     return {'area': t.areas_np().astype(np.int64), 'bbox': bb,
             'moments': mom[:6 * n].cpu().numpy().view(np.uint64).reshape(n, 6),
             'perimeter_hist': hist[:10 * n].cpu().numpy().reshape(n, 10).astype(np.int64),
             'convex_area': convex[:n].cpu().numpy().astype(np.int64)}
+
+
+def polygons_to_bool(polys, h, w):
+    """list of flat [x0,y0,x1,y1,...] polygons -> bool[n, h, w] host array by skimage's polygon2mask
+    rule (structures._poly2mask), rasterised on the GPU."""
+    dev = require_cuda()
+    n = len(polys)
+    if n == 0:
+        return np.zeros((0, int(h), int(w)), bool)
+    lens = np.fromiter((len(p) for p in polys), np.int64, n)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    xy = np.concatenate([np.asarray(p, np.float64).ravel() for p in polys])
+    out = torch.empty((n, int(h), int(w)), dtype=torch.uint8, device=dev)
+    d_xy, d_off = _dev(xy, torch.float64, dev), _dev(off, torch.int64, dev)      # keep both alive for the launch
+    N.call('ampis_polygon2mask', _p(d_xy), _p(d_off), n, int(h), int(w), _p(out), _stream())
+    return out.cpu().numpy().view(np.bool_)

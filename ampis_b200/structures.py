@@ -324,24 +324,30 @@ def _rle_to_bool(rle):
     return engine.unpack_bool(t, np.arange(len(rle)), int(h), int(w)).cpu().numpy()
 
 
+def _poly2mask(masks, size):
+    """list of [x0,y0,x1,y1,...] polygons -> bool[n, r, c] with skimage.draw.polygon2mask's rule
+    (reference structures.py:693-715), rasterised on the GPU (csrc/poly.cu polygon2mask_kernel)."""
+    return engine.polygons_to_bool([np.asarray(p, np.float64).ravel() for p in masks], size[0], size[1])
+
+
 def masks_to_bitmask_array(masks, size=None):
     """Anything -> bool[n_mask, r, c] (reference structures.py:717-774).  RLE input is decoded
-    and transposed on the GPU.  Polygon input is rasterised with the same rleFrPoly rule as
-    ``masks_to_rle`` -- the reference uses skimage.draw.polygon2mask here (structures.py:711),
-    a different rasteriser that is not available offline; see DESIGN.md."""
+    and transposed on the GPU.  Polygon input goes through ``_poly2mask`` like the reference
+    (first polygon of every instance, skimage's point-in-polygon rule -- NOT the pycocotools
+    rasteriser ``masks_to_rle`` uses; the two differ on boundary pixels, as in the reference)."""
     dtype = type(masks)
     if dtype == np.ndarray:
         assert masks.dtype == np.bool_
         return masks
     elif dtype == PolygonMasks:
         assert size is not None
-        return _rle_to_bool(masks_to_rle(masks, size))
+        return _poly2mask([p[0] for p in masks.polygons], size)
     elif dtype == list:
         if type(masks[0]) == dict:
             return _rle_to_bool(masks)
         elif type(masks[0]) == list or type(masks[0]) == np.ndarray:
             assert size is not None
-            return _rle_to_bool(masks_to_rle(PolygonMasks([[p] for p in masks]), size))
+            return _poly2mask(masks, size)
         else:
             raise NotImplementedError
     elif dtype == RLEMasks:

@@ -327,6 +327,13 @@ int ampis_poly_to_rle(const double *d_xy, const int64_t *d_xy_off, const uint32_
                       const uint32_t *d_w, int32_t n, uint32_t *d_cnt, const int64_t *d_cnt_off,
                       int32_t *d_cnt_len, void *stream);
 
+/* skimage.draw.polygon2mask as used by structures._poly2mask (structures.py:693-715, reached from
+ * masks_to_bitmask_array(PolygonMasks), structures.py:743-747): pixel (r, c) is set when the
+ * crossing-number test of skimage's _pnpoly.pxd holds for (x = c, y = r).  d_xy holds x0,y0,x1,y1,...
+ * of all polygons (the same layout as ampis_poly_to_rle).  d_out: u8[n][h][w], zeroed here. */
+int ampis_polygon2mask(const double *d_xy, const int64_t *d_xy_off, int32_t n, int32_t h, int32_t w,
+                       uint8_t *d_out, void *stream);
+
 /* ---- synthetic micrograph generator (bench / test data only; HOST code, host buffers) ----
  * Deterministic powder-like images: per image n_gt primary blobs followed by n_sec secondary
  * masks (kind 0: predictions of the primaries -- jitter, scale, drop_frac dropped and replaced

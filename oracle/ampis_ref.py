@@ -477,3 +477,28 @@ def regionprops_one(mask):
             'major_axis_length': float(4 * np.sqrt(l1)), 'minor_axis_length': float(4 * np.sqrt(l2)),
             'orientation': float(orientation), 'perimeter': float(_perimeter4(img)),
             'solidity': area / convex_area, 'label': 1}
+
+
+def poly2mask(polygons, size):
+    """structures.py:693-715 -- skimage.draw.polygon2mask of every [x0,y0,x1,y1,...] polygon:
+    draw.polygon's integer bounding range, skimage 0.18 _pnpoly crossing rule on (x = col, y = row)."""
+    out = np.zeros((len(polygons), size[0], size[1]), bool)
+    for k, p in enumerate(polygons):
+        p = np.asarray(p, float)
+        c, r = p[0::2], p[1::2]                       # vertex columns (x) and rows (y)
+        minr, maxr = int(max(0, r.min())), min(size[0] - 1, int(np.ceil(r.max())))
+        minc, maxc = int(max(0, c.min())), min(size[1] - 1, int(np.ceil(c.max())))
+        if maxr < minr or maxc < minc:
+            continue
+        yy, xx = np.mgrid[minr:maxr + 1, minc:maxc + 1]
+        x, y = xx.astype(float), yy.astype(float)
+        inside = np.zeros(x.shape, bool)
+        j = len(c) - 1
+        for i in range(len(c)):
+            cond = ((r[i] <= y) & (y < r[j])) | ((r[j] <= y) & (y < r[i]))
+            with np.errstate(divide='ignore', invalid='ignore'):
+                xi = (c[j] - c[i]) * (y - r[i]) / (r[j] - r[i]) + c[i]
+            inside ^= cond & (x < xi)
+            j = i
+        out[k, minr:maxr + 1, minc:maxc + 1] = inside
+    return out

@@ -717,3 +717,27 @@ def test_region_properties_vs_skimage_restatement(mods):
     assert list(df.columns) == ['centroid-0', 'centroid-1', 'bbox-0', 'bbox-1', 'bbox-2', 'bbox-3', 'class_idx']
     with pytest.raises(NotImplementedError):
         iset.compute_rprops(keys=['euler_number'])
+
+
+def test_polygon_bitmasks_follow_skimage_rule(mods):
+    """masks_to_bitmask_array(PolygonMasks / list of polygons) == polygon2mask restatement, bit for bit
+    (shipped VIA polygons and random polygons incl. ones sticking out of the frame); and it is NOT
+    the pycocotools rasterisation masks_to_rle uses -- both behaviours are the reference's."""
+    S, R = mods.structures, mods.R
+    from ampis_b200.containers import PolygonMasks
+    p = U.load('powder_polygons.npz')
+    xy, off = p['0_poly_xy'], p['0_poly_off']
+    size = tuple(int(v) for v in p['0_size'])
+    polys = [xy[off[i]:off[i + 1]] for i in range(60)]
+    got = S.masks_to_bitmask_array(PolygonMasks([[q] for q in polys]), size)
+    want = R.poly2mask(polys, size)
+    assert got.dtype == np.bool_ and got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(S.masks_to_bitmask_array([list(q) for q in polys[:5]], size), want[:5])
+    via_rle = S.masks_to_bitmask_array(S.masks_to_rle(PolygonMasks([[q] for q in polys]), size))
+    assert (via_rle != want).any() and abs(int(via_rle.sum()) - int(want.sum())) < 0.02 * want.sum()
+    rng = np.random.default_rng(17)
+    h, w = 45, 60
+    rnd = [np.round(rng.uniform(-10, 70, size=2 * rng.integers(3, 12)) * 2) / 2 for _ in range(40)]
+    assert np.array_equal(S.masks_to_bitmask_array(rnd, (h, w)), R.poly2mask(rnd, (h, w)))
+    with pytest.raises(AssertionError):
+        S.masks_to_bitmask_array(PolygonMasks([[polys[0]]]))
