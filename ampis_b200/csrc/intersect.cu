@@ -62,32 +62,7 @@ __device__ __forceinline__ u32 warp_intersect(const uint4 *__restrict__ A, const
     return warp_sum(acc);
 }
 
-// CROP layout: popcount(A & B) over the overlap of two bounding-box windows.  A window stores, for
-// every column of the box, the absolute 32-row bands (y0>>5)..(y1>>5); words of the same column
-// and band line up without shifts.  rb / cb: tight boxes (x0,y0,x1,y1) of the two masks, which
-// must overlap.  Lanes stride over the (column, band) pairs of the overlap.
-__device__ __forceinline__ u32 warp_intersect_crop(const u32 *__restrict__ A, const int4 rb,
-                                                   const u32 *__restrict__ B, const int4 cb, u32 lane)
-{
-    const u32 xa = (u32)max(rb.x, cb.x), xb = (u32)min(rb.z, cb.z);
-    const u32 rw0 = (u32)rb.y >> 5, rw1 = (u32)rb.w >> 5, cw0 = (u32)cb.y >> 5, cw1 = (u32)cb.w >> 5;
-    const u32 wa = max(rw0, cw0), wb = min(rw1, cw1);
-    const u32 nw = wb - wa + 1u, total = (xb - xa + 1u) * nw;
-    const u32 rn = rw1 - rw0 + 1u, cn = cw1 - cw0 + 1u;
-    const u32 *A0 = A + (xa - (u32)rb.x) * rn + (wa - rw0);
-    const u32 *B0 = B + (xa - (u32)cb.x) * cn + (wa - cw0);
-    u32 dx = lane / nw, dw = lane - dx * nw;
-    const u32 sdx = 32u / nw, sdw = 32u - sdx * nw;
-    u32 acc = 0;
-    for (u32 idx = lane; idx < total; idx += 32) {
-        acc += __popc(__ldg(A0 + dx * rn + dw) & __ldg(B0 + dx * cn + dw));
-        dw += sdw; dx += sdx;
-        if (dw >= nw) { dw -= nw; dx++; }
-    }
-    return warp_sum(acc);
-}
-
-template <int MODE, bool CROP>
+template <int MODE>
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32, 6)
 intersect_rows_kernel(const RowArgs p)
 {
@@ -113,8 +88,8 @@ intersect_rows_kernel(const RowArgs p)
         const int rm = p.row_mask[r];
         rb = p.bbox[rm];
         ra = p.area[rm];
-        if (CROP) A = p.bits + p.bits_off[rm];
-        else { rs = p.span[rm]; A = p.bits + p.bits_off[rm] - p.reg[rm].x; }
+        rs = p.span[rm];
+        A = p.bits + p.bits_off[rm] - p.reg[rm].x;
     }
 
     // lane-local running best over the columns this lane owns (increasing index => first max)
@@ -129,8 +104,8 @@ intersect_rows_kernel(const RowArgs p)
             const int cm = cb + t0 + k;
             s_bbox[k] = p.bbox[cm];
             s_area[k] = p.area[cm];
-            if (CROP) s_base[k] = p.bits + p.bits_off[cm];
-            else { s_span[k] = p.span[cm]; s_base[k] = p.bits + p.bits_off[cm] - p.reg[cm].x; }
+            s_span[k] = p.span[cm];
+            s_base[k] = p.bits + p.bits_off[cm] - p.reg[cm].x;
         }
         __syncthreads();
         if (!valid) continue;
@@ -142,22 +117,17 @@ intersect_rows_kernel(const RowArgs p)
             if (k < tn && ra > 0) {
                 const int4 b = s_bbox[k];
                 ca = s_area[k];
-                cand = max(rb.x, b.x) <= min(rb.z, b.z) && max(rb.y, b.y) <= min(rb.w, b.w);
-                if (!CROP) { cs = s_span[k]; cand = cand && max(rs.x, cs.x) < min(rs.y, cs.y); }
+                cs = s_span[k];
+                cand = max(rb.x, b.x) <= min(rb.z, b.z) && max(rb.y, b.y) <= min(rb.w, b.w) &&
+                       max(rs.x, cs.x) < min(rs.y, cs.y);
             }
             u32 inter = 0;
             u32 todo = __ballot_sync(0xffffffffu, cand);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                u32 v;
-                if (CROP) {
-                    v = warp_intersect_crop(reinterpret_cast<const u32 *>(A), rb,
-                                            reinterpret_cast<const u32 *>(s_base[c0 + src]), s_bbox[c0 + src], lane);
-                } else {
-                    const uint2 ss = s_span[c0 + src];
-                    v = warp_intersect(A, s_base[c0 + src], max(rs.x, ss.x), min(rs.y, ss.y), lane);
-                }
+                const uint2 ss = s_span[c0 + src];
+                const u32 v = warp_intersect(A, s_base[c0 + src], max(rs.x, ss.x), min(rs.y, ss.y), lane);
                 if ((int)lane == src) inter = v;
             }
             if (k < tn) {
@@ -218,41 +188,10 @@ extern "C" int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_of
     a.grp_imat_off = d_grp_imat_off; a.imat = d_imat;
     a.best_col = d_best_col; a.best_inter = d_best_inter; a.best_score = d_best_score;
     if (mode == AMPIS_MODE_IOU)
-        intersect_rows_kernel<AMPIS_MODE_IOU, false><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
+        intersect_rows_kernel<AMPIS_MODE_IOU><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
     else
-        intersect_rows_kernel<AMPIS_MODE_SAT, false><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
+        intersect_rows_kernel<AMPIS_MODE_SAT><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
     AMPIS_CHECK_LAUNCH("intersect_rows_kernel");
-    return AMPIS_OK;
-}
-
-extern "C" int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
-                                         const uint32_t *d_area, const int32_t *d_row_mask,
-                                         const int32_t *d_blk_grp, const int32_t *d_blk_row0, int32_t n_blocks,
-                                         const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
-                                         const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
-                                         const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
-                                         int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
-                                         void *stream)
-{
-    AMPIS_REQUIRE(n_blocks >= 0, "n_blocks < 0");
-    AMPIS_REQUIRE(mode == AMPIS_MODE_IOU || mode == AMPIS_MODE_SAT, "bad mode");
-    if (n_blocks == 0) return AMPIS_OK;
-    AMPIS_REQUIRE(d_bits_off && d_bbox && d_area && d_row_mask && d_blk_grp && d_blk_row0 && d_grp_row_begin &&
-                      d_grp_row_count && d_grp_col_begin && d_grp_col_count && d_best_col && d_best_inter &&
-                      d_best_score, "null pointer");
-    RowArgs a;
-    a.bits = (const uint4 *)d_bits; a.bits_off = d_bits_off; a.reg = nullptr; a.span = nullptr;
-    a.bbox = (const int4 *)d_bbox; a.area = d_area;
-    a.row_mask = d_row_mask; a.blk_grp = d_blk_grp; a.blk_row0 = d_blk_row0;
-    a.grp_row_begin = d_grp_row_begin; a.grp_row_count = d_grp_row_count;
-    a.grp_col_begin = d_grp_col_begin; a.grp_col_count = d_grp_col_count;
-    a.grp_imat_off = d_grp_imat_off; a.imat = d_imat;
-    a.best_col = d_best_col; a.best_inter = d_best_inter; a.best_score = d_best_score;
-    if (mode == AMPIS_MODE_IOU)
-        intersect_rows_kernel<AMPIS_MODE_IOU, true><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
-    else
-        intersect_rows_kernel<AMPIS_MODE_SAT, true><<<n_blocks, ROWS_PER_CTA * 32, 0, as_stream(stream)>>>(a);
-    AMPIS_CHECK_LAUNCH("intersect_rows_kernel<crop>");
     return AMPIS_OK;
 }
 

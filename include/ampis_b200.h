@@ -164,7 +164,8 @@ int ampis_intersect_rows(const void *d_bits, const int64_t *d_bits_off, const ui
 
 /* The same kernel over AMPIS_LAYOUT_CROP tables: AND+popc only over the overlap of the two
  * bounding-box windows (words of the same column and the same 32-row band line up without
- * shifts because bands are absolute).  Same outputs, bit for bit. */
+ * shifts because bands are absolute).  Same outputs, bit for bit.  The column metadata is staged
+ * by TMA bulk copies: d_bbox, d_area and d_bits_off must be 16-byte aligned. */
 int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
                               const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_blk_grp,
                               const int32_t *d_blk_row0, int32_t n_blocks, const int32_t *d_grp_row_begin,
