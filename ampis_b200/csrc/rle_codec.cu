@@ -30,42 +30,85 @@ extern "C" int ampis_sm_count(void)
     return sms;
 }
 
-// One thread per mask: the format is a byte-serial varint stream with a second-order
-// delta (count i>2 is stored relative to count i-2), ~1.4 bytes per count and ~130
-// counts per mask, so a mask is ~200 dependent byte steps.  A batch has 10^5..10^6
-// masks, which is all the parallelism the chip needs; the strings are read through L1.
-__global__ void __launch_bounds__(128)
+// rleFrString, one WARP per mask, 32 characters per step.  The format is a
+// varint stream (5 payload bits per character, bit 0x20 = "more", bit 0x10 of the last character =
+// sign) with a second-order delta: count m > 2 is stored relative to count m-2.
+//   1. a ballot of the "last character of a number" flags splits the 32 characters into numbers;
+//   2. every character contributes payload << 5*(its position inside its number); the last lane of
+//      a number ORs the contributions of up to 6 lanes below it (a number that matters has at most
+//      7 characters: only the low 32 bits of the sum are kept, exactly what the reference's
+//      (uint) cast of its long keeps);
+//   3. numbers are compacted to the low lanes (__fns) and the delta is undone by a stride-2 warp
+//      scan (two interleaved chains; count 0 belongs to no chain: count 2 is stored absolute);
+//   4. a number cut by the 32-character boundary carries its partial value into the next step.
+// Reads and writes are coalesced; the previous thread-per-mask version spent its time in
+// 32-way divergent byte loads.
+__global__ void __launch_bounds__(256)
 rle_string_decode_kernel(const uint8_t *__restrict__ chars, const i64 *__restrict__ chr_off, int n,
                          u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off, int *__restrict__ cnt_len)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)((blockIdx.x * (u32)blockDim.x + threadIdx.x) >> 5);
     if (i >= n) return;
+    const u32 lane = lane_id();
+    const u32 lt = (1u << lane) - 1u;
     const uint8_t *s = chars + chr_off[i];
     const i64 len = chr_off[i + 1] - chr_off[i];
     u32 *out = cnt + cnt_off[i];
-    i64 p = 0;
-    int m = 0;
-    long long prev1 = 0, prev2 = 0;   // cnts[m-1], cnts[m-2]
-    while (p < len) {
-        long long x = 0;
-        int k = 0;
-        bool more = true;
-        while (more && p < len) {
-            long long c = (long long)s[p] - 48;
-            if (k < 12) x |= (c & 0x1f) << (5 * k);
-            more = (c & 0x20) != 0;
-            p++;
-            k++;
-            if (!more && (c & 0x10) && k < 12) x |= (long long)(~0ULL << (5 * k));
+    u32 m_base = 0;                       // numbers emitted so far
+    u32 carry_x = 0, carry_k = 0;         // partial number continued from the previous step
+    u32 carry_e = 0, carry_o = 0;         // last value of the even / odd delta chain (count 0 excluded)
+    for (i64 p0 = 0; p0 < len; p0 += 32) {
+        const i64 pos = p0 + lane;
+        const bool valid = pos < len;
+        const u32 c = valid ? (u32)s[pos] - 48u : 0u;
+        // a string that stops in the middle of a number still yields that number (as the serial code does)
+        const bool end = valid && (!(c & 0x20u) || pos == len - 1);
+        const u32 e_mask = __ballot_sync(0xffffffffu, end);
+        const u32 below = e_mask & lt;
+        const u32 k_in = lane - (below ? 32u - (u32)__clz(below) : 0u);      // characters of my number below me, this step
+        const u32 k = k_in + (below ? 0u : carry_k);                         // my position inside my number
+        const u32 contrib = (valid && k < 7u) ? (c & 0x1fu) << (5u * k) : 0u;
+        u32 x = contrib;
+#pragma unroll
+        for (u32 d = 1; d <= 6; d++) {
+            const u32 t = __shfl_up_sync(0xffffffffu, contrib, d);
+            if (d <= k_in) x |= t;
         }
-        if (m > 2) x += prev2;
-        u32 v = (u32)x;
-        out[m] = v;
-        prev2 = prev1;
-        prev1 = (long long)v;
-        m++;
+        if (!below) x |= carry_x;
+        if (end && !(c & 0x20u) && (c & 0x10u)) {
+            const u32 sh = 5u * (k + 1u);
+            if (sh < 32u) x |= 0xffffffffu << sh;
+        }
+        const u32 nn = __popc(e_mask);
+        // number t of this step sits in the lane of the (t+1)-th end flag
+        const u32 src = __fns(e_mask, 0, lane + 1);
+        const u32 xv = __shfl_sync(0xffffffffu, x, src & 31u);
+        const u32 m = m_base + lane;
+        const bool have = lane < nn;
+        u32 y = (have && m != 0) ? xv : 0u;
+#pragma unroll
+        for (u32 d = 2; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, y, d);
+            if (lane >= d) y += t;
+        }
+        const u32 w = y + ((m & 1u) ? carry_o : carry_e);
+        if (have) out[m] = m == 0 ? xv : w;
+        // chains continue from the last two numbers of this step
+        if (nn >= 1) {
+            const u32 w1 = __shfl_sync(0xffffffffu, w, nn - 1);
+            const u32 w2 = __shfl_sync(0xffffffffu, w, nn >= 2 ? nn - 2 : 0);
+            const u32 m1 = m_base + nn - 1;
+            if (m1 & 1u) { carry_o = w1; if (nn >= 2) carry_e = w2; }
+            else { carry_e = w1; if (nn >= 2) carry_o = w2; }
+        }
+        m_base += nn;
+        // characters above the last end flag start a number that finishes in a later step
+        const int last_end = e_mask ? 31 - __clz(e_mask) : -1;
+        const u32 tail = __reduce_or_sync(0xffffffffu, (int)lane > last_end ? contrib : 0u);
+        carry_x = (e_mask ? 0u : carry_x) | tail;
+        carry_k = (e_mask ? 0u : carry_k) + (u32)(31 - last_end);
     }
-    cnt_len[i] = m;
+    if (lane == 0) cnt_len[i] = (int)m_base;
 }
 
 __global__ void __launch_bounds__(128)
@@ -105,8 +148,8 @@ extern "C" int ampis_rle_string_decode(const uint8_t *d_chars, const int64_t *d_
     AMPIS_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_chars && d_chr_off && d_cnt && d_cnt_off && d_cnt_len, "null pointer");
-    rle_string_decode_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(d_chars, d_chr_off, n, d_cnt,
-                                                                            d_cnt_off, d_cnt_len);
+    rle_string_decode_kernel<<<(unsigned)(((i64)n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+        d_chars, d_chr_off, n, d_cnt, d_cnt_off, d_cnt_len);
     AMPIS_CHECK_LAUNCH("rle_string_decode_kernel");
     return AMPIS_OK;
 }

@@ -512,15 +512,33 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
     totals = torch.zeros(n_thr * 3, dtype=torch.int64, device=dev)
     spp_hist = torch.zeros(64, dtype=torch.int64, device=dev)
 
+    # the strings of launch group i+1 are uploaded on a copy stream while group i is evaluated:
+    # two device buffers, handed back and forth with events
+    copy_stream = torch.cuda.Stream(device=dev)
+    max_off = max(p[1].numel() for p in pinned)
+    bufs = [(d_chars, torch.empty(max_off, dtype=torch.int64, device=dev)),
+            (torch.empty_like(d_chars), torch.empty(max_off, dtype=torch.int64, device=dev))]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    max_masks = max(b.host.n_masks for b in subs)
+    d_cnt_len = torch.empty(max_masks, dtype=torch.int32, device=dev)
+
     def step():
         totals.zero_()
         spp_hist.zero_()
-        for (blob, off, b), (hc, hb, hs) in zip(pinned, h_out):
+        comp = torch.cuda.current_stream()
+        copy_stream.wait_stream(comp)                 # uploads of this step start inside the timed region
+        for i, ((blob, off, b), (hc, hb, hs)) in enumerate(zip(pinned, h_out)):
             n = b.host.n_masks
-            dc = d_chars[:blob.numel()]
-            dc.copy_(blob, non_blocking=True)
-            d_off = off.to(dev, non_blocking=True)
-            cnt_len = torch.empty(n, dtype=torch.int32, device=dev)
+            k = i & 1
+            dc, d_off = bufs[k][0][:blob.numel()], bufs[k][1][:off.numel()]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[k])    # the evaluation that last read this buffer has finished
+                dc.copy_(blob, non_blocking=True)
+                d_off.copy_(off, non_blocking=True)
+                ev_ready[k].record(copy_stream)
+            comp.wait_event(ev_ready[k])
+            cnt_len = d_cnt_len[:n]
             N.call('ampis_rle_string_decode', _p(dc), _p(d_off), n, _p(d_cnt), _p(d_off), _p(cnt_len), _s())
             t = engine.MaskTable(dev, n, d_cnt, d_off, cnt_len, b.h, b.w, layout)
             if args.unfused:
@@ -536,6 +554,7 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
             hc.copy_(counts, non_blocking=True)
             hb.copy_(rows.best_col[:b.groups.n_rows], non_blocking=True)
             hs.copy_(rows.best_score[:b.groups.n_rows], non_blocking=True)
+            ev_free[k].record(comp)
         red = totals if subs[0].mode == engine.MODE_IOU else spp_hist
         if world > 1:
             dist.all_reduce(red)
@@ -558,7 +577,8 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
     pairs = world * n_img * subs[0].host.n_rows * subs[0].host.n_cols
     return {'value': pairs * args.steps / (ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
             'd2h_bytes_per_step': int(d2h), 'ms_per_step': ms / args.steps,
-            'input': 'COCO-compressed RLE strings in pinned host memory, decoded on the GPU'}
+            'input': 'COCO-compressed RLE strings in pinned host memory, uploaded on a copy stream (double-buffered) '
+                     'and decoded on the GPU'}
 
 
 def cpu_baseline(args):
