@@ -45,8 +45,12 @@ def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False):
     """One image: rows x cols through the fused kernel. Returns host arrays + device handles."""
     _check_same_size(rows_rle, cols_rle)
     table = engine.table_from_rle(list(rows_rle) + list(cols_rle))
-    groups = engine.Groups.interleaved(table.device, [len(rows_rle)], [len(cols_rle)], dense=dense)
-    res = engine.intersect_rows(table, groups, mode)
+    # crowded images (operand fill above the measured crossover) go through the tensor-core contraction,
+    # everything else through the bbox-culled AND+popc walk; the results are identical
+    crowded = min(len(rows_rle), len(cols_rle)) >= engine.MMA_MIN_SIDE and \
+        engine.operand_fill(table) >= engine.MMA_FILL_THRESHOLD
+    groups = engine.Groups.interleaved(table.device, [len(rows_rle)], [len(cols_rle)], dense=dense or crowded)
+    res = engine.intersect(table, groups, mode, kernel='mma' if crowded else 'rows')
     return table, groups, res
 
 

@@ -305,6 +305,8 @@ def intersect_mma(table, groups, mode, out=None):
 #: operand fill above which the dense tensor-core contraction beats the culled AND+popc walk
 #: (measured crossover, profiles/crossover_r01.md)
 MMA_FILL_THRESHOLD = 0.30
+#: below this many rows / columns a 128 x 256 tile is mostly padding and the contraction cannot win
+MMA_MIN_SIDE = 64
 
 
 def operand_fill(table, groups=None):

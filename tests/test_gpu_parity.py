@@ -741,3 +741,25 @@ def test_polygon_bitmasks_follow_skimage_rule(mods):
     assert np.array_equal(S.masks_to_bitmask_array(rnd, (h, w)), R.poly2mask(rnd, (h, w)))
     with pytest.raises(AssertionError):
         S.masks_to_bitmask_array(PolygonMasks([[polys[0]]]))
+
+
+def test_public_api_takes_the_tensor_core_path_on_crowded_images(mods, monkeypatch):
+    """A crowded image (operand fill above engine.MMA_FILL_THRESHOLD) is evaluated by the tcgen05
+    contraction from the drop-in API; results equal the oracle like on the culled path."""
+    A, B, E, R, rle = mods.analyze, mods.batch, mods.engine, mods.R, mods.rle
+    cfg = dict(B.CONFIGS['dense_overlap'], h=128, w=128, n_rows=70, n_cols=90, median_diam=70.0)
+    host = B.synth(cfg, 1, 5)
+    rows, cols = host.image_masks(0)
+    gt, pr = _counts_to_rle(rle, rows, host.h, host.w), _counts_to_rle(rle, cols, host.h, host.w)
+    used = []
+    real = E.intersect
+    monkeypatch.setattr(E, 'intersect', lambda t, g, m, out=None, kernel='auto': (used.append(kernel), real(t, g, m, out, kernel))[1])
+    got = A.det_seg_scores(gt, pr, 0.5)
+    assert used == ['mma']
+    want = R.det_seg_scores(gt, pr, 0.5)
+    for k in want:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+    assert np.array_equal(A._piecewise_iou(gt, pr), R.piecewise_iou(gt, pr)) and used == ['mma', 'mma']
+    _, g2, p2 = U.powder_match_image(0)
+    A.rle_instance_matcher(g2, p2)
+    assert used[-1] == 'rows'
