@@ -66,7 +66,7 @@ def _gpu_match_counts(gt_lists, pred_lists, thresholds):
     masks = []
     for g, p in zip(gt_lists, pred_lists):
         masks += list(g) + list(p)
-    table = engine.table_from_rle(masks)
+    table = engine.table_from_rle(masks, layout=engine.LAYOUT_CROP)     # smallest storage, same results
     groups = engine.Groups.interleaved(table.device, [len(g) for g in gt_lists], [len(p) for p in pred_lists])
     rows = engine.intersect_rows(table, groups, engine.MODE_IOU)
     counts, _ = engine.match_counts(rows, groups, thresholds)
@@ -111,7 +111,7 @@ def _gpu_satellite_counts(part_lists, sat_lists, thresh, n_bins):
     masks = []
     for p, s in zip(part_lists, sat_lists):
         masks += list(s) + list(p)
-    table = engine.table_from_rle(masks)
+    table = engine.table_from_rle(masks, layout=engine.LAYOUT_CROP)
     groups = engine.Groups.interleaved(table.device, [len(s) for s in sat_lists], [len(p) for p in part_lists])
     rows = engine.intersect_rows(table, groups, engine.MODE_SAT)
     counts, hist = engine.satellite_counts(table, rows, groups, thresh, n_bins)

@@ -135,3 +135,54 @@ def test_sharded_gpu_pipeline_single_rank():
     from oracle import cocomask as rle
     areas = np.concatenate([rle.area(g) for g in gts]).astype(np.int64)
     assert np.array_equal(D.area_histogram_sharded(gts, 0, 50, 8), np.bincount(np.clip(areas // 50, 0, 7), minlength=8))
+
+
+def _nccl_worker(rank, world, port, n_img, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from ampis_b200 import distributed as D
+    gts, prs = _dataset(n_img)
+    th = [0.5, 0.75]
+    r = D.evaluate_sharded(gts, prs, th)                     # GPU pipeline on this rank's device + NCCL all-reduce
+    s = D.satellites_sharded(prs, gts, 0.3, 16)
+    h = D.area_histogram_sharded(gts, 0, 50, 8)
+    q.put((rank, r['totals'], r['per_image'], r['index'], {k: v for k, v in s.items() if k != 'index'}, h))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_two_rank_nccl_on_two_gpus():
+    """Same check as the gloo test with the real thing: two processes, two GPUs, the CUDA pipeline on
+    each shard and NCCL for the reduction / gather.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    n_img = 7
+    gts, prs = _dataset(n_img)
+    th = [0.5, 0.75]
+    want = _oracle_counts(gts, prs, th)
+    want_sat, want_hist = _oracle_sat(prs, gts, 0.3, 16)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, n_img, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    from oracle import cocomask as rle
+    areas = np.concatenate([rle.area(g) for g in gts]).astype(np.int64)
+    for rank, totals, per_image, index, sat, hist in sorted(res, key=lambda x: x[0]):
+        assert np.array_equal(index, np.arange(rank, n_img, 2))
+        assert np.array_equal(totals, want.sum(axis=0)) and np.array_equal(per_image, want)
+        assert sat['n_satellites'] == want_sat[:, 0].sum() and sat['n_satellited_particles'] == want_sat[:, 2].sum()
+        assert np.array_equal(sat['spp_hist'], want_hist)
+        assert np.array_equal(hist, np.bincount(np.clip(areas // 50, 0, 7), minlength=8))
