@@ -31,6 +31,11 @@ CONFIGS = {
     # C4: 2048x2048 spheroidite, 5000 x 5000 small elongated instances
     'c4_spheroidite': dict(h=2048, w=2048, n_rows=5000, n_cols=5000, kind=0, median_diam=13.5, sigma_ln=0.6,
                            max_aspect=3.0, sec_median_diam=0.0, mode=engine.MODE_IOU),
+    # C5: the whole synthetic dataset (10,000 C2 images) split over the ranks of one box -- strong scaling;
+    # the all-reduce carries TP/FP/FN and a binned area histogram (size distribution)
+    'c5_dataset': dict(h=1024, w=1024, n_rows=500, n_cols=500, kind=0, median_diam=34.0, sigma_ln=0.45,
+                       max_aspect=1.3, sec_median_diam=0.0, mode=engine.MODE_IOU, dataset_images=10000,
+                       area_bins=4096, area_bin_width=64),
     # crowded frame: 512 x 512 large overlapping instances in 256x256 px (about a quarter of all pairs have
     # overlapping boxes) -- the regime of the tensor-core contraction (engine.intersect_mma), not a
     # BASELINE.json config
@@ -152,8 +157,9 @@ class Pipeline(object):
     fused measure+paint -> intersect rows -> counts."""
 
     def __init__(self, batch, layout, arena, rows_out=None, thresholds=COCO_THRESHOLDS, totals=None,
-                 sat_thresh=0.5, fused=True, kernel='rows'):
+                 sat_thresh=0.5, fused=True, kernel='rows', area_hist=None, area_bin_width=64):
         dev = batch.device
+        self.area_hist, self.area_bin_width = area_hist, area_bin_width     # optional int64 histogram (+=)
         self.batch, self.layout, self.arena, self.fused = batch, layout, arena, fused
         assert kernel in ('rows', 'mma')
         self.kernel = kernel        # 'rows': bbox-culled AND+popc; 'mma': dense int8 tcgen05 contraction
@@ -200,6 +206,8 @@ class Pipeline(object):
         else:
             self.counts, _ = engine.satellite_counts(t, self.rows, self.batch.groups, self.sat_thresh,
                                                      hist=self.spp_hist, counts=self.counts_buf)
+        if self.area_hist is not None:
+            engine.hist_u32(t.area[:t.n], 0, self.area_bin_width, self.area_hist.numel(), hist=self.area_hist)
         if mark: mark(4)
 
 

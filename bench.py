@@ -227,11 +227,17 @@ class LayoutRun(object):
                                          torch.empty(max(b.groups.imat_size for b in self.subs), dtype=torch.int32,
                                                      device=dev))
         self.thresholds = batch.COCO_THRESHOLDS
-        self.totals = torch.zeros(len(self.thresholds) * 3, dtype=torch.int64, device=dev)
+        cfg = batch.CONFIGS[args.config]
+        n_tot = len(self.thresholds) * 3
+        # one int64 payload for the all-reduce: TP/FP/FN x thresholds [+ binned area histogram]
+        self.payload = torch.zeros(n_tot + cfg.get('area_bins', 0), dtype=torch.int64, device=dev)
+        self.totals = self.payload[:n_tot]
+        self.area_hist = self.payload[n_tot:] if cfg.get('area_bins') else None
         self.kernel = args.kernel
-        self.mode = batch.CONFIGS[args.config]['mode']
+        self.mode = cfg['mode']
         self.pipes = [batch.Pipeline(b, layout, self.arena, self.rows_out, self.thresholds, self.totals,
-                                     fused=self.fused, kernel=args.kernel) for b in self.subs]
+                                     fused=self.fused, kernel=args.kernel, area_hist=self.area_hist,
+                                     area_bin_width=cfg.get('area_bin_width', 64)) for b in self.subs]
         if self.mode != 0:
             for p in self.pipes[1:]:
                 p.spp_hist = self.pipes[0].spp_hist
@@ -239,7 +245,7 @@ class LayoutRun(object):
 
     def launch_all(self, record=None):
         import torch
-        self.totals.zero_()
+        self.payload.zero_()
         if self.mode != 0:
             self.pipes[0].spp_hist.zero_()
         for p in self.pipes:
@@ -270,7 +276,7 @@ class LayoutRun(object):
         else:
             self.launch_all(record)
         if world > 1:       # TP/FP/FN x thresholds (or the satellites-per-particle histogram): the only exchange
-            dist.all_reduce(self.totals if self.mode == 0 else self.pipes[0].spp_hist)
+            dist.all_reduce(self.payload if self.mode == 0 else self.pipes[0].spp_hist)
         return self.totals
 
     def timed(self, args, world, dist, sync):
@@ -372,6 +378,11 @@ def main():
         torch.cuda.synchronize()
 
     cfg = batch.CONFIGS[args.config]
+    strong = 'dataset_images' in cfg
+    if strong:          # a fixed dataset split over the ranks (strong scaling); every rank gets its share
+        total_images = cfg['dataset_images']
+        args.images = total_images // world + (1 if rank < total_images % world else 0)
+    job_images = cfg['dataset_images'] if strong else world * args.images        # images all ranks evaluate per step
     layout = {'full': engine.LAYOUT_FULL, 'span': engine.LAYOUT_SPAN, 'crop': engine.LAYOUT_CROP}[args.layout]
     per_image = cfg['n_rows'] + cfg['n_cols']
     B_m = ((cfg['h'] * cfg['w'] + 127) // 128) * 16
@@ -409,8 +420,8 @@ def main():
             srun.capture()
         sms, skt, stot = srun.timed(args, world, dist, sync)
         assert np.array_equal(stot, final_totals), 'span and full layouts disagree'
-        span = {'value': world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (sms / 1e3), 'unit': UNIT,
-                'images_per_s': world * args.images * args.steps / (sms / 1e3), 'ms_per_step': sms / args.steps,
+        span = {'value': job_images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (sms / 1e3), 'unit': UNIT,
+                'images_per_s': job_images * args.steps / (sms / 1e3), 'ms_per_step': sms / args.steps,
                 'images_per_launch': srun.sub, 'roofline': roofline_of(args, cfg, srun, sms, skt, world),
                 'note': 'same inputs and bit-identical results; only first..last 1-pixel of each mask is stored'}
         if not args.no_e2e:
@@ -425,8 +436,8 @@ def main():
             crun.capture()
         cms, ckt, ctot = crun.timed(args, world, dist, sync)
         assert np.array_equal(ctot, final_totals), 'crop and full layouts disagree'
-        crop = {'value': world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (cms / 1e3), 'unit': UNIT,
-                'images_per_s': world * args.images * args.steps / (cms / 1e3), 'ms_per_step': cms / args.steps,
+        crop = {'value': job_images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (cms / 1e3), 'unit': UNIT,
+                'images_per_s': job_images * args.steps / (cms / 1e3), 'ms_per_step': cms / args.steps,
                 'images_per_launch': crun.sub, 'roofline': roofline_of(args, cfg, crun, cms, ckt, world),
                 'stored_bytes_per_image': crun.stored_chunks * 16 / args.images,
                 'note': 'same inputs and bit-identical results; only the bounding-box window of each mask is '
@@ -441,21 +452,23 @@ def main():
 
     host0 = run.subs[0].host
     n_masks = args.images * per_image
-    value = world * args.images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (ms / 1e3)
+    value = job_images * cfg['n_rows'] * cfg['n_cols'] * args.steps / (ms / 1e3)
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u32', 'data': 'synthetic',
-        'images_per_s': world * args.images * args.steps / (ms / 1e3),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
+        'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
+        'images_per_s': job_images * args.steps / (ms / 1e3),
         'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
                    'layout': args.layout, 'intersection_kernel': args.kernel, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
                    'runs_per_mask': run.total_runs / n_masks,
                    'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
                          'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
                                                                           run.stored_chunks * 16 / len(run.subs) / 1e9),
-                   'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN per step' % world},
+                   'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN%s per step' % (
+                       world, ' + %d-bin area histogram' % cfg['area_bins'] if cfg.get('area_bins') else '')},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
-        'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel == 'mma' else 0))),
+        'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel == 'mma' else 0) +
+                                                            (1 if cfg.get('area_bins') else 0))),
         ('totals_tp_fp_fn_at_0.50' if cfg['mode'] == 0 else 'sat_matched_unmatched_satellited_particles+spp_hist'): final_totals[0].tolist(),
         'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},
     }
