@@ -321,13 +321,10 @@ extern "C" int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits
     AMPIS_REQUIRE(d_bits && d_bits_off && d_reg && d_span && d_row_mask && d_tile_grp && d_tile_m0 && d_tile_n0 &&
                       d_grp_row_begin && d_grp_row_count && d_grp_col_begin && d_grp_col_count && d_grp_imat_off &&
                       d_imat, "null pointer");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(intersect_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             MMA_SMEM_BYTES);
-        if (e != cudaSuccess) { ampis_set_error("intersect_mma_kernel smem: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
-        configured = true;
-    }
+    // per launch: the attribute is per device, and a process may drive more than one
+    cudaError_t e = cudaFuncSetAttribute(intersect_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MMA_SMEM_BYTES);
+    if (e != cudaSuccess) { ampis_set_error("intersect_mma_kernel smem: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     MmaArgs a;
     a.bits = (const uint4 *)d_bits; a.bits_off = d_bits_off; a.reg = (const uint2 *)d_reg;
     a.span = (const uint2 *)d_span; a.row_mask = d_row_mask;

@@ -200,13 +200,9 @@ extern "C" int ampis_poly_to_rle(const double *d_xy, const int64_t *d_xy_off, co
     if (n == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_xy && d_xy_off && d_h && d_w && d_cnt && d_cnt_off && d_cnt_len, "null pointer");
     const size_t smem = (size_t)(POLY_MAX_VERTS + 1 + 2 * POLY_MAX_CROSS) * sizeof(u32);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(poly_to_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) { ampis_set_error("poly smem attr: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
-        configured = true;
-    }
+    // per launch: the attribute is per device, and a process may drive more than one
+    cudaError_t e = cudaFuncSetAttribute(poly_to_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ampis_set_error("poly smem attr: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     poly_to_rle_kernel<<<n, POLY_THREADS, smem, as_stream(stream)>>>(d_xy, d_xy_off, d_h, d_w, d_cnt, d_cnt_off,
                                                                     d_cnt_len);
     AMPIS_CHECK_LAUNCH("poly_to_rle_kernel");
