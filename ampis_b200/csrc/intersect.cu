@@ -18,7 +18,7 @@
 //   * Candidates are then intersected four at a time, eight lanes per candidate: 128-bit loads of
 //     both packed masks over the overlap of their spans, AND + popc, 8-lane reduction -- so the
 //     loads of four candidates are in flight together instead of one exposed round trip each
-//     (61 % of the stall samples of the first version, profiles/kernels_r01c.md).  Long overlaps
+//     (61 % of the stall samples of the first version, ncu stall sampling, round 1).  Long overlaps
 //     take the whole warp.
 //   * The dense row of the intersection matrix is zero-filled with coalesced stores during the
 //     scan; candidates patch their cells.

@@ -1,7 +1,7 @@
 // Intersection rows over AMPIS_LAYOUT_CROP tables, second generation (same outputs as
 // intersect_rows_kernel: analyze.py:149-164 / powder.py:80-86 semantics, see intersect.cu).
 //
-// What bounded the first version (profiles/kernels_r01c.md): 61 % of the stall samples were loads
+// What bounded the first version (ncu source-level stall sampling, round 1): 61 % of the stall samples were loads
 // -- every candidate pair cost one exposed global round trip, one after another, and every CTA
 // re-staged the column metadata through registers.  Here
 //   * the column metadata of the image (tight boxes, areas, arena offsets: three contiguous arrays)

@@ -3,8 +3,9 @@
 
     python profiles/summarize.py <tag>      # e.g. r01
 
-Reads  gpurun_out/launches_<tag>_{full,span}.csv         (ncu --metrics gpu__time_duration.sum)
-       gpurun_out/{paint,rows}_<tag>_{full,span}.ncu-rep (ncu --set full)
+Reads  gpurun_out/launches_<tag>_{full,span,crop}.csv         (ncu --metrics gpu__time_duration.sum)
+       gpurun_out/{paint,rows}_<tag>_{full,span,crop}.ncu-rep (ncu --set full)
+       gpurun_out/mma_<tag>.ncu-rep                           (ncu --set full of the tcgen05 contraction)
 Writes profiles/launches_<tag>_<layout>.md, profiles/kernels_<tag>.md and updates profiles/traffic.json
 (per-launch dram bytes of the hot kernels, read by bench.py for roofline.traffic).
 """
@@ -96,7 +97,7 @@ def main():
           'Command: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 6 -c 2 python '
           'bench.py --steps 2 --warmup 3 --images 182 --sub 91 --layout <layout> --no-e2e --no-cpu --no-span` '
           '(c2_powder_batch: 91 images = 91,000 masks of 1024x1024 per launch).', '']
-    for layout in ('full', 'span'):
+    for layout in ('full', 'span', 'crop'):
         launches(tag, layout)
         for kern in ('paint', 'rows'):
             path = os.path.join(OUT, '%s_%s_%s.ncu-rep' % (kern, tag, layout))
@@ -119,6 +120,34 @@ def main():
             traffic['c2_powder_batch/%s/%s' % (layout, kern)] = {
                 'bytes_per_launch': rd + wr, 'images_per_launch': 91, 'bytes_per_image': (rd + wr) / 91,
                 'source': 'profiles/kernels_%s.md' % tag}
+    mpath = os.path.join(OUT, 'mma_%s.ncu-rep' % tag)
+    if os.path.exists(mpath):
+        extra = ['sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active',
+                 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+                 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+        METRICS.extend(m for m in extra if m not in METRICS)
+        ms = rep_metrics(mpath)
+        if ms:
+            md += ['## %s (int8 tcgen05 contraction), C2 frames' % ms[0]['kernel'], '',
+                   'Command (profiles/run_ncu_mma.sh): `ncu --set full --clock-control none --import-source on -k '
+                   'regex:intersect_mma -s 3 -c 2 python bench.py --images 37 --kernel mma --layout full --no-cpu '
+                   '--no-span --no-e2e --steps 2 --warmup 3` (37 images x 8 tiles of 128x256 = 296 CTAs = two waves, '
+                   '8192 slabs of 128 pixels per tile).', '',
+                   '| metric | ' + ' | '.join('launch %d' % i for i in range(len(ms))) + ' |', '|---|' + '---|' * len(ms)]
+            for m in METRICS:
+                if m in ms[0]:
+                    md.append('| %s | ' % m + ' | '.join(
+                        ('%.6g' % x[m]) if isinstance(x.get(m), float) else str(x.get(m)) for x in ms) + ' |')
+            t = sum(x['gpu__time_duration.sum'] for x in ms) / len(ms)
+            ops = 2.0 * 37 * 250000 * 1024 * 1024
+            md += ['', 'per launch: %.3f ms for 2*G*P*H*W = %.3g integer ops -> %.0f TOP/s algorithmic (%.0f executed with '
+                   'the 512x512 tile padding); tensor pipe (IMMA) active %.1f %% of cycles; DRAM %.0f MB.' % (
+                       t * 1e3, ops, ops / t / 1e12, ops / t / 1e12 * (512 * 512) / (500 * 500),
+                       ms[0]['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'],
+                       (ms[0]['dram__bytes_read.sum'] + ms[0]['dram__bytes_write.sum']) / 1e6),
+                   'SASS (`cuobjdump -sass ampis_b200/libampis_b200.so`): `UTCIMMA` (tcgen05.mma kind::i8), `UTCBAR` '
+                   '(tcgen05.commit), `LDTM.x32` (tcgen05.ld), `UBLKCP` (cp.async.bulk in the rows kernels), '
+                   '`SYNCS.*` (mbarrier).', '']
     open(os.path.join(PROF, 'kernels_%s.md' % tag), 'w').write('\n'.join(md) + '\n')
     json.dump(traffic, open(tpath, 'w'), indent=1, sort_keys=True)
     print('\n'.join(md))
