@@ -27,8 +27,8 @@ SIGNATURES = {
     'ampis_exclusive_scan_i64': (C.c_int, [_p, _p, _i64, _p, C.c_size_t, _p]),
     'ampis_rle_decode_packed': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     'ampis_unpack_bool_nrc': (C.c_int, [_p, _p, _p, _p, _i32, _u32, _u32, _p, _p]),
-    'ampis_bool_area_bbox': (C.c_int, [_p, _i32, _u32, _u32, _p, _p, _p]),
-    'ampis_pack_bool_nrc': (C.c_int, [_p, _i32, _u32, _u32, _p, _p, _p]),
+    'ampis_bool_area_bbox': (C.c_int, [_p, _i32, _u32, _u32, _i32, _p, _p, _p]),
+    'ampis_pack_bool_nrc': (C.c_int, [_p, _i32, _u32, _u32, _i32, _p, _p, _p]),
     'ampis_rows_per_block': (C.c_int, []),
     'ampis_intersect_rows': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p,
                                        _p, _p, _p]),

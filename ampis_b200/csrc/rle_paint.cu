@@ -445,6 +445,7 @@ extern "C" int ampis_unpack_bool_nrc(const void *d_bits, const int64_t *d_bits_o
 
 // ---- bool[n][h][w] -> packed (FULL layout) -------------------------------------------------
 // Thread per output 32-bit word: gathers 32 pixels of one or two columns.
+template <bool Y_MAJOR>
 __global__ void __launch_bounds__(256)
 pack_bool_nrc_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, uint4 *__restrict__ bits,
                      const i64 *__restrict__ bits_off)
@@ -460,14 +461,16 @@ pack_bool_nrc_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, uint4 *__r
     u32 x = (u32)(p / h), y = (u32)(p - (u64)x * h);
 #pragma unroll 4
     for (int b = 0; b < 32; b++) {
-        if (p + b < hw && m[(u64)y * w + x]) v |= 1u << b;
+        // Y_MAJOR: the array is stored [n][w][h] (a transposed view of a Fortran-ordered stack, what
+        // RLE.decode returns), i.e. already in COCO pixel order
+        if (p + b < hw && (Y_MAJOR ? m[p + b] : m[(u64)y * w + x])) v |= 1u << b;
         if (++y == h) { y = 0; x++; }
     }
     reinterpret_cast<u32 *>(bits + bits_off[k])[wi] = v;
 }
 
-extern "C" int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w, void *d_bits,
-                                   const int64_t *d_bits_off, void *stream)
+extern "C" int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w, int32_t y_major,
+                                   void *d_bits, const int64_t *d_bits_off, void *stream)
 {
     AMPIS_REQUIRE(n >= 0, "n < 0");
     if (n == 0 || h == 0 || w == 0) return AMPIS_OK;
@@ -475,28 +478,58 @@ extern "C" int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h
     AMPIS_REQUIRE(n <= 65535, "at most 65535 masks per call");
     const u64 nwords = (((u64)h * w + 127) / 128) * 4;
     dim3 grid((unsigned)((nwords + 255) / 256), n);
-    pack_bool_nrc_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_masks, h, w, (uint4 *)d_bits, d_bits_off);
+    if (y_major)
+        pack_bool_nrc_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(d_masks, h, w, (uint4 *)d_bits, d_bits_off);
+    else
+        pack_bool_nrc_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(d_masks, h, w, (uint4 *)d_bits, d_bits_off);
     AMPIS_CHECK_LAUNCH("pack_bool_nrc_kernel");
     return AMPIS_OK;
 }
 
 // ---- bool[n][h][w] -> area + tight bbox ------------------------------------------------------
+// The array is [n][h][w] (x fastest) or, with y_major, [n][w][h] (y fastest: a transposed view of a
+// Fortran-ordered stack).  Threads read 16 bytes at a time along the fastest axis when rows allow it.
 __global__ void __launch_bounds__(256)
-bool_area_bbox_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, u64 *__restrict__ area,
+bool_area_bbox_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, int y_major, u64 *__restrict__ area,
                       int *__restrict__ bbox)
 {
     const int k = blockIdx.x;
     const u64 hw = (u64)h * w;
     const uint8_t *m = masks + (u64)k * hw;
-    u32 a = 0, x0 = 0xffffffffu, y0 = 0xffffffffu, x1 = 0, y1 = 0;
-    for (u64 p = threadIdx.x; p < hw; p += blockDim.x) {
-        if (m[p]) {
-            const u32 y = (u32)(p / w), x = (u32)(p - (u64)y * w);
-            a++;
-            x0 = min(x0, x); x1 = max(x1, x + 1);
-            y0 = min(y0, y); y1 = max(y1, y + 1);
+    const u32 inner = y_major ? h : w;                  // length of the fastest axis
+    u32 a = 0, i0 = 0xffffffffu, o0 = 0xffffffffu, i1 = 0, o1 = 0;      // inner / outer coordinate ranges
+    if ((inner & 15u) == 0 && (((uintptr_t)m) & 15u) == 0) {
+        const uint4 *m4 = reinterpret_cast<const uint4 *>(m);
+        for (u64 q = threadIdx.x; q < hw / 16; q += blockDim.x) {
+            const uint4 v = m4[q];
+            if ((v.x | v.y | v.z | v.w) == 0u) continue;
+            const u64 p = q * 16;
+            const u32 o = (u32)(p / inner), ib = (u32)(p - (u64)o * inner);
+            const u32 wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if ((wv[j] >> (8 * b)) & 0xffu) {
+                        const u32 i = ib + 4u * j + b;
+                        a++;
+                        i0 = min(i0, i); i1 = max(i1, i + 1);
+                    }
+                }
+            }
+            o0 = min(o0, o); o1 = max(o1, o + 1);
+        }
+    } else {
+        for (u64 p = threadIdx.x; p < hw; p += blockDim.x) {
+            if (m[p]) {
+                const u32 o = (u32)(p / inner), i = (u32)(p - (u64)o * inner);
+                a++;
+                i0 = min(i0, i); i1 = max(i1, i + 1);
+                o0 = min(o0, o); o1 = max(o1, o + 1);
+            }
         }
     }
+    u32 x0 = y_major ? o0 : i0, x1 = y_major ? o1 : i1, y0 = y_major ? i0 : o0, y1 = y_major ? i1 : o1;
     __shared__ u32 sa[8], sx0[8], sy0[8], sx1[8], sy1[8];
     a = warp_sum(a); x0 = warp_min(x0); y0 = warp_min(y0); x1 = warp_max(x1); y1 = warp_max(y1);
     const u32 wid = threadIdx.x >> 5;
@@ -513,13 +546,13 @@ bool_area_bbox_kernel(const uint8_t *__restrict__ masks, u32 h, u32 w, u64 *__re
     }
 }
 
-extern "C" int ampis_bool_area_bbox(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w,
+extern "C" int ampis_bool_area_bbox(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w, int32_t y_major,
                                     uint64_t *d_area, int32_t *d_bbox, void *stream)
 {
     AMPIS_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_masks && d_area && d_bbox, "null pointer");
-    bool_area_bbox_kernel<<<n, 256, 0, as_stream(stream)>>>(d_masks, h, w, (u64 *)d_area, d_bbox);
+    bool_area_bbox_kernel<<<n, 256, 0, as_stream(stream)>>>(d_masks, h, w, y_major, (u64 *)d_area, d_bbox);
     AMPIS_CHECK_LAUNCH("bool_area_bbox_kernel");
     return AMPIS_OK;
 }

@@ -7,6 +7,7 @@ import json
 from pathlib import Path
 
 import numpy as np
+import torch
 
 from . import engine
 from .containers import BoxMode
@@ -28,7 +29,8 @@ def extract_boxes(masks, mask_mode='detectron2', box_mode='detectron2'):
     boxes = np.zeros((masks.shape[0], 4), dtype=dtype)
     if masks.shape[0] == 0:
         return boxes
-    area, bb = engine.bool_area_bbox(np.ascontiguousarray(masks != 0))
+    # bool input is uploaded as it is; anything else is reduced to "non-zero" first (numpy truthiness)
+    area, bb = engine.bool_area_bbox(masks if masks.dtype in (np.bool_, np.uint8) else masks != 0)
     ne = area > 0
     x1, y1, x2, y2 = bb[ne, 0], bb[ne, 1], bb[ne, 2], bb[ne, 3]
     if box_mode == 'detectron2':
@@ -51,11 +53,12 @@ def compress_pred(pred):
     The reference encodes mask by mask with pycocotools on the CPU; here the whole ``n x h x w``
     stack is packed, run-length encoded and string-encoded on the GPU in one go."""
     masks = pred.pred_masks
-    if hasattr(masks, 'detach'):                       # torch bool [n, h, w], possibly already on the GPU
-        masks = masks.detach().to('cpu').numpy()
+    if hasattr(masks, 'detach'):                       # torch bool [n, h, w]: encoded on the device it lives on
+        masks = masks.detach()
+        pred.pred_masks = engine.encode_bool(masks.to(torch.bool)) if len(masks) else []
     else:
         masks = np.stack([_to_numpy(x) for x in masks]) if len(masks) else np.zeros((0, 1, 1), bool)
-    pred.pred_masks = engine.encode_bool(masks.astype(np.bool_)) if len(masks) else []
+        pred.pred_masks = engine.encode_bool(masks.astype(np.bool_)) if len(masks) else []
     pred.pred_boxes = _to_numpy(pred.pred_boxes)
     pred.scores = _to_numpy(pred.scores)
     pred.pred_classes = _to_numpy(pred.pred_classes)

@@ -30,8 +30,13 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+#: host arrays up to this size are staged through a pinned copy (asynchronous upload); larger ones are copied
+#: straight from pageable memory -- allocating hundreds of MB of pinned memory per call costs more than it saves
+PIN_LIMIT_BYTES = 8 << 20
+
+
 def _dev(a, dtype, device):
-    """numpy array -> device tensor of the given torch dtype (async copy from pinned memory)."""
+    """numpy array -> device tensor of the given torch dtype."""
     t = torch.from_numpy(np.ascontiguousarray(a))
     if t.dtype != dtype:
         t = t.to(dtype)
@@ -39,6 +44,8 @@ def _dev(a, dtype, device):
         return torch.empty(0, dtype=dtype, device=device)
     if torch.device(device).type != 'cuda':
         return t.clone()
+    if t.numel() * t.element_size() > PIN_LIMIT_BYTES:
+        return t.to(device)
     return t.pin_memory().to(device, non_blocking=True)
 
 
@@ -434,15 +441,45 @@ def unpack_bool(table, ids, h, w):
     return out.view(torch.bool)
 
 
+def _stack_memory(a):
+    """bool/uint8 [n, h, w] host array -> (flat uint8 memory, y_major).  The two layouts that occur --
+    C order, and the transposed view of a Fortran-ordered h x w x n stack that RLE.decode(...)
+    .transpose(2, 0, 1) yields (memory [n][w][h]) -- are uploaded as they are; anything else is
+    copied to C order first."""
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    assert a.ndim == 3 and a.dtype == np.uint8
+    if a.flags.c_contiguous:
+        return a.reshape(-1), 0
+    t = a.transpose(0, 2, 1)
+    if t.flags.c_contiguous:
+        return t.reshape(-1), 1
+    return np.ascontiguousarray(a).reshape(-1), 0
+
+
+def to_host(t):
+    """Device tensor -> numpy array.  Large results land in pinned memory (PyTorch caches the
+    allocation, so repeated calls pay for it once): a pageable read-back of a few hundred MB runs at a
+    fraction of the link rate."""
+    if t.numel() * t.element_size() <= PIN_LIMIT_BYTES:
+        return t.cpu().numpy()
+    view_bool = t.dtype == torch.bool
+    src = t.view(torch.uint8) if view_bool else t
+    host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    host.copy_(src)
+    out = host.numpy()
+    return out.view(np.bool_) if view_bool else out
+
+
 def bool_area_bbox(masks_np):
     """bool[n, h, w] host array -> (uint64 areas, int32 tight boxes x0,y0,x1,y1) on the host."""
     dev = require_cuda()
-    m = np.ascontiguousarray(masks_np).view(np.uint8)
-    n, h, w = m.shape
-    d = _dev(m.reshape(-1), torch.uint8, dev)
+    flat, y_major = _stack_memory(masks_np)
+    n, h, w = masks_np.shape
+    d = _dev(flat, torch.uint8, dev)
     area = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     bbox = torch.empty(4 * max(n, 1), dtype=torch.int32, device=dev)
-    N.call('ampis_bool_area_bbox', _p(d), n, h, w, _p(area), _p(bbox), _stream())
+    N.call('ampis_bool_area_bbox', _p(d), n, h, w, y_major, _p(area), _p(bbox), _stream())
     return area[:n].cpu().numpy().view(np.uint64), bbox[:4 * n].cpu().numpy().reshape(-1, 4)
 
 
@@ -525,22 +562,28 @@ def frames_to_rle(bits, n, h, w):
     return [{'size': [int(h), int(w)], 'counts': s} for s in strings]
 
 
-def encode_bool(masks_np):
-    """bool/uint8 [n, h, w] host array -> list of COCO RLE dicts (RLE.encode of the Fortran-ordered
-    h x w x n stack, data_utils.py:275,423): pack, run-length encode and string-encode on the GPU."""
+def encode_bool(masks):
+    """bool/uint8 [n, h, w] host array OR CUDA tensor -> list of COCO RLE dicts (RLE.encode of the
+    Fortran-ordered h x w x n stack, data_utils.py:275,423): pack, run-length encode and string-encode
+    on the GPU.  A CUDA tensor (model output) is encoded where it is -- no round trip through the host."""
     dev = require_cuda()
-    m = np.ascontiguousarray(masks_np)
-    if m.dtype == np.bool_:
-        m = m.view(np.uint8)
-    assert m.ndim == 3 and m.dtype == np.uint8
-    n, h, w = m.shape
-    if n == 0:
-        return []
+    y_major = 0
+    if isinstance(masks, torch.Tensor):
+        assert masks.dim() == 3 and masks.dtype in (torch.bool, torch.uint8)
+        n, h, w = (int(v) for v in masks.shape)
+        if n == 0:
+            return []
+        d = masks.to(dev).contiguous().view(torch.uint8).reshape(-1)
+    else:
+        n, h, w = masks.shape
+        if n == 0:
+            return []
+        flat, y_major = _stack_memory(np.asarray(masks))
+        d = _dev(flat, torch.uint8, dev)
     chunks = (h * w + 127) // 128
-    d = _dev(m.reshape(-1), torch.uint8, dev)
     bits = torch.empty(4 * n * chunks, dtype=torch.int32, device=dev)
     d_off = torch.arange(n, dtype=torch.int64, device=dev) * chunks
-    N.call('ampis_pack_bool_nrc', _p(d), n, h, w, _p(bits), _p(d_off), _stream())
+    N.call('ampis_pack_bool_nrc', _p(d), n, h, w, y_major, _p(bits), _p(d_off), _stream())
     return frames_to_rle(bits, n, h, w)
 
 

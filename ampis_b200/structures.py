@@ -321,7 +321,7 @@ def _rle_to_bool(rle):
     for m in rle:
         if list(m['size']) != [h, w]:
             raise ValueError('all masks must share one image size')
-    return engine.unpack_bool(t, np.arange(len(rle)), int(h), int(w)).cpu().numpy()
+    return engine.to_host(engine.unpack_bool(t, np.arange(len(rle)), int(h), int(w)))
 
 
 def _poly2mask(masks, size):

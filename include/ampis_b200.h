@@ -127,13 +127,14 @@ int ampis_unpack_bool_nrc(const void *d_bits, const int64_t *d_bits_off, const u
                           uint8_t *d_out, void *stream);
 
 /* bool[n][h][w] -> area (u64) and tight bbox (mask_areas on ndarray, structures.py:558-560;
- * extract_boxes, data_utils.py:229-239). */
-int ampis_bool_area_bbox(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w,
+ * extract_boxes, data_utils.py:229-239).  y_major != 0: the memory is [n][w][h] (row index fastest),
+ * the layout behind RLE.decode(...).transpose(2,0,1) -- accepted as it is, no host-side re-layout. */
+int ampis_bool_area_bbox(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w, int32_t y_major,
                          uint64_t *d_area, int32_t *d_bbox, void *stream);
 
 /* bool[n][h][w] (row-major) -> packed FULL-layout bits (RLE.encode producer side,
  * data_utils.py:275,423): region of mask i is chunk 0..ceil(h*w/128) at d_bits_off[i]. */
-int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w,
+int ampis_pack_bool_nrc(const uint8_t *d_masks, int32_t n, uint32_t h, uint32_t w, int32_t y_major,
                         void *d_bits, const int64_t *d_bits_off, void *stream);
 
 /* ---- intersection / IoU rows ----------------------------------------------------
