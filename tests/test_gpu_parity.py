@@ -763,3 +763,73 @@ def test_public_api_takes_the_tensor_core_path_on_crowded_images(mods, monkeypat
     _, g2, p2 = U.powder_match_image(0)
     A.rle_instance_matcher(g2, p2)
     assert used[-1] == 'rows'
+
+
+def _host_csr_from_bool(B, masks_per_image, n_rows, h, w, rle):
+    """list of bool[n_rows + n_cols, h, w] stacks -> batch.HostCSR (run counts via the oracle encoder)."""
+    cnts = []
+    for stack in masks_per_image:
+        for m in stack:
+            cnts.append(rle.counts_from_string(rle.encode(np.asfortranarray(m.astype(np.uint8)))['counts']))
+    lens = np.array([len(c) for c in cnts], np.int32)
+    off = np.zeros(len(cnts), np.int64)
+    if len(cnts) > 1:
+        off[1:] = np.cumsum(lens[:-1])
+    n_cols = masks_per_image[0].shape[0] - n_rows
+    cfg = dict(h=h, w=w, n_rows=n_rows, n_cols=n_cols, kind=0, mode=0)
+    return B.HostCSR(cfg, len(masks_per_image), np.concatenate(cnts).astype(np.uint32), off, lens)
+
+
+@pytest.mark.parametrize('seed', range(int(os.environ.get('AMPIS_FUZZ_SEEDS', '4'))))      # soak: AMPIS_FUZZ_SEEDS=200
+def test_randomised_batches_all_layouts_and_kernels_vs_dense_numpy(mods, seed):
+    """Randomised sweep over frame shapes (1x1 .. odd sizes, not multiples of 32 or 128), mask kinds
+    (blobs, full frames, empty, single pixels, stripes that wrap column ends, noise) and group shapes:
+    every layout (span / full / crop, fused and unfused construction) and both intersection kernels
+    against a dense numpy formulation (bool AND + sum), independent of the run-walk oracle."""
+    B, E, rle, torch = mods.batch, mods.engine, mods.rle, mods.torch
+    rng = np.random.default_rng(1000 + seed)
+    for trial in range(6):
+        h, w = int(rng.integers(1, 150)), int(rng.integers(1, 150))
+        G, Pn, n_img = int(rng.integers(1, 40)), int(rng.integers(1, 70)), int(rng.integers(1, 4))
+        stacks = []
+        for _ in range(n_img):
+            m = U.rand_masks(rng, G + Pn, h, w, p_empty=0.15)
+            kind = rng.integers(0, 6, G + Pn)
+            for i, k in enumerate(kind):
+                if k == 0:
+                    m[i] = True
+                elif k == 1:
+                    m[i] = False
+                    m[i, rng.integers(0, h), rng.integers(0, w)] = True
+                elif k == 2:
+                    m[i] = False
+                    m[i, :, rng.integers(0, w):] = True           # full-height stripe: runs wrap column ends
+                elif k == 3:
+                    m[i] = rng.random((h, w)) < 0.5
+            stacks.append(m)
+        host = _host_csr_from_bool(B, stacks, G, h, w, rle)
+        dev = B.DeviceBatch(host, dense=True)
+        want_I = np.stack([(s[:G, None].astype(np.int64) * s[None, G:].astype(np.int64)).sum(axis=(2, 3)) for s in stacks])
+        area = np.stack([s.sum(axis=(1, 2)) for s in stacks]).astype(np.int64)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            iou = np.where(want_I > 0, want_I / (area[:, :G, None] + area[:, None, G:] - want_I), 0.0)
+        want_best = np.where(iou.max(axis=2) > 0, iou.argmax(axis=2), -1)
+        ref = None
+        for layout in (E.LAYOUT_SPAN, E.LAYOUT_FULL, E.LAYOUT_CROP):
+            for fused in (False, True):
+                arena = None
+                if fused:
+                    arena = torch.empty(4 * max(B.arena_chunks_needed(dev, layout), 1), dtype=torch.int32, device='cuda')
+                kernels = ('rows',) if layout == E.LAYOUT_CROP else ('rows', 'mma')
+                for kernel in kernels:
+                    r = B.eval_step(dev, layout=layout, check=True, arena=arena, kernel=kernel)
+                    I = r.rows.imat.cpu().numpy()[:n_img * G * Pn].reshape(n_img, G, Pn)
+                    tag = (trial, h, w, G, Pn, layout, fused, kernel)
+                    assert np.array_equal(I, want_I), tag
+                    assert np.array_equal(r.rows.best_col.cpu().numpy()[:n_img * G].reshape(n_img, G), want_best), tag
+                    assert np.array_equal(r.rows.best_score.cpu().numpy()[:n_img * G].reshape(n_img, G), iou.max(axis=2)), tag
+                    assert np.array_equal(r.table.area.cpu().numpy()[:n_img * (G + Pn)].reshape(n_img, -1), area), tag
+                    if ref is None:
+                        ref = r.counts.cpu().numpy()
+                    else:
+                        assert np.array_equal(r.counts.cpu().numpy(), ref), tag
