@@ -668,6 +668,11 @@ def _check_rprops(got, want):
         for k in w:
             if k in ('area', 'bbox', 'bbox_area', 'convex_area', 'label'):
                 assert g[k] == w[k], (i, k, g[k], w[k])             # integers: exact
+            elif k == 'orientation':
+                # an axis direction: +pi/2 and -pi/2 are the same line, and which one the float pipeline of
+                # skimage lands on for an exactly axis-aligned shape depends on the sign of a ~1e-17 residue
+                d = (g[k] - w[k] + np.pi / 2) % np.pi - np.pi / 2
+                assert abs(d) < 1e-6, (i, k, g[k], w[k])
             else:                                                   # derived floats: 1e-6 (north_star)
                 assert np.allclose(g[k], w[k], rtol=1e-6, atol=1e-6), (i, k, g[k], w[k])
 
@@ -833,3 +838,56 @@ def test_randomised_batches_all_layouts_and_kernels_vs_dense_numpy(mods, seed):
                         ref = r.counts.cpu().numpy()
                     else:
                         assert np.array_equal(r.counts.cpu().numpy(), ref), tag
+
+
+@pytest.mark.parametrize('seed', range(int(os.environ.get('AMPIS_FUZZ_SEEDS', '3'))))
+def test_randomised_measurement_kernels_vs_oracle(mods, seed):
+    """Randomised sweep of the kernels either side of the matching path on odd frame shapes: RLE
+    encoder, string codec round trip, connected components / label instances, region properties,
+    polygon rasterisers, boundary distances, pixel-class maps."""
+    A, E, S, R, D, rle = mods.analyze, mods.engine, mods.structures, mods.R, mods.data_utils, mods.rle
+    rng = np.random.default_rng(7000 + seed)
+    for trial in range(3):
+        h, w, n = int(rng.integers(1, 140)), int(rng.integers(1, 140)), int(rng.integers(2, 24))
+        a = U.rand_masks(rng, n, h, w, p_empty=0.1)
+        a[0] = rng.random((h, w)) < 0.5
+        a[1] = True
+        tag = (seed, trial, h, w, n)
+        # encoder (both memory layouts) + decoder round trip
+        want = rle.encode(np.asfortranarray(a.transpose(1, 2, 0).astype(np.uint8)))
+        assert [m['counts'] for m in E.encode_bool(a)] == [m['counts'] for m in want], tag
+        y_major = np.asfortranarray(a.transpose(1, 2, 0)).transpose(2, 0, 1)          # the RLE.decode layout
+        assert [m['counts'] for m in E.encode_bool(y_major)] == [m['counts'] for m in want], tag
+        assert np.array_equal(S.masks_to_bitmask_array(want), a), tag
+        assert np.array_equal(D.extract_boxes(y_major), R.extract_boxes(a)), tag
+        # label images: connected components of the union and arbitrary label values
+        union = a[2:].any(axis=0)
+        for binary, img in ((True, union), (False, (rng.integers(0, 5, (h, w)) * rng.integers(1, 300)).astype(np.int64))):
+            got, bb = E.label_image_to_instances(img, binary=binary)
+            wl = R.annotations_from_label_image(img, binary=binary)
+            assert [m['counts'] for m in got] == [m['counts'] for _, m in wl], tag
+            if wl:
+                assert np.array_equal(bb.astype(np.float64), np.stack([b for b, _ in wl])), tag
+        # region properties
+        got, wantp = S.region_properties(want), [R.regionprops_one(x) for x in a]
+        _check_rprops(got, wantp)
+        # polygons: pycocotools rule (RLE) and skimage rule (bitmask)
+        polys = [np.round(rng.uniform(-5, max(h, w) + 5, size=2 * rng.integers(3, 9)) * 2) / 2 for _ in range(6)]
+        from ampis_b200.containers import PolygonMasks
+        assert [m['counts'] for m in S.masks_to_rle(PolygonMasks([[p] for p in polys]), (h, w))] == \
+            [m['counts'] for m in R.polygons_to_rle([[p] for p in polys], (h, w))], tag
+        assert np.array_equal(S.masks_to_bitmask_array(polys, (h, w)), R.poly2mask(polys, (h, w))), tag
+        # boundary distances and pixel classes of "matches" between shifted copies
+        b = np.roll(a, 1, axis=2)
+        b[:, :, 0] = False
+        eb = rle.encode(np.asfortranarray(b.transpose(1, 2, 0).astype(np.uint8)))
+        pairs = np.array([[i, i] for i in range(n) if a[i].any() and b[i].any()]).reshape(-1, 2)
+        boxes = np.tile(np.array([0, h, 0, w]), (n, 1))
+        if len(pairs):
+            fp, fn = A.mask_edge_distance(want, eb, boxes, boxes, pairs)
+            wfp, wfn = R.mask_edge_distance(want, eb, boxes, boxes, pairs)
+            assert all(np.array_equal(x.numpy(), y) for x, y in zip(fp + fn, wfp + wfn)), tag
+            for mode in ('reduced', 'all'):
+                iset, _ = A.seg_perf_iset(want, eb, {'tp': pairs}, mode=mode)
+                assert [m['counts'] for m in iset.instances.masks.rle] == \
+                    [m['counts'] for m in R.seg_perf_masks(want, eb, pairs, mode)], tag
