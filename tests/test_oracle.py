@@ -209,3 +209,74 @@ def test_match_edge_cases():
     assert res['particles_unmatched'].tolist() == [1] and res['match_pairs'] == {0: [1]}
     with pytest.raises(IndexError):
         R.rle_satellite_match([half], [z], 0.5)
+
+
+def test_regionprops_restatement_closed_forms():
+    """Known answers for the skimage restatement (oracle/ampis_ref.regionprops_one): filled rectangles
+    have closed-form moments, skimage's 4-neighbourhood perimeter of an a x b rectangle is 2(a-1)+2(b-1),
+    a one-pixel-wide line of n pixels has perimeter n-2... (skimage documents perimeter(10x10 square) = 36)."""
+    from oracle import ampis_ref as R
+    m = np.zeros((40, 50), bool)
+    m[5:15, 10:20] = True                                         # 10 x 10 square
+    p = R.regionprops_one(m)
+    assert p['area'] == 100 and p['bbox'] == (5, 10, 15, 20) and p['bbox_area'] == 100
+    assert p['perimeter'] == 36.0 and p['convex_area'] == 100 and p['solidity'] == 1.0 and p['extent'] == 1.0
+    assert p['centroid'] == (9.5, 14.5) and p['local_centroid'] == (4.5, 4.5)
+    assert np.isclose(p['major_axis_length'], 4 * np.sqrt(99 / 12)) and np.isclose(p['minor_axis_length'], 4 * np.sqrt(99 / 12))
+    assert np.isclose(p['eccentricity'], 0.0, atol=1e-7) and np.isclose(p['equivalent_diameter'], np.sqrt(400 / np.pi))
+    m[:] = False
+    m[8:12, 3:33] = True                                          # 4 rows x 30 columns: long axis along the columns
+    p = R.regionprops_one(m)
+    assert p['perimeter'] == 2 * 3 + 2 * 29
+    assert np.isclose(p['major_axis_length'], 4 * np.sqrt((30 ** 2 - 1) / 12))
+    assert np.isclose(p['minor_axis_length'], 4 * np.sqrt((4 ** 2 - 1) / 12))
+    assert np.isclose(abs(p['orientation']), np.pi / 2)           # skimage: angle to the row axis
+    assert np.isclose(R.regionprops_one(m.T)['orientation'], 0.0)
+    m[:] = False
+    m[7, 2:12] = True                                             # a 10-pixel line
+    p = R.regionprops_one(m)
+    assert p['perimeter'] == 8.0 and p['convex_area'] == 10       # end pixels (one border neighbour) carry no weight
+    assert p['minor_axis_length'] == 0.0 and p['eccentricity'] == 1.0
+    m[:] = False
+    m[[3, 4, 4], [3, 3, 4]] = True                                # three-pixel corner: its hull holds no fourth pixel centre
+    assert R.regionprops_one(m)['convex_area'] == 3
+    m[:] = False
+    m[10:21, 10] = m[10, 10:21] = m[20, 10:21] = m[10:21, 20] = True      # hollow square ring: hull = filled square
+    p = R.regionprops_one(m)
+    assert p['area'] == 40 and p['convex_area'] == 121 and np.isclose(p['solidity'], 40 / 121)
+    assert R.regionprops_one(np.zeros((5, 5), bool)) == {}
+
+
+def test_polygon2mask_and_labelling_restatements_known_answers():
+    from oracle import ampis_ref as R
+    # an axis-aligned square with corners on pixel centres: the crossing rule keeps the top / left edges
+    sq = [2.0, 3.0, 6.0, 3.0, 6.0, 7.0, 2.0, 7.0]                 # x0,y0,... : x in [2,6], y in [3,7]
+    mask = R.poly2mask([sq], (10, 10))[0]
+    assert mask.sum() == 16 and mask[3:7, 2:6].all()
+    # 8-connectivity, raster numbering
+    img = np.array([[1, 0, 0, 1],
+                    [0, 1, 0, 1],
+                    [0, 0, 0, 0],
+                    [1, 1, 0, 1]], bool)
+    lab = R.label_binary(img)
+    assert lab.tolist() == [[1, 0, 0, 2], [0, 1, 0, 2], [0, 0, 0, 0], [3, 3, 0, 4]]
+    anns = R.annotations_from_label_image(img, binary=True)
+    assert [a[0].tolist() for a in anns] == [[0, 0, 1, 1], [3, 0, 3, 1], [0, 3, 1, 3], [3, 3, 3, 3]]
+    lab2 = np.array([[0, 7, 7], [3, 3, 0], [0, 0, 9]])
+    anns = R.annotations_from_label_image(lab2, binary=False)
+    assert [a[0].tolist() for a in anns] == [[0, 1, 1, 1], [1, 0, 2, 0], [2, 2, 2, 2]]       # values 3, 7, 9
+
+
+def test_edge_distance_and_class_maps_known_answers():
+    from oracle import ampis_ref as R
+    from oracle import cocomask as rle
+    g = np.zeros((8, 8), np.uint8)
+    p = np.zeros((8, 8), np.uint8)
+    g[2:6, 2:6] = 1
+    p[2:6, 3:7] = 1                                                # shifted one pixel to the right
+    ge, pe = [rle.encode(np.asfortranarray(g))], [rle.encode(np.asfortranarray(p))]
+    fp, fn = R.mask_edge_distance(ge, pe, [np.array([2, 6, 2, 6])], [np.array([2, 6, 3, 7])], np.array([[0, 0]]))
+    assert fp[0].tolist() == [1.0] * 4 and fn[0].tolist() == [1.0] * 4
+    masks = R.seg_perf_masks(ge, pe, np.array([[0, 0]]), 'reduced')
+    assert [int(rle.area(m)) for m in masks] == [12, 4, 4, 0]     # TP, FN, FP, overlap classes
+    assert R.merge_boxes([2, 6, 2, 6], [2, 6, 3, 7]).tolist() == [2, 6, 2, 7]
