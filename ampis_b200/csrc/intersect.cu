@@ -28,7 +28,7 @@
 #define ROWS_PER_CTA 8
 #define COL_TILE 512
 #define CAND_LIST 64
-#define LONG_OVERLAP 48       // chunks (768 B per operand) from which a candidate gets the whole warp
+#define LONG_OVERLAP 128      // chunks (2 KB per operand) from which a candidate gets the whole warp
 
 struct RowArgs {
     const uint4 *bits;

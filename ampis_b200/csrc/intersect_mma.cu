@@ -55,6 +55,8 @@ struct MmaArgs {
     const uint2 *reg;
     const uint2 *span;
     const int *row_mask;
+    const int *row_order;      // optional: position inside the group's sorted row list -> row index in the group
+    const int *col_order;      // optional, indexed by grp_col_begin + sorted position -> column index in the group
     const int *tile_grp, *tile_m0, *tile_n0;
     const int *grp_row_begin, *grp_row_count, *grp_col_begin, *grp_col_count;
     const i64 *grp_imat_off;
@@ -187,9 +189,16 @@ intersect_mma_kernel(const MmaArgs p)
     u32 lo = 0, hi = 0;
     const uint4 *src = nullptr;
     if (wid > 0) {
+        // tiles are cut from the SORTED row / column lists (by first occupied slab) when orders are given:
+        // masks of a tile are then neighbours in the image and the slab range of the tile shrinks
         int mask = -1;
-        if (!is_b) { if (m0 + (int)slot < G) mask = p.row_mask[rb + m0 + (int)slot]; }
-        else if (n0 + (int)(slot - MMA_TM) < P) mask = cb + n0 + (int)(slot - MMA_TM);
+        if (!is_b) {
+            const int pos = m0 + (int)slot;
+            if (pos < G) mask = p.row_mask[rb + (p.row_order ? p.row_order[rb + pos] : pos)];
+        } else {
+            const int pos = n0 + (int)(slot - MMA_TM);
+            if (pos < P) mask = cb + (p.col_order ? p.col_order[cb + pos] : pos);
+        }
         if (mask >= 0) {
             const uint2 sp = p.span[mask];
             lo = sp.x; hi = sp.y;
@@ -271,7 +280,8 @@ intersect_mma_kernel(const MmaArgs p)
         if (wid <= 8) {
             const i64 off = p.grp_imat_off[g];
             const u32 quarter = wid & 3u, half = (wid - 1u) >> 2;   // TMEM lanes 32*quarter.., columns 128*half..
-            const int row = m0 + (int)(32u * quarter + lane);
+            const int rpos = m0 + (int)(32u * quarter + lane);
+            const int row = (rpos < G && p.row_order) ? p.row_order[rb + rpos] : rpos;      // unsorted index for the output
             if (niter) {
                 mbar_wait(bar_acc, 0u);
                 tc_fence_after();
@@ -286,12 +296,12 @@ intersect_mma_kernel(const MmaArgs p)
 #pragma unroll
                     for (int t = 0; t < 32; t++) v[t] = 0u;
                 }
-                if (row < G) {
+                if (rpos < G) {
                     int *orow = p.imat + off + (i64)row * P;
 #pragma unroll
                     for (int t = 0; t < 32; t++) {
-                        const int c = n0 + (int)col0 + t;
-                        if (c < P) orow[c] = (int)(v[t] >> 7);
+                        const int cpos = n0 + (int)col0 + t;
+                        if (cpos < P) orow[p.col_order ? p.col_order[cb + cpos] : cpos] = (int)(v[t] >> 7);
                     }
                 }
             }
@@ -310,6 +320,7 @@ extern "C" int ampis_mma_tile_cols(void) { return MMA_TN; }
 
 extern "C" int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
                                        const uint32_t *d_span, const int32_t *d_row_mask,
+                                       const int32_t *d_row_order, const int32_t *d_col_order,
                                        const int32_t *d_tile_grp, const int32_t *d_tile_m0,
                                        const int32_t *d_tile_n0, int32_t n_tiles,
                                        const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
@@ -328,6 +339,7 @@ extern "C" int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits
     MmaArgs a;
     a.bits = (const uint4 *)d_bits; a.bits_off = d_bits_off; a.reg = (const uint2 *)d_reg;
     a.span = (const uint2 *)d_span; a.row_mask = d_row_mask;
+    a.row_order = d_row_order; a.col_order = d_col_order;
     a.tile_grp = d_tile_grp; a.tile_m0 = d_tile_m0; a.tile_n0 = d_tile_n0;
     a.grp_row_begin = d_grp_row_begin; a.grp_row_count = d_grp_row_count;
     a.grp_col_begin = d_grp_col_begin; a.grp_col_count = d_grp_col_count;

@@ -285,10 +285,45 @@ def intersect_rows(table, groups, mode, out=None):
     return out
 
 
-def intersect_mma(table, groups, mode, out=None):
+def _span_orders(table, groups):
+    """Per-group orders of the rows and of the columns by first occupied slab (device int32 arrays in
+    the index spaces ampis_intersect_tcgen05 expects).  Index plumbing with torch sorts; the masks
+    themselves are not touched."""
+    n = table.n
+    lo = table.span[:2 * n].view(n, 2)[:, 0].to(torch.int64) & 0xffffffff
+    if getattr(groups, '_col_grp', None) is None:
+        col_grp = np.full(n, -1, np.int64)          # group of every column mask (host bookkeeping, cached)
+        cb, cc = groups.grp_col_begin.cpu().numpy(), groups.h_col_count
+        for g in range(groups.n_groups):
+            col_grp[cb[g]:cb[g] + cc[g]] = g
+        groups._col_grp = _dev(col_grp, torch.int64, table.device)
+        groups._row_begin_of_row = groups.grp_row_begin.long()[groups.row_grp.long()]
+    # rows: sort (group, span start); group blocks stay where they are, subtract the block start
+    key_r = (groups.row_grp.long() << 32) | lo[groups.row_mask.long()]
+    row_order = (torch.argsort(key_r, stable=True) - groups._row_begin_of_row).to(torch.int32)
+    # columns: same over mask ids; non-column masks get the largest key and stay out of every block
+    cg = groups._col_grp
+    key_c = torch.where(cg >= 0, (cg << 32) | lo, torch.full_like(lo, 1 << 62))
+    order_c = torch.argsort(key_c, stable=True)               # sorted position -> mask id, grouped by image
+    n_cols = int((cg >= 0).sum().item()) if getattr(groups, '_n_cols', None) is None else groups._n_cols
+    groups._n_cols = n_cols
+    col_ids = order_c[:n_cols]
+    g_of = cg[col_ids]
+    begin = groups.grp_col_begin.long()[g_of]
+    # position of every sorted column inside its group: columns of a group are consecutive in the sort
+    first_of_group = torch.zeros(groups.n_groups + 1, dtype=torch.int64, device=table.device)
+    first_of_group[1:] = torch.cumsum(torch.from_numpy(groups.h_col_count).to(table.device), 0)
+    pos = torch.arange(n_cols, device=table.device) - first_of_group[g_of]
+    col_order = torch.zeros(max(n, 1), dtype=torch.int32, device=table.device)
+    col_order[begin + pos] = (col_ids - begin).to(torch.int32)
+    return row_order, col_order
+
+
+def intersect_mma(table, groups, mode, out=None, sort=True):
     """Dense intersection matrices by the int8 tcgen05 contraction (no pruning), then the per-row
     arg-max from the matrices.  Same RowResult as intersect_rows(), bit for bit; the choice
-    between the two is a cost decision."""
+    between the two is a cost decision.  sort=True cuts the tiles from rows / columns
+    ordered by position in the image, which shortens the pixel range each tile contracts."""
     dev = table.device
     assert table.layout != LAYOUT_CROP, 'the contraction reads linear packed masks (span or full layout)'
     nr = max(groups.n_rows, 1)
@@ -299,8 +334,10 @@ def intersect_mma(table, groups, mode, out=None):
                         torch.empty(nr, dtype=torch.float64, device=dev),
                         torch.empty(max(groups.imat_size, 1), dtype=torch.int32, device=dev))
     assert out.imat is not None
+    row_order, col_order = _span_orders(table, groups) if sort and groups.n_rows else (None, None)
     N.call('ampis_intersect_tcgen05', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
-           _p(groups.row_mask), _p(tile_grp), _p(tile_m0), _p(tile_n0), n_tiles, _p(groups.grp_row_begin),
+           _p(groups.row_mask), _p(row_order), _p(col_order), _p(tile_grp), _p(tile_m0), _p(tile_n0), n_tiles,
+           _p(groups.grp_row_begin),
            _p(groups.grp_row_count), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off),
            _p(out.imat), _stream())
     N.call('ampis_rows_from_imat', _p(out.imat), _p(groups.imat_off), _p(table.area), _p(groups.row_mask),
@@ -311,7 +348,7 @@ def intersect_mma(table, groups, mode, out=None):
 
 #: operand fill above which the dense tensor-core contraction beats the culled AND+popc walk
 #: (measured crossover, profiles/crossover_r01.md)
-MMA_FILL_THRESHOLD = 0.30
+MMA_FILL_THRESHOLD = 0.25
 #: below this many rows / columns a 128 x 256 tile is mostly padding and the contraction cannot win
 MMA_MIN_SIDE = 64
 

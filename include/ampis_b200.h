@@ -184,11 +184,17 @@ int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, con
  * culled AND+popc kernel is the one for sparse images ("choice of intersection kernel").
  * A tile is ampis_mma_tile_rows() x ampis_mma_tile_cols() cells of one group's matrix:
  *   tile_grp[t], tile_m0[t], tile_n0[t]   group and first row / first column of tile t
- * Every group with at least one tile must have a dense matrix (grp_imat_off[g] >= 0). */
+ * Every group with at least one tile must have a dense matrix (grp_imat_off[g] >= 0).
+ * Optional d_row_order / d_col_order (NULL = identity): tiles are cut from per-group SORTED lists --
+ * row_order[grp_row_begin[g] + pos] = row index inside group g, col_order[grp_col_begin[g] + pos] =
+ * column index inside group g.  Sorting by span start makes the masks of a tile neighbours in the image,
+ * so the slab range a tile has to contract (rows' range AND columns' range) shrinks; results are
+ * written at the unsorted indices. */
 int ampis_mma_tile_rows(void);
 int ampis_mma_tile_cols(void);
 int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
                             const uint32_t *d_span, const int32_t *d_row_mask,
+                            const int32_t *d_row_order, const int32_t *d_col_order,
                             const int32_t *d_tile_grp, const int32_t *d_tile_m0, const int32_t *d_tile_n0,
                             int32_t n_tiles, const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
                             const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
