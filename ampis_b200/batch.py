@@ -157,12 +157,13 @@ class Pipeline(object):
     fused measure+paint -> intersect rows -> counts."""
 
     def __init__(self, batch, layout, arena, rows_out=None, thresholds=COCO_THRESHOLDS, totals=None,
-                 sat_thresh=0.5, fused=True, kernel='rows', area_hist=None, area_bin_width=64):
+                 sat_thresh=0.5, fused=True, kernel='rows', area_hist=None, area_bin_width=64, mma_sort=True):
         dev = batch.device
         self.area_hist, self.area_bin_width = area_hist, area_bin_width     # optional int64 histogram (+=)
         self.batch, self.layout, self.arena, self.fused = batch, layout, arena, fused
         assert kernel in ('rows', 'mma')
         self.kernel = kernel        # 'rows': bbox-culled AND+popc; 'mma': dense int8 tcgen05 contraction
+        self.mma_sort = mma_sort    # tiles from spatially sorted masks (contracts fewer slabs on large frames)
         if kernel == 'mma':
             batch.groups.mma_tiles()
         self.table = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
@@ -197,7 +198,7 @@ class Pipeline(object):
             t.paint(self.arena)
         if mark: mark(2)
         if self.kernel == 'mma':
-            engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows)
+            engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows, sort=self.mma_sort)
         else:
             engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows)
         if mark: mark(3)

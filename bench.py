@@ -46,6 +46,9 @@ def parse():
     ap.add_argument('--kernel', default='rows', choices=['rows', 'mma'],
                     help='intersection kernel: rows = bbox-culled AND+popc (default); mma = dense int8 tcgen05 '
                          'contraction (for crowded images, e.g. --config dense_overlap)')
+    ap.add_argument('--mma-sort', action='store_true',
+                    help='with --kernel mma: cut the tiles from spatially sorted masks (fewer slabs contracted; the '
+                         'default contracts the full pixel range so that the tensor roofline counts executed work)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--graph', action='store_true', help='replay each step from a CUDA graph')
@@ -236,7 +239,8 @@ class LayoutRun(object):
         self.kernel = args.kernel
         self.mode = cfg['mode']
         self.pipes = [batch.Pipeline(b, layout, self.arena, self.rows_out, self.thresholds, self.totals,
-                                     fused=self.fused, kernel=args.kernel, area_hist=self.area_hist,
+                                     fused=self.fused, kernel=args.kernel, mma_sort=args.mma_sort,
+                                     area_hist=self.area_hist,
                                      area_bin_width=cfg.get('area_bin_width', 64)) for b in self.subs]
         if self.mode != 0:
             for p in self.pipes[1:]:
@@ -459,7 +463,7 @@ def main():
         'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
         'images_per_s': job_images * args.steps / (ms / 1e3),
         'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
-                   'layout': args.layout, 'intersection_kernel': args.kernel, 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
+                   'layout': args.layout, 'intersection_kernel': args.kernel + ('+sorted tiles' if args.kernel == 'mma' and args.mma_sort else ''), 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
                    'runs_per_mask': run.total_runs / n_masks,
                    'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
                          'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
@@ -558,8 +562,10 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
                 t.measure().paint(arena)
             else:
                 t.measure_paint(arena)
-            rows = (engine.intersect_mma if args.kernel == 'mma' else engine.intersect_rows)(
-                t, b.groups, b.mode, out=rows_out)
+            if args.kernel == 'mma':
+                rows = engine.intersect_mma(t, b.groups, b.mode, out=rows_out, sort=args.mma_sort)
+            else:
+                rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out)
             if b.mode == engine.MODE_IOU:
                 counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
             else:       # satellites: per-image (matched, unmatched, satellited particles, particles) + global histogram
