@@ -44,11 +44,15 @@ def _check_same_size(*mask_lists):
 def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False):
     """One image: rows x cols through the fused kernel. Returns host arrays + device handles."""
     _check_same_size(rows_rle, cols_rle)
-    table = engine.table_from_rle(list(rows_rle) + list(cols_rle))
-    # crowded images (operand fill above the measured crossover) go through the tensor-core contraction,
-    # everything else through the bbox-culled AND+popc walk; the results are identical
+    # measured as bounding-box windows (the smallest storage, the fastest culled walk) ...
+    table = engine.table_from_rle(list(rows_rle) + list(cols_rle), layout=engine.MATCH_LAYOUT, paint=False)
+    # ... unless the image is crowded (operand fill above the measured crossover): then linear spans and the
+    # tensor-core contraction.  The results are identical either way.
     crowded = min(len(rows_rle), len(cols_rle)) >= engine.MMA_MIN_SIDE and \
         engine.operand_fill(table) >= engine.MMA_FILL_THRESHOLD
+    if crowded and table.layout == engine.LAYOUT_CROP:
+        table.relayout(engine.LAYOUT_SPAN)
+    table.paint()
     groups = engine.Groups.interleaved(table.device, [len(rows_rle)], [len(cols_rle)], dense=dense or crowded)
     res = engine.intersect(table, groups, mode, kernel='mma' if crowded else 'rows')
     return table, groups, res

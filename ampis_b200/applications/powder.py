@@ -30,7 +30,7 @@ def _rle_satellite_match(particles, satellites, match_thresh=0.5):
         for m in list(particles) + list(satellites):
             if list(m['size']) != list(particles[0]['size']):
                 raise ValueError('particle and satellite masks must share one image size')
-        table = engine.table_from_rle(list(satellites) + list(particles))
+        table = engine.table_from_rle(list(satellites) + list(particles), layout=engine.MATCH_LAYOUT)
         groups = engine.Groups.interleaved(table.device, [S], [Np])
         res = engine.intersect_rows(table, groups, engine.MODE_SAT)
         best = res.best_col[:S].cpu().numpy().astype(np.int64)

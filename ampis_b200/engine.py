@@ -13,6 +13,8 @@ from . import _native as N
 LAYOUT_SPAN, LAYOUT_FULL, LAYOUT_CROP = N.LAYOUT_SPAN, N.LAYOUT_FULL, N.LAYOUT_CROP
 MODE_IOU, MODE_SAT = N.MODE_IOU, N.MODE_SAT
 DEFAULT_LAYOUT = LAYOUT_SPAN
+#: storage the matching / satellite functions of the drop-in API paint (crowded images switch to SPAN + contraction)
+MATCH_LAYOUT = LAYOUT_CROP
 
 
 def require_cuda():
@@ -106,6 +108,14 @@ class MaskTable(object):
         N.call('ampis_rle_measure_paint', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h), _p(self.w),
                self.n, self.layout, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
                _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor), _stream())
+        return self
+
+    def relayout(self, layout):
+        """Switch the storage layout of a measured, not yet painted table (re-derives the stored regions)."""
+        assert self.bits is None
+        if layout != self.layout:
+            self.layout = layout
+            self.measure()
         return self
 
     def check(self):

@@ -129,10 +129,10 @@ def test_bitmask_array_and_extract_boxes(mods):
         assert np.array_equal(D.extract_boxes(a), R.extract_boxes(a))
 
 
-@pytest.mark.parametrize('layout', ['span', 'full'])
+@pytest.mark.parametrize('layout', ['span', 'full', 'crop'])
 def test_golden_matching_all_images(mods, layout, monkeypatch):
     A, E = mods.analyze, mods.engine
-    monkeypatch.setattr(E, 'DEFAULT_LAYOUT', E.LAYOUT_FULL if layout == 'full' else E.LAYOUT_SPAN)
+    monkeypatch.setattr(E, 'MATCH_LAYOUT', {'full': E.LAYOUT_FULL, 'span': E.LAYOUT_SPAN, 'crop': E.LAYOUT_CROP}[layout])
     g = U.load('powder_match.npz')
     for k in range(len(g['names'])):
         _, gt, pr = U.powder_match_image(k)
