@@ -331,10 +331,14 @@ def roofline_of(args, cfg, run, ms, kt, world):
     dur_ms = kt[KERNELS.index(dom)] / ((2 if run.graph is not None else args.steps) * launches)
     achieved = alg[dom] / launches / (dur_ms / 1e3) / 1e9
     lay = {engine.LAYOUT_FULL: 'full', engine.LAYOUT_SPAN: 'span', engine.LAYOUT_CROP: 'crop'}[run.layout]
-    traffic = None
+    # DRAM bytes per launch of the dominant kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum of the
+    # capture summarised in profiles/), scaled from the captured images per launch to this run's
+    traffic, traffic_detail = None, None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get('%s/%s/%s' % (args.config, lay, dom))
+        traffic_detail = json.load(open(tp)).get('%s/%s/%s' % (args.config, lay, dom))
+        if traffic_detail:
+            traffic = traffic_detail['bytes_per_image'] * n_img / launches
     step_gbs = canonical_img * n_img * args.steps / (ms / 1e3) / 1e9
     if run.kernel == 'mma' and dom == 'rows':
         # dense contraction: 2*G*P*H*W integer ops per image, tensor-pipe bound
@@ -349,6 +353,7 @@ def roofline_of(args, cfg, run, ms, kt, world):
     pk = 'rle_paint_kernel' if args.unfused else 'rle_measure_paint_kernel'
     return {'bound': 'hbm', 'kernel': {'paint': pk, 'rows': 'intersect_rows_kernel'}[dom],
             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+            'traffic_detail': traffic_detail,
             'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom] / launches, 'launch_ms': dur_ms,
             'step_canonical': {'bytes_per_image': canonical_img, 'achieved': step_gbs, 'frac': step_gbs / peak,
                                'note': 'whole step per GPU vs the two-pass full-frame accounting of SURVEY 8d; '
