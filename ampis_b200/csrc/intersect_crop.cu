@@ -182,7 +182,7 @@ intersect_rows_crop_kernel(const CropRowArgs p)
             bool cand = false;
             if (k < tn) {
                 const int4 b = s_bbox[k];
-                cand = max(rb.x, b.x) <= min(rb.z, b.z) && max(rb.y, b.y) <= min(rb.w, b.w);
+                cand = b.x <= rb.z && b.z >= rb.x && b.y <= rb.w && b.w >= rb.y;      // boxes are non-empty here
             }
             const u32 bal = __ballot_sync(0xffffffffu, cand);
             if (cand) list[n + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)k;

@@ -273,16 +273,30 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
         }
         if (lane == 0) { s_span[team] = sp; s_reg[team] = rg; }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        i64 tot = 0;
-        for (int k = 0; k < MASKS; k++) { s_off[k] = tot; tot += (i64)(s_reg[k].y - s_reg[k].x); }
-        s_base = tot ? (i64)atomicAdd(cursor, (unsigned long long)tot) : 0;
+    i64 off;
+    if (TEAM_WARPS == 1) {
+        // a warp is its own team: it reserves its region with its own atomicAdd, no CTA-wide barrier
+        // (the two __syncthreads of the shared reservation were 21 % of this kernel's stall samples)
+        __syncwarp();
+        if (!valid) return;
+        unsigned long long o = 0;
+        if (lane == 0) {
+            const u32 sz = s_reg[team].y - s_reg[team].x;
+            o = sz ? atomicAdd(cursor, (unsigned long long)sz) : 0ull;
+        }
+        off = (i64)__shfl_sync(0xffffffffu, o, 0);
+    } else {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            i64 tot = 0;
+            for (int k = 0; k < MASKS; k++) { s_off[k] = tot; tot += (i64)(s_reg[k].y - s_reg[k].x); }
+            s_base = tot ? (i64)atomicAdd(cursor, (unsigned long long)tot) : 0;
+        }
+        __syncthreads();
+        if (!valid) return;
+        off = s_base + s_off[team];
     }
-    __syncthreads();
-    if (!valid) return;
     const uint2 rg = s_reg[team], sp = s_span[team];
-    const i64 off = s_base + s_off[team];
     if (off + (i64)(rg.y - rg.x) > capacity) {
         // arena exhausted: leave the mask empty so later kernels stay inside the arena; the
         // caller sees *cursor > capacity and retries (ampis_rle_measure_paint contract)
