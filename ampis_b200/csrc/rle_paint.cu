@@ -213,7 +213,11 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
             while (s < e) {
                 const u32 x = (u32)(s / H);
                 const u64 cs = (u64)x * H;
-                const u32 ys = (u32)(s - cs), ye = (u32)(min(e, cs + H) - cs);      // rows [ys,ye) of column x
+                // rows [ys,ye) of column x, clipped to the box rows (a well-formed mask never needs the clip;
+                // a malformed one -- flagged in status -- must not write outside its window)
+                const u32 ys = max((u32)(s - cs), (u32)bb.y), ye = min((u32)(min(e, cs + H) - cs), (u32)bb.w + 1u);
+                s = cs + H;
+                if (ye <= ys) continue;
                 u32 *col = tile + (x - xa) * nwy - wy0;
                 const u32 w0 = ys >> 5, w1 = (ye - 1) >> 5;
                 if (w0 == w1) {
@@ -223,7 +227,6 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
                     for (u32 w = w0 + 1; w < w1; w++) col[w] = 0xffffffffu;
                     atomicOr(&col[w1], bit_range(0u, ((ye - 1) & 31u) + 1u));
                 }
-                s = cs + H;
             }
         }
         __syncwarp();
