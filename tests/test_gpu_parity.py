@@ -277,6 +277,14 @@ def test_empty_and_error_conventions(mods):
         S.masks_to_rle(PolygonMasks([[np.array([1., 1, 5, 1, 5, 5])]]))
     with pytest.raises(ValueError):
         S.mask_areas([{'size': [6, 5], 'counts': rle.string_from_counts(np.array([3, 3], np.uint32))}])
+    # counts that overshoot the frame are flagged in every storage layout (and painted without writing outside
+    # the mask's region: the run below would reach far beyond a 45 x 37 frame)
+    good = _enc(rle, np.ones((45, 37)))
+    bad = [{'size': [45, 37], 'counts': rle.string_from_counts(np.array([3, 5000, 7, 900], np.uint32))}, good, good]
+    for lay in (mods.engine.LAYOUT_SPAN, mods.engine.LAYOUT_FULL, mods.engine.LAYOUT_CROP):
+        with pytest.raises(ValueError, match='malformed RLE'):
+            mods.engine.table_from_rle(bad, layout=lay)
+    assert S.mask_areas([good]).tolist() == [45 * 37]
 
 
 @pytest.mark.parametrize('cfg,n_img', [('c1_powder_example', 2), ('c2_powder_batch', 2)])
