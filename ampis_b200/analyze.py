@@ -213,47 +213,43 @@ def mask_edge_distance(gt_mask, pred_mask, gt_box, pred_box, matches, device='au
     return FP, FN
 
 
+_DET_COLORS = {'TP': (0.5, 0., 1.), 'FP': (0., 1., 1.), 'FN': (1., 0., 0.)}
+
+
+def _boxes_array(instances):
+    b = instances.boxes
+    return b if type(b) == np.ndarray else b.tensor.numpy()
+
+
 def det_perf_iset(gt, pred, match_results=None, colormap=None, tp_gt=False):
-    """Detection TP / FP / FN instances gathered in one InstanceSet for display
-    (analyze.py:502-586).  Host bookkeeping over the matcher's output."""
+    """Detection outcome of an image as one InstanceSet for display (analyze.py:502-586): the matched
+    instances (taken from the predictions, or from the ground truth with *tp_gt*), then the
+    unmatched predictions (FP), then the unmatched ground truth (FN), each group in its colour.
+    Returns ``(iset, colormap)`` when no colormap was passed, else ``iset``.  Host bookkeeping over
+    the matcher's output."""
     if match_results is None:
         match_results = rle_instance_matcher(gt, pred)
-    return_colormap = colormap is None
+    default_colors = colormap is None
+    if default_colors:
+        colormap = {k: np.asarray(v, np.float64) for k, v in _DET_COLORS.items()}
     size = gt.instances.image_size
-    gt_masks = masks_to_rle(gt.instances.masks, size)
-    pred_masks = masks_to_rle(pred.instances.masks, size)
-    gt_bbox = gt.instances.boxes if type(gt.instances.boxes) == np.ndarray else gt.instances.boxes.tensor.numpy()
-    pred_bbox = pred.instances.boxes if type(pred.instances.boxes) == np.ndarray \
-        else pred.instances.boxes.tensor.numpy()
-    if colormap is None:
-        colormap = {'TP': np.asarray([0.5, 0., 1.], np.float64),
-                    'FP': np.asarray([0., 1., 1.], np.float64),
-                    'FN': np.asarray([1., 0., 0.], np.float64)}
-    if tp_gt:
-        tp_idx = match_results['tp'][:, 0]
-        tp_masks = [gt_masks[i] for i in tp_idx]
-        tp_bbox = gt_bbox[tp_idx]
-    else:
-        tp_idx = match_results['tp'][:, 1]
-        tp_masks = [pred_masks[i] for i in tp_idx]
-        tp_bbox = pred_bbox[tp_idx]
-    tp_colors = np.tile(colormap['TP'], (len(tp_masks), 1))
-    fp_idx = match_results['fp']
-    fp_masks = [pred_masks[i] for i in fp_idx]
-    fp_bbox = pred_bbox[fp_idx]
-    fp_colors = np.tile(colormap['FP'], (len(fp_masks), 1))
-    fn_idx = match_results['fn']
-    fn_masks = [gt_masks[i] for i in fn_idx]
-    fn_bbox = gt_bbox[fn_idx]
-    fn_colors = np.tile(colormap['FN'], (len(fn_masks), 1))
-    masks = RLEMasks(tp_masks + fp_masks + fn_masks)
-    bbox = np.concatenate((tp_bbox, fp_bbox, fn_bbox), axis=0)
-    colors = np.concatenate((tp_colors, fp_colors, fn_colors), axis=0)
+    sources = {'gt': (masks_to_rle(gt.instances.masks, size), _boxes_array(gt.instances)),
+               'pred': (masks_to_rle(pred.instances.masks, size), _boxes_array(pred.instances))}
+    tp = match_results['tp']
+    parts = [('TP', 'gt', tp[:, 0]) if tp_gt else ('TP', 'pred', tp[:, 1]),
+             ('FP', 'pred', match_results['fp']),
+             ('FN', 'gt', match_results['fn'])]
+    masks, boxes, colors = [], [], []
+    for kind, side, idx in parts:
+        rles, bb = sources[side]
+        masks += [rles[i] for i in idx]
+        boxes.append(bb[idx])
+        colors.append(np.tile(colormap[kind], (len(idx), 1)))
+    masks = RLEMasks(masks)
     iset = InstanceSet()
-    iset.instances = Instances(image_size=masks.rle[0]['size'], **{'masks': masks, 'boxes': bbox, 'colors': colors})
-    if return_colormap:
-        return iset, colormap
-    return iset
+    iset.instances = Instances(image_size=masks.rle[0]['size'], masks=masks, boxes=np.concatenate(boxes, axis=0),
+                               colors=np.concatenate(colors, axis=0))
+    return (iset, colormap) if default_colors else iset
 
 
 _SEG_COLORS_ALL = np.array([[0., 0., 0.], [0.153, 0.153, 0.000], [0.286, 1., 0.], [1., 0.857, 0.], [1., 0., 0.],

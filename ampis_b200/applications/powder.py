@@ -93,132 +93,128 @@ class PowderSatelliteImage(object):
         return copy.deepcopy(self)
 
 
+def _pixel_scale(isets):
+    """Length per pixel of every image from its horizontal field width (HFW / image width), and the
+    unit string, for psd(distance='length') without an explicit c (reference powder.py:370-388)."""
+    if type(isets[0]) != InstanceSet:
+        raise ValueError('Cannot infer c from particles (must be list of InstanceSet or PowderSatelliteImage '
+                         'objects')
+    if isets[0].HFW is None:
+        raise ValueError('Cannot infer c because HFW is not defined')
+    widths_um = [s.HFW for s in isets]
+    assert None not in widths_um, 'all HFW values must be specified if c is not defined'
+    units = isets[0].HFW_units
+    assert all(s.HFW_units == units for s in isets), 'all HFW values should have same units'
+    widths_px = [int(s.instances.image_size[1]) for s in isets]
+    return [um / px for um, px in zip(widths_um, widths_px)], units
+
+
+_PSD_X = {'d_eq': ('Equivalent diameter', ', {}'), 'area': ('Mask area', '- ${}^2$')}
+_PSD_Y = {'cvf': 'cumulative volume fraction', 'counts': 'counts (cumulative)'}
+
+
 def psd(particles, xvals='d_eq', yvals='cvf', c=None, distance='length', ax=None, plot=True, return_results=False):
-    """Cumulative particle size distribution from segmentation masks (reference
-    powder.py:288-461).  Same argument handling and ValueErrors; the numerics (exact-value
-    histogram via np.unique, d_eq = 2*sqrt(A/pi), V = 4/3*pi^(-1/2)*A^(3/2), normalised cumsum)
-    follow powder.py:417-444 on areas measured on the GPU.  Drawing needs matplotlib and happens
-    only on an axis passed by the caller."""
+    """Cumulative particle size distribution (reference powder.py:288-461).
+
+    Areas come from the GPU measurement pass; they are scaled to length units by *c* (a number, one
+    number per image, or ``(c, unit)``; inferred from HFW when omitted), or left in pixels with
+    ``distance='pixels'``.  Distinct areas are counted exactly (``np.unique``), mapped to
+    ``d_eq = 2 sqrt(A / pi)`` when ``xvals='d_eq'``, weighted by the sphere volume
+    ``4/3 pi^(-1/2) A^(3/2)`` when ``yvals='cvf'``, accumulated and normalised to end at 1.  The same
+    arguments raise the same ``ValueError``s as the reference.  Nothing is drawn unless an axis is
+    passed (matplotlib is not a dependency); ``return_results=True`` returns the curve and labels."""
+    xkey, ykey, how = xvals.lower(), yvals.lower(), distance.lower()
+    units = ''
     if type(c) == tuple:
-        length_units = c[1]
-        c = c[0]
-    else:
-        length_units = ''
+        c, units = c
     if type(particles) in (InstanceSet, PowderSatelliteImage):
         particles = [particles]
     if type(particles[0]) == PowderSatelliteImage:
-        particles = [x.particles for x in particles]
-    areas = [mask_areas(x) for x in particles]      # powder.py:363 is always truthy (quirk B.6)
+        particles = [item.particles for item in particles]
+    per_image = [mask_areas(item) for item in particles]          # the reference's list branch is dead (quirk B.6)
 
-    if distance.lower() == 'length':
+    if how == 'length':
         if c is None:
-            if type(particles[0]) == InstanceSet:
-                if particles[0].HFW is not None:
-                    HFW = [x.HFW for x in particles]
-                    assert all([x is not None for x in HFW]), 'all HFW values must be specified if c is not defined'
-                    for iset in particles:
-                        assert iset.HFW_units == particles[0].HFW_units, 'all HFW values should have same units'
-                    length_units = particles[0].HFW_units
-                    HFW = np.asarray([x.HFW for x in particles])
-                    image_widths = np.asarray([x.instances.image_size[1] for x in particles], np.int64)
-                    c = [h / w for h, w in zip(HFW, image_widths)]
-                else:
-                    raise ValueError('Cannot infer c because HFW is not defined')
-            else:
-                raise ValueError('Cannot infer c from particles (must be list of InstanceSet or PowderSatelliteImage '
-                                 'objects')
+            c, units = _pixel_scale(particles)
         if type(c) in [list, np.ndarray]:
-            assert len(c) == len(areas), 'if c (or c[0] if passed as tuple) is a list or array ' \
-                                         'it must have the same length as particles.'
-            areas = [a_i * c_i ** 2 for a_i, c_i in zip(areas, c)]
-        elif type(c) in [int, float]:
-            areas = [a_i * c ** 2 for a_i in areas]
+            assert len(c) == len(per_image), 'if c (or c[0] if passed as tuple) is a list or array ' \
+                                             'it must have the same length as particles.'
+            per_image = [a * k ** 2 for a, k in zip(per_image, c)]
+        elif type(c) in [int, float]:                                # numpy scalars are rejected, as in the reference
+            per_image = [a * c ** 2 for a in per_image]
         else:
             raise ValueError('c (or c[0] if passed as tuple) must be a list, array, int, or float')
-    elif distance.lower() == 'pixels':
-        length_units = 'px'
-        areas = mask_areas(particles)
+    elif how == 'pixels':
+        units = 'px'
+        per_image = mask_areas(particles)                            # recomputed, as in the reference (powder.py:410)
     else:
         raise ValueError('distance must be "length" or "pixels"')
+    areas = np.concatenate(per_image, axis=0) if type(per_image[0]) in (list, np.ndarray) else per_image
 
-    if type(areas[0]) in (list, np.ndarray):
-        areas = np.concatenate(areas, axis=0)
-
-    unique, counts = np.unique(areas, return_counts=True)
-    if xvals.lower() == 'd_eq':
-        unique = 2 * np.sqrt(unique / np.pi)
-        xlabel = 'Equivalent diameter{}'.format(', {}'.format(length_units) if length_units else '')
-    elif xvals.lower() == 'area':
-        xlabel = 'Mask area{}'.format('- ${}^2$'.format(length_units) if length_units else '')
-    else:
+    x, weight = np.unique(areas, return_counts=True)
+    if xkey not in _PSD_X:
         raise ValueError('xvals must be "d_eq" or "area"')
-
-    if yvals.lower() == 'cvf':
-        volumes = 4 / 3 * np.pi ** (-1 / 2) * unique ** (3 / 2)
-        counts = volumes * counts
-        ylabel = 'cumulative volume fraction'
-    elif yvals.lower() == 'counts':
-        ylabel = 'counts (cumulative)'
-    else:
+    if xkey == 'd_eq':
+        x = 2 * np.sqrt(x / np.pi)
+    name, unit_fmt = _PSD_X[xkey]
+    xlabel = name + (unit_fmt.format(units) if units else '')
+    if ykey not in _PSD_Y:
         raise ValueError('yvals must be "cvf" or "counts"')
-
-    counts = counts.cumsum()
-    counts = counts / counts[-1]
-    x, y = unique, counts
+    if ykey == 'cvf':
+        weight = 4 / 3 * np.pi ** (-1 / 2) * x ** (3 / 2) * weight
+    ylabel = _PSD_Y[ykey]
+    y = weight.cumsum()
+    y = y / y[-1]
 
     if ax is not None:
         ax.grid(axis='both', which='both', color=(0.85, 0.85, 0.85), linewidth=1, linestyle='--')
         ax.plot(x, y, '-.k')
         ax.set_xlabel(xlabel)
         ax.set_ylabel(ylabel)
-
     if return_results:
         return {'x': x, 'y': y, 'x_label': xlabel, 'y_label': ylabel}
 
 
+_SUMMARY_ROWS = (('n_images', 'number of images'),
+                 ('n_particles', 'number of particles'),
+                 ('n_satellites', 'number of matched satellites'),
+                 ('n_satellites_unmatched', 'number of unmatched satellites'),
+                 ('n_satellited_particels', 'number of satellited particles'),            # key spelled as in the reference
+                 ('sat_frac', 'fraction of satellited particles'),
+                 ('mspp', 'median number of satellites per\nsatellited particle             '))
+
+
 def satellite_measurements(psi, print_summary=True, output_dict=False):
-    """Satellite content of a list of PowderSatelliteImage objects (reference powder.py:463-569)."""
-    if type(psi) == PowderSatelliteImage:
-        psi = [psi]
-    assert all([type(x) == PowderSatelliteImage for x in psi]), 'psi must be list of PowderSatelliteImage objects!'
-    matches = [x.matches for x in psi]
-    if any([x is None for x in matches]):
-        for x in psi:
-            x.compute_matches()
-        matches = [x.matches for x in psi]
+    """Satellite content of a set of images (reference powder.py:463-569): totals, the fraction of
+    particles that carry satellites, the median number of satellites per satellited particle and
+    the cumulative distribution of that number.  Images without matches get them computed first.
+    The same sums are what ``distributed.satellites_sharded`` all-reduces over GPUs."""
+    images = [psi] if type(psi) == PowderSatelliteImage else psi
+    assert all(type(im) == PowderSatelliteImage for im in images), 'psi must be list of PowderSatelliteImage objects!'
+    if any(im.matches is None for im in images):
+        for im in images:
+            im.compute_matches()
+    found = [im.matches for im in images]
 
-    n_images = len(psi)
-    n_particles_matched = sum([len(x['match_pairs'].keys()) for x in matches])
-    n_particles = n_particles_matched + sum([len(x['particles_unmatched']) for x in matches])
-    spp_list = []
-    for m in matches:
-        for v in m['match_pairs'].values():
-            spp_list.append(len(v))
-    spp_list = np.asarray(spp_list)
-    n_satellites_matched = sum(spp_list)
-    mspp = np.median(spp_list)
-    n_satellites_unmatched = sum([len(x['satellites_unmatched']) for x in matches])
-    sat_frac = n_particles_matched / n_particles
-    unique, counts = np.unique(spp_list, return_counts=True)
-    assert counts.sum() == n_particles_matched
-    assert n_particles == sum([len(x.particles.instances) for x in psi])
-    assert n_satellites_matched + n_satellites_unmatched == sum([len(x.satellites.instances) for x in psi])
-    counts = counts.cumsum() / counts.sum()
+    per_particle = np.asarray([len(sats) for m in found for sats in m['match_pairs'].values()])
+    out = {'n_images': len(images)}
+    satellited = sum(len(m['match_pairs']) for m in found)
+    out['n_particles'] = satellited + sum(len(m['particles_unmatched']) for m in found)
+    out['n_satellites'] = sum(per_particle)
+    out['n_satellites_unmatched'] = sum(len(m['satellites_unmatched']) for m in found)
+    out['n_satellited_particels'] = satellited
+    out['sat_frac'] = satellited / out['n_particles']
+    out['mspp'] = np.median(per_particle)
+    values, freq = np.unique(per_particle, return_counts=True)
+    # consistency with the instance lists themselves (the reference asserts the same three sums)
+    assert freq.sum() == satellited
+    assert out['n_particles'] == sum(len(im.particles.instances) for im in images)
+    assert out['n_satellites'] + out['n_satellites_unmatched'] == sum(len(im.satellites.instances) for im in images)
+    out['unique_satellites_per_particle'] = values
+    out['counts_satellites_per_particle'] = freq.cumsum() / freq.sum()
 
-    keys = ['n_images', 'n_particles', 'n_satellites', 'n_satellites_unmatched', 'n_satellited_particels',
-            'sat_frac', 'mspp', 'unique_satellites_per_particle', 'counts_satellites_per_particle']
-    labels = ['number of images',
-              'number of particles',
-              'number of matched satellites',
-              'number of unmatched satellites',
-              'number of satellited particles',
-              'fraction of satellited particles',
-              'median number of satellites per\n'
-              'satellited particle             ']
-    values = [n_images, n_particles, n_satellites_matched, n_satellites_unmatched, n_particles_matched,
-              sat_frac, mspp, unique, counts]
     if print_summary:
-        for lab, v in zip(labels, values[:-2]):
-            print('{:35}\t{}'.format(lab, v))
+        for key, label in _SUMMARY_ROWS:
+            print('{:35}\t{}'.format(label, out[key]))
     if output_dict:
-        return dict(zip(keys, values))
+        return out

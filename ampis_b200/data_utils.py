@@ -80,113 +80,96 @@ def _imread(path, as_gray=False):
     return np.asarray(im)
 
 
+def _record(idx, image_path, annotation_file, height, width, mask_format, dataset_class, annotations, **extra):
+    """One detectron2-style data dict (the key set of data_utils.py:398-404 / 452-459 / 503-509)."""
+    d = {'file_name': str(image_path), 'annotation_file': annotation_file, 'height': height, 'width': width,
+         'mask_format': mask_format, 'image_id': idx}
+    d.update(extra)
+    d['dataset_class'] = dataset_class
+    d['annotations'] = annotations
+    d['num_instances'] = len(annotations)
+    return d
+
+
+def _instance(bbox, segmentation):
+    return {'bbox': bbox, 'bbox_mode': BoxMode.XYXY_ABS, 'segmentation': segmentation, 'category_id': 0}
+
+
+def _from_annotation_images(binary, im_root, ann_root, pattern, dataset_class, cwd):
+    """'binary' / 'label': one annotation image (or .npy) per picture, matched by file stem."""
+    out = []
+    for idx, picture in enumerate(Path(im_root).glob(pattern)):
+        hits = list(Path(ann_root).glob('*{}*'.format(picture.stem)))
+        n = len(hits)
+        assert n == 1, f'There must be exactly 1 annotation file for, {picture.name}, but {n} were found'
+        ann_path = hits[0].relative_to(cwd)
+        ann = np.load(str(ann_path)) if ann_path.suffix == '.npy' else _imread(ann_path)
+        # labelling, boxes and RLE of every instance from ONE pass over the image on the GPU (csrc/label.cu)
+        rles, boxes = engine.label_image_to_instances(ann, binary=binary)
+        instances = [_instance(b.astype(np.float64), m) for m, b in zip(rles, boxes)]     # box = x1, y1, x2, y2
+        out.append(_record(idx, picture.relative_to(cwd), str(ann_path), ann.shape[0], ann.shape[1], 'bitmask',
+                           dataset_class, instances))
+    return out
+
+
+def _from_via2(json_path, dataset_class, cwd):
+    """VIA 2 project file -> polygon annotations; vertices move to pixel centres (+0.5)."""
+    with open(json_path, 'rb') as f:
+        project = json.load(f)
+    picture_dir = Path(json_path.parent, project['_via_settings']['core']['default_filepath'])
+    out = []
+    for idx, entry in enumerate(project['_via_img_metadata'].values()):
+        picture = Path(picture_dir, entry['filename'])
+        attrs = entry['file_attributes']
+        size = attrs.get('Size (width, height)', None)
+        if size:
+            width, height = (int(v) for v in size.split(', '))
+        else:
+            height, width = _imread(picture, as_gray=True).shape
+        instances = []
+        for region in entry['regions']:
+            xs, ys = region['shape_attributes']['all_points_x'], region['shape_attributes']['all_points_y']
+            ring = [v + 0.5 for xy in zip(xs, ys) for v in xy]
+            instances.append(_instance(np.asarray((np.min(xs), np.min(ys), np.max(xs), np.max(ys))), [ring]))
+        out.append(_record(idx, picture.relative_to(cwd), json_path.name, height, width, 'polygon', dataset_class,
+                           instances, HFW=attrs.get('HFW', None)))
+    return out
+
+
+def _from_rle_json(json_path, dataset_class, cwd):
+    """JSON list of {'file_name', 'segmentations': [COCO RLE with str counts]}; boxes straight from the runs."""
+    with open(json_path, 'r') as f:
+        listing = json.load(f)
+    out = []
+    for idx, item in enumerate(listing):
+        masks = item['segmentations']
+        for m in masks:
+            m['counts'] = m['counts'].encode('utf-8')
+        height, width = masks[0]['size']
+        table = engine.table_from_rle(masks, paint=False)
+        area, tight = table.areas_np(), table.bbox_np()
+        instances = [_instance(tight[k].astype(np.float64) if area[k] else np.zeros(4), m) for k, m in enumerate(masks)]
+        out.append(_record(idx, Path(json_path.parent, Path(item['file_name'])).relative_to(cwd), str(json_path),
+                           height, width, 'bitmask', dataset_class, instances))
+    return out
+
+
 def get_ddicts(label_fmt, im_root, ann_root=None, pattern='*', dataset_class=None):
     """Images + ground-truth annotations -> detectron2-style data dicts (data_utils.py:313-530).
 
     label_fmt 'binary' / 'label': annotation images (or .npy) in *ann_root*; instances are the
     connected components of the binary image (8-connectivity, raster order, as
-    skimage.measure.label) or the distinct non-zero label values in ascending order.  Labelling,
-    boxes and RLE encoding run on the GPU (csrc/label.cu) from ONE pass over the image instead of a
-    full-frame pass per instance.  'via2': VIA 2 JSON -> polygons (+0.5 pixel-centre shift).
-    'rle': JSON list of {'file_name', 'segmentations'}; boxes come from the runs
-    (csrc/rle_measure.cu) without decoding."""
+    skimage.measure.label) or the distinct non-zero label values in ascending order.
+    'via2': *im_root* is a VIA 2 JSON project -> polygons.  'rle': *im_root* is a JSON list of
+    {'file_name', 'segmentations'}.  All instances get category 0 (single-class, like the reference)."""
     cwd = Path()
     im_root = Path(im_root)
-    ann_root = Path(ann_root) if ann_root else None
-    ddicts = []
-
-    if label_fmt.lower() in ['binary', 'label']:
-        img_paths = Path(im_root).glob(pattern)
-        for idx, p in enumerate(img_paths):
-            file_annotations = list(Path(ann_root).glob('*{}*'.format(p.stem)))
-            n = len(file_annotations)
-            assert n == 1, f'There must be exactly 1 annotation file for, {p.name}, but {n} were found'
-            ann_path = file_annotations[0].relative_to(cwd)
-            ann = np.load(str(ann_path)) if ann_path.suffix == '.npy' else _imread(ann_path)
-            height, width = ann.shape[:2]
-            ddict = {'file_name': str(p.relative_to(cwd)),
-                     'annotation_file': str(ann_path),
-                     'height': height,
-                     'width': width,
-                     'mask_format': 'bitmask',
-                     'image_id': idx,
-                     'dataset_class': dataset_class}
-            rles, bb = engine.label_image_to_instances(ann, binary=(label_fmt == 'binary'))
-            annotations = []
-            for mask, b in zip(rles, bb):
-                annotations.append({'bbox': b.astype(np.float64),          # extract_boxes(mask)[0]: x1, y1, x2, y2
-                                    'bbox_mode': BoxMode.XYXY_ABS,
-                                    'segmentation': mask,
-                                    'category_id': 0})
-            ddict['annotations'] = annotations
-            ddict['num_instances'] = len(annotations)
-            ddicts.append(ddict)
-
-    elif label_fmt.lower() == 'via2':
-        with open(Path(im_root), 'rb') as f:
-            j = json.load(f)
-        img_dir = Path(im_root.parent, j['_via_settings']['core']['default_filepath'])
-        for idx, annos in enumerate(j['_via_img_metadata'].values()):
-            filename = Path(img_dir, annos['filename'])
-            size = annos['file_attributes'].get('Size (width, height)', None)
-            if size:
-                width, height = tuple((int(x) for x in size.split(', ')))
-            else:
-                im = _imread(filename, as_gray=True)
-                height, width = im.shape
-            hfw = annos['file_attributes'].get('HFW', None)
-            ddict = {'file_name': str(filename.relative_to(cwd)),
-                     'annotation_file': im_root.name,
-                     'height': height,
-                     'width': width,
-                     'mask_format': 'polygon',
-                     'image_id': idx,
-                     'HFW': hfw,
-                     'dataset_class': dataset_class}
-            annotations = []
-            for obj in annos['regions']:
-                shape = obj['shape_attributes']
-                px = shape['all_points_x']
-                py = shape['all_points_y']
-                poly = [(x + 0.5, y + 0.5) for x, y in zip(px, py)]
-                poly = [p for x in poly for p in x]
-                annotations.append({'bbox': np.asarray((np.min(px), np.min(py), np.max(px), np.max(py))),
-                                    'bbox_mode': BoxMode.XYXY_ABS,
-                                    'segmentation': [poly],
-                                    'category_id': 0})
-            ddict['annotations'] = annotations
-            ddict['num_instances'] = len(annotations)
-            ddicts.append(ddict)
-
-    elif label_fmt.lower() == 'rle':
-        with open(im_root, 'r') as f:
-            data = json.load(f)
-        for i, anns in enumerate(data):
-            for jj, ann in enumerate(anns['segmentations']):
-                data[i]['segmentations'][jj]['counts'] = ann['counts'].encode('utf-8')
-        for idx, p in enumerate(data):
-            img_path = Path(im_root.parent, Path(p['file_name']))
-            ann = p['segmentations']
-            height, width = ann[0]['size']
-            ddict = {'file_name': str(img_path.relative_to(cwd)),
-                     'annotation_file': str(im_root),
-                     'height': height,
-                     'width': width,
-                     'mask_format': 'bitmask',
-                     'image_id': idx,
-                     'dataset_class': dataset_class}
-            table = engine.table_from_rle(ann, paint=False)          # boxes straight from the runs
-            area, bb = table.areas_np(), table.bbox_np()
-            annotations = []
-            for k, mask in enumerate(ann):
-                bbox = bb[k].astype(np.float64) if area[k] else np.zeros(4)
-                annotations.append({'bbox': bbox,
-                                    'bbox_mode': BoxMode.XYXY_ABS,
-                                    'segmentation': mask,
-                                    'category_id': 0})
-            ddict['annotations'] = annotations
-            ddict['num_instances'] = len(annotations)
-            ddicts.append(ddict)
-    else:
-        raise (ValueError("label_fmt must be 'binary','label', or 'via2'"))
-    return ddicts
+    fmt = label_fmt.lower()
+    if fmt in ('binary', 'label'):
+        return _from_annotation_images(label_fmt == 'binary', im_root, Path(ann_root) if ann_root else None, pattern,
+                                       dataset_class, cwd)
+    if fmt == 'via2':
+        return _from_via2(im_root, dataset_class, cwd)
+    if fmt == 'rle':
+        return _from_rle_json(im_root, dataset_class, cwd)
+    raise (ValueError("label_fmt must be 'binary','label', or 'via2'"))

@@ -19,161 +19,132 @@ from .containers import BitMasks, Boxes, Instances, PolygonMasks
 
 
 def random_colors(n, seed, bright=True):
-    """Seeded HSV colours (reference ampis/visualize.py:19-56; only used to fill the ``colors``
-    field the InstanceSet readers attach)."""
-    rs = np.random.RandomState(seed=seed)
-    brightness = 1.0 if bright else 0.7
-    hsv = [(i / n, 1, brightness) for i in range(n)]
-    colors = list(map(lambda c: colorsys.hsv_to_rgb(*c), hsv))
-    rs.shuffle(colors)
-    return np.asarray(colors)
+    """n distinguishable RGB colours in a seeded random order (reference ampis/visualize.py:19-56; the
+    InstanceSet readers attach them as the ``colors`` field): evenly spaced hues, full saturation,
+    value 1.0 (0.7 when not *bright*), shuffled by RandomState(seed)."""
+    value = 1.0 if bright else 0.7
+    palette = [colorsys.hsv_to_rgb(k / n, 1, value) for k in range(n)]
+    np.random.RandomState(seed=seed).shuffle(palette)
+    return np.asarray(palette)
+
+
+def _is_bool_selector(item):
+    """Boolean masks in the forms RLEMasks.__getitem__ accepts: torch bool tensor, numpy bool array,
+    list whose first element is a bool."""
+    if type(item) == torch.BoolTensor or (type(item) == torch.Tensor and item.dtype == torch.bool):
+        return True
+    if type(item) == np.ndarray:
+        return item.dtype == np.bool_
+    return type(item) == list and type(item[0]) == bool
 
 
 class RLEMasks(object):
-    """List of COCO RLE dicts with fancy indexing (reference structures.py:24-95)."""
+    """List of COCO RLE dicts that indexes like detectron2's mask containers (reference
+    structures.py:24-95): int, slice, boolean mask (same length) or a sequence of indices."""
 
     def __init__(self, rle):
         super().__init__()
         self.rle = rle
 
     def __getitem__(self, item: Union[int, slice, List[int], List[bool], torch.BoolTensor, np.ndarray]):
-        idx_list = False
-        if type(item) == int:
-            return RLEMasks(self.rle[item])          # wraps a dict, like the reference (quirk B.13)
-        elif type(item) == torch.BoolTensor or (type(item) == torch.Tensor and item.dtype == torch.bool):
-            return RLEMasks([mask for mask, bool_ in zip(self.rle, item) if bool_])
-        elif type(item) == np.ndarray:
-            if item.dtype == np.bool_:
-                assert item.shape[0] == len(self)
-                return RLEMasks([mask for mask, bool_ in zip(self.rle, item) if bool_])
-            else:
-                idx_list = True
-        elif type(item) == slice:
-            return RLEMasks(self.rle[item])
-        elif type(item) == list:
-            if type(item[0]) == bool:
+        if type(item) in (int, slice):
+            return RLEMasks(self.rle[item])          # an int wraps ONE dict, like the reference (quirk B.13)
+        if _is_bool_selector(item):
+            if type(item) in (np.ndarray, list):
                 assert len(item) == len(self)
-                return RLEMasks([mask for mask, bool_ in zip(self.rle, item) if bool_])
-            else:
-                idx_list = True
-        else:
-            idx_list = True
-        if idx_list:
-            return RLEMasks([self.rle[idx] for idx in item])
+            return RLEMasks([m for m, keep in zip(self.rle, item) if keep])
+        return RLEMasks([self.rle[k] for k in item])
 
     def __len__(self):
         return len(self.rle)
 
 
+def _parse_hfw(value):
+    """'103.6 um' -> (103.6, 'um'); a bare number -> (number, None); None -> (None, None); anything else
+    is kept as it is (reference structures.py:294-305)."""
+    if value is None:
+        return None, None
+    try:
+        return float(value), None
+    except ValueError:
+        parts = value.split(' ')
+        if len(parts) == 2:
+            return float(parts[0]), parts[1]
+        return value, None
+
+
 class InstanceSet(object):
-    """Instances of one image (reference structures.py:98-533)."""
+    """Everything AMPIS keeps about the instances of one image (reference structures.py:98-533): the
+    ``Instances`` (masks, boxes, class_idx, scores, colors), where they came from (``filepath``,
+    ``dataset_class``, ``pred_or_gt``, ``mask_format``), the physical scale (``HFW``, ``HFW_units``)
+    and the measured ``rprops``."""
 
     def __init__(self, mask_format=None, bbox_mode=None, filepath=None, annotations=None, instances=None, img=None,
                  dataset_class=None, pred_or_gt=None, HFW=None, HFW_units=None, randomstate=None):
         super().__init__()
-        self.mask_format = mask_format
-        self.bbox_mode = bbox_mode
-        self.img = img
-        self.filepath = filepath
-        self.dataset_class = dataset_class
-        self.pred_or_gt = pred_or_gt
-        self.HFW = HFW
-        self.HFW_units = HFW_units
+        self.mask_format, self.bbox_mode = mask_format, bbox_mode
+        self.filepath, self.img = filepath, img
+        self.annotations, self.instances = annotations, instances
+        self.dataset_class, self.pred_or_gt = dataset_class, pred_or_gt
+        self.HFW, self.HFW_units = HFW, HFW_units
         self.rprops = None
-        self.instances = instances
-        self.annotations = annotations
-        if randomstate is None:
-            randomstate = np.random.randint(2 ** 32 - 1)
-        self.randomstate = randomstate
         self.colors = None
+        self.randomstate = np.random.randint(2 ** 32 - 1) if randomstate is None else randomstate
+
+    def _attach(self, instances):
+        self.instances = instances
+        self.instances.colors = random_colors(len(instances), self.randomstate)
 
     def read_from_ddict(self, ddict, inplace=True):
-        """Ground-truth data dict -> InstanceSet (reference structures.py:203-309)."""
-        self.pred_or_gt = 'gt'
-        self.filepath = Path(ddict['file_name'])
-        self.mask_format = ddict['mask_format']
-        image_size = (ddict['height'], ddict['width'])
-        class_idx = np.asarray([anno['category_id'] for anno in ddict['annotations']], np.int64)
-        bbox = np.stack([anno['bbox'] for anno in ddict['annotations']])
-        segs = [anno['segmentation'] for anno in ddict['annotations']]
-        segtype = type(segs[0])
-        if segtype == dict:
+        """Fill the set from a ground-truth data dict (reference structures.py:203-309): RLE dicts
+        become RLEMasks, bool arrays BitMasks, coordinate lists PolygonMasks; ``HFW`` strings like
+        '103.6 um' are split into value and unit."""
+        annos = ddict['annotations']
+        self.pred_or_gt, self.filepath, self.mask_format = 'gt', Path(ddict['file_name']), ddict['mask_format']
+        segs = [a['segmentation'] for a in annos]
+        kind = type(segs[0])
+        if kind == dict:
             masks = RLEMasks(segs)
-        elif segtype == np.ndarray:
+        elif kind == np.ndarray:
             if segs[0].dtype == np.bool_:
                 masks = BitMasks(np.stack(segs))
         else:
             masks = PolygonMasks(segs)
-        instances = Instances(image_size, **{'masks': masks, 'boxes': bbox, 'class_idx': class_idx})
-        self.instances = instances
-        self.instances.colors = random_colors(len(instances), self.randomstate)
+        self._attach(Instances((ddict['height'], ddict['width']), masks=masks,
+                               boxes=np.stack([a['bbox'] for a in annos]),
+                               class_idx=np.asarray([a['category_id'] for a in annos], np.int64)))
         self.dataset_class = ddict.get('dataset_class', None)
-        HFW = ddict.get('HFW', None)
-        HFW_units = None
-        if HFW is not None:
-            try:
-                HFW = float(HFW)
-            except ValueError:
-                split = HFW.split(' ')
-                if len(split) == 2:
-                    HFW = float(split[0])
-                    HFW_units = split[1]
-        self.HFW = HFW
-        self.HFW_units = HFW_units
-        if not inplace:
-            return self
-        return
+        self.HFW, self.HFW_units = _parse_hfw(ddict.get('HFW', None))
+        return None if inplace else self
 
     def read_from_model_out(self, outs, inplace=True):
-        """Formatted model output -> InstanceSet (reference structures.py:312-371)."""
-        self.pred_or_gt = 'pred'
-        self.mask_format = 'bitmask'
-        self.filepath = outs['file_name']
-        split = outs['dataset'].split('_')
-        if len(split) > 1:
-            self.dataset_class = outs['dataset'].split('_')[-1]
-        else:
-            self.dataset_class = outs['dataset']
-        instances_pred = outs['pred']['instances']
-        instances = Instances(instances_pred.image_size,
-                              **{'masks': RLEMasks(instances_pred.pred_masks),
-                                 'boxes': instances_pred.pred_boxes,
-                                 'class_idx': instances_pred.pred_classes,
-                                 'scores': instances_pred.scores})
-        self.instances = instances
-        self.instances.colors = random_colors(len(self.instances), self.randomstate)
-        if not inplace:
-            return self
-        return
+        """Fill the set from ``data_utils.format_outputs`` output (reference structures.py:312-371).
+        A dataset name like 'powder_Validation' yields dataset_class 'Validation'."""
+        self.pred_or_gt, self.mask_format, self.filepath = 'pred', 'bitmask', outs['file_name']
+        self.dataset_class = outs['dataset'].split('_')[-1]
+        pred = outs['pred']['instances']
+        self._attach(Instances(pred.image_size, masks=RLEMasks(pred.pred_masks), boxes=pred.pred_boxes,
+                               class_idx=pred.pred_classes, scores=pred.scores))
+        return None if inplace else self
 
     def filter_mask_size(self, min_thresh=100, max_thresh=100000, to_rle=False):
-        """Instances with min_thresh < area < max_thresh, strict (reference structures.py:374-442)."""
+        """New ``Instances`` holding the instances with min_thresh < area < max_thresh (both strict,
+        ``None`` disables a side); the set itself is not modified (reference structures.py:374-442)."""
         masks = self.instances.masks
         if to_rle:
             masks = RLEMasks(masks_to_rle(masks, self.instances.image_size))
-        masktype = type(masks)
         areas = mask_areas(masks)
-        if min_thresh is None:
-            inlier_min = np.ones(areas.shape, np.bool_)
+        keep = np.ones(areas.shape, np.bool_)
+        if min_thresh is not None:
+            keep &= areas > min_thresh
+        if max_thresh is not None:
+            keep &= areas < max_thresh
+        if type(masks) == PolygonMasks:
+            masks = PolygonMasks([p for p, k in zip(masks.polygons, keep) if k])
         else:
-            inlier_min = areas > min_thresh
-        if max_thresh is None:
-            inlier_max = np.ones(areas.shape, np.bool_)
-        else:
-            inlier_max = areas < max_thresh
-        inliers_bool = np.logical_and(inlier_min, inlier_max)
-        if masktype == PolygonMasks:
-            polygons = [p for p, b in zip(masks.polygons, inliers_bool) if b]
-            masks = PolygonMasks(polygons)
-        else:
-            masks = masks[inliers_bool]
-        new_instance_fields = {}
-        for key, value in self.instances._fields.items():
-            if key == 'masks':
-                new_instance_fields[key] = masks
-            else:
-                new_instance_fields[key] = value[inliers_bool]
-        return Instances(self.instances.image_size, **new_instance_fields)
+            masks = masks[keep]
+        fields = {name: (masks if name == 'masks' else value[keep]) for name, value in self.instances._fields.items()}
+        return Instances(self.instances.image_size, **fields)
 
     def remove_edge_instances(self, k=1):
         """Drop instances that touch the k-pixel image border, in place (reference
@@ -250,25 +221,20 @@ class InstanceSet(object):
 def mask_areas(masks):
     """Area in pixels of each mask (reference structures.py:536-583): ndarray -> uint64 sums,
     PolygonMasks -> shoelace float64, RLE -> uint32 pixel counts (GPU), containers recurse."""
-    masktype = type(masks)
-    if masktype == np.ndarray:
+    kind = type(masks)
+    if kind == np.ndarray:
         if masks.dtype == np.bool_ and masks.ndim == 3 and masks.size:
             return engine.bool_area_bbox(masks)[0].astype(np.uint)
         return masks.sum(axis=(1, 2), dtype=np.uint)
-    elif masktype == PolygonMasks:
-        return np.asarray([_shoelace_area(coords[0][::2], coords[0][1::2]) for coords in masks.polygons])
-    elif masktype == list and type(masks[0]) == dict:
-        return engine.table_from_rle(masks, paint=False).areas_np()
-    elif masktype == RLEMasks:
-        return engine.table_from_rle(masks.rle, paint=False).areas_np()
-    elif masktype == Instances:
-        return mask_areas(masks.masks)
-    elif masktype == InstanceSet:
-        return mask_areas(masks.instances)
-    elif masktype == list:
-        return [mask_areas(x) for x in masks]
-    else:
-        raise NotImplementedError('Not implemented for type {}'.format(masktype))
+    if kind == PolygonMasks:
+        return np.asarray([_shoelace_area(ring[0][::2], ring[0][1::2]) for ring in masks.polygons])
+    if kind == RLEMasks or (kind == list and type(masks[0]) == dict):
+        return engine.table_from_rle(masks.rle if kind == RLEMasks else masks, paint=False).areas_np()
+    if kind in (Instances, InstanceSet):
+        return mask_areas(masks.masks if kind == Instances else masks.instances)
+    if kind == list:
+        return [mask_areas(m) for m in masks]
+    raise NotImplementedError('Not implemented for type {}'.format(kind))
 
 
 def _shoelace_area(x, y):
@@ -277,42 +243,40 @@ def _shoelace_area(x, y):
 
 
 def boxes_to_array(boxes):
-    """Boxes / list / array -> n x 4 ndarray (reference structures.py:613-639)."""
-    dtype = type(boxes)
-    if dtype == np.ndarray:
+    """n x 4 ndarray from an ndarray, a list of 4-sequences or detectron2 ``Boxes`` (reference
+    structures.py:613-639); other types give None, as in the reference."""
+    if type(boxes) == np.ndarray:
         return boxes
-    elif dtype == list:
+    if type(boxes) == list:
         assert len(boxes[0]) == 4
         return np.asarray(boxes)
-    elif dtype == Boxes:
+    if type(boxes) == Boxes:
         return boxes.tensor.to('cpu').numpy()
 
 
 def masks_to_rle(masks, size=None):
-    """Anything -> list of COCO RLE dicts (reference structures.py:643-690).  Polygons are
-    rasterised by the GPU restatement of rleFrPoly (first polygon of each instance only, as
-    ``RLE.frPyObjects(p, *size)[0]`` does) and compressed by the GPU string encoder."""
-    dtype = type(masks)
-    if dtype == list:
+    """Any supported mask container -> list of COCO RLE dicts (reference structures.py:643-690).
+    RLE input is returned as it is.  Polygons need *size* and are rasterised by the GPU restatement of
+    pycocotools' rleFrPoly -- the first polygon of each instance only, as ``RLE.frPyObjects(p, *size)[0]``
+    does -- and compressed by the GPU string encoder."""
+    kind = type(masks)
+    if kind == list:
         if type(masks[0]) == dict:
             return masks
-        elif type(masks[0]) == list:
+        if type(masks[0]) == list:
             raise NotImplementedError('):')
-    if dtype == RLEMasks:
+    if kind == RLEMasks:
         return masks.rle
-    elif dtype == PolygonMasks:
+    if kind == PolygonMasks:
         assert size is not None
         h, w = int(size[0]), int(size[1])
-        polys = [np.asarray(p[0], np.float64) for p in masks.polygons]
-        cnt, cnt_off, cnt_len, _, _ = engine.polygons_to_counts(polys, h, w)
-        strings = engine.counts_to_strings(cnt, cnt_off, cnt_len, len(polys))
-        return [{'size': [h, w], 'counts': s} for s in strings]
-    elif dtype == InstanceSet:
-        return masks_to_rle(masks.instances.masks, masks.instances.image_size)
-    elif dtype == Instances:
-        return masks_to_rle(masks.masks, masks.image_size)
-    else:
-        raise NotImplementedError('cannot convert mask type {} to RLE'.format(masks))
+        rings = [np.asarray(p[0], np.float64) for p in masks.polygons]
+        cnt, cnt_off, cnt_len, _, _ = engine.polygons_to_counts(rings, h, w)
+        return [{'size': [h, w], 'counts': c} for c in engine.counts_to_strings(cnt, cnt_off, cnt_len, len(rings))]
+    if kind in (Instances, InstanceSet):
+        inst = masks if kind == Instances else masks.instances
+        return masks_to_rle(inst.masks, inst.image_size)
+    raise NotImplementedError('cannot convert mask type {} to RLE'.format(masks))
 
 
 def _rle_to_bool(rle):
