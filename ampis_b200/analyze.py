@@ -100,7 +100,7 @@ def _piecewise_rle_match(gt, pred, iou_thresh=0.5, interval=80, _details=None):
         best_inter = res.best_inter[:G].cpu().numpy().view(np.uint32).astype(np.int64)
         areas = table.areas_np()
     if _details is not None:
-        _details.update(best_col=best_col, best_inter=best_inter, areas=areas)
+        _details.update(best_col=best_col, best_iou=best_iou, best_inter=best_inter, areas=areas)
     return _match_from_rows(best_col, best_iou, P, iou_thresh)
 
 
@@ -116,43 +116,73 @@ fast_instance_match = rle_instance_matcher
 
 
 def det_seg_scores(gt, pred, iou_thresh=0.5, size=None):
-    """Detection and segmentation precision/recall (analyze.py:226-339).  Raises
-    ZeroDivisionError like the reference when TP+FP or TP+FN is zero."""
-    gtmasks = masks_to_rle(gt, size)
-    predmasks = masks_to_rle(pred, size)
-    det = {}
-    detection_results_ = _piecewise_rle_match(gtmasks, predmasks, iou_thresh, _details=det)
-    matches_ = np.asarray(detection_results_['tp'])
-    TP_det_ = len(matches_)
-    FN_det_ = len(detection_results_['fn'])
-    FP_det_ = len(detection_results_['fp'])
-    det_precision = TP_det_ / (TP_det_ + FP_det_)
-    det_recall = TP_det_ / (TP_det_ + FN_det_)
-    if TP_det_:
-        G = len(gtmasks)
-        gi, pi = matches_[:, 0], matches_[:, 1]
-        # the intersection of every matched pair was already produced by the row kernel
-        seg_true_positive = det['best_inter'][gi].astype(np.int64)
-        tp_gt_area = det['areas'][gi].astype(np.int64)
-        tp_pred_area = det['areas'][G + pi].astype(np.int64)
+    """Detection and segmentation precision / recall of one image (analyze.py:226-339): eleven keys --
+    ``det_precision``, ``det_recall`` (floats), per-match ``seg_precision``, ``seg_recall``, ``seg_tp``,
+    ``seg_fp``, ``seg_fn`` and the matcher's ``det_tp``, ``det_fn``, ``det_fp``, ``det_tp_iou``.  The
+    intersection of every matched pair is a by-product of the row kernel, so there is no second pass
+    of merges.  Raises ZeroDivisionError like the reference when TP+FP or TP+FN is zero."""
+    gtmasks, predmasks = masks_to_rle(gt, size), masks_to_rle(pred, size)
+    rows = {}
+    _piecewise_rle_match(gtmasks, predmasks, iou_thresh, _details=rows)
+    G, P = len(gtmasks), len(predmasks)
+    areas = rows['areas']
+    return _scores_from_rows(G, P, rows['best_col'], rows['best_iou'], rows['best_inter'],
+                             None if areas is None else areas[:G], None if areas is None else areas[G:], iou_thresh)
+
+
+def _scores_from_rows(G, P, best_col, best_iou, best_inter, areas_gt, areas_pred, iou_thresh):
+    """The dict of det_seg_scores from one image's row results (analyze.py:300-339)."""
+    det = _match_from_rows(best_col, best_iou, P, iou_thresh)
+    tp = np.asarray(det['tp'])
+    n_tp, n_fn, n_fp = len(tp), len(det['fn']), len(det['fp'])
+    out = {'det_precision': n_tp / (n_tp + n_fp), 'det_recall': n_tp / (n_tp + n_fn)}     # ZeroDivisionError as in the reference
+    if n_tp:
+        gi, pi = tp[:, 0], tp[:, 1]
+        inter = best_inter[gi].astype(np.int64)
+        a_gt, a_pr = areas_gt[gi].astype(np.int64), areas_pred[pi].astype(np.int64)
     else:
-        seg_true_positive = tp_gt_area = tp_pred_area = np.array([], np.int64)
-    seg_false_positive = tp_pred_area - seg_true_positive
-    seg_false_negative = tp_gt_area - seg_true_positive
+        inter = a_gt = a_pr = np.array([], np.int64)
     with np.errstate(invalid='ignore', divide='ignore'):
-        seg_precision = seg_true_positive / (seg_true_positive + seg_false_positive)
-        seg_recall = seg_true_positive / (seg_true_positive + seg_false_negative)
-    return {'det_precision': det_precision,
-            'det_recall': det_recall,
-            'seg_precision': seg_precision,
-            'seg_recall': seg_recall,
-            'det_tp': matches_,
-            'det_fn': detection_results_['fn'],
-            'det_fp': detection_results_['fp'],
-            'seg_tp': seg_true_positive,
-            'seg_fn': seg_false_negative,
-            'seg_fp': seg_false_positive,
-            'det_tp_iou': detection_results_['iou']}
+        out['seg_precision'] = inter / (inter + (a_pr - inter))
+        out['seg_recall'] = inter / (inter + (a_gt - inter))
+    out.update(det_tp=tp, det_fn=det['fn'], det_fp=det['fp'], seg_tp=inter, seg_fn=a_gt - inter, seg_fp=a_pr - inter,
+               det_tp_iou=det['iou'])
+    return out
+
+
+def det_seg_scores_batch(gt_list, pred_list, iou_thresh=0.5, size=None):
+    """``det_seg_scores`` for many images at once -- not in the reference API, which scores one image
+    per Python call (Colab cell 44 loops over the dataset).  All images go through ONE mask table and
+    ONE launch of each kernel; the result is the list of per-image dicts the loop would have produced,
+    key for key and bit for bit.  Images with no ground truth or no predictions raise ZeroDivisionError
+    like the per-image function."""
+    assert len(gt_list) == len(pred_list)
+    gts = [masks_to_rle(g, size) for g in gt_list]
+    prs = [masks_to_rle(p, size) for p in pred_list]
+    for g, p in zip(gts, prs):
+        _check_same_size(g, p)
+    n_img = len(gts)
+    if n_img == 0:
+        return []
+    flat = [m for g, p in zip(gts, prs) for m in list(g) + list(p)]
+    Gs, Ps = [len(g) for g in gts], [len(p) for p in prs]
+    if not flat:
+        raise ZeroDivisionError('division by zero')
+    table = engine.table_from_rle(flat, layout=engine.MATCH_LAYOUT)
+    groups = engine.Groups.interleaved(table.device, Gs, Ps)
+    res = engine.intersect_rows(table, groups, engine.MODE_IOU)
+    n_rows = groups.n_rows
+    best_col = res.best_col[:n_rows].cpu().numpy().astype(np.int64)
+    best_iou = res.best_score[:n_rows].cpu().numpy()
+    best_inter = res.best_inter[:n_rows].cpu().numpy().view(np.uint32).astype(np.int64)
+    areas = table.areas_np()
+    out, r0, m0 = [], 0, 0
+    for G, P in zip(Gs, Ps):
+        out.append(_scores_from_rows(G, P, best_col[r0:r0 + G], best_iou[r0:r0 + G], best_inter[r0:r0 + G],
+                                     areas[m0:m0 + G], areas[m0 + G:m0 + G + P], iou_thresh))
+        r0 += G
+        m0 += G + P
+    return out
 
 
 def merge_boxes(box1, box2):

@@ -899,3 +899,21 @@ def test_randomised_measurement_kernels_vs_oracle(mods, seed):
                 iset, _ = A.seg_perf_iset(want, eb, {'tp': pairs}, mode=mode)
                 assert [m['counts'] for m in iset.instances.masks.rle] == \
                     [m['counts'] for m in R.seg_perf_masks(want, eb, pairs, mode)], tag
+
+
+def test_det_seg_scores_batch_equals_per_image_calls(mods):
+    """The batch form (one table, one launch per kernel for all images) returns exactly the dicts the
+    reference-style per-image loop returns -- shipped images of different instance counts."""
+    A = mods.analyze
+    g = U.load('powder_match.npz')
+    images = [U.powder_match_image(k)[1:] for k in range(len(g['names']))]
+    got = A.det_seg_scores_batch([x[0] for x in images], [x[1] for x in images], 0.5)
+    assert len(got) == len(images)
+    for (gt, pr), res in zip(images, got):
+        want = A.det_seg_scores(gt, pr, 0.5)
+        assert list(res) == list(want)
+        for k in want:
+            assert np.array_equal(np.asarray(res[k]), np.asarray(want[k])) and np.asarray(res[k]).dtype == np.asarray(want[k]).dtype, k
+    assert A.det_seg_scores_batch([], []) == []
+    with pytest.raises(ZeroDivisionError):
+        A.det_seg_scores_batch([images[0][0], mods.structures.RLEMasks([])], [images[0][1], mods.structures.RLEMasks([])])
