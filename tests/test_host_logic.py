@@ -159,3 +159,29 @@ def test_get_ddicts_via2_json(tmp_path, monkeypatch):
     assert dd[1]['num_instances'] == 0 and dd[1]['HFW'] is None and (dd[1]['height'], dd[1]['width']) == (32, 64)
     with pytest.raises(ValueError):
         D.get_ddicts('coco', 'via/anns.json')
+
+
+@pytest.mark.timeout(600)
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs without a GPU (the oracle port on the host cores) and prints the
+    contract's JSON line; a non-zero rank exits silently."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+           '--config', 'c1_powder_example', '--cpu-images', '1']
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1')
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=500)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['unit'] == 'pairs/s' and d['value'] > 0 and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and 'model' not in d['config']
+    r = subprocess.run(cmd, env=dict(env, RANK='1', WORLD_SIZE='2'), capture_output=True, text=True, timeout=100)
+    assert r.returncode == 0 and r.stdout.strip() == ''
