@@ -29,8 +29,11 @@ CONFIGS = {
     'c3_satellites': dict(h=2048, w=2048, n_rows=200, n_cols=2000, kind=1, median_diam=34.0, sigma_ln=0.45,
                           max_aspect=1.3, sec_median_diam=17.0, mode=engine.MODE_SAT),
     # C4: 2048x2048 spheroidite, 5000 x 5000 small elongated instances
+    # (+ the exact area distribution of all instances, one bin per pixel count: equivalent-diameter
+    # histograms and the PSD follow from it on the host, d_eq being a function of the area)
     'c4_spheroidite': dict(h=2048, w=2048, n_rows=5000, n_cols=5000, kind=0, median_diam=13.5, sigma_ln=0.6,
-                           max_aspect=3.0, sec_median_diam=0.0, mode=engine.MODE_IOU),
+                           max_aspect=3.0, sec_median_diam=0.0, mode=engine.MODE_IOU, area_bins=4096,
+                           area_bin_width=1),
     # C5: the whole synthetic dataset (10,000 C2 images) split over the ranks of one box -- strong scaling;
     # the all-reduce carries TP/FP/FN and a binned area histogram (size distribution)
     'c5_dataset': dict(h=1024, w=1024, n_rows=500, n_cols=500, kind=0, median_diam=34.0, sigma_ln=0.45,
@@ -123,10 +126,13 @@ class StepResult(object):
 
 
 def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_out=None,
-              sat_thresh=0.5, check=False, fused=None, kernel='rows'):
+              sat_thresh=0.5, check=False, fused=None, kernel='rows', sparse=None):
     """One pass of the hot path over a device-resident batch: measure -> paint -> fused
     intersect/arg-max rows -> per-image and total counts.  No host synchronisation when an
-    arena is supplied and check is False.  Returns device tensors."""
+    arena is supplied and check is False.  Returns device tensors.  kernel: 'rows' (bbox-culled
+    AND+popc; crop tables with many columns per image prune through a grid), 'grid' / 'scan' (crop
+    layout: force / forbid the grid), 'mma' (dense tcgen05 contraction).  sparse: an engine.SparseRows
+    that receives the non-zero intersections as triplets (crop layout)."""
     layout = engine.DEFAULT_LAYOUT if layout is None else layout
     t = engine.MaskTable(batch.device, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
                          batch.w, layout)
@@ -139,7 +145,10 @@ def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_o
     if kernel == 'mma':
         rows = engine.intersect_mma(t, batch.groups, batch.mode, out=rows_out)
     else:
-        rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out)
+        assert kernel in ('rows', 'scan') or layout == engine.LAYOUT_CROP, 'the grid kernel reads crop tables'
+        grid = engine.ColumnGrid(batch.device, batch.groups.n_groups) if kernel == 'grid' else \
+            ('scan' if kernel == 'scan' else None)
+        rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out, grid=grid, sparse=sparse)
     r = StepResult()
     r.table, r.rows = t, rows
     if batch.mode == engine.MODE_IOU:
@@ -157,12 +166,26 @@ class Pipeline(object):
     fused measure+paint -> intersect rows -> counts."""
 
     def __init__(self, batch, layout, arena, rows_out=None, thresholds=COCO_THRESHOLDS, totals=None,
-                 sat_thresh=0.5, fused=True, kernel='rows', area_hist=None, area_bin_width=64, mma_sort=True):
+                 sat_thresh=0.5, fused=True, kernel='rows', area_hist=None, area_bin_width=64, mma_sort=True,
+                 sparse_capacity=None):
         dev = batch.device
         self.area_hist, self.area_bin_width = area_hist, area_bin_width     # optional int64 histogram (+=)
         self.batch, self.layout, self.arena, self.fused = batch, layout, arena, fused
-        assert kernel in ('rows', 'mma')
+        assert kernel in ('rows', 'mma', 'grid', 'scan')
         self.kernel = kernel        # 'rows': bbox-culled AND+popc; 'mma': dense int8 tcgen05 contraction
+        # crop layout: candidates through a uniform grid ('grid', or 'rows' with many columns per image)
+        # instead of the scan of all columns ('scan'); the entry list is sized once from a dry run
+        self.grid, self.sparse = None, None
+        if layout == engine.LAYOUT_CROP and (kernel == 'grid' or sparse_capacity is not None or (
+                kernel == 'rows' and batch.groups.max_cols >= engine.ROWS_GRID_MIN_COLS)):
+            probe = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
+                                     batch.w, layout).measure()
+            need = engine.ColumnGrid(dev, batch.groups.n_groups).build(probe, batch.groups).capacity
+            self.grid = engine.ColumnGrid(dev, batch.groups.n_groups, capacity=need)
+            if sparse_capacity is not None:
+                self.sparse = engine.SparseRows(dev, sparse_capacity)
+        elif layout == engine.LAYOUT_CROP and kernel == 'scan':
+            self.grid = 'scan'
         self.mma_sort = mma_sort    # tiles from spatially sorted masks (contracts fewer slabs on large frames)
         if kernel == 'mma':
             batch.groups.mma_tiles()
@@ -200,7 +223,8 @@ class Pipeline(object):
         if self.kernel == 'mma':
             engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows, sort=self.mma_sort)
         else:
-            engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows)
+            engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows, grid=self.grid,
+                                  sparse=self.sparse)
         if mark: mark(3)
         if self.batch.mode == engine.MODE_IOU:
             engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)

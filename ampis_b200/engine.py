@@ -4,6 +4,7 @@ the kernels of libampis_b200.so.  PyTorch is used only for device memory, stream
 hand-written sm_100a kernels.  There is no CPU fallback anywhere in this module.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -270,8 +271,75 @@ class RowResult(object):
         self.best_col, self.best_inter, self.best_score, self.imat = best_col, best_inter, best_score, imat
 
 
-def intersect_rows(table, groups, mode, out=None):
-    """Run the fused row kernel.  Returns device tensors (no sync)."""
+#: from this many column masks per image on, the crop rows kernel finds its candidates through a
+#: uniform grid over the image (ampis_intersect_rows_grid) instead of scanning every column's box
+ROWS_GRID_MIN_COLS = int(os.environ.get('AMPIS_ROWS_GRID_MIN_COLS', 1024))
+
+
+class ColumnGrid(object):
+    """Uniform 32 x 32 grid over every image of a batch with the column masks binned by bounding box
+    (the spatial index of ampis_intersect_rows_grid).  build() needs the measured boxes of `table`;
+    without a capacity the number of entries is read back (one sync) and the entry list sized exactly."""
+
+    def __init__(self, device, n_groups, capacity=None):
+        self.device, self.n_groups = device, int(n_groups)
+        cells = N.lib().ampis_grid_cells() * max(self.n_groups, 1)
+        self.n_cells = cells
+        self.shift = torch.empty(max(self.n_groups, 1), dtype=torch.int32, device=device)
+        self.cell_count = torch.empty(cells, dtype=torch.int64, device=device)
+        self.cell_off = torch.empty(cells + 1, dtype=torch.int64, device=device)
+        self.cell_fill = torch.empty(cells, dtype=torch.int32, device=device)
+        self.tmp_bytes = N.lib().ampis_scan_tmp_bytes(cells)
+        self.tmp = torch.empty(max(self.tmp_bytes // 8, 1), dtype=torch.int64, device=device)
+        self.entries = None if capacity is None else torch.empty(max(int(capacity), 1), dtype=torch.int32,
+                                                                 device=device)
+        self.capacity = None if capacity is None else int(capacity)
+
+    def build(self, table, groups):
+        N.call('ampis_grid_count', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
+               groups.n_groups, groups.max_cols, _p(self.shift), _p(self.cell_count), _p(self.cell_fill), _stream())
+        N.call('ampis_exclusive_scan_i64', _p(self.cell_count), _p(self.cell_off), self.n_cells, _p(self.tmp),
+               self.tmp_bytes, _stream())
+        if self.entries is None:
+            self.capacity = self.needed()
+            self.entries = torch.empty(max(self.capacity, 1), dtype=torch.int32, device=self.device)
+        N.call('ampis_grid_fill', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
+               groups.n_groups, groups.max_cols, _p(self.shift), _p(self.cell_off), _p(self.cell_fill),
+               _p(self.entries), self.capacity, _stream())
+        return self
+
+    def needed(self):
+        """Entries the last build() wanted (read-back; compare with .capacity)."""
+        return int(self.cell_off[self.n_cells].item())
+
+
+class SparseRows(object):
+    """Sparse output of ampis_intersect_rows_grid: the non-zero intersections as (row, column-in-group,
+    intersection) triplets, unordered; `count` may exceed `capacity` (the excess was dropped)."""
+
+    def __init__(self, device, capacity):
+        self.capacity = int(capacity)
+        c = max(self.capacity, 1)
+        self.row = torch.empty(c, dtype=torch.int32, device=device)
+        self.col = torch.empty(c, dtype=torch.int32, device=device)
+        self.inter = torch.empty(c, dtype=torch.int32, device=device)      # uint32 payload
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def triplets(self):
+        """(row, col, inter) as int64 device tensors sorted by (row, col); raises if entries were dropped."""
+        n = int(self.count.item())
+        if n > self.capacity:
+            raise N.AmpisNativeError('sparse intersection list too small: %d triplets, capacity %d'
+                                     % (n, self.capacity))
+        r, c = self.row[:n].long(), self.col[:n].long()
+        order = torch.argsort((r << 32) | c)
+        return r[order], c[order], (self.inter[:n].long() & 0xffffffff)[order]
+
+
+def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None):
+    """Run the fused row kernel.  Returns device tensors (no sync).  Crop-layout tables with many
+    columns per image (ROWS_GRID_MIN_COLS), or whenever a ColumnGrid / SparseRows is passed, go through
+    the grid-pruned kernel; grid='scan' forces the all-columns scan."""
     dev = table.device
     nr = max(groups.n_rows, 1)
     if out is None:
@@ -280,6 +348,25 @@ def intersect_rows(table, groups, mode, out=None):
         out = RowResult(torch.empty(nr, dtype=torch.int32, device=dev),
                         torch.empty(nr, dtype=torch.int32, device=dev),
                         torch.empty(nr, dtype=torch.float64, device=dev), imat)
+    use_grid = table.layout == LAYOUT_CROP and not isinstance(grid, str) and \
+        (grid is not None or sparse is not None or groups.max_cols >= ROWS_GRID_MIN_COLS)
+    assert use_grid or sparse is None, 'sparse output comes from the grid kernel (crop layout)'
+    if use_grid:
+        if grid is None:
+            grid = ColumnGrid(dev, groups.n_groups)
+        grid.build(table, groups)
+        out.grid = grid
+        if sparse is not None:
+            sparse.count.zero_()
+        N.call('ampis_intersect_rows_grid', _p(table.bits), _p(table.bits_off), _p(table.bbox), _p(table.area),
+               _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0), groups.n_blocks,
+               _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),
+               _p(groups.grp_col_count), _p(grid.shift), _p(grid.cell_off), _p(grid.entries), grid.capacity,
+               _p(groups.imat_off), mode, _p(out.imat), _p(out.best_col), _p(out.best_inter), _p(out.best_score),
+               _p(sparse.row) if sparse else None, _p(sparse.col) if sparse else None,
+               _p(sparse.inter) if sparse else None, sparse.capacity if sparse else 0,
+               _p(sparse.count) if sparse else None, _stream())
+        return out
     if table.layout == LAYOUT_CROP:
         N.call('ampis_intersect_rows_crop', _p(table.bits), _p(table.bits_off), _p(table.bbox), _p(table.area),
                _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0), groups.n_blocks,

@@ -43,9 +43,14 @@ def parse():
                          'span = culled storage (only first..last 1-pixel of each mask); '
                          'crop = bounding-box windows (the cropped accounting of SURVEY 8d)')
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
-    ap.add_argument('--kernel', default='rows', choices=['rows', 'mma'],
-                    help='intersection kernel: rows = bbox-culled AND+popc (default); mma = dense int8 tcgen05 '
-                         'contraction (for crowded images, e.g. --config dense_overlap)')
+    ap.add_argument('--kernel', default='rows', choices=['rows', 'mma', 'grid', 'scan'],
+                    help='intersection kernel: rows = bbox-culled AND+popc (default; crop layout with >= 1024 '
+                         'columns per image prunes through a uniform grid); grid / scan = crop layout with the grid '
+                         'forced / forbidden; mma = dense int8 tcgen05 contraction (for crowded images, e.g. '
+                         '--config dense_overlap)')
+    ap.add_argument('--sparse', action='store_true',
+                    help='crop layout: no dense G x P matrix, the non-zero intersections come out as triplets '
+                         '(bbox-pruned sparse IoU, the C4 form of SURVEY 8d)')
     ap.add_argument('--mma-sort', action='store_true',
                     help='with --kernel mma: cut the tiles from spatially sorted masks (fewer slabs contracted; the '
                          'default contracts the full pixel range so that the tensor roofline counts executed work)')
@@ -217,7 +222,7 @@ class LayoutRun(object):
         for s0 in range(0, args.images, sub):
             k = min(sub, args.images - s0)
             host = batch.synth(args.config, k, 1_000_003 * (rank + 1) + s0)
-            self.subs.append(batch.DeviceBatch(host, dev, dense=True))
+            self.subs.append(batch.DeviceBatch(host, dev, dense=not (args.sparse and layout == engine.LAYOUT_CROP)))
         self.t_gen = time.time() - t0
         self.total_runs = sum(b.host.total_runs() for b in self.subs)
         need = [batch.arena_chunks_needed(b, layout) for b in self.subs]
@@ -227,8 +232,8 @@ class LayoutRun(object):
         self.rows_out = engine.RowResult(torch.empty(n_rows, dtype=torch.int32, device=dev),
                                          torch.empty(n_rows, dtype=torch.int32, device=dev),
                                          torch.empty(n_rows, dtype=torch.float64, device=dev),
-                                         torch.empty(max(b.groups.imat_size for b in self.subs), dtype=torch.int32,
-                                                     device=dev))
+                                         torch.empty(max(max(b.groups.imat_size for b in self.subs), 1),
+                                                     dtype=torch.int32, device=dev))
         self.thresholds = batch.COCO_THRESHOLDS
         cfg = batch.CONFIGS[args.config]
         n_tot = len(self.thresholds) * 3
@@ -240,8 +245,9 @@ class LayoutRun(object):
         self.mode = cfg['mode']
         self.pipes = [batch.Pipeline(b, layout, self.arena, self.rows_out, self.thresholds, self.totals,
                                      fused=self.fused, kernel=args.kernel, mma_sort=args.mma_sort,
-                                     area_hist=self.area_hist,
-                                     area_bin_width=cfg.get('area_bin_width', 64)) for b in self.subs]
+                                     area_hist=self.area_hist, area_bin_width=cfg.get('area_bin_width', 64),
+                                     sparse_capacity=(32 * b.groups.n_rows if args.sparse and
+                                                      layout == engine.LAYOUT_CROP else None)) for b in self.subs]
         if self.mode != 0:
             for p in self.pipes[1:]:
                 p.spp_hist = self.pipes[0].spp_hist
@@ -308,6 +314,14 @@ class LayoutRun(object):
             for i in range(4):
                 kt[i] += ev[i].elapsed_time(ev[i + 1])
         self.pipes[-1].table.check()      # arena large enough, RLE well-formed (after the timed region)
+        self.sparse_pairs = None
+        if self.pipes[0].sparse is not None:
+            cnt = [int(p.sparse.count.item()) for p in self.pipes]
+            assert all(c <= p.sparse.capacity for c, p in zip(cnt, self.pipes)), 'sparse triplet list overflowed'
+            self.sparse_pairs = sum(cnt)
+        for p in self.pipes:
+            if getattr(p.grid, 'capacity', None):
+                assert p.grid.needed() <= p.grid.capacity, 'grid entry list overflowed'
         if self.mode != 0:      # satellites: per-image counts summed over the batch + the global histogram
             c = sum(p.counts.cpu().numpy().sum(axis=0) for p in self.pipes)
             return float(ms.item()), kt, np.concatenate([c, self.pipes[0].spp_hist.cpu().numpy()[:8]]).reshape(1, -1)
@@ -403,6 +417,8 @@ def main():
             by_imat = max(1, int(4e9 // (4 * cfg['n_rows'] * cfg['n_cols'])))
             return max(1, min(args.images, int(12e9 // (per_image * B_m)), by_imat))       # ~12 GB arena
         by_imat = max(1, int(4e9 // (4 * cfg['n_rows'] * cfg['n_cols'])))          # dense matrices <= 4 GB per launch
+        if args.sparse and lay == engine.LAYOUT_CROP:
+            by_imat = args.images
         return min(args.images, 250, by_imat)
 
     sampler = ClockSampler(local) if rank == 0 else None       # samples cover warm-up + timed steps
@@ -418,7 +434,8 @@ def main():
     # decode -> same pipeline -> D2H of per-image counts and per-GT matches
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, run.subs, dev, layout, run.arena, run.rows_out, run.thresholds, world, dist, sync)
+        e2e = run_e2e(args, run.subs, dev, layout, run.arena, run.rows_out, run.thresholds, world, dist, sync,
+                      pipes=run.pipes)
 
     # ---- the culled storage layout (product default), measured beside the canonical one
     span = None
@@ -449,11 +466,12 @@ def main():
                 'images_per_s': job_images * args.steps / (cms / 1e3), 'ms_per_step': cms / args.steps,
                 'images_per_launch': crun.sub, 'roofline': roofline_of(args, cfg, crun, cms, ckt, world),
                 'stored_bytes_per_image': crun.stored_chunks * 16 / args.images,
+                'intersection_kernel': 'grid' if getattr(crun.pipes[0].grid, 'capacity', None) else 'scan',
                 'note': 'same inputs and bit-identical results; only the bounding-box window of each mask is '
                         'stored (32-row bands of the box columns)'}
         if not args.no_e2e:
             crop['e2e'] = run_e2e(args, crun.subs, dev, engine.LAYOUT_CROP, crun.arena, crun.rows_out,
-                                  crun.thresholds, world, dist, sync)
+                                  crun.thresholds, world, dist, sync, pipes=crun.pipes)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -468,7 +486,7 @@ def main():
         'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
         'images_per_s': job_images * args.steps / (ms / 1e3),
         'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
-                   'layout': args.layout, 'intersection_kernel': args.kernel + ('+sorted tiles' if args.kernel == 'mma' and args.mma_sort else ''), 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
+                   'layout': args.layout, 'sparse_output': bool(run.pipes[0].sparse), 'intersection_kernel': ('grid' if getattr(run.pipes[0].grid, 'capacity', None) else args.kernel) + ('+sorted tiles' if args.kernel == 'mma' and args.mma_sort else ''), 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
                    'runs_per_mask': run.total_runs / n_masks,
                    'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
                          'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
@@ -476,11 +494,15 @@ def main():
                    'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN%s per step' % (
                        world, ' + %d-bin area histogram' % cfg['area_bins'] if cfg.get('area_bins') else '')},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
+        # grid-pruned crop rows: + setup, count, 3 scan kernels, fill
         'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel == 'mma' else 0) +
+                                                            (6 if getattr(run.pipes[0].grid, 'capacity', None) else 0) +
                                                             (1 if cfg.get('area_bins') else 0))),
         ('totals_tp_fp_fn_at_0.50' if cfg['mode'] == 0 else 'sat_matched_unmatched_satellited_particles+spp_hist'): final_totals[0].tolist(),
         'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},
     }
+    if run.sparse_pairs is not None:
+        out['config']['nonzero_pairs_per_image'] = run.sparse_pairs / args.images
     if e2e:
         out['e2e'] = e2e
     if span:
@@ -494,7 +516,7 @@ def main():
         dist.destroy_process_group()
 
 
-def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, sync):
+def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, sync, pipes=None):
     """Same metric through host buffers: every step copies the compressed RLE strings (what the
     reference API receives) from pinned host memory, decodes them on the GPU, runs the pipeline
     and reads the per-image counts and per-GT matches back."""
@@ -570,7 +592,8 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
             if args.kernel == 'mma':
                 rows = engine.intersect_mma(t, b.groups, b.mode, out=rows_out, sort=args.mma_sort)
             else:
-                rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out)
+                rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out, grid=pipes[i].grid if pipes else None,
+                                             sparse=pipes[i].sparse if pipes else None)
             if b.mode == engine.MODE_IOU:
                 counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
             else:       # satellites: per-image (matched, unmatched, satellited particles, particles) + global histogram

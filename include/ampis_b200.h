@@ -175,6 +175,35 @@ int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, con
                               int32_t *d_imat, int32_t *d_best_col, uint32_t *d_best_inter,
                               double *d_best_score, void *stream);
 
+/* The crop rows kernel with the bbox pre-pruning (rleIou's bbIou pass, analyze.py:108,158) done through a
+ * uniform grid instead of a scan of all G x P boxes -- for images with thousands of instances
+ * (spheroidite, satellites vs 2,000 particles).  The column masks of every group are binned into
+ * ampis_grid_cells() = 32 x 32 square cells of side 2^grp_shift[g] pixels:
+ *   ampis_grid_count   d_grp_shift[g], d_cell_count i64[n_groups * cells] (+ clears d_cell_fill u32[same])
+ *   ampis_exclusive_scan_i64(d_cell_count -> d_cell_off[n_groups * cells + 1]); d_cell_off[last] = entries needed
+ *   ampis_grid_fill    d_entries i32[capacity]: column indices (inside the group) cell by cell
+ * ampis_intersect_rows_grid then gives the same per-row outputs (and dense rows, if asked) as
+ * ampis_intersect_rows_crop, bit for bit.  Optional sparse output: the non-zero intersections as
+ * (row, column-in-group, intersection) triplets in no particular order; *d_coo_count (zeroed by the
+ * caller) counts them and may exceed coo_capacity, in which case the excess was dropped. */
+int ampis_grid_cells(void);
+int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                     int32_t n_groups, int32_t max_cols, int32_t *d_grp_shift, int64_t *d_cell_count,
+                     uint32_t *d_cell_fill, void *stream);
+int ampis_grid_fill(const int32_t *d_bbox, const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                    int32_t n_groups, int32_t max_cols, const int32_t *d_grp_shift, const int64_t *d_cell_off,
+                    uint32_t *d_cell_fill, int32_t *d_entries, int64_t capacity, void *stream);
+int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
+                              const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_blk_grp,
+                              const int32_t *d_blk_row0, int32_t n_blocks, const int32_t *d_grp_row_begin,
+                              const int32_t *d_grp_row_count, const int32_t *d_grp_col_begin,
+                              const int32_t *d_grp_col_count, const int32_t *d_grp_shift,
+                              const int64_t *d_cell_off, const int32_t *d_entries, int64_t capacity,
+                              const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
+                              int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
+                              int32_t *d_coo_row, int32_t *d_coo_col, uint32_t *d_coo_inter,
+                              int64_t coo_capacity, uint64_t *d_coo_count, void *stream);
+
 /* ---- dense intersection matrices on the tensor cores (tcgen05, int8 contraction) -----------
  * Same quantity as the dense output of ampis_intersect_rows -- I[r][c] = popcount(row AND col),
  * what rleIou's run walk accumulates per pair (analyze.py:108,158; powder.py:82) -- computed for

@@ -389,6 +389,48 @@ def test_crop_layout_equals_span_layout(mods, cfg, over, n_img):
     assert int(a.rows.imat.max()) > 0
 
 
+@pytest.mark.parametrize('cfg,over,n_img', [
+    ('c2_powder_batch', {}, 3),
+    ('c4_spheroidite', dict(n_rows=1500, n_cols=1500, h=1024, w=1024), 2),
+    ('c4_spheroidite', dict(n_rows=700, n_cols=900, h=300, w=2000), 2),                    # cells clamp on one axis
+    ('dense_overlap', {}, 1),                                                              # boxes over many cells
+    ('c3_satellites', dict(n_cols=1200, h=1024, w=1024), 2),
+    ('c2_powder_batch', dict(h=70, w=45, n_rows=9, n_cols=11, median_diam=30.0), 4),
+])
+def test_grid_pruned_rows_equal_scanned_rows(mods, cfg, over, n_img):
+    """Crop rows kernel with the box pre-pruning through the uniform grid == the kernel that tests every
+    column's box, bit for bit (dense matrix, arg-max, scores, counts); its sparse output is exactly the
+    set of non-zero cells of the dense matrix."""
+    B, E, torch = mods.batch, mods.engine, mods.torch
+    host = B.synth(dict(B.CONFIGS[cfg], **over), n_img, 4242)
+    dev = B.DeviceBatch(host, dense=True)
+    a = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, kernel='scan')
+    sp = E.SparseRows('cuda', dev.groups.imat_size)
+    b = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, kernel='grid', sparse=sp)
+    assert b.rows.grid.needed() == b.rows.grid.capacity > 0
+    assert torch.equal(a.rows.imat, b.rows.imat)
+    assert torch.equal(a.rows.best_col, b.rows.best_col) and torch.equal(a.rows.best_inter, b.rows.best_inter)
+    assert np.array_equal(a.rows.best_score.cpu().numpy(), b.rows.best_score.cpu().numpy(), equal_nan=True)
+    assert torch.equal(a.counts, b.counts)
+    r, c, v = (x.cpu().numpy() for x in sp.triplets())
+    G, Pn = host.n_rows, host.n_cols
+    I = a.rows.imat.cpu().numpy()[:n_img * G * Pn].reshape(n_img * G, Pn)
+    wr, wc = np.nonzero(I)
+    assert np.array_equal(r, wr) and np.array_equal(c, wc) and np.array_equal(v, I[wr, wc])
+    # no dense matrix at all: same rows
+    dev2 = B.DeviceBatch(host, dense=False)
+    d = B.eval_step(dev2, layout=E.LAYOUT_CROP, kernel='grid')
+    assert torch.equal(a.rows.best_col, d.rows.best_col) and torch.equal(a.counts, d.counts)
+    # pre-sized pipeline form (what bench.py runs)
+    arena = torch.empty(4 * B.arena_chunks_needed(dev2, E.LAYOUT_CROP), dtype=torch.int32, device='cuda')
+    pipe = B.Pipeline(dev2, E.LAYOUT_CROP, arena, kernel='grid', sparse_capacity=sp.capacity)
+    pipe.launch()
+    pipe.launch()
+    assert torch.equal(pipe.rows.best_col[:dev2.groups.n_rows], a.rows.best_col[:dev2.groups.n_rows])
+    assert int(pipe.sparse.count.item()) == len(wr)
+    assert pipe.grid.needed() == pipe.grid.capacity
+
+
 def test_full_size_properties(mods):
     """BASELINE config sizes (C2 image count reduced): size-independent properties --
     span and full layouts agree bit for bit, I(gt,pred) == I(pred,gt)^T, area == popcount of the
@@ -833,7 +875,7 @@ def test_randomised_batches_all_layouts_and_kernels_vs_dense_numpy(mods, seed):
                 arena = None
                 if fused:
                     arena = torch.empty(4 * max(B.arena_chunks_needed(dev, layout), 1), dtype=torch.int32, device='cuda')
-                kernels = ('rows',) if layout == E.LAYOUT_CROP else ('rows', 'mma')
+                kernels = ('rows', 'grid') if layout == E.LAYOUT_CROP else ('rows', 'mma')
                 for kernel in kernels:
                     r = B.eval_step(dev, layout=layout, check=True, arena=arena, kernel=kernel)
                     I = r.rows.imat.cpu().numpy()[:n_img * G * Pn].reshape(n_img, G, Pn)
