@@ -51,6 +51,25 @@ __device__ __forceinline__ u32 warp_max(u32 v)
     return v;
 }
 
+// Division of 32-bit positions by a per-mask constant (the image height: position -> column) without the
+// ~20-instruction IDIV sequence: q = umulhi(s, floor((2^32-1)/d)) is floor(s/d) or one less.
+struct FastDiv {
+    u32 d, m;
+};
+__device__ __forceinline__ FastDiv fastdiv_make(u32 d)
+{
+    FastDiv f;
+    f.d = d;
+    f.m = 0xffffffffu / d;
+    return f;
+}
+__device__ __forceinline__ u32 fastdiv(u32 s, const FastDiv f)
+{
+    u32 q = __umulhi(s, f.m);
+    if (s - q * f.d >= f.d) q++;
+    return q;
+}
+
 // streaming 128-bit store / load (data is written once and read by a later kernel)
 __device__ __forceinline__ void st_v4_stream(uint4 *p, uint4 v)
 {

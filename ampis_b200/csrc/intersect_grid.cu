@@ -279,17 +279,18 @@ extern "C" int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_
     if (n_groups == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_bbox && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_count && d_cell_fill,
                   "null pointer");
-    AMPIS_REQUIRE(n_groups <= 65535, "more than 65535 groups per launch");
     grid_setup_kernel<<<n_groups, 256, 0, as_stream(stream)>>>((const int4 *)d_bbox, d_grp_col_begin,
                                                                d_grp_col_count, d_grp_shift, d_cell_count,
                                                                d_cell_fill);
     AMPIS_CHECK_LAUNCH("grid_setup_kernel");
     if (max_cols == 0) return AMPIS_OK;
-    const dim3 grid((max_cols + 255) / 256, n_groups);
-    grid_bin_kernel<false><<<grid, 256, 0, as_stream(stream)>>>((const int4 *)d_bbox, d_grp_col_begin,
-                                                                 d_grp_col_count, d_grp_shift, d_cell_count,
-                                                                 nullptr, nullptr, nullptr, 0);
-    AMPIS_CHECK_LAUNCH("grid_bin_kernel<count>");
+    for (int32_t g0 = 0; g0 < n_groups; g0 += 65535) {             // gridDim.y limit
+        const dim3 grid((max_cols + 255) / 256, min(n_groups - g0, 65535));
+        grid_bin_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
+            (const int4 *)d_bbox, d_grp_col_begin + g0, d_grp_col_count + g0, d_grp_shift + g0,
+            d_cell_count + (i64)g0 * GR_CELLS, nullptr, nullptr, nullptr, 0);
+        AMPIS_CHECK_LAUNCH("grid_bin_kernel<count>");
+    }
     return AMPIS_OK;
 }
 
@@ -302,12 +303,14 @@ extern "C" int ampis_grid_fill(const int32_t *d_bbox, const int32_t *d_grp_col_b
     if (n_groups == 0 || max_cols == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_bbox && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_off && d_cell_fill &&
                       d_entries, "null pointer");
-    AMPIS_REQUIRE(n_groups <= 65535, "more than 65535 groups per launch");
-    const dim3 grid((max_cols + 255) / 256, n_groups);
-    grid_bin_kernel<true><<<grid, 256, 0, as_stream(stream)>>>((const int4 *)d_bbox, d_grp_col_begin,
-                                                                d_grp_col_count, d_grp_shift, nullptr, d_cell_off,
-                                                                d_cell_fill, d_entries, capacity);
-    AMPIS_CHECK_LAUNCH("grid_bin_kernel<fill>");
+    for (int32_t g0 = 0; g0 < n_groups; g0 += 65535) {
+        const dim3 grid((max_cols + 255) / 256, min(n_groups - g0, 65535));
+        // cell_off holds absolute entry positions, so only the per-group arrays are shifted
+        grid_bin_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(
+            (const int4 *)d_bbox, d_grp_col_begin + g0, d_grp_col_count + g0, d_grp_shift + g0, nullptr,
+            d_cell_off + (i64)g0 * GR_CELLS, d_cell_fill + (i64)g0 * GR_CELLS, d_entries, capacity);
+        AMPIS_CHECK_LAUNCH("grid_bin_kernel<fill>");
+    }
     return AMPIS_OK;
 }
 

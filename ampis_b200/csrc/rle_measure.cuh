@@ -18,6 +18,7 @@ __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt,
                                                     u32 *cum_s, int cum_s_cap, u32 *cum_g)
 {
     const u32 lane = lane_id();
+    const FastDiv byH = fastdiv_make(H);
     u64 carry = 0;
     u32 a = 0, first = 0xffffffffu, last = 0, ymin = 0xffffffffu, ymax = 0;
     // 128 runs per outer step: the four loads are independent, so a typical mask (~75 runs)
@@ -52,7 +53,7 @@ __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt,
                 a += c;
                 first = min(first, start);
                 last = max(last, end);
-                const u32 xs = start / H, xe = (end - 1) / H;
+                const u32 xs = fastdiv(start, byH), xe = fastdiv(end - 1, byH);
                 if (xs != xe) { ymin = 0; ymax = H - 1; }
                 else { ymin = min(ymin, start - xs * H); ymax = max(ymax, end - 1 - xe * H); }
             }

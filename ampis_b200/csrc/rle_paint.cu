@@ -195,6 +195,7 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
     const u32 x_end = (u32)bb.z + 1u;
     const u32 cols_per_tile = max(1u, tile_words / nwy);
     const bool one_tile = (x_end - (u32)bb.x) <= cols_per_tile;
+    const FastDiv byH = fastdiv_make(H);
     for (u32 xa = (u32)bb.x; xa < x_end; xa += cols_per_tile) {
         const u32 xb = min(xa + cols_per_tile, x_end);
         const u32 tw = (xb - xa) * nwy;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
             u64 s = rs > b0 ? rs : b0;
             const u64 e = re < b1 ? re : b1;
             while (s < e) {
-                const u32 x = (u32)(s / H);
+                const u32 x = fastdiv((u32)s, byH);               // s < e <= a run end, which is a u32
                 const u64 cs = (u64)x * H;
                 // rows [ys,ye) of column x, clipped to the box rows (a well-formed mask never needs the clip;
                 // a malformed one -- flagged in status -- must not write outside its window)
