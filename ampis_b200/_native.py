@@ -38,9 +38,9 @@ SIGNATURES = {
                                             _p, _p]),
     'ampis_grid_cells': (C.c_int, []),
     'ampis_grid_count': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
-    'ampis_grid_fill': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p, _i64, _p]),
-    'ampis_intersect_rows_grid': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
-                                            _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
+    'ampis_grid_fill': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _p]),
+    'ampis_intersect_rows_grid': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64,
+                                            _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     'ampis_rle_decode_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     'ampis_mma_tile_rows': (C.c_int, []),
     'ampis_mma_tile_cols': (C.c_int, []),

@@ -27,8 +27,11 @@
 
 #define GR_N 32                 // cells per axis
 #define GR_CELLS (GR_N * GR_N)
-#define GR_ROWS 8
-#define GR_LIST 64
+#define GR_ROWS 8               // rows per CTA (= ampis_rows_per_block())
+#define GR_TILE 8               // lanes per row
+#define GR_THREADS (GR_ROWS * GR_TILE)
+#define GR_LIST 16              // candidates a tile collects before it intersects them
+#define GR_BIGLIST 16           // large overlaps a warp parks for its warp-wide phase
 #define GR_BIG 256              // overlap words from which a candidate gets the whole warp
 
 __device__ __forceinline__ int bits_of(u32 x) { return 32 - __clz(x); }
@@ -70,7 +73,7 @@ grid_setup_kernel(const int4 *bbox, const int *grp_col_begin, const int *grp_col
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 grid_bin_kernel(const int4 *bbox, const int *grp_col_begin, const int *grp_col_count, const int *grp_shift,
-                i64 *cell_count, const i64 *cell_off, u32 *cell_fill, int *entries, i64 capacity)
+                i64 *cell_count, const i64 *cell_off, u32 *cell_fill, int *entries, int4 *entry_bbox, i64 capacity)
 {
     const int g = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +87,7 @@ grid_bin_kernel(const int4 *bbox, const int *grp_col_begin, const int *grp_col_c
             const i64 cell = (i64)g * GR_CELLS + cy * GR_N + cx;
             if (FILL) {
                 const i64 pos = cell_off[cell] + (i64)atomicAdd(cell_fill + cell, 1u);
-                if (pos < capacity) entries[pos] = k;
+                if (pos < capacity) { entries[pos] = k; entry_bbox[pos] = b; }
             } else {
                 atomicAdd(reinterpret_cast<unsigned long long *>(cell_count + cell), 1ull);
             }
@@ -102,6 +105,7 @@ struct GridRowArgs {
     const int *grp_shift;
     const i64 *cell_off;
     const int *entries;
+    const int4 *entry_bbox;
     i64 capacity;
     const i64 *grp_imat_off;
     int *imat;
@@ -114,92 +118,122 @@ struct GridRowArgs {
     unsigned long long *coo_count;
 };
 
+// Eight lanes per row (a warp works on four rows at once): with a handful of cells, entries and candidates per
+// row, a whole warp per row left most lanes idle and the kernel latency bound (ncu: 53 % of the stall samples on
+// dependent loads at 39 % occupancy).  The four 8-lane tiles of a warp run independently (tile-masked shuffles,
+// ballots and syncs); candidates with large overlaps are parked in a per-warp list and handled by all 32 lanes
+// once every tile is through, so big masks still get the whole warp.
 template <int MODE>
-__global__ void __launch_bounds__(GR_ROWS * 32, 4)
+__global__ void __launch_bounds__(GR_THREADS, 20)
 intersect_rows_grid_kernel(const GridRowArgs p)
 {
-    __shared__ int s_cand[GR_ROWS][GR_LIST];
-    __shared__ int s_pre[GR_ROWS][32];          // exclusive prefix of the entry counts of the warp's 32 cells
-    __shared__ int s_base[GR_ROWS][32];         // first entry of the cell (relative to the image) - prefix
+    __shared__ int s_k[GR_ROWS][GR_LIST];
+    __shared__ int4 s_bb[GR_ROWS][GR_LIST];
+    __shared__ int s_pre[GR_ROWS][GR_TILE];         // exclusive prefix of the entry counts of the tile's 8 cells
+    __shared__ int s_base[GR_ROWS][GR_TILE];        // first entry of the cell (relative to the image) - prefix
+    __shared__ int s_nbig[GR_THREADS / 32];
+    __shared__ int s_big_k[GR_THREADS / 32][GR_BIGLIST], s_big_slot[GR_THREADS / 32][GR_BIGLIST];
+    __shared__ u32 s_big_area[GR_THREADS / 32][GR_BIGLIST];
+    __shared__ i64 s_big_off[GR_THREADS / 32][GR_BIGLIST];
+    __shared__ int4 s_big_bb[GR_THREADS / 32][GR_BIGLIST];
+    __shared__ int4 s_row_bb[GR_ROWS];
+    __shared__ const u32 *s_row_A[GR_ROWS];
 
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const u32 t = lane & (GR_TILE - 1), tsh = lane & ~(GR_TILE - 1);
+    const u32 tmask = ((1u << GR_TILE) - 1u) << tsh;
+    const int slot = (int)threadIdx.x / GR_TILE;
     const int g = p.blk_grp[blockIdx.x];
-    const int r = p.blk_row0[blockIdx.x] + (int)wid;
-    if (r >= p.grp_row_begin[g] + p.grp_row_count[g]) return;      // no CTA-wide barrier below
+    const int r = p.blk_row0[blockIdx.x] + slot;
+    const bool valid = r < p.grp_row_begin[g] + p.grp_row_count[g];
     const int cb = p.grp_col_begin[g];
     const int P = p.grp_col_count[g];
     const i64 imat_off = (p.imat && p.grp_imat_off) ? p.grp_imat_off[g] : -1;
-    int *irow = imat_off >= 0 ? p.imat + imat_off + (i64)(r - p.grp_row_begin[g]) * P : nullptr;
+    int *irow = (valid && imat_off >= 0) ? p.imat + imat_off + (i64)(r - p.grp_row_begin[g]) * P : nullptr;
 
-    const int rm = p.row_mask[r];
-    const int4 rb = p.bbox[rm];
-    const u32 ra = p.area[rm];
-    const u32 *A = p.words + p.bits_off[rm] * 4;
-    double best_s = 0.0;
+    int4 rb = make_int4(0, 0, -1, -1);
+    u32 ra = 0;
+    const u32 *A = nullptr;
+    if (valid) {
+        const int rm = p.row_mask[r];
+        rb = p.bbox[rm];
+        ra = p.area[rm];
+        A = p.words + p.bits_off[rm] * 4;
+    }
+    if (t == 0) { s_row_bb[slot] = rb; s_row_A[slot] = A; }
+    if (lane == 0) s_nbig[wid] = 0;
+    __syncwarp();
+    double best_s = 0.0;                             // identical in the 8 lanes of a tile
     u32 best_i = 0;
     int best_c = MODE == AMPIS_MODE_IOU ? -1 : (P > 0 ? 0 : -1);
-    int *list = s_cand[wid];
 
-    if (irow) {                                                    // dense row: zeros now, candidates patch later
-        for (int k = (int)lane; k < P; k += 32) irow[k] = 0;
-        __syncwarp();
-    }
-
-    auto flush = [&](int n) {
-        for (int j0 = 0; j0 < n; j0 += 4) {
-            const int j = j0 + (int)(lane >> 3);
-            const bool have = j < n;
-            const int k = have ? list[j] : 0;
-            Overlap o;
-            o.total = 0;
-            if (have) o = overlap_of(A, rb, p.words + p.bits_off[cb + k] * 4, p.bbox[cb + k]);
-            u32 inter = 0;
-            if (__any_sync(0xffffffffu, have && o.total >= GR_BIG)) {
-                for (int q = 0; q < 4 && j0 + q < n; q++) {
-                    const int kq = list[j0 + q];
-                    const Overlap oq = overlap_of(A, rb, p.words + p.bits_off[cb + kq] * 4, p.bbox[cb + kq]);
-                    const u32 v = warp_sum(overlap_popc(oq, lane, 32));
-                    if ((int)(lane >> 3) == q) inter = v;
-                }
-            } else {
-                u32 v = have ? overlap_popc(o, lane & 7u, 8) : 0u;
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                inter = v;
+    auto update = [&](int k, u32 inter, u32 ca) {
+        if (!inter) return;
+        if (t == 0) {
+            if (irow) irow[k] = (int)inter;
+            if (p.coo_count) {
+                const unsigned long long pos = atomicAdd(p.coo_count, 1ull);
+                if ((i64)pos < p.coo_capacity) { p.coo_row[pos] = r; p.coo_col[pos] = k; p.coo_inter[pos] = inter; }
             }
-            if (have && (lane & 7u) == 0 && inter) {
-                if (irow) irow[k] = (int)inter;
-                if (p.coo_count) {
-                    const unsigned long long pos = atomicAdd(p.coo_count, 1ull);
-                    if ((i64)pos < p.coo_capacity) {
-                        p.coo_row[pos] = r; p.coo_col[pos] = k; p.coo_inter[pos] = inter;
+        }
+        if (MODE == AMPIS_MODE_IOU) {
+            const double s = (double)inter / (double)(ra + ca - inter);
+            if (s > best_s || (s == best_s && (unsigned)k < (unsigned)best_c)) { best_s = s; best_i = inter; best_c = k; }
+        } else {
+            if (inter > best_i || (inter == best_i && (unsigned)k < (unsigned)best_c)) { best_i = inter; best_c = k; }
+        }
+    };
+
+    // the tile's candidate list -> intersections; metadata of up to 8 candidates is fetched by one lane each
+    auto flush = [&](int n) {
+        for (int j0 = 0; j0 < n; j0 += GR_TILE) {
+            const int mine = j0 + (int)t;
+            int k_m = 0;
+            i64 off_m = 0;
+            u32 area_m = 0;
+            if (mine < n) {
+                k_m = s_k[slot][mine];
+                off_m = p.bits_off[cb + k_m];
+                area_m = p.area[cb + k_m];
+            }
+            const int nq = min(GR_TILE, n - j0);
+            for (int q = 0; q < nq; q++) {
+                const int k = __shfl_sync(tmask, k_m, q, GR_TILE);
+                const i64 off = __shfl_sync(tmask, off_m, q, GR_TILE);
+                const u32 ca = __shfl_sync(tmask, area_m, q, GR_TILE);
+                const int4 cbx = s_bb[slot][j0 + q];
+                const Overlap o = overlap_of(A, rb, p.words + off * 4, cbx);
+                if (o.total >= GR_BIG) {             // park it for the whole warp
+                    int pos = 0;
+                    if (t == 0) pos = atomicAdd(&s_nbig[wid], 1);
+                    pos = __shfl_sync(tmask, pos, 0, GR_TILE);
+                    if (pos < GR_BIGLIST) {
+                        if (t == 0) {
+                            s_big_k[wid][pos] = k; s_big_slot[wid][pos] = slot; s_big_area[wid][pos] = ca;
+                            s_big_off[wid][pos] = off; s_big_bb[wid][pos] = cbx;
+                        }
+                        continue;
                     }
                 }
-                if (MODE == AMPIS_MODE_IOU) {
-                    const double s = (double)inter / (double)(ra + p.area[cb + k] - inter);
-                    if (s > best_s || (s == best_s && (unsigned)k < (unsigned)best_c)) {
-                        best_s = s; best_i = inter; best_c = k;
-                    }
-                } else {
-                    if (inter > best_i || (inter == best_i && (unsigned)k < (unsigned)best_c)) {
-                        best_i = inter; best_c = k;
-                    }
-                }
+                u32 v = overlap_popc(o, t, GR_TILE);
+                v += __shfl_xor_sync(tmask, v, 4);
+                v += __shfl_xor_sync(tmask, v, 2);
+                v += __shfl_xor_sync(tmask, v, 1);
+                update(k, v, ca);
             }
         }
     };
 
-    if (ra != 0 && P > 0) {
+    if (valid && ra != 0 && P > 0) {
         const int s = p.grp_shift[g];
         const i64 *off = p.cell_off + (i64)g * GR_CELLS;
         const i64 gbase = off[0];
         const int rcx0 = cell_of(rb.x, s), rcy0 = cell_of(rb.y, s);
         const int ncx = cell_of(rb.z, s) - rcx0 + 1, ncell = ncx * (cell_of(rb.w, s) - rcy0 + 1);
         int n = 0;
-        for (int c0 = 0; c0 < ncell; c0 += 32) {
-            // one cell per lane: entry range, flattened by an exclusive warp scan of the lengths
-            const int ci = c0 + (int)lane;
+        for (int c0 = 0; c0 < ncell; c0 += GR_TILE) {
+            // one cell per lane: entry range, flattened by an exclusive scan of the lengths over the tile
+            const int ci = c0 + (int)t;
             int st = 0, len = 0;
             if (ci < ncell) {
                 const int cell = (rcy0 + ci / ncx) * GR_N + rcx0 + ci % ncx;
@@ -208,60 +242,63 @@ intersect_rows_grid_kernel(const GridRowArgs p)
             }
             int incl = len;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int)lane >= d) incl += t;
+            for (int d = 1; d < GR_TILE; d <<= 1) {
+                const int v = __shfl_up_sync(tmask, incl, d, GR_TILE);
+                if ((int)t >= d) incl += v;
             }
-            const int T = __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();                                          // previous round's readers are done
-            s_pre[wid][lane] = incl - len;
-            s_base[wid][lane] = st - (incl - len);
-            __syncwarp();
-            for (int t0 = 0; t0 < T; t0 += 32) {
-                const int t = t0 + (int)lane;
+            const int T = __shfl_sync(tmask, incl, GR_TILE - 1, GR_TILE);
+            __syncwarp(tmask);                                     // previous round's readers are done
+            s_pre[slot][t] = incl - len;
+            s_base[slot][t] = st - (incl - len);
+            __syncwarp(tmask);
+            for (int t0 = 0; t0 < T; t0 += GR_TILE) {
+                const int idx = t0 + (int)t;
                 bool cand = false;
                 int k = 0;
-                if (t < T) {
-                    int j = 0;                                     // last cell with prefix <= t (empty cells share a prefix)
+                int4 b = make_int4(0, 0, -1, -1);
+                if (idx < T) {
+                    int j = 0;                                     // last cell with prefix <= idx (empty cells share a prefix)
 #pragma unroll
-                    for (int d = 16; d; d >>= 1)
-                        if (s_pre[wid][j + d] <= t) j += d;
-                    const i64 e = gbase + s_base[wid][j] + t;
+                    for (int d = GR_TILE / 2; d; d >>= 1)
+                        if (s_pre[slot][j + d] <= idx) j += d;
+                    const i64 e = gbase + s_base[slot][j] + idx;
                     if (e < p.capacity) {
                         k = p.entries[e];
-                        const int4 b = p.bbox[cb + k];
+                        b = p.entry_bbox[e];
                         const int cj = c0 + j;
                         cand = b.x <= rb.z && b.z >= rb.x && b.y <= rb.w && b.w >= rb.y &&
                                max(rcx0, cell_of(b.x, s)) == rcx0 + cj % ncx &&
                                max(rcy0, cell_of(b.y, s)) == rcy0 + cj / ncx;
                     }
                 }
-                const u32 bal = __ballot_sync(0xffffffffu, cand);
-                if (cand) list[n + __popc(bal & ((1u << lane) - 1u))] = k;
+                const u32 bal = (__ballot_sync(tmask, cand) >> tsh) & ((1u << GR_TILE) - 1u);
+                if (cand) {
+                    const int pos = n + __popc(bal & ((1u << t) - 1u));
+                    s_k[slot][pos] = k;
+                    s_bb[slot][pos] = b;
+                }
                 n += __popc(bal);
-                if (n > GR_LIST - 32) {
-                    __syncwarp();
+                if (n > GR_LIST - GR_TILE) {
+                    __syncwarp(tmask);
                     flush(n);
                     n = 0;
-                    __syncwarp();
+                    __syncwarp(tmask);
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(tmask);
         flush(n);
     }
-    // warp arg-max: larger key wins, ties go to the smaller column index (np.argmax)
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, best_s, d);
-        const u32 oi = __shfl_xor_sync(0xffffffffu, best_i, d);
-        const int oc = __shfl_xor_sync(0xffffffffu, best_c, d);
-        bool take;
-        if (MODE == AMPIS_MODE_IOU) take = os > best_s || (os == best_s && (unsigned)oc < (unsigned)best_c);
-        else take = oi > best_i || (oi == best_i && (unsigned)oc < (unsigned)best_c);
-        if (take) { best_s = os; best_i = oi; best_c = oc; }
+    // ---- large overlaps parked by the warp's tiles: all 32 lanes on one candidate at a time
+    __syncwarp();
+    const int nbig = min(s_nbig[wid], GR_BIGLIST);
+    for (int i = 0; i < nbig; i++) {
+        const int os = s_big_slot[wid][i];
+        const Overlap o = overlap_of(s_row_A[os], s_row_bb[os], p.words + s_big_off[wid][i] * 4, s_big_bb[wid][i]);
+        const u32 v = warp_sum(overlap_popc(o, lane, 32));
+        if (os == slot) update(s_big_k[wid][i], v, s_big_area[wid][i]);
     }
-    if (lane == 0) {
+    if (valid && t == 0) {
         if (MODE == AMPIS_MODE_SAT) best_s = (double)best_i / (double)ra;   // 0/0 = NaN like numpy
         p.best_col[r] = best_c;
         p.best_inter[r] = best_i;
@@ -288,7 +325,7 @@ extern "C" int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_
         const dim3 grid((max_cols + 255) / 256, min(n_groups - g0, 65535));
         grid_bin_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
             (const int4 *)d_bbox, d_grp_col_begin + g0, d_grp_col_count + g0, d_grp_shift + g0,
-            d_cell_count + (i64)g0 * GR_CELLS, nullptr, nullptr, nullptr, 0);
+            d_cell_count + (i64)g0 * GR_CELLS, nullptr, nullptr, nullptr, nullptr, 0);
         AMPIS_CHECK_LAUNCH("grid_bin_kernel<count>");
     }
     return AMPIS_OK;
@@ -297,18 +334,19 @@ extern "C" int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_
 extern "C" int ampis_grid_fill(const int32_t *d_bbox, const int32_t *d_grp_col_begin,
                                const int32_t *d_grp_col_count, int32_t n_groups, int32_t max_cols,
                                const int32_t *d_grp_shift, const int64_t *d_cell_off, uint32_t *d_cell_fill,
-                               int32_t *d_entries, int64_t capacity, void *stream)
+                               int32_t *d_entries, int32_t *d_entry_bbox, int64_t capacity, void *stream)
 {
     AMPIS_REQUIRE(n_groups >= 0 && max_cols >= 0 && capacity >= 0, "negative size");
     if (n_groups == 0 || max_cols == 0) return AMPIS_OK;
     AMPIS_REQUIRE(d_bbox && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_off && d_cell_fill &&
-                      d_entries, "null pointer");
+                      d_entries && d_entry_bbox, "null pointer");
     for (int32_t g0 = 0; g0 < n_groups; g0 += 65535) {
         const dim3 grid((max_cols + 255) / 256, min(n_groups - g0, 65535));
         // cell_off holds absolute entry positions, so only the per-group arrays are shifted
         grid_bin_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(
             (const int4 *)d_bbox, d_grp_col_begin + g0, d_grp_col_count + g0, d_grp_shift + g0, nullptr,
-            d_cell_off + (i64)g0 * GR_CELLS, d_cell_fill + (i64)g0 * GR_CELLS, d_entries, capacity);
+            d_cell_off + (i64)g0 * GR_CELLS, d_cell_fill + (i64)g0 * GR_CELLS, d_entries, (int4 *)d_entry_bbox,
+            capacity);
         AMPIS_CHECK_LAUNCH("grid_bin_kernel<fill>");
     }
     return AMPIS_OK;
@@ -320,8 +358,9 @@ extern "C" int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bi
                                          const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
                                          const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
                                          const int32_t *d_grp_shift, const int64_t *d_cell_off,
-                                         const int32_t *d_entries, int64_t capacity,
+                                         const int32_t *d_entries, const int32_t *d_entry_bbox, int64_t capacity,
                                          const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
+                                         int64_t imat_ints,
                                          int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                                          int32_t *d_coo_row, int32_t *d_coo_col, uint32_t *d_coo_inter,
                                          int64_t coo_capacity, uint64_t *d_coo_count, void *stream)
@@ -332,7 +371,8 @@ extern "C" int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bi
     AMPIS_REQUIRE(d_bits_off && d_bbox && d_area && d_row_mask && d_blk_grp && d_blk_row0 && d_grp_row_begin &&
                       d_grp_row_count && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_off &&
                       d_best_col && d_best_inter && d_best_score, "null pointer");
-    AMPIS_REQUIRE(d_entries || capacity == 0, "entries missing");
+    AMPIS_REQUIRE((d_entries && d_entry_bbox) || capacity == 0, "entries missing");
+    AMPIS_REQUIRE(imat_ints >= 0, "imat_ints < 0");
     AMPIS_REQUIRE(!d_coo_count || (d_coo_row && d_coo_col && d_coo_inter && coo_capacity >= 0) || coo_capacity == 0,
                   "sparse output arrays missing");
     GridRowArgs a;
@@ -340,15 +380,19 @@ extern "C" int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bi
     a.row_mask = d_row_mask; a.blk_grp = d_blk_grp; a.blk_row0 = d_blk_row0;
     a.grp_row_begin = d_grp_row_begin; a.grp_row_count = d_grp_row_count;
     a.grp_col_begin = d_grp_col_begin; a.grp_col_count = d_grp_col_count;
-    a.grp_shift = d_grp_shift; a.cell_off = d_cell_off; a.entries = d_entries; a.capacity = capacity;
+    a.grp_shift = d_grp_shift; a.cell_off = d_cell_off; a.entries = d_entries; a.entry_bbox = (const int4 *)d_entry_bbox; a.capacity = capacity;
     a.grp_imat_off = d_grp_imat_off; a.imat = d_imat;
     a.best_col = d_best_col; a.best_inter = d_best_inter; a.best_score = d_best_score;
     a.coo_row = d_coo_row; a.coo_col = d_coo_col; a.coo_inter = d_coo_inter; a.coo_capacity = coo_capacity;
     a.coo_count = (unsigned long long *)d_coo_count;
+    if (d_imat && d_grp_imat_off && imat_ints > 0) {               // dense rows: zeros first, the kernel patches cells
+        const cudaError_t e = cudaMemsetAsync(d_imat, 0, (size_t)imat_ints * 4, as_stream(stream));
+        if (e != cudaSuccess) { ampis_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+    }
     if (mode == AMPIS_MODE_IOU)
-        intersect_rows_grid_kernel<AMPIS_MODE_IOU><<<n_blocks, GR_ROWS * 32, 0, as_stream(stream)>>>(a);
+        intersect_rows_grid_kernel<AMPIS_MODE_IOU><<<n_blocks, GR_THREADS, 0, as_stream(stream)>>>(a);
     else
-        intersect_rows_grid_kernel<AMPIS_MODE_SAT><<<n_blocks, GR_ROWS * 32, 0, as_stream(stream)>>>(a);
+        intersect_rows_grid_kernel<AMPIS_MODE_SAT><<<n_blocks, GR_THREADS, 0, as_stream(stream)>>>(a);
     AMPIS_CHECK_LAUNCH("intersect_rows_grid_kernel");
     return AMPIS_OK;
 }

@@ -252,7 +252,7 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
 {
     constexpr int MASKS = MP_WARPS / TEAM_WARPS;
     constexpr int CUM_CAP = MP_CUM_WORDS / MASKS;
-    __shared__ u32 s_cum[MP_CUM_WORDS];
+    __shared__ __align__(16) u32 s_cum[MP_CUM_WORDS];
     constexpr bool TILED = KIND == 1;
     __shared__ __align__(16) u32 s_tile[KIND ? MP_WARPS : 1][KIND ? MP_TILE * 4 : 4];
     __shared__ uint2 s_span[MASKS], s_reg[MASKS];

@@ -291,9 +291,15 @@ class ColumnGrid(object):
         self.cell_fill = torch.empty(cells, dtype=torch.int32, device=device)
         self.tmp_bytes = N.lib().ampis_scan_tmp_bytes(cells)
         self.tmp = torch.empty(max(self.tmp_bytes // 8, 1), dtype=torch.int64, device=device)
-        self.entries = None if capacity is None else torch.empty(max(int(capacity), 1), dtype=torch.int32,
-                                                                 device=device)
-        self.capacity = None if capacity is None else int(capacity)
+        self.entries = self.entry_bbox = None
+        self.capacity = None
+        if capacity is not None:
+            self._alloc(int(capacity))
+
+    def _alloc(self, capacity):
+        self.capacity = capacity
+        self.entries = torch.empty(max(capacity, 1), dtype=torch.int32, device=self.device)
+        self.entry_bbox = torch.empty(4 * max(capacity, 1), dtype=torch.int32, device=self.device)
 
     def build(self, table, groups):
         N.call('ampis_grid_count', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
@@ -301,11 +307,10 @@ class ColumnGrid(object):
         N.call('ampis_exclusive_scan_i64', _p(self.cell_count), _p(self.cell_off), self.n_cells, _p(self.tmp),
                self.tmp_bytes, _stream())
         if self.entries is None:
-            self.capacity = self.needed()
-            self.entries = torch.empty(max(self.capacity, 1), dtype=torch.int32, device=self.device)
+            self._alloc(self.needed())
         N.call('ampis_grid_fill', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
                groups.n_groups, groups.max_cols, _p(self.shift), _p(self.cell_off), _p(self.cell_fill),
-               _p(self.entries), self.capacity, _stream())
+               _p(self.entries), _p(self.entry_bbox), self.capacity, _stream())
         return self
 
     def needed(self):
@@ -361,8 +366,10 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None):
         N.call('ampis_intersect_rows_grid', _p(table.bits), _p(table.bits_off), _p(table.bbox), _p(table.area),
                _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0), groups.n_blocks,
                _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),
-               _p(groups.grp_col_count), _p(grid.shift), _p(grid.cell_off), _p(grid.entries), grid.capacity,
-               _p(groups.imat_off), mode, _p(out.imat), _p(out.best_col), _p(out.best_inter), _p(out.best_score),
+               _p(groups.grp_col_count), _p(grid.shift), _p(grid.cell_off), _p(grid.entries), _p(grid.entry_bbox),
+               grid.capacity, _p(groups.imat_off), mode, _p(out.imat),
+               groups.imat_size if groups.imat_off is not None and out.imat is not None else 0,
+               _p(out.best_col), _p(out.best_inter), _p(out.best_score),
                _p(sparse.row) if sparse else None, _p(sparse.col) if sparse else None,
                _p(sparse.inter) if sparse else None, sparse.capacity if sparse else 0,
                _p(sparse.count) if sparse else None, _stream())

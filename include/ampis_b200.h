@@ -181,9 +181,11 @@ int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, con
  * ampis_grid_cells() = 32 x 32 square cells of side 2^grp_shift[g] pixels:
  *   ampis_grid_count   d_grp_shift[g], d_cell_count i64[n_groups * cells] (+ clears d_cell_fill u32[same])
  *   ampis_exclusive_scan_i64(d_cell_count -> d_cell_off[n_groups * cells + 1]); d_cell_off[last] = entries needed
- *   ampis_grid_fill    d_entries i32[capacity]: column indices (inside the group) cell by cell
- * ampis_intersect_rows_grid then gives the same per-row outputs (and dense rows, if asked) as
- * ampis_intersect_rows_crop, bit for bit.  Optional sparse output: the non-zero intersections as
+ *   ampis_grid_fill    d_entries i32[capacity]: column indices (inside the group) cell by cell, and
+ *                      d_entry_bbox i32[4 * capacity]: their boxes (saves the rows kernel a dependent load)
+ * ampis_intersect_rows_grid then gives the same per-row outputs (and dense rows, if asked: the first
+ * imat_ints values of d_imat are zeroed by a memset node, the kernel patches the non-zero cells) as
+ * ampis_intersect_rows_crop, bit for bit.  Eight lanes per row, four rows per warp.  Optional sparse output: the non-zero intersections as
  * (row, column-in-group, intersection) triplets in no particular order; *d_coo_count (zeroed by the
  * caller) counts them and may exceed coo_capacity, in which case the excess was dropped. */
 int ampis_grid_cells(void);
@@ -192,14 +194,16 @@ int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_begin, cons
                      uint32_t *d_cell_fill, void *stream);
 int ampis_grid_fill(const int32_t *d_bbox, const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
                     int32_t n_groups, int32_t max_cols, const int32_t *d_grp_shift, const int64_t *d_cell_off,
-                    uint32_t *d_cell_fill, int32_t *d_entries, int64_t capacity, void *stream);
+                    uint32_t *d_cell_fill, int32_t *d_entries, int32_t *d_entry_bbox, int64_t capacity,
+                    void *stream);
 int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
                               const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_blk_grp,
                               const int32_t *d_blk_row0, int32_t n_blocks, const int32_t *d_grp_row_begin,
                               const int32_t *d_grp_row_count, const int32_t *d_grp_col_begin,
                               const int32_t *d_grp_col_count, const int32_t *d_grp_shift,
-                              const int64_t *d_cell_off, const int32_t *d_entries, int64_t capacity,
-                              const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
+                              const int64_t *d_cell_off, const int32_t *d_entries,
+                              const int32_t *d_entry_bbox, int64_t capacity,
+                              const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat, int64_t imat_ints,
                               int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                               int32_t *d_coo_row, int32_t *d_coo_col, uint32_t *d_coo_inter,
                               int64_t coo_capacity, uint64_t *d_coo_count, void *stream);
