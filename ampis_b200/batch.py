@@ -142,10 +142,10 @@ def eval_step(batch, layout=None, thresholds=COCO_THRESHOLDS, arena=None, rows_o
         t.measure_paint(arena)       # one launch: measure + arena allocation + paint
     else:
         t.measure().paint(arena)     # five launches; sizes the arena exactly when none is given
-    if kernel == 'mma':
-        rows = engine.intersect_mma(t, batch.groups, batch.mode, out=rows_out)
+    if kernel in ('mma', 'mma2'):       # 'mma2': CTA pairs (cta_group::2)
+        rows = engine.intersect_mma(t, batch.groups, batch.mode, out=rows_out, pair=kernel == 'mma2')
     else:
-        assert kernel in ('rows', 'scan') or layout == engine.LAYOUT_CROP, 'the grid kernel reads crop tables'
+        assert kernel in ('rows', 'scan', 'mma', 'mma2') or layout == engine.LAYOUT_CROP, 'the grid kernel reads crop tables'
         grid = engine.ColumnGrid(batch.device, batch.groups.n_groups) if kernel == 'grid' else \
             ('scan' if kernel == 'scan' else None)
         rows = engine.intersect_rows(t, batch.groups, batch.mode, out=rows_out, grid=grid, sparse=sparse)
@@ -171,7 +171,7 @@ class Pipeline(object):
         dev = batch.device
         self.area_hist, self.area_bin_width = area_hist, area_bin_width     # optional int64 histogram (+=)
         self.batch, self.layout, self.arena, self.fused = batch, layout, arena, fused
-        assert kernel in ('rows', 'mma', 'grid', 'scan')
+        assert kernel in ('rows', 'mma', 'mma2', 'grid', 'scan')
         self.kernel = kernel        # 'rows': bbox-culled AND+popc; 'mma': dense int8 tcgen05 contraction
         # crop layout: candidates through a uniform grid ('grid', or 'rows' with many columns per image)
         # instead of the scan of all columns ('scan'); the entry list is sized once from a dry run
@@ -187,8 +187,8 @@ class Pipeline(object):
         elif layout == engine.LAYOUT_CROP and kernel == 'scan':
             self.grid = 'scan'
         self.mma_sort = mma_sort    # tiles from spatially sorted masks (contracts fewer slabs on large frames)
-        if kernel == 'mma':
-            batch.groups.mma_tiles()
+        if kernel in ('mma', 'mma2'):
+            batch.groups.mma_tiles(kernel == 'mma2')
         self.table = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
                                       batch.w, layout)
         g = batch.groups
@@ -220,8 +220,9 @@ class Pipeline(object):
             if mark: mark(1)
             t.paint(self.arena)
         if mark: mark(2)
-        if self.kernel == 'mma':
-            engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows, sort=self.mma_sort)
+        if self.kernel in ('mma', 'mma2'):
+            engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows, sort=self.mma_sort,
+                                 pair=self.kernel == 'mma2')
         else:
             engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows, grid=self.grid,
                                   sparse=self.sparse)

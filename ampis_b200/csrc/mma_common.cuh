@@ -111,3 +111,51 @@ __device__ __forceinline__ void expand_chunk(uint4 c, u32 row_addr, u32 r7)
     sts_v4(row_addr + ((6u ^ r7) << 4), o0); sts_v4(row_addr + ((7u ^ r7) << 4), o1);
 }
 
+
+// ---- CTA-pair (cta_group::2) and cluster helpers -------------------------------------------------
+__device__ __forceinline__ u32 cluster_ctarank()
+{
+    u32 r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in the CTA of rank `rank`
+__device__ __forceinline__ u32 cluster_map(u32 local, u32 rank)
+{
+    u32 r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ u32 cluster_lds_u32(u32 cluster_addr)
+{
+    u32 v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+// arrive on a barrier of another CTA of the cluster.  Plain form (release at CTA scope): a cluster-scope release
+// compiles to MEMBAR.ALL.GPU + ERRBAR per arrive (measured: 19 % of the pair kernel's stall samples, stage
+// handshake ~0.8 us).  The operand bytes the arrive publishes were written to this CTA's OWN shared memory and
+// made visible to the async proxy by fence.proxy.async before it -- the same pattern as CUTLASS's 2-SM
+// pipelines (umma_arrive_2x1SM_sm0 / ClusterBarrier::arrive(cta_id)).
+__device__ __forceinline__ void mbar_arrive_cluster(u32 cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T over the pair: M256 (128 rows per CTA) N256 (128 columns of B per CTA) K32
+__device__ __forceinline__ void tc_mma_i8_pair(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the pair's earlier MMAs have completed) on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(u32 bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}

@@ -231,12 +231,17 @@ class Groups(object):
             self.imat_size = int(off[-1])
             self.imat_off = _dev(off[:-1], torch.int64, device)
 
-    def mma_tiles(self):
-        """Tile list of the tensor-core contraction (ampis_intersect_tcgen05): every group's dense
-        matrix cut into ampis_mma_tile_rows() x ampis_mma_tile_cols() tiles; built once, cached."""
-        if getattr(self, '_mma', None) is None:
+    def mma_tiles(self, pair=False):
+        """Tile list of the tensor-core contraction (ampis_intersect_tcgen05[_pair]): every group's dense
+        matrix cut into tiles of the kernel's size (128 x 256, or 256 x 256 for CTA pairs); built once, cached."""
+        cache = getattr(self, '_mma', None)
+        if cache is None:
+            cache = self._mma = {}
+        if pair not in cache:
             assert self.imat_off is not None, 'the tensor-core path writes dense matrices: Groups(dense=True)'
-            tm, tn = N.lib().ampis_mma_tile_rows(), N.lib().ampis_mma_tile_cols()
+            lib = N.lib()
+            tm, tn = (lib.ampis_mma_pair_tile_rows(), lib.ampis_mma_pair_tile_cols()) if pair else \
+                (lib.ampis_mma_tile_rows(), lib.ampis_mma_tile_cols())
             grp, m0, n0 = [], [], []
             for g in range(self.n_groups):
                 G, P = int(self.h_row_count[g]), int(self.h_col_count[g])
@@ -247,9 +252,9 @@ class Groups(object):
                 m0.append(mm.ravel().astype(np.int32))
                 n0.append(nn.ravel().astype(np.int32))
             cat = lambda v: np.concatenate(v) if v else np.zeros(0, np.int32)
-            self._mma = (len(cat(grp)), _dev(cat(grp), torch.int32, self.device),
-                         _dev(cat(m0), torch.int32, self.device), _dev(cat(n0), torch.int32, self.device))
-        return self._mma
+            cache[pair] = (len(cat(grp)), _dev(cat(grp), torch.int32, self.device),
+                           _dev(cat(m0), torch.int32, self.device), _dev(cat(n0), torch.int32, self.device))
+        return cache[pair]
 
     @staticmethod
     def interleaved(device, n_rows_per_group, n_cols_per_group, dense=False):
@@ -273,7 +278,9 @@ class RowResult(object):
 
 #: from this many column masks per image on, the crop rows kernel finds its candidates through a
 #: uniform grid over the image (ampis_intersect_rows_grid) instead of scanning every column's box
-ROWS_GRID_MIN_COLS = int(os.environ.get('AMPIS_ROWS_GRID_MIN_COLS', 1024))
+#: (measured: C2, 500 columns per image, rows kernel 1.25 -> 1.00 ms per 1,000 images; C4, 5,000 columns, 2.4 ->
+#: 0.25 ms per 40 images; below a few hundred columns the six small launches that build the grid cost more)
+ROWS_GRID_MIN_COLS = int(os.environ.get('AMPIS_ROWS_GRID_MIN_COLS', 384))
 
 
 class ColumnGrid(object):
@@ -423,7 +430,15 @@ def _span_orders(table, groups):
     return row_order, col_order
 
 
-def intersect_mma(table, groups, mode, out=None, sort=True):
+#: tensor-core contraction on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) instead of single CTAs
+#: (128 x 256 tiles): 'auto' = pairs when the tiles contract the full pixel range (sort=False: tensor pipe 90 % vs
+#: 78 % busy, 1.15-1.22x), single CTAs when tiles are cut from spatially sorted masks (the smaller tile contracts a
+#: shorter slab range: 2.27 vs 3.08 ms on C2 frames, 1.89 vs 2.01 ms on crowded 256 x 256 frames;
+#: profiles/mma_pair_r01.md); '0' / '1' force one of them
+MMA_PAIR = os.environ.get('AMPIS_MMA_PAIR', 'auto')
+
+
+def intersect_mma(table, groups, mode, out=None, sort=True, pair=None):
     """Dense intersection matrices by the int8 tcgen05 contraction (no pruning), then the per-row
     arg-max from the matrices.  Same RowResult as intersect_rows(), bit for bit; the choice
     between the two is a cost decision.  sort=True cuts the tiles from rows / columns
@@ -431,7 +446,9 @@ def intersect_mma(table, groups, mode, out=None, sort=True):
     dev = table.device
     assert table.layout != LAYOUT_CROP, 'the contraction reads linear packed masks (span or full layout)'
     nr = max(groups.n_rows, 1)
-    n_tiles, tile_grp, tile_m0, tile_n0 = groups.mma_tiles()
+    if pair is None:
+        pair = (not sort) if MMA_PAIR == 'auto' else MMA_PAIR != '0'
+    n_tiles, tile_grp, tile_m0, tile_n0 = groups.mma_tiles(pair)
     if out is None:
         out = RowResult(torch.empty(nr, dtype=torch.int32, device=dev),
                         torch.empty(nr, dtype=torch.int32, device=dev),
@@ -439,7 +456,7 @@ def intersect_mma(table, groups, mode, out=None, sort=True):
                         torch.empty(max(groups.imat_size, 1), dtype=torch.int32, device=dev))
     assert out.imat is not None
     row_order, col_order = _span_orders(table, groups) if sort and groups.n_rows else (None, None)
-    N.call('ampis_intersect_tcgen05', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
+    N.call('ampis_intersect_tcgen05_pair' if pair else 'ampis_intersect_tcgen05', _p(table.bits), _p(table.bits_off), _p(table.reg), _p(table.span),
            _p(groups.row_mask), _p(row_order), _p(col_order), _p(tile_grp), _p(tile_m0), _p(tile_n0), n_tiles,
            _p(groups.grp_row_begin),
            _p(groups.grp_row_count), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off),

@@ -43,7 +43,7 @@ def parse():
                          'span = culled storage (only first..last 1-pixel of each mask); '
                          'crop = bounding-box windows (the cropped accounting of SURVEY 8d)')
     ap.add_argument('--sub', type=int, default=0, help='images per launch group (0 = auto)')
-    ap.add_argument('--kernel', default='rows', choices=['rows', 'mma', 'grid', 'scan'],
+    ap.add_argument('--kernel', default='rows', choices=['rows', 'mma', 'mma2', 'grid', 'scan'],
                     help='intersection kernel: rows = bbox-culled AND+popc (default; crop layout with >= 1024 '
                          'columns per image prunes through a uniform grid); grid / scan = crop layout with the grid '
                          'forced / forbidden; mma = dense int8 tcgen05 contraction (for crowded images, e.g. '
@@ -354,7 +354,7 @@ def roofline_of(args, cfg, run, ms, kt, world):
         if traffic_detail:
             traffic = traffic_detail['bytes_per_image'] * n_img / launches
     step_gbs = canonical_img * n_img * args.steps / (ms / 1e3) / 1e9
-    if run.kernel == 'mma' and dom == 'rows':
+    if run.kernel in ('mma', 'mma2') and dom == 'rows':
         # dense contraction: 2*G*P*H*W integer ops per image, tensor-pipe bound
         tpeak, tsrc = tensor_peak_tops()
         ops = 2.0 * pairs_img * cfg['h'] * cfg['w'] * n_img / launches
@@ -486,7 +486,7 @@ def main():
         'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
         'images_per_s': job_images * args.steps / (ms / 1e3),
         'config': {'workload': workload_name(args, host0), 'images_per_gpu_per_step': args.images,
-                   'layout': args.layout, 'sparse_output': bool(run.pipes[0].sparse), 'intersection_kernel': ('grid' if getattr(run.pipes[0].grid, 'capacity', None) else args.kernel) + ('+sorted tiles' if args.kernel == 'mma' and args.mma_sort else ''), 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
+                   'layout': args.layout, 'sparse_output': bool(run.pipes[0].sparse), 'intersection_kernel': ('grid' if getattr(run.pipes[0].grid, 'capacity', None) else args.kernel) + ('+sorted tiles' if args.kernel in ('mma', 'mma2') and args.mma_sort else ''), 'images_per_launch': run.sub, 'thresholds': 'IoU 0.50:0.05:0.95' if cfg['mode'] == 0 else 'satellite overlap > 0.5',
                    'runs_per_mask': run.total_runs / n_masks,
                    'l2': 'per step the kernels stream %.0f MB of run counts and a %.1f GB packed-mask arena, both '
                          'larger than the 126 MB L2; no explicit flush' % (4 * run.total_runs / 1e6,
@@ -495,7 +495,7 @@ def main():
                        world, ' + %d-bin area histogram' % cfg['area_bins'] if cfg.get('area_bins') else '')},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
         # grid-pruned crop rows: + setup, count, 3 scan kernels, fill
-        'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel == 'mma' else 0) +
+        'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel in ('mma', 'mma2') else 0) +
                                                             (6 if getattr(run.pipes[0].grid, 'capacity', None) else 0) +
                                                             (1 if cfg.get('area_bins') else 0))),
         ('totals_tp_fp_fn_at_0.50' if cfg['mode'] == 0 else 'sat_matched_unmatched_satellited_particles+spp_hist'): final_totals[0].tolist(),
@@ -589,8 +589,8 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
                 t.measure().paint(arena)
             else:
                 t.measure_paint(arena)
-            if args.kernel == 'mma':
-                rows = engine.intersect_mma(t, b.groups, b.mode, out=rows_out, sort=args.mma_sort)
+            if args.kernel in ('mma', 'mma2'):
+                rows = engine.intersect_mma(t, b.groups, b.mode, out=rows_out, sort=args.mma_sort, pair=args.kernel == 'mma2')
             else:
                 rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out, grid=pipes[i].grid if pipes else None,
                                              sparse=pipes[i].sparse if pipes else None)

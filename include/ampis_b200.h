@@ -233,6 +233,20 @@ int ampis_intersect_tcgen05(const void *d_bits, const int64_t *d_bits_off, const
                             const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
                             const int64_t *d_grp_imat_off, int32_t *d_imat, void *stream);
 
+/* The same contraction on CTA pairs (tcgen05 cta_group::2, clusters of two CTAs on one TPC): one
+ * M256 N256 K32 instruction per step over a 256 x 256 tile, each CTA expanding only its own 128 rows and
+ * 128 columns.  Tiles are ampis_mma_pair_tile_rows() x ampis_mma_pair_tile_cols(); otherwise the same
+ * arguments and the same output, bit for bit. */
+int ampis_mma_pair_tile_rows(void);
+int ampis_mma_pair_tile_cols(void);
+int ampis_intersect_tcgen05_pair(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
+                            const uint32_t *d_span, const int32_t *d_row_mask,
+                            const int32_t *d_row_order, const int32_t *d_col_order,
+                            const int32_t *d_tile_grp, const int32_t *d_tile_m0, const int32_t *d_tile_n0,
+                            int32_t n_tiles, const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
+                            const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                            const int64_t *d_grp_imat_off, int32_t *d_imat, void *stream);
+
 /* Per-row results (same outputs and tie rules as ampis_intersect_rows) from dense matrices:
  * row_grp[r] = group of row r. */
 int ampis_rows_from_imat(const int32_t *d_imat, const int64_t *d_grp_imat_off, const uint32_t *d_area,

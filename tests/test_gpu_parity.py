@@ -431,6 +431,26 @@ def test_grid_pruned_rows_equal_scanned_rows(mods, cfg, over, n_img):
     assert pipe.grid.needed() == pipe.grid.capacity
 
 
+def test_sparse_iou_equals_nonzeros_of_the_dense_matrix(mods):
+    """analyze.sparse_iou == the non-zero cells of analyze._piecewise_iou (which the oracle pins), golden
+    powder image and a synthetic spheroidite frame; also the empty conventions."""
+    A, B, rle = mods.analyze, mods.batch, mods.rle
+    _, gt, pr = U.powder_match_image(0)
+    host = B.synth(dict(B.CONFIGS['c4_spheroidite'], n_rows=1200, n_cols=1100, h=1024, w=1024), 1, 99)
+    rows, cols = host.image_masks(0)
+    mk = lambda cs: [{'size': [host.h, host.w], 'counts': rle.string_from_counts(c)} for c in cs]
+    for a, b in ((gt, pr), (mk(rows), mk(cols))):
+        dense = A._piecewise_iou(a, b)
+        sp = A.sparse_iou(a, b)
+        wr, wc = np.nonzero(dense)
+        assert sp['shape'] == dense.shape and len(wr) > 0
+        assert np.array_equal(sp['row'], wr) and np.array_equal(sp['col'], wc)
+        assert np.array_equal(sp['iou'], dense[wr, wc])
+        assert sp['inter'].dtype == np.uint32 and sp['inter'].min() > 0
+    e = A.sparse_iou([], pr)
+    assert e['shape'] == (0, len(pr)) and len(e['row']) == 0
+
+
 def test_full_size_properties(mods):
     """BASELINE config sizes (C2 image count reduced): size-independent properties --
     span and full layouts agree bit for bit, I(gt,pred) == I(pred,gt)^T, area == popcount of the
@@ -495,9 +515,14 @@ def test_tensor_core_contraction_equals_culled_popc(mods, cfg, over, n_img, layo
     t = E.MaskTable(dev.device, host.n_masks, dev.cnt, dev.cnt_off, dev.cnt_len, dev.h, dev.w, lay)
     t.measure().paint().check()
     a = E.intersect_rows(t, dev.groups, dev.mode)
-    m = E.intersect_mma(t, dev.groups, dev.mode)
+    m = E.intersect_mma(t, dev.groups, dev.mode, pair=False)
     torch.cuda.synchronize()
     assert torch.equal(a.imat, m.imat)
+    for sort in (True, False):                       # CTA pairs (cta_group::2, 256 x 256 tiles): the same matrix
+        m2 = E.intersect_mma(t, dev.groups, dev.mode, pair=True, sort=sort)
+        torch.cuda.synchronize()
+        assert torch.equal(a.imat, m2.imat), 'pair kernel, sort=%s' % sort
+        assert torch.equal(a.best_col, m2.best_col) and torch.equal(a.best_inter, m2.best_inter)
     assert torch.equal(a.best_col, m.best_col) and torch.equal(a.best_inter, m.best_inter)
     sa, sm = a.best_score.cpu().numpy(), m.best_score.cpu().numpy()
     assert np.array_equal(sa, sm, equal_nan=True)
