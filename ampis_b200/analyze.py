@@ -31,14 +31,14 @@ def align_instance_sets(a, b):
 
 
 def _check_same_size(*mask_lists):
-    size = None
-    for ml in mask_lists:
-        for m in ml:
-            s = (int(m['size'][0]), int(m['size'][1]))
-            if size is None:
-                size = s
-            elif s != size:
-                raise ValueError('masks of different image sizes cannot be compared (%s vs %s)' % (size, s))
+    sizes = [m['size'] for ml in mask_lists for m in ml]
+    if not sizes:
+        return
+    a = np.asarray(sizes, np.int64).reshape(len(sizes), -1)[:, :2]
+    bad = np.nonzero((a != a[0]).any(axis=1))[0]
+    if len(bad):
+        raise ValueError('masks of different image sizes cannot be compared (%s vs %s)'
+                         % (tuple(a[0].tolist()), tuple(a[bad[0]].tolist())))
 
 
 def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False):
@@ -75,7 +75,7 @@ def sparse_iou(a, b, size=None):
     zeros around a few thousand overlapping pairs; this is the bbox-pruned form (grid-pruned crop rows
     kernel, engine.SparseRows)."""
     from .structures import masks_to_rle
-    a, b = masks_to_rle(a, size), masks_to_rle(b, size)
+    a, b = (masks_to_rle(m, size) if len(m) else [] for m in (a, b))
     out = {'row': np.zeros(0, np.int64), 'col': np.zeros(0, np.int64), 'inter': np.zeros(0, np.uint32),
            'iou': np.zeros(0), 'shape': (len(a), len(b))}
     if len(a) == 0 or len(b) == 0:

@@ -153,17 +153,44 @@ def table_from_counts(cnt, cnt_off, cnt_len, h, w, layout=None, arena=None, chec
 def _rle_fields(masks):
     """list of COCO RLE dicts -> (list of bytes, h array, w array); mirrors the input
     handling of pycocotools' _frString (str counts are accepted and encoded)."""
-    strings, hs, ws = [], [], []
-    for m in masks:
-        c = m['counts']
-        if type(c) == str:
-            c = c.encode('ascii')
-        elif not isinstance(c, (bytes, bytearray)):
-            raise TypeError('RLE counts must be compressed bytes/str, got %s' % type(c))
-        strings.append(bytes(c))
-        hs.append(m['size'][0])
-        ws.append(m['size'][1])
-    return strings, hs, ws
+    strings = [m['counts'] for m in masks]
+    if not all(type(c) is bytes for c in strings):
+        for i, c in enumerate(strings):
+            if type(c) == str:
+                strings[i] = c.encode('ascii')
+            elif isinstance(c, (bytes, bytearray)):
+                strings[i] = bytes(c)
+            else:
+                raise TypeError('RLE counts must be compressed bytes/str, got %s' % type(c))
+    hw = np.asarray([m['size'] for m in masks], np.int64).reshape(len(strings), -1)
+    return strings, hw[:, 0], hw[:, 1]
+
+
+def _upload(device, *arrays):
+    """Several small host arrays -> device tensors through ONE pinned staging buffer and ONE copy
+    (each numpy array keeps its dtype; pieces are 16-byte aligned views of the same allocation)."""
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    offs, total = [], 0
+    for a in arrays:
+        offs.append(total)
+        total += (a.nbytes + 15) & ~15
+    if torch.device(device).type != 'cuda' or total > PIN_LIMIT_BYTES:
+        return [_dev(a.view(np.int32) if a.dtype == np.uint32 else a, _TORCH_DTYPE[a.dtype.name], device)
+                for a in arrays]
+    stage = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+    host = stage.numpy()
+    for a, o in zip(arrays, offs):
+        host[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+    dev = stage.to(device, non_blocking=True)
+    out = []
+    for a, o in zip(arrays, offs):
+        t = dev[o:o + a.nbytes].view(_TORCH_DTYPE[a.dtype.name])
+        out.append(t if a.size else torch.empty(0, dtype=t.dtype, device=device))
+    return out
+
+
+_TORCH_DTYPE = {'uint8': torch.uint8, 'int32': torch.int32, 'int64': torch.int64, 'float64': torch.float64,
+                'uint32': torch.int32}
 
 
 def table_from_rle(masks, layout=None, paint=True):
@@ -172,14 +199,11 @@ def table_from_rle(masks, layout=None, paint=True):
     device = require_cuda()
     strings, hs, ws = _rle_fields(masks)
     n = len(strings)
-    lens = np.fromiter((len(s) for s in strings), np.int64, n)
+    lens = np.fromiter(map(len, strings), np.int64, n)
     off = np.zeros(n + 1, np.int64)
     np.cumsum(lens, out=off[1:])
-    blob = np.frombuffer(b''.join(strings), np.uint8).copy() if n else np.zeros(0, np.uint8)
-    d_chars = _dev(blob, torch.uint8, device)
-    d_off = _dev(off, torch.int64, device)
-    d_h = _dev(np.asarray(hs, np.int64), torch.int32, device)
-    d_w = _dev(np.asarray(ws, np.int64), torch.int32, device)
+    blob = np.frombuffer(b''.join(strings), np.uint8) if n else np.zeros(0, np.uint8)
+    d_off, d_h, d_w, d_chars = _upload(device, off, hs.astype(np.int32), ws.astype(np.int32), blob)
     cnt = torch.empty(max(int(off[-1]), 1), dtype=torch.int32, device=device)
     cnt_len = torch.empty(max(n, 1), dtype=torch.int32, device=device)
     N.call('ampis_rle_string_decode', _p(d_chars), _p(d_off), n, _p(cnt), _p(d_off), _p(cnt_len), _stream())
@@ -204,9 +228,6 @@ class Groups(object):
         self.h_row_count = np.asarray(grp_row_count, np.int64)
         self.h_col_count = np.asarray(grp_col_count, np.int64)
         self.h_row_begin = np.asarray(grp_row_begin, np.int64)
-        i32 = torch.int32
-        self.row_mask = _dev(np.asarray(row_mask, np.int32), i32, device)
-        self.row_grp = _dev(np.asarray(row_grp, np.int32), i32, device)
         rpb = N.lib().ampis_rows_per_block()
         nb = (self.h_row_count + rpb - 1) // rpb                    # CTAs per group
         blk_grp = np.repeat(np.arange(self.n_groups, dtype=np.int64), nb)
@@ -214,12 +235,12 @@ class Groups(object):
         np.cumsum(nb, out=first[1:])
         blk_row0 = self.h_row_begin[blk_grp] + rpb * (np.arange(int(first[-1]), dtype=np.int64) - first[blk_grp])
         self.n_blocks = int(first[-1])
-        self.blk_grp = _dev(blk_grp.astype(np.int32), i32, device)
-        self.blk_row0 = _dev(blk_row0.astype(np.int32), i32, device)
-        self.grp_row_begin = _dev(np.asarray(grp_row_begin, np.int32), i32, device)
-        self.grp_row_count = _dev(np.asarray(grp_row_count, np.int32), i32, device)
-        self.grp_col_begin = _dev(np.asarray(grp_col_begin, np.int32), i32, device)
-        self.grp_col_count = _dev(np.asarray(grp_col_count, np.int32), i32, device)
+        i32 = np.int32
+        (self.row_mask, self.row_grp, self.blk_grp, self.blk_row0, self.grp_row_begin, self.grp_row_count,
+         self.grp_col_begin, self.grp_col_count) = _upload(
+            device, np.asarray(row_mask, i32), np.asarray(row_grp, i32), blk_grp.astype(i32), blk_row0.astype(i32),
+            np.asarray(grp_row_begin, i32), np.asarray(grp_row_count, i32), np.asarray(grp_col_begin, i32),
+            np.asarray(grp_col_count, i32))
         self.imat_off = None
         self.h_imat_off = None
         self.imat_size = 0

@@ -396,6 +396,8 @@ def test_crop_layout_equals_span_layout(mods, cfg, over, n_img):
     ('dense_overlap', {}, 1),                                                              # boxes over many cells
     ('c3_satellites', dict(n_cols=1200, h=1024, w=1024), 2),
     ('c2_powder_batch', dict(h=70, w=45, n_rows=9, n_cols=11, median_diam=30.0), 4),
+    ('c2_powder_batch', dict(h=512, w=512, n_rows=40, n_cols=40, median_diam=150.0), 2),   # large overlaps: warp-wide phase
+    ('dense_overlap', dict(h=512, w=512, n_rows=64, n_cols=64, median_diam=220.0), 2),     # ... more than a warp parks
 ])
 def test_grid_pruned_rows_equal_scanned_rows(mods, cfg, over, n_img):
     """Crop rows kernel with the box pre-pruning through the uniform grid == the kernel that tests every
