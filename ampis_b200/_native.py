@@ -33,7 +33,7 @@ SIGNATURES = {
     'ampis_intersect_rows': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p,
                                        _p, _p, _p]),
     'ampis_rle_measure_paint': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
-                                          _p]),
+                                          _i32, _p]),
     'ampis_intersect_rows_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p,
                                             _p, _p]),
     'ampis_grid_cells': (C.c_int, []),

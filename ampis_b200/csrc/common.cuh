@@ -51,6 +51,35 @@ __device__ __forceinline__ u32 warp_max(u32 v)
     return v;
 }
 
+// Sub-warp groups of L = 8 / 16 / 32 consecutive lanes (one small mask per group): lane mask of the caller's group
+// and reductions that stay inside it.
+template <int L>
+__device__ __forceinline__ u32 group_mask()
+{
+    return L == 32 ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (lane_id() & ~(u32)(L - 1)));
+}
+template <int L>
+__device__ __forceinline__ u32 group_sum(u32 v, u32 gm)
+{
+#pragma unroll
+    for (int d = L / 2; d; d >>= 1) v += __shfl_xor_sync(gm, v, d);
+    return v;
+}
+template <int L>
+__device__ __forceinline__ u32 group_min(u32 v, u32 gm)
+{
+#pragma unroll
+    for (int d = L / 2; d; d >>= 1) v = min(v, __shfl_xor_sync(gm, v, d));
+    return v;
+}
+template <int L>
+__device__ __forceinline__ u32 group_max(u32 v, u32 gm)
+{
+#pragma unroll
+    for (int d = L / 2; d; d >>= 1) v = max(v, __shfl_xor_sync(gm, v, d));
+    return v;
+}
+
 // Division of 32-bit positions by a per-mask constant (the image height: position -> column) without the
 // ~20-instruction IDIV sequence: q = umulhi(s, floor((2^32-1)/d)) is floor(s/d) or one less.
 struct FastDiv {

@@ -11,20 +11,23 @@ struct MaskMeasure {
     u64 total;    // sum of all run counts
 };
 
-// One warp walks the m run counts of a mask 128 at a time: every lane takes FOUR consecutive runs (two
+// One group of L lanes (a warp by default) walks the m run counts of a mask 4*L at a time: every lane takes FOUR consecutive runs (two
 // 0-runs and two 1-runs, so all lanes do the same work), sums them locally, and ONE warp scan of the lane
 // totals places them -- a typical mask (~75 runs) costs one scan instead of three and keeps 19 lanes busy
 // on the per-run statistics instead of 16 lanes three times.
 // Run end positions are written to cum_s[j] for j < cum_s_cap (shared memory, may be null)
-// and to cum_g[j] (global memory, may be null).  Result valid in all lanes.
+// and to cum_g[j] (global memory, may be null).  Result valid in all lanes of the group.  Small masks
+// (30-75 runs) leave most of a warp idle: L = 8 or 16 puts four or two masks on a warp.
+template <int L = 32>
 __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt, int m, u32 H, u64 HW,
                                                     u32 *cum_s, int cum_s_cap, u32 *cum_g)
 {
-    const u32 lane = lane_id();
+    const u32 lane = lane_id() & (u32)(L - 1);
+    const u32 gm = group_mask<L>();
     const FastDiv byH = fastdiv_make(H);
     u64 carry = 0;
     u32 a = 0, first = 0xffffffffu, last = 0, ymin = 0xffffffffu, ymax = 0;
-    for (int jb = 0; jb < m; jb += 128) {
+    for (int jb = 0; jb < m; jb += 4 * L) {
         const int j0 = jb + 4 * (int)lane;
         u32 c[4];
 #pragma unroll
@@ -35,8 +38,8 @@ __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt,
         for (int q = 1; q < 4; q++) loc[q] = loc[q - 1] + c[q];
         u64 incl = loc[3];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u64 t = __shfl_up_sync(0xffffffffu, incl, d);
+        for (int d = 1; d < L; d <<= 1) {
+            const u64 t = __shfl_up_sync(gm, incl, d, L);
             if ((int)lane >= d) incl += t;
         }
         const u64 base = carry + incl - loc[3];
@@ -66,14 +69,14 @@ __device__ __forceinline__ MaskMeasure warp_measure(const u32 *__restrict__ cnt,
                 else { ymin = min(ymin, start - xs * H); ymax = max(ymax, end - 1 - xe * H); }
             }
         }
-        carry = __shfl_sync(0xffffffffu, carry + incl, 31);
+        carry = __shfl_sync(gm, carry + incl, L - 1, L);
     }
     MaskMeasure r;
-    r.area = warp_sum(a);
-    r.first = warp_min(first);
-    r.last = warp_max(last);
-    r.ymin = warp_min(ymin);
-    r.ymax = warp_max(ymax);
+    r.area = group_sum<L>(a, gm);
+    r.first = group_min<L>(first, gm);
+    r.last = group_max<L>(last, gm);
+    r.ymin = group_min<L>(ymin, gm);
+    r.ymax = group_max<L>(ymax, gm);
     r.total = carry;
     return r;
 }

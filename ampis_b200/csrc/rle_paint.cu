@@ -187,9 +187,12 @@ __device__ __forceinline__ void warp_paint_tile_smem(const u32 *sC, int m, u32 t
 // 1-runs, cuts them at column boundaries (a run that reaches the bottom of a column continues at
 // the top of the next) and sets the bits of every piece.  `searched` = false when all runs are
 // known to fall in one tile (small masks: no binary search at all).
+template <int L = 32>
 __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, const int4 bb, u32 *tile,
                                                 u32 tile_words, u32 *out, u32 lane)
 {
+    // `lane` = lane inside the group of L lanes that owns the mask (see warp_measure)
+    const u32 gm = group_mask<L>();
     if (bb.z < bb.x) return;
     const u32 wy0 = (u32)bb.y >> 5, nwy = ((u32)bb.w >> 5) - wy0 + 1u;
     const u32 x_end = (u32)bb.z + 1u;
@@ -199,15 +202,15 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
     for (u32 xa = (u32)bb.x; xa < x_end; xa += cols_per_tile) {
         const u32 xb = min(xa + cols_per_tile, x_end);
         const u32 tw = (xb - xa) * nwy;
-        for (u32 k = lane; k < tw; k += 32) tile[k] = 0u;
-        __syncwarp();
+        for (u32 k = lane; k < tw; k += L) tile[k] = 0u;
+        __syncwarp(gm);
         const u64 b0 = (u64)xa * H, b1 = (u64)xb * H;
         int r0 = 0, r1 = m - 1;
         if (!one_tile) {
             r0 = upper_bound_u32(C, m, b0);          // run that owns bit b0
             r1 = upper_bound_u32(C, m, b1 - 1);      // run that owns bit b1-1 (m if beyond the runs)
         }
-        for (int r = (r0 | 1) + 2 * (int)lane; r <= r1 && r < m; r += 64) {   // odd runs are the 1-runs
+        for (int r = (r0 | 1) + 2 * (int)lane; r <= r1 && r < m; r += 2 * L) {   // odd runs are the 1-runs
             const u64 rs = (u64)C[r - 1], re = (u64)C[r];
             u64 s = rs > b0 ? rs : b0;
             const u64 e = re < b1 ? re : b1;
@@ -230,10 +233,10 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(gm);
         u32 *o = out + (xa - (u32)bb.x) * nwy;
-        for (u32 k = lane; k < tw; k += 32) o[k] = tile[k];
-        __syncwarp();
+        for (u32 k = lane; k < tw; k += L) o[k] = tile[k];
+        __syncwarp(gm);
     }
 }
 
@@ -340,6 +343,78 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
     }
 }
 
+// Fused measure + paint for AMPIS_LAYOUT_CROP with a GROUP of L = 8 or 16 lanes per mask (four or two masks per
+// warp): small instances (spheroidite carbides ~30 runs, powder particles ~75) leave most of a warp idle in the
+// warp-per-mask kernel above, whose ~850 instructions per mask are mostly straight-line code paid per warp.
+// Same steps: the group measures its mask (4 runs per lane and pass), lane 0 reserves arena space with its own
+// atomicAdd, the group paints the bounding-box window through its slice of the shared tile.
+template <int L>
+__global__ void __launch_bounds__(MP_WARPS * 32, 5)
+rle_measure_paint_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
+                              const int *__restrict__ cnt_len, const u32 *__restrict__ hh,
+                              const u32 *__restrict__ ww, int n, u32 *cum_g, u32 *__restrict__ area,
+                              int *__restrict__ bbox, u32 *__restrict__ span, u32 *__restrict__ reg,
+                              i64 *__restrict__ bits_off, int *__restrict__ status, uint4 *__restrict__ bits,
+                              i64 capacity, unsigned long long *__restrict__ cursor)
+{
+    constexpr int GROUPS = MP_WARPS * 32 / L;
+    constexpr int CUM_CAP = MP_CUM_WORDS / GROUPS;
+    constexpr int TILE_WORDS = MP_WARPS * MP_TILE * 4 / GROUPS;
+    __shared__ __align__(16) u32 s_cum[MP_CUM_WORDS];
+    __shared__ __align__(16) u32 s_tile[MP_WARPS * MP_TILE * 4];
+    __shared__ uint2 s_span[GROUPS], s_reg[GROUPS];
+    __shared__ int4 s_bbox[GROUPS];
+    const u32 gl = threadIdx.x & (u32)(L - 1);
+    const int grp = (int)threadIdx.x / L;
+    const u32 gm = group_mask<L>();
+    const int i = blockIdx.x * GROUPS + grp;
+    const bool valid = i < n;
+    int m = 0;
+    i64 base = 0;
+    u32 H = 1;
+    uint2 rg = make_uint2(0u, 0u);
+    if (valid) {
+        m = cnt_len[i];
+        base = cnt_off[i];
+        H = hh[i];
+        const u64 HW = (u64)H * ww[i];
+        const MaskMeasure ms = warp_measure<L>(cnt + base, m, H, HW, s_cum + grp * CUM_CAP, CUM_CAP,
+                                               m > CUM_CAP ? cum_g + base : nullptr);
+        if (gl == 0)
+            store_measure(ms, H, HW, AMPIS_LAYOUT_CROP, i, area, bbox, span, reg, status, &s_span[grp], &s_reg[grp],
+                          &s_bbox[grp]);
+        __syncwarp(gm);
+        rg = s_reg[grp];
+    }
+    // arena space: ONE atomicAdd per warp for its 32 / L masks (a single cursor takes ~1 G atomics/s, which is what
+    // bounded this kernel with an atomic per mask)
+    __syncwarp();
+    const u32 sz = (valid && gl == 0) ? rg.y - rg.x : 0u;
+    u32 before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 32 / L; k++) {
+        const u32 v = __shfl_sync(0xffffffffu, sz, k * L);
+        if (k < (int)(lane_id() / L)) before += v;
+        total += v;
+    }
+    unsigned long long o = 0;
+    if (lane_id() == 0 && total) o = atomicAdd(cursor, (unsigned long long)total);
+    const i64 off = (i64)__shfl_sync(0xffffffffu, o, 0) + (i64)before;
+    if (!valid) return;
+    if (off + (i64)(rg.y - rg.x) > capacity) {           // arena exhausted: see rle_measure_paint_kernel
+        if (gl == 0) {
+            bits_off[i] = 0;
+            reinterpret_cast<uint2 *>(span)[i] = make_uint2(0u, 0u);
+            reinterpret_cast<uint2 *>(reg)[i] = make_uint2(0u, 0u);
+        }
+        return;
+    }
+    if (gl == 0) bits_off[i] = off;
+    const u32 *C = m > CUM_CAP ? cum_g + base : s_cum + grp * CUM_CAP;
+    warp_paint_crop<L>(C, m, H, s_bbox[grp], s_tile + grp * TILE_WORDS, TILE_WORDS,
+                       reinterpret_cast<u32 *>(bits + off), gl);
+}
+
 // CROP layout painter for tables measured by ampis_rle_measure (offsets from the scan): one warp
 // per mask, run ends read from global memory.
 __global__ void __launch_bounds__(256)
@@ -373,12 +448,16 @@ extern "C" int ampis_rle_decode_crop(const uint32_t *d_cum, const int64_t *d_cnt
     return AMPIS_OK;
 }
 
+// typical runs per mask (caller's hint) up to which 8 / 16 lanes work on one mask in the crop kernel
+#define PAINT_L8_MAX_RUNS 40
+#define PAINT_L16_MAX_RUNS 112
+
 extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off,
                                        const int32_t *d_cnt_len, const uint32_t *d_h, const uint32_t *d_w,
                                        int32_t n, int32_t layout, uint32_t *d_cum, uint32_t *d_area,
                                        int32_t *d_bbox, uint32_t *d_span, uint32_t *d_reg, int64_t *d_bits_off,
                                        int32_t *d_status, void *d_bits, int64_t bits_capacity,
-                                       uint64_t *d_cursor, void *stream)
+                                       uint64_t *d_cursor, int32_t runs_hint, void *stream)
 {
     AMPIS_REQUIRE(n >= 0, "n < 0");
     AMPIS_REQUIRE(layout == AMPIS_LAYOUT_SPAN || layout == AMPIS_LAYOUT_FULL || layout == AMPIS_LAYOUT_CROP,
@@ -393,6 +472,14 @@ extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_c
         rle_measure_paint_kernel<MP_WARPS, 0><<<n, MP_WARPS * 32, 0, as_stream(stream)>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
             d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
+    else if (layout == AMPIS_LAYOUT_CROP && runs_hint > 0 && runs_hint <= PAINT_L8_MAX_RUNS)
+        rle_measure_paint_crop_kernel<8><<<(n + 31) / 32, MP_WARPS * 32, 0, as_stream(stream)>>>(
+            d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off, d_status,
+            (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
+    else if (layout == AMPIS_LAYOUT_CROP && runs_hint > 0 && runs_hint <= PAINT_L16_MAX_RUNS)
+        rle_measure_paint_crop_kernel<16><<<(n + 15) / 16, MP_WARPS * 32, 0, as_stream(stream)>>>(
+            d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off, d_status,
+            (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
     else if (layout == AMPIS_LAYOUT_CROP)
         rle_measure_paint_kernel<1, 2><<<(n + MP_WARPS - 1) / MP_WARPS, MP_WARPS * 32, 0, as_stream(stream)>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,

@@ -52,6 +52,10 @@ def _dev(a, dtype, device):
     return t.pin_memory().to(device, non_blocking=True)
 
 
+#: runs per mask hinted to the fused crop decode kernel (-1: the table's own average; 0: always a warp per mask)
+PAINT_RUNS_HINT = int(os.environ.get('AMPIS_PAINT_RUNS_HINT', -1))
+
+
 class MaskTable(object):
     """Structure-of-arrays table of n masks on the GPU (see include/ampis_b200.h)."""
 
@@ -108,7 +112,8 @@ class MaskTable(object):
         self.fused = True
         N.call('ampis_rle_measure_paint', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h), _p(self.w),
                self.n, self.layout, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
-               _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor), _stream())
+               _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor),
+               PAINT_RUNS_HINT if PAINT_RUNS_HINT >= 0 else (self.cnt.numel() // max(self.n, 1)), _stream())
         return self
 
     def relayout(self, layout):

@@ -113,12 +113,14 @@ int ampis_rle_decode_crop(const uint32_t *d_cum, const int64_t *d_cnt_off, const
  * and paints.  Arena order is arbitrary (d_bits_off[i] is still written per mask; there is no
  * d_bits_off[n]).  After the stream has completed, *d_cursor = uint4 chunks needed; if it exceeds
  * bits_capacity some masks were not painted and the caller must retry with a larger arena.
- * d_cum is only touched for masks with more runs than fit in shared memory. */
+ * d_cum is only touched for masks with more runs than fit in shared memory.
+ * runs_hint: typical number of runs per mask (0 = unknown).  CROP layout only: small masks (<= 40 / <= 112 runs)
+ * are handled by 8 / 16 lanes each instead of a warp; results do not depend on it. */
 int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
                             const uint32_t *d_h, const uint32_t *d_w, int32_t n, int32_t layout,
                             uint32_t *d_cum, uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span,
                             uint32_t *d_reg, int64_t *d_bits_off, int32_t *d_status, void *d_bits,
-                            int64_t bits_capacity, uint64_t *d_cursor, void *stream);
+                            int64_t bits_capacity, uint64_t *d_cursor, int32_t runs_hint, void *stream);
 
 /* bits -> bool[n][h][w] row-major bytes (RLE.decode(...).astype(bool).transpose(2,0,1),
  * structures.py:752,765).  All n masks must share (h,w). d_mask_ids selects masks. */

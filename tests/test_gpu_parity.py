@@ -453,6 +453,30 @@ def test_sparse_iou_equals_nonzeros_of_the_dense_matrix(mods):
     assert e['shape'] == (0, len(pr)) and len(e['row']) == 0
 
 
+@pytest.mark.parametrize('cfg,over,n_img', [
+    ('c2_powder_batch', {}, 2),
+    ('c4_spheroidite', dict(n_rows=900, n_cols=900, h=1024, w=1024), 2),
+    ('c2_powder_batch', dict(h=600, w=500, n_rows=30, n_cols=30, median_diam=170.0), 2),   # > 64 / 128 runs: global run ends, several tiles
+    ('c2_powder_batch', dict(h=70, w=45, n_rows=9, n_cols=11, median_diam=30.0), 3),
+])
+def test_crop_decode_lane_groups_agree(mods, cfg, over, n_img, monkeypatch):
+    """The fused crop decode kernel with 8, 16 or 32 lanes per mask (chosen from a runs-per-mask hint) writes the
+    same measurements and, through the rows kernel, the same intersections as the unfused measure / scan / paint."""
+    B, E, torch = mods.batch, mods.engine, mods.torch
+    host = B.synth(dict(B.CONFIGS[cfg], **over), n_img, 31337)
+    dev = B.DeviceBatch(host, dense=True)
+    ref = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, fused=False, kernel='scan')
+    arena = torch.empty(4 * B.arena_chunks_needed(dev, E.LAYOUT_CROP), dtype=torch.int32, device='cuda')
+    for hint in (0, 30, 100):                       # warp per mask, 8 lanes, 16 lanes
+        monkeypatch.setattr(E, 'PAINT_RUNS_HINT', hint)
+        got = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, arena=arena, kernel='scan')
+        n = host.n_masks
+        assert torch.equal(got.table.area[:n], ref.table.area[:n]) and torch.equal(got.table.bbox[:4 * n], ref.table.bbox[:4 * n])
+        assert torch.equal(got.table.status[:n], ref.table.status[:n])
+        assert torch.equal(got.rows.imat, ref.rows.imat), hint
+        assert torch.equal(got.rows.best_col, ref.rows.best_col) and torch.equal(got.counts, ref.counts)
+
+
 def test_full_size_properties(mods):
     """BASELINE config sizes (C2 image count reduced): size-independent properties --
     span and full layouts agree bit for bit, I(gt,pred) == I(pred,gt)^T, area == popcount of the
