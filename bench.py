@@ -365,7 +365,12 @@ def roofline_of(args, cfg, run, ms, kt, world):
                 'step_canonical': {'bytes_per_image': canonical_img, 'achieved': step_gbs, 'frac': step_gbs / peak},
                 'kernel_share': {k: float(v) for k, v in zip(KERNELS, kt / kt.sum())}}
     pk = 'rle_paint_kernel' if args.unfused else 'rle_measure_paint_kernel'
-    return {'bound': 'hbm', 'kernel': {'paint': pk, 'rows': 'intersect_rows_kernel'}[dom],
+    rk = 'intersect_rows_kernel'
+    if run.layout == engine.LAYOUT_CROP:
+        rk = 'intersect_rows_grid_kernel' if getattr(run.pipes[0].grid, 'capacity', None) else 'intersect_rows_crop_kernel'
+        if not args.unfused and 0 < run.total_runs / max(n_masks, 1) <= 112:
+            pk = 'rle_measure_paint_crop_kernel'       # 8 or 16 lanes per mask
+    return {'bound': 'hbm', 'kernel': {'paint': pk, 'rows': rk}[dom],
             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
             'traffic_detail': traffic_detail,
             'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom] / launches, 'launch_ms': dur_ms,
