@@ -10,13 +10,14 @@
 // columns registered in the cells its own box touches: ~15 box tests per row instead of 5,000.
 //
 //   grid_setup_kernel   CTA per image: cell shift from the column boxes, clears the cell counters
-//   grid_count_kernel   thread per column mask: += 1 in every cell its box touches
+//   grid_bin_kernel<0>  thread per column mask: += 1 in every cell its box touches
 //   (exclusive scan of the counters by scan_*_kernel: cell -> first entry)
-//   grid_fill_kernel    thread per column mask: writes its index into every cell it touches
-//   intersect_rows_grid_kernel   warp per row: the cells of the row's box are read by one lane each,
-//       their entry lists are flattened by a warp scan, lanes test one entry each (a pair is taken
-//       only in the cell holding the top-left corner of the two boxes' overlap, so it is seen once),
-//       candidates are intersected four at a time, eight lanes per candidate, as in intersect_crop.cu.
+//   grid_bin_kernel<1>  thread per column mask: writes its index and its box into every cell it touches
+//   intersect_rows_grid_kernel   eight lanes per row, four rows per warp: the cells of the row's box are read by
+//       one lane each, their entry lists are flattened by a scan over the tile, lanes test one entry each (a pair
+//       is taken only in the cell holding the top-left corner of the two boxes' overlap, so it is seen once),
+//       candidates are intersected one after another by the row's eight lanes; overlaps of 256 words or more
+//       are parked and intersected by the whole warp afterwards.
 // Entries inside a cell are in no particular order: every arg-max tie is broken explicitly on the
 // column index, so the result does not depend on it.
 // Optional sparse output: (row, column, intersection) triplets of the non-zero intersections appended
