@@ -11,6 +11,7 @@ from . import build as _build
 LAYOUT_SPAN, LAYOUT_FULL, LAYOUT_CROP = 0, 1, 2
 MODE_IOU, MODE_SAT = 0, 1
 ST_BAD_TOTAL = 1
+OK, EINVAL, ECUDA, ENOSPC = 0, -1, -2, -3
 
 _p = C.c_void_p
 _i32, _i64, _u32, _u64, _f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
@@ -45,6 +46,8 @@ SIGNATURES = {
     'ampis_mma_tile_rows': (C.c_int, []),
     'ampis_mma_tile_cols': (C.c_int, []),
     'ampis_intersect_tcgen05': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    'ampis_eval_image_host': (C.c_int, [_p, _p, _i32, _i32, _u32, _u32, _i32, _i32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p,
+                                        _p, _p, _p, _p]),
     'ampis_mma_pair_tile_rows': (C.c_int, []),
     'ampis_mma_pair_tile_cols': (C.c_int, []),
     'ampis_intersect_tcgen05_pair': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p,

@@ -8,6 +8,7 @@ mask, the first-arg-max prediction, its IoU and its intersection, so the matcher
 det/seg scores are read off a single pass.  ``interval`` is accepted for signature
 compatibility; it never affected results.
 """
+import os
 from pathlib import Path
 
 import numpy as np
@@ -56,6 +57,30 @@ def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False):
     groups = engine.Groups.interleaved(table.device, [len(rows_rle)], [len(cols_rle)], dense=dense or crowded)
     res = engine.intersect(table, groups, mode, kernel='mma' if crowded else 'rows')
     return table, groups, res
+
+
+#: one library call per image (engine.eval_image) instead of the table API driven kernel by kernel from Python
+FUSED_CALL = os.environ.get('AMPIS_FUSED_CALL', '1') != '0'
+
+
+def _image_rows(rows_rle, cols_rle, mode):
+    """Per-row arg-max results of one image as host arrays: (best_col int64, best_score float64, best_inter int64,
+    areas uint32 of rows then columns).  Normally ONE call into the library (ampis_eval_image_host: bounding-box
+    windows, culled AND+popc); an image that turns out to be crowded (operand fill above the measured crossover,
+    known from the spans the call returns) is evaluated again through the table API with the tensor-core
+    contraction, which is where the time goes on such images.  Identical results either way."""
+    G = len(rows_rle)
+    if FUSED_CALL:
+        _check_same_size(rows_rle, cols_rle)
+        try:
+            r = engine.eval_image(rows_rle, cols_rle, mode)
+        except engine.N.AmpisNativeError:
+            r = None                      # e.g. boxes spread over very many grid cells: the table API sizes things exactly
+        if r is not None and not (min(G, len(cols_rle)) >= engine.MMA_MIN_SIDE and r.fill() >= engine.MMA_FILL_THRESHOLD):
+            return r.best_col.astype(np.int64), r.best_score, r.best_inter.astype(np.int64), r.area
+    table, groups, res = _rows_vs_cols(rows_rle, cols_rle, mode)
+    return (res.best_col[:G].cpu().numpy().astype(np.int64), res.best_score[:G].cpu().numpy(),
+            res.best_inter[:G].cpu().numpy().view(np.uint32).astype(np.int64), table.areas_np())
 
 
 def _piecewise_iou(a, b, interval=80):
@@ -126,11 +151,7 @@ def _piecewise_rle_match(gt, pred, iou_thresh=0.5, interval=80, _details=None):
         best_inter = np.zeros(G, np.int64)
         areas = None
     else:
-        table, groups, res = _rows_vs_cols(gt, pred, engine.MODE_IOU)
-        best_col = res.best_col[:G].cpu().numpy().astype(np.int64)
-        best_iou = res.best_score[:G].cpu().numpy()
-        best_inter = res.best_inter[:G].cpu().numpy().view(np.uint32).astype(np.int64)
-        areas = table.areas_np()
+        best_col, best_iou, best_inter, areas = _image_rows(gt, pred, engine.MODE_IOU)
     if _details is not None:
         _details.update(best_col=best_col, best_iou=best_iou, best_inter=best_inter, areas=areas)
     return _match_from_rows(best_col, best_iou, P, iou_thresh)

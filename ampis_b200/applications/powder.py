@@ -7,7 +7,7 @@ import copy
 
 import numpy as np
 
-from .. import engine
+from .. import analyze, engine
 from ..containers import Instances
 from ..structures import InstanceSet, mask_areas, masks_to_rle
 
@@ -30,11 +30,8 @@ def _rle_satellite_match(particles, satellites, match_thresh=0.5):
         for m in list(particles) + list(satellites):
             if list(m['size']) != list(particles[0]['size']):
                 raise ValueError('particle and satellite masks must share one image size')
-        table = engine.table_from_rle(list(satellites) + list(particles), layout=engine.MATCH_LAYOUT)
-        groups = engine.Groups.interleaved(table.device, [S], [Np])
-        res = engine.intersect_rows(table, groups, engine.MODE_SAT)
-        best = res.best_col[:S].cpu().numpy().astype(np.int64)
-        score = res.best_score[:S].cpu().numpy()          # NaN for zero-area satellites, as numpy's 0/0
+        best, score, _, _ = analyze._image_rows(satellites, particles, engine.MODE_SAT)   # NaN score for zero-area
+                                                                                         # satellites, as numpy's 0/0
     else:
         best, score = np.zeros(0, np.int64), np.zeros(0)
     with np.errstate(invalid='ignore'):

@@ -1,0 +1,155 @@
+// One image through the whole matching path in ONE library call (host-side orchestration only; every
+// computation is one of the kernels of this library):
+//
+//   compressed RLE strings (host) -> pinned staging -> one H2D copy -> rleFrString on the GPU -> fused measure +
+//   crop decode -> rows kernel (all-columns scan, or grid-pruned from `grid_min_cols` columns on) -> one D2H copy
+//   of the per-row results and per-mask measurements -> one stream synchronisation.
+//
+// This is what analyze.py:149-164 (G x ceil(P/80) RLE.iou calls + arg-max) and powder.py:80-86 (S x N RLE.merge +
+// RLE.area) cost per image in the reference.  The drop-in functions evaluate one image per Python call; driving the
+// ten kernels from Python costs ~1 ms of interpreter, allocator and launch overhead per call for ~0.1 ms of GPU
+// work, which is what this entry point removes.  It allocates nothing: the caller passes a device workspace and a
+// pinned host workspace and is told how much is needed when they are too small.
+#include <string.h>
+
+#include "common.cuh"
+
+static inline int64_t al256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+struct Carve {
+    int64_t off = 0;
+    int64_t take(int64_t bytes) { const int64_t o = off; off = al256(off + bytes); return o; }
+};
+
+extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_off, int32_t n_rows, int32_t n_cols,
+                                     uint32_t h, uint32_t w, int32_t mode, int32_t grid_min_cols,
+                                     void *d_ws, int64_t d_ws_bytes, void *h_ws, int64_t h_ws_bytes,
+                                     int32_t *best_col, uint32_t *best_inter, double *best_score, uint32_t *area,
+                                     int32_t *bbox, uint32_t *span, int32_t *status, int64_t *need_bytes, void *stream)
+{
+    AMPIS_REQUIRE(n_rows >= 0 && n_cols >= 0, "negative size");
+    AMPIS_REQUIRE(mode == AMPIS_MODE_IOU || mode == AMPIS_MODE_SAT, "bad mode");
+    AMPIS_REQUIRE(chr_off && d_ws && h_ws && best_col && best_inter && best_score && area && bbox && span && status && need_bytes,
+                  "null pointer");
+    AMPIS_REQUIRE(((uintptr_t)d_ws & 255u) == 0, "device workspace must be 256-byte aligned");
+    const int64_t n = (int64_t)n_rows + n_cols;
+    if (n == 0) return AMPIS_OK;
+    const int64_t n_chars = chr_off[n] - chr_off[0];
+    AMPIS_REQUIRE(chr_off[0] == 0 && n_chars >= 0 && (chars || n_chars == 0), "bad string offsets");
+    const int32_t nb = (n_rows + ampis_rows_per_block() - 1) / ampis_rows_per_block();
+    const bool use_grid = n_cols >= grid_min_cols && n_rows > 0;
+    const int cells = ampis_grid_cells();
+    const int64_t grid_cap = use_grid ? 16 * (int64_t)n_cols + 4096 : 0;
+
+    // ---- layout: [upload block][download block][device-only][arena] ---------------------------------------
+    Carve c;
+    const int64_t u_chars = c.take(n_chars), u_off = c.take(8 * (n + 1)), u_h = c.take(4 * n), u_w = c.take(4 * n);
+    const int64_t u_rowmask = c.take(4 * (int64_t)n_rows), u_blkgrp = c.take(4 * (int64_t)nb), u_blkrow = c.take(4 * (int64_t)nb);
+    const int64_t u_grb = c.take(4), u_grc = c.take(4), u_gcb = c.take(4), u_gcc = c.take(4);
+    const int64_t upload_bytes = c.off;
+    const int64_t dl0 = c.off;
+    const int64_t o_col = c.take(4 * (int64_t)n_rows), o_inter = c.take(4 * (int64_t)n_rows), o_score = c.take(8 * (int64_t)n_rows);
+    const int64_t o_area = c.take(4 * n), o_bbox = c.take(16 * n), o_span = c.take(8 * n), o_status = c.take(4 * n), o_cursor = c.take(8);
+    const int64_t o_gridtot = c.take(8);
+    const int64_t download_bytes = c.off - dl0;
+    const int64_t host_bytes = c.off;
+    const int64_t d_cnt = c.take(4 * n_chars), d_cum = c.take(4 * n_chars), d_cntlen = c.take(4 * n);
+    const int64_t d_reg = c.take(8 * n), d_bitsoff = c.take(8 * (n + 1));
+    int64_t g_shift = 0, g_count = 0, g_off = 0, g_fill = 0, g_tmp = 0, g_ent = 0, g_entbb = 0;
+    size_t scan_tmp = 0;
+    if (use_grid) {
+        scan_tmp = ampis_scan_tmp_bytes(cells);
+        g_shift = c.take(4); g_count = c.take(8 * (int64_t)cells); g_off = c.take(8 * ((int64_t)cells + 1));
+        g_fill = c.take(4 * (int64_t)cells); g_tmp = c.take((int64_t)scan_tmp); g_ent = c.take(4 * grid_cap);
+        g_entbb = c.take(16 * grid_cap);
+    }
+    const int64_t arena0 = c.off;
+    // arena: what is left, at least a window of 64 bytes per mask to start with
+    if (h_ws_bytes < host_bytes || d_ws_bytes < arena0 + 64 * n + 4096) {
+        *need_bytes = arena0 + 2048 * n + 65536;
+        if (h_ws_bytes < host_bytes) *need_bytes = -(host_bytes);      // negative: the HOST workspace is the short one
+        return AMPIS_ENOSPC;
+    }
+    const int64_t arena_chunks = (d_ws_bytes - arena0) / 16;
+    uint8_t *H = (uint8_t *)h_ws, *D = (uint8_t *)d_ws;
+    cudaStream_t st = as_stream(stream);
+
+    // ---- fill the upload block ---------------------------------------------------------------------------
+    if (n_chars) memcpy(H + u_chars, chars, (size_t)n_chars);
+    memcpy(H + u_off, chr_off, (size_t)(8 * (n + 1)));
+    uint32_t *ph = (uint32_t *)(H + u_h), *pw = (uint32_t *)(H + u_w);
+    for (int64_t i = 0; i < n; i++) { ph[i] = h; pw[i] = w; }
+    int32_t *prm = (int32_t *)(H + u_rowmask), *pbg = (int32_t *)(H + u_blkgrp), *pbr = (int32_t *)(H + u_blkrow);
+    for (int32_t i = 0; i < n_rows; i++) prm[i] = i;
+    for (int32_t b = 0; b < nb; b++) { pbg[b] = 0; pbr[b] = b * ampis_rows_per_block(); }
+    *(int32_t *)(H + u_grb) = 0; *(int32_t *)(H + u_grc) = n_rows;
+    *(int32_t *)(H + u_gcb) = n_rows; *(int32_t *)(H + u_gcc) = n_cols;
+    cudaError_t e = cudaMemcpyAsync(D, H, (size_t)upload_bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { ampis_set_error("upload: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+
+    // ---- kernels --------------------------------------------------------------------------------------------
+    int rc;
+#define STEP(call) do { rc = (call); if (rc != AMPIS_OK) return rc; } while (0)
+    STEP(ampis_rle_string_decode(D + u_chars, (const int64_t *)(D + u_off), (int32_t)n, (uint32_t *)(D + d_cnt),
+                                 (const int64_t *)(D + u_off), (int32_t *)(D + d_cntlen), stream));
+    STEP(ampis_rle_measure_paint((const uint32_t *)(D + d_cnt), (const int64_t *)(D + u_off), (const int32_t *)(D + d_cntlen),
+                                 (const uint32_t *)(D + u_h), (const uint32_t *)(D + u_w), (int32_t)n, AMPIS_LAYOUT_CROP,
+                                 (uint32_t *)(D + d_cum), (uint32_t *)(D + o_area), (int32_t *)(D + o_bbox),
+                                 (uint32_t *)(D + o_span), (uint32_t *)(D + d_reg), (int64_t *)(D + d_bitsoff),
+                                 (int32_t *)(D + o_status), D + arena0, arena_chunks, (uint64_t *)(D + o_cursor),
+                                 (int32_t)(n_chars / n), stream));
+    if (n_rows > 0 && n_cols > 0) {
+        if (use_grid) {
+            STEP(ampis_grid_count((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
+                                  n_cols, (int32_t *)(D + g_shift), (int64_t *)(D + g_count), (uint32_t *)(D + g_fill), stream));
+            STEP(ampis_exclusive_scan_i64((const int64_t *)(D + g_count), (int64_t *)(D + g_off), cells, D + g_tmp, scan_tmp,
+                                          stream));
+            STEP(ampis_grid_fill((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
+                                 n_cols, (const int32_t *)(D + g_shift), (const int64_t *)(D + g_off), (uint32_t *)(D + g_fill),
+                                 (int32_t *)(D + g_ent), (int32_t *)(D + g_entbb), grid_cap, stream));
+            STEP(ampis_intersect_rows_grid(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
+                                           (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
+                                           (const int32_t *)(D + u_blkgrp), (const int32_t *)(D + u_blkrow), nb,
+                                           (const int32_t *)(D + u_grb), (const int32_t *)(D + u_grc),
+                                           (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc),
+                                           (const int32_t *)(D + g_shift), (const int64_t *)(D + g_off),
+                                           (const int32_t *)(D + g_ent), (const int32_t *)(D + g_entbb), grid_cap, nullptr, mode,
+                                           nullptr, 0, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter),
+                                           (double *)(D + o_score), nullptr, nullptr, nullptr, 0, nullptr, stream));
+            e = cudaMemcpyAsync(D + o_gridtot, D + g_off + 8 * (int64_t)cells, 8, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { ampis_set_error("grid total: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+        } else {
+            STEP(ampis_intersect_rows_crop(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
+                                           (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
+                                           (const int32_t *)(D + u_blkgrp), (const int32_t *)(D + u_blkrow), nb,
+                                           (const int32_t *)(D + u_grb), (const int32_t *)(D + u_grc),
+                                           (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), nullptr, mode, nullptr,
+                                           (int32_t *)(D + o_col), (uint32_t *)(D + o_inter), (double *)(D + o_score), stream));
+        }
+    }
+#undef STEP
+    e = cudaMemcpyAsync(H + dl0, D + dl0, (size_t)download_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { ampis_set_error("download: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+
+    // ---- did everything fit? ------------------------------------------------------------------------------------
+    const uint64_t used = *(const uint64_t *)(H + o_cursor);
+    if ((int64_t)used > arena_chunks) {
+        *need_bytes = arena0 + 16 * (int64_t)used + 65536;
+        return AMPIS_ENOSPC;
+    }
+    if (use_grid && n_cols > 0 && *(const int64_t *)(H + o_gridtot) > grid_cap) {
+        ampis_set_error("grid entry list too small (%lld entries)", (long long)*(const int64_t *)(H + o_gridtot));
+        return AMPIS_EINVAL;          // boxes spread over far more cells than 16 per mask: use the table API
+    }
+    if (n_rows > 0 && n_cols > 0) {
+        memcpy(best_col, H + o_col, (size_t)(4 * (int64_t)n_rows));
+        memcpy(best_inter, H + o_inter, (size_t)(4 * (int64_t)n_rows));
+        memcpy(best_score, H + o_score, (size_t)(8 * (int64_t)n_rows));
+    }
+    memcpy(area, H + o_area, (size_t)(4 * n));
+    memcpy(bbox, H + o_bbox, (size_t)(16 * n));
+    memcpy(span, H + o_span, (size_t)(8 * n));
+    memcpy(status, H + o_status, (size_t)(4 * n));
+    return AMPIS_OK;
+}

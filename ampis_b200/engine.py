@@ -5,6 +5,7 @@ hand-written sm_100a kernels.  There is no CPU fallback anywhere in this module.
 """
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -218,6 +219,70 @@ def table_from_rle(masks, layout=None, paint=True):
         t.paint()
     t.check()
     return t
+
+
+class ImageRows(object):
+    """Result of eval_image(): per-row arg-max results and per-mask measurements of one image (numpy)."""
+    __slots__ = ('best_col', 'best_inter', 'best_score', 'area', 'bbox', 'span', 'n_rows', 'n_cols', 'hw')
+
+    def fill(self):
+        """Operand fill (see operand_fill) from the returned spans."""
+        slabs = (self.hw[0] * self.hw[1] + 127) // 128
+        n = len(self.area)
+        return float((self.span[:, 1].astype(np.int64) - self.span[:, 0]).sum()) / max(slabs * n, 1)
+
+
+_image_ws = {}          # device index -> [device workspace, pinned host workspace]
+_image_ws_lock = threading.Lock()
+
+
+def eval_image(rows_rle, cols_rle, mode):
+    """One image, rows x columns, through ampis_eval_image_host: ONE library call stages the compressed strings,
+    runs string decode -> fused measure + crop decode -> rows kernel and brings the per-row results back with one
+    synchronisation (the drop-in matching functions call this once per image).  The caller has checked that all
+    masks share one image size.  Raises ValueError on malformed RLE like MaskTable.check()."""
+    device = require_cuda()
+    strings, hs, ws = _rle_fields(list(rows_rle) + list(cols_rle))
+    n_rows, n_cols = len(rows_rle), len(cols_rle)
+    n = n_rows + n_cols
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(np.fromiter(map(len, strings), np.int64, n), out=off[1:])
+    blob = b''.join(strings)
+    r = ImageRows()
+    r.n_rows, r.n_cols, r.hw = n_rows, n_cols, (int(hs[0]), int(ws[0])) if n else (0, 0)
+    r.best_col = np.empty(n_rows, np.int32)
+    r.best_inter = np.empty(n_rows, np.uint32)
+    r.best_score = np.empty(n_rows, np.float64)
+    r.area = np.empty(n, np.uint32)
+    r.bbox = np.empty((n, 4), np.int32)
+    r.span = np.empty((n, 2), np.uint32)
+    status = np.empty(n, np.int32)
+    if n == 0:
+        return r
+    need = C.c_int64(0)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib = N.lib()
+    with _image_ws_lock:
+        ws_pair = _image_ws.setdefault(device.index, [torch.empty(1 << 22, dtype=torch.uint8, device=device),
+                                                      torch.empty(1 << 20, dtype=torch.uint8, pin_memory=True)])
+        for _ in range(8):
+            d_ws, h_ws = ws_pair
+            rc = lib.ampis_eval_image_host(blob, ptr(off), n_rows, n_cols, r.hw[0], r.hw[1], mode, ROWS_GRID_MIN_COLS,
+                                           _p(d_ws), d_ws.numel(), _p(h_ws), h_ws.numel(), ptr(r.best_col),
+                                           ptr(r.best_inter), ptr(r.best_score), ptr(r.area), ptr(r.bbox), ptr(r.span),
+                                           ptr(status), C.byref(need), _stream())
+            if rc != N.ENOSPC:
+                break
+            if need.value < 0:          # pinned host workspace too small
+                ws_pair[1] = torch.empty(int(-need.value * 3 // 2), dtype=torch.uint8, pin_memory=True)
+            else:
+                torch.cuda.current_stream().synchronize()
+                ws_pair[0] = None
+                ws_pair[0] = torch.empty(int(need.value * 3 // 2), dtype=torch.uint8, device=device)
+        N.check(rc, 'ampis_eval_image_host')
+    if status.any():
+        raise ValueError('malformed RLE: run counts do not sum to h*w for masks %s' % np.nonzero(status)[0][:8].tolist())
+    return r
 
 
 class Groups(object):

@@ -129,10 +129,13 @@ def test_bitmask_array_and_extract_boxes(mods):
         assert np.array_equal(D.extract_boxes(a), R.extract_boxes(a))
 
 
-@pytest.mark.parametrize('layout', ['span', 'full', 'crop'])
+@pytest.mark.parametrize('layout', ['span', 'full', 'crop', 'one_call'])
 def test_golden_matching_all_images(mods, layout, monkeypatch):
     A, E = mods.analyze, mods.engine
-    monkeypatch.setattr(E, 'MATCH_LAYOUT', {'full': E.LAYOUT_FULL, 'span': E.LAYOUT_SPAN, 'crop': E.LAYOUT_CROP}[layout])
+    # 'one_call': the product default (ampis_eval_image_host per image); the others: the table API in each layout
+    monkeypatch.setattr(A, 'FUSED_CALL', layout == 'one_call')
+    if layout != 'one_call':
+        monkeypatch.setattr(E, 'MATCH_LAYOUT', {'full': E.LAYOUT_FULL, 'span': E.LAYOUT_SPAN, 'crop': E.LAYOUT_CROP}[layout])
     g = U.load('powder_match.npz')
     for k in range(len(g['names'])):
         _, gt, pr = U.powder_match_image(k)
@@ -475,6 +478,42 @@ def test_crop_decode_lane_groups_agree(mods, cfg, over, n_img, monkeypatch):
         assert torch.equal(got.table.status[:n], ref.table.status[:n])
         assert torch.equal(got.rows.imat, ref.rows.imat), hint
         assert torch.equal(got.rows.best_col, ref.rows.best_col) and torch.equal(got.counts, ref.counts)
+
+
+def test_one_call_image_entry_equals_table_api(mods, monkeypatch):
+    """engine.eval_image (ampis_eval_image_host: one library call per image) == the table API kernel by kernel:
+    both modes, the scanned and the grid-pruned rows kernel, workspace growth on a large image, malformed RLE."""
+    A, B, E, P, rle = mods.analyze, mods.batch, mods.engine, mods.powder, mods.rle
+    cases = [('c1_powder_example', {}, E.MODE_IOU),                                              # scan (300 columns)
+             ('c2_powder_batch', {}, E.MODE_IOU),                                                # grid (500 columns)
+             ('c3_satellites', dict(h=1024, w=1024, n_cols=700), E.MODE_SAT),                    # satellites, grid
+             ('c4_spheroidite', dict(n_rows=3000, n_cols=3500), E.MODE_IOU),                     # grows the workspaces
+             ('c2_powder_batch', dict(h=640, w=480, n_rows=20, n_cols=25, median_diam=200.0), E.MODE_IOU)]
+    for cfg, over, mode in cases:
+        host = B.synth(dict(B.CONFIGS[cfg], **over), 1, 2024)
+        rows, cols = host.image_masks(0)
+        mk = lambda cs: [{'size': [host.h, host.w], 'counts': rle.string_from_counts(c)} for c in cs]
+        r_, c_ = mk(rows), mk(cols)
+        got = E.eval_image(r_, c_, mode)
+        table, groups, res = A._rows_vs_cols(r_, c_, mode)
+        G = len(r_)
+        assert np.array_equal(got.best_col, res.best_col[:G].cpu().numpy()), cfg
+        assert np.array_equal(got.best_inter, res.best_inter[:G].cpu().numpy().view(np.uint32)), cfg
+        assert np.array_equal(got.best_score, res.best_score[:G].cpu().numpy(), equal_nan=True), cfg
+        assert np.array_equal(got.area, table.areas_np()) and np.array_equal(got.bbox, table.bbox_np()), cfg
+        assert abs(got.fill() - E.operand_fill(table)) < 1e-12
+    bad = [{'size': [45, 37], 'counts': rle.string_from_counts(np.array([3, 5000, 7, 900], np.uint32))}]
+    with pytest.raises(ValueError, match='malformed RLE'):
+        E.eval_image(bad, bad, E.MODE_IOU)
+    # the satellite function end to end, both ways
+    host = B.synth(dict(B.CONFIGS['c3_satellites'], h=1024, w=1024, n_cols=500), 1, 7)
+    sat, part = host.image_masks(0)
+    mk = lambda cs: [{'size': [host.h, host.w], 'counts': rle.string_from_counts(c)} for c in cs]
+    a = P._rle_satellite_match(mk(part), mk(sat), 0.5)
+    monkeypatch.setattr(A, 'FUSED_CALL', False)
+    b = P._rle_satellite_match(mk(part), mk(sat), 0.5)
+    assert all(np.array_equal(a[k], b[k]) for k in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched',
+                                                    'intersection_scores')) and a['match_pairs'].keys() == b['match_pairs'].keys()
 
 
 def test_full_size_properties(mods):
@@ -867,8 +906,15 @@ def test_public_api_takes_the_tensor_core_path_on_crowded_images(mods, monkeypat
         assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
     assert np.array_equal(A._piecewise_iou(gt, pr), R.piecewise_iou(gt, pr)) and used == ['mma', 'mma']
     _, g2, p2 = U.powder_match_image(0)
-    A.rle_instance_matcher(g2, p2)
-    assert used[-1] == 'rows'
+    calls = []
+    real_eval = E.eval_image
+    monkeypatch.setattr(E, 'eval_image', lambda *a: (calls.append(1), real_eval(*a))[1])
+    n_before = len(used)
+    one_call = A.rle_instance_matcher(g2, p2)                  # ordinary image: ONE library call, no table API
+    assert calls == [1] and len(used) == n_before
+    monkeypatch.setattr(A, 'FUSED_CALL', False)                # the table API gives the same answer
+    by_table = A.rle_instance_matcher(g2, p2)
+    assert used[-1] == 'rows' and all(np.array_equal(one_call[k], by_table[k]) for k in by_table)
 
 
 def _host_csr_from_bool(B, masks_per_image, n_rows, h, w, rle):
