@@ -71,7 +71,6 @@ def _image_rows(rows_rle, cols_rle, mode):
     contraction, which is where the time goes on such images.  Identical results either way."""
     G = len(rows_rle)
     if FUSED_CALL:
-        _check_same_size(rows_rle, cols_rle)
         try:
             r = engine.eval_image(rows_rle, cols_rle, mode)
         except engine.N.AmpisNativeError:

@@ -160,7 +160,7 @@ def _rle_fields(masks):
     """list of COCO RLE dicts -> (list of bytes, h array, w array); mirrors the input
     handling of pycocotools' _frString (str counts are accepted and encoded)."""
     strings = [m['counts'] for m in masks]
-    if not all(type(c) is bytes for c in strings):
+    if set(map(type, strings)) - {bytes}:
         for i, c in enumerate(strings):
             if type(c) == str:
                 strings[i] = c.encode('ascii')
@@ -239,12 +239,16 @@ _image_ws_lock = threading.Lock()
 def eval_image(rows_rle, cols_rle, mode):
     """One image, rows x columns, through ampis_eval_image_host: ONE library call stages the compressed strings,
     runs string decode -> fused measure + crop decode -> rows kernel and brings the per-row results back with one
-    synchronisation (the drop-in matching functions call this once per image).  The caller has checked that all
-    masks share one image size.  Raises ValueError on malformed RLE like MaskTable.check()."""
+    synchronisation (the drop-in matching functions call this once per image).  Raises ValueError when the masks
+    do not share one image size and on malformed RLE (like MaskTable.check())."""
     device = require_cuda()
     strings, hs, ws = _rle_fields(list(rows_rle) + list(cols_rle))
     n_rows, n_cols = len(rows_rle), len(cols_rle)
     n = n_rows + n_cols
+    if n and ((hs != hs[0]).any() or (ws != ws[0]).any()):
+        k = int(np.nonzero((hs != hs[0]) | (ws != ws[0]))[0][0])
+        raise ValueError('masks of different image sizes cannot be compared (%s vs %s)'
+                         % ((int(hs[0]), int(ws[0])), (int(hs[k]), int(ws[k]))))
     off = np.zeros(n + 1, np.int64)
     np.cumsum(np.fromiter(map(len, strings), np.int64, n), out=off[1:])
     blob = b''.join(strings)
