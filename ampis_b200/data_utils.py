@@ -146,8 +146,7 @@ def _from_rle_json(json_path, dataset_class, cwd):
         for m in masks:
             m['counts'] = m['counts'].encode('utf-8')
         height, width = masks[0]['size']
-        table = engine.table_from_rle(masks, paint=False)
-        area, tight = table.areas_np(), table.bbox_np()
+        area, tight = engine.measure_rle(masks)
         instances = [_instance(tight[k].astype(np.float64) if area[k] else np.zeros(4), m) for k, m in enumerate(masks)]
         out.append(_record(idx, Path(json_path.parent, Path(item['file_name'])).relative_to(cwd), str(json_path),
                            height, width, 'bitmask', dataset_class, instances))

@@ -289,6 +289,22 @@ def eval_image(rows_rle, cols_rle, mode):
     return r
 
 
+def measure_rle(masks):
+    """(area uint32[n], tight bbox int32[n, 4]) of a list of RLE dicts: rleArea and the box extract_boxes reads off
+    the decoded mask.  Masks of one image size go through the one-call entry point (no intersection is run); mixed
+    sizes through the table API."""
+    masks = list(masks)
+    if masks:
+        try:
+            r = eval_image(masks, [], MODE_IOU)
+            return r.area, r.bbox
+        except ValueError as e:
+            if 'different image sizes' not in str(e):
+                raise
+    t = table_from_rle(masks, paint=False)
+    return t.areas_np(), t.bbox_np()
+
+
 class Groups(object):
     """Row/column bookkeeping of a batch: group g (an image) owns rows (ground truth or
     satellites) and columns (predictions or particles); all are mask ids of one MaskTable."""

@@ -154,8 +154,7 @@ class InstanceSet(object):
         quirk: the slice is empty, the frame is the whole image and every non-empty mask goes."""
         r, c = self.instances.image_size
         rle = masks_to_rle(self.instances.masks, (r, c))
-        t = engine.table_from_rle(rle, paint=False)
-        bb, area = t.bbox_np(), t.areas_np()
+        area, bb = engine.measure_rle(rle)
         # ``border[k:-k, k:-k] = 0`` zeroes nothing when the slice is empty
         if k <= 0 or r - 2 * k <= 0 or c - 2 * k <= 0:
             touches = area > 0
@@ -229,7 +228,7 @@ def mask_areas(masks):
     if kind == PolygonMasks:
         return np.asarray([_shoelace_area(ring[0][::2], ring[0][1::2]) for ring in masks.polygons])
     if kind == RLEMasks or (kind == list and type(masks[0]) == dict):
-        return engine.table_from_rle(masks.rle if kind == RLEMasks else masks, paint=False).areas_np()
+        return engine.measure_rle(masks.rle if kind == RLEMasks else masks)[0]
     if kind in (Instances, InstanceSet):
         return mask_areas(masks.masks if kind == Instances else masks.instances)
     if kind == list:
