@@ -198,29 +198,40 @@ intersect_rows_grid_kernel(const GridRowArgs p)
                 area_m = p.area[cb + k_m];
             }
             const int nq = min(GR_TILE, n - j0);
-            for (int q = 0; q < nq; q++) {
-                const int k = __shfl_sync(tmask, k_m, q, GR_TILE);
-                const i64 off = __shfl_sync(tmask, off_m, q, GR_TILE);
-                const u32 ca = __shfl_sync(tmask, area_m, q, GR_TILE);
-                const int4 cbx = s_bb[slot][j0 + q];
+            // two candidates at a time, four lanes each: their window words are in flight together (the kernel is
+            // bound by the latency of these dependent loads, not by lanes)
+            const u32 sub = t >> 2, t4 = t & 3u;
+            for (int q0 = 0; q0 < nq; q0 += 2) {
+                const int q = q0 + (int)sub;
+                const bool have = q < nq;
+                const int qs = have ? q : q0;
+                const int k = __shfl_sync(tmask, k_m, qs, GR_TILE);
+                const i64 off = __shfl_sync(tmask, off_m, qs, GR_TILE);
+                const u32 ca = __shfl_sync(tmask, area_m, qs, GR_TILE);
+                const int4 cbx = s_bb[slot][j0 + qs];
                 const Overlap o = overlap_of(A, rb, p.words + off * 4, cbx);
-                if (o.total >= GR_BIG) {             // park it for the whole warp
-                    int pos = 0;
-                    if (t == 0) pos = atomicAdd(&s_nbig[wid], 1);
-                    pos = __shfl_sync(tmask, pos, 0, GR_TILE);
-                    if (pos < GR_BIGLIST) {
-                        if (t == 0) {
-                            s_big_k[wid][pos] = k; s_big_slot[wid][pos] = slot; s_big_area[wid][pos] = ca;
-                            s_big_off[wid][pos] = off; s_big_bb[wid][pos] = cbx;
-                        }
-                        continue;
-                    }
+                // large overlaps are parked for the whole warp (the four lanes of a candidate decide alike; the
+                // shuffle is executed by all eight lanes whatever the two halves decide)
+                const bool big = have && o.total >= GR_BIG;
+                int pos = GR_BIGLIST;
+                if (big && t4 == 0) pos = atomicAdd(&s_nbig[wid], 1);
+                pos = __shfl_sync(tmask, pos, (int)(sub * 4u), GR_TILE);
+                const bool parked = big && pos < GR_BIGLIST;
+                if (parked && t4 == 0) {
+                    s_big_k[wid][pos] = k; s_big_slot[wid][pos] = slot; s_big_area[wid][pos] = ca;
+                    s_big_off[wid][pos] = off; s_big_bb[wid][pos] = cbx;
                 }
-                u32 v = overlap_popc(o, t, GR_TILE);
-                v += __shfl_xor_sync(tmask, v, 4);
+                u32 v = (have && !parked) ? overlap_popc(o, t4, 4) : 0u;
                 v += __shfl_xor_sync(tmask, v, 2);
                 v += __shfl_xor_sync(tmask, v, 1);
-                update(k, v, ca);
+                // both results to all eight lanes, applied in candidate order (every lane keeps the same best)
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const u32 vu = __shfl_sync(tmask, v, u * 4, GR_TILE);
+                    const int ku = __shfl_sync(tmask, k, u * 4, GR_TILE);
+                    const u32 cau = __shfl_sync(tmask, ca, u * 4, GR_TILE);
+                    if (q0 + u < nq) update(ku, vu, cau);     // parked or empty: vu == 0, nothing happens
+                }
             }
         }
     };
