@@ -38,8 +38,7 @@ SIGNATURES = {
     'ampis_intersect_rows_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p,
                                             _p, _p]),
     'ampis_grid_cells': (C.c_int, []),
-    'ampis_grid_count': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
-    'ampis_grid_fill': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _p]),
+    'ampis_grid_build': (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _p, _p]),
     'ampis_intersect_rows_grid': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64,
                                             _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     'ampis_rle_decode_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),

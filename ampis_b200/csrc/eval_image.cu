@@ -55,12 +55,9 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
     const int64_t host_bytes = c.off;
     const int64_t d_cnt = c.take(4 * n_chars), d_cum = c.take(4 * n_chars), d_cntlen = c.take(4 * n);
     const int64_t d_reg = c.take(8 * n), d_bitsoff = c.take(8 * (n + 1));
-    int64_t g_shift = 0, g_count = 0, g_off = 0, g_fill = 0, g_tmp = 0, g_ent = 0, g_entbb = 0;
-    size_t scan_tmp = 0;
+    int64_t g_shift = 0, g_off = 0, g_ent = 0, g_entbb = 0;
     if (use_grid) {
-        scan_tmp = ampis_scan_tmp_bytes(cells);
-        g_shift = c.take(4); g_count = c.take(8 * (int64_t)cells); g_off = c.take(8 * ((int64_t)cells + 1));
-        g_fill = c.take(4 * (int64_t)cells); g_tmp = c.take((int64_t)scan_tmp); g_ent = c.take(4 * grid_cap);
+        g_shift = c.take(4); g_off = c.take(8 * ((int64_t)cells + 1)); g_ent = c.take(4 * grid_cap);
         g_entbb = c.take(16 * grid_cap);
     }
     const int64_t arena0 = c.off;
@@ -100,13 +97,9 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
                                  (int32_t)(n_chars / n), stream));
     if (n_rows > 0 && n_cols > 0) {
         if (use_grid) {
-            STEP(ampis_grid_count((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
-                                  n_cols, (int32_t *)(D + g_shift), (int64_t *)(D + g_count), (uint32_t *)(D + g_fill), stream));
-            STEP(ampis_exclusive_scan_i64((const int64_t *)(D + g_count), (int64_t *)(D + g_off), cells, D + g_tmp, scan_tmp,
-                                          stream));
-            STEP(ampis_grid_fill((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
-                                 n_cols, (const int32_t *)(D + g_shift), (const int64_t *)(D + g_off), (uint32_t *)(D + g_fill),
-                                 (int32_t *)(D + g_ent), (int32_t *)(D + g_entbb), grid_cap, stream));
+            STEP(ampis_grid_build((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
+                                  (int32_t *)(D + g_shift), (int64_t *)(D + g_off), (int32_t *)(D + g_ent),
+                                  (int32_t *)(D + g_entbb), grid_cap, (uint64_t *)(D + o_gridtot), stream));
             STEP(ampis_intersect_rows_grid(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
                                            (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
                                            (const int32_t *)(D + u_blkgrp), (const int32_t *)(D + u_blkrow), nb,
@@ -116,8 +109,6 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
                                            (const int32_t *)(D + g_ent), (const int32_t *)(D + g_entbb), grid_cap, nullptr, mode,
                                            nullptr, 0, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter),
                                            (double *)(D + o_score), nullptr, nullptr, nullptr, 0, nullptr, stream));
-            e = cudaMemcpyAsync(D + o_gridtot, D + g_off + 8 * (int64_t)cells, 8, cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) { ampis_set_error("grid total: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
         } else {
             STEP(ampis_intersect_rows_crop(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
                                            (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),

@@ -9,10 +9,9 @@
 // side of the image's columns so that a mask lands in ~1-4 cells); a row then only looks at the
 // columns registered in the cells its own box touches: ~15 box tests per row instead of 5,000.
 //
-//   grid_setup_kernel   CTA per image: cell shift from the column boxes, clears the cell counters
-//   grid_bin_kernel<0>  thread per column mask: += 1 in every cell its box touches
-//   (exclusive scan of the counters by scan_*_kernel: cell -> first entry)
-//   grid_bin_kernel<1>  thread per column mask: writes its index and its box into every cell it touches
+//   grid_build_kernel   CTA per image: cell shift from the column boxes, per-cell counts and their scan in shared
+//       memory, one atomicAdd on a global cursor for the image's entries, then every column mask writes its
+//       index and its box into the cells it touches
 //   intersect_rows_grid_kernel   eight lanes per row, four rows per warp: the cells of the row's box are read by
 //       one lane each, their entry lists are flattened by a scan over the tile, lanes test one entry each (a pair
 //       is taken only in the cell holding the top-left corner of the two boxes' overlap, so it is seen once),
@@ -38,18 +37,32 @@
 __device__ __forceinline__ int bits_of(u32 x) { return 32 - __clz(x); }
 __device__ __forceinline__ int cell_of(int v, int shift) { return min(v >> shift, GR_N - 1); }
 
-__global__ void __launch_bounds__(256)
-grid_setup_kernel(const int4 *bbox, const int *grp_col_begin, const int *grp_col_count, int *grp_shift,
-                  i64 *cell_count, u32 *cell_fill)
+// One CTA builds the grid of one image: cell shift from the column boxes, per-cell counts in shared memory,
+// exclusive scan, ONE atomicAdd on the global cursor for the image's entries, then the entries themselves
+// (shared-memory cursors per cell).  cell_off has GR_CELLS + 1 values per image (absolute entry positions).
+#define GB_THREADS 512
+
+__global__ void __launch_bounds__(GB_THREADS)
+grid_build_kernel(const int4 *__restrict__ bbox, const int *__restrict__ grp_col_begin,
+                  const int *__restrict__ grp_col_count, int *__restrict__ grp_shift, i64 *__restrict__ cell_off,
+                  int *__restrict__ entries, int4 *__restrict__ entry_bbox, i64 capacity,
+                  unsigned long long *__restrict__ cursor)
 {
+    __shared__ u32 s_cnt[GR_CELLS], s_off[GR_CELLS];
+    __shared__ u32 s_wsum[GB_THREADS / 32];
     __shared__ unsigned long long s_sum;
-    __shared__ u32 s_n, s_ext;
+    __shared__ u32 s_n, s_ext, s_total;
+    __shared__ int s_shift;
+    __shared__ i64 s_base;
     const int g = blockIdx.x;
-    if (threadIdx.x == 0) { s_sum = 0; s_n = 0; s_ext = 0; }
-    __syncthreads();
+    const u32 tid = threadIdx.x, lane = lane_id(), wid = tid >> 5;
     const int cb = grp_col_begin[g], P = grp_col_count[g];
+    if (tid == 0) { s_sum = 0; s_n = 0; s_ext = 0; }
+    for (int c = tid; c < GR_CELLS; c += GB_THREADS) s_cnt[c] = 0;
+    __syncthreads();
+    // ---- cell size: 2^shift >= mean box side, and the image's extent fits 32 cells
     u32 sum = 0, n = 0, ext = 0;
-    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+    for (int k = tid; k < P; k += GB_THREADS) {
         const int4 b = bbox[cb + k];
         if (b.z < b.x) continue;
         sum += (u32)max(b.z - b.x, b.w - b.y) + 1u;
@@ -57,42 +70,73 @@ grid_setup_kernel(const int4 *bbox, const int *grp_col_begin, const int *grp_col
         n++;
     }
     sum = warp_sum(sum); n = warp_sum(n); ext = warp_max(ext);
-    if (lane_id() == 0) { atomicAdd(&s_sum, (unsigned long long)sum); atomicAdd(&s_n, n); atomicMax(&s_ext, ext); }
-    for (int c = threadIdx.x; c < GR_CELLS; c += blockDim.x) {
-        cell_count[(i64)g * GR_CELLS + c] = 0;
-        cell_fill[(i64)g * GR_CELLS + c] = 0;
-    }
+    if (lane == 0) { atomicAdd(&s_sum, (unsigned long long)sum); atomicAdd(&s_n, n); atomicMax(&s_ext, ext); }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         const u32 mean = s_n ? (u32)((s_sum + s_n - 1) / s_n) : 1u;
         const int by_frame = max(0, bits_of(s_ext) - 5);               // extent >> shift < 32
         const int by_size = bits_of(max(mean, 1u) - 1u);                // 2^shift >= mean box side
-        grp_shift[g] = min(max(by_frame, by_size), 30);
+        s_shift = min(max(by_frame, by_size), 30);
+        grp_shift[g] = s_shift;
     }
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(256)
-grid_bin_kernel(const int4 *bbox, const int *grp_col_begin, const int *grp_col_count, const int *grp_shift,
-                i64 *cell_count, const i64 *cell_off, u32 *cell_fill, int *entries, int4 *entry_bbox, i64 capacity)
-{
-    const int g = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= grp_col_count[g]) return;
-    const int4 b = bbox[grp_col_begin[g] + k];
-    if (b.z < b.x) return;
-    const int s = grp_shift[g];
-    const int cx0 = cell_of(b.x, s), cx1 = cell_of(b.z, s), cy0 = cell_of(b.y, s), cy1 = cell_of(b.w, s);
-    for (int cy = cy0; cy <= cy1; cy++)
-        for (int cx = cx0; cx <= cx1; cx++) {
-            const i64 cell = (i64)g * GR_CELLS + cy * GR_N + cx;
-            if (FILL) {
-                const i64 pos = cell_off[cell] + (i64)atomicAdd(cell_fill + cell, 1u);
-                if (pos < capacity) { entries[pos] = k; entry_bbox[pos] = b; }
-            } else {
-                atomicAdd(reinterpret_cast<unsigned long long *>(cell_count + cell), 1ull);
-            }
+    __syncthreads();
+    const int s = s_shift;
+    // ---- count
+    for (int k = tid; k < P; k += GB_THREADS) {
+        const int4 b = bbox[cb + k];
+        if (b.z < b.x) continue;
+        const int cx0 = cell_of(b.x, s), cx1 = cell_of(b.z, s), cy0 = cell_of(b.y, s), cy1 = cell_of(b.w, s);
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int cx = cx0; cx <= cx1; cx++) atomicAdd(&s_cnt[cy * GR_N + cx], 1u);
+    }
+    __syncthreads();
+    // ---- exclusive scan of the 1024 counts: two cells per thread, warp scan, scan of the warp sums
+    const u32 c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+    u32 incl = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        u32 w = lane < GB_THREADS / 32 ? s_wsum[lane] : 0u, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 v = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += v;
         }
+        if (lane < GB_THREADS / 32) s_wsum[lane] = wi - w;             // exclusive
+        if (lane == 31) {
+            s_total = wi;
+            s_base = wi ? (i64)atomicAdd(cursor, (unsigned long long)wi) : 0;
+        }
+    }
+    __syncthreads();
+    const u32 excl = s_wsum[wid] + incl - (c0 + c1);
+    s_off[2 * tid] = excl;
+    s_off[2 * tid + 1] = excl + c0;
+    s_cnt[2 * tid] = 0;                                                 // reused as the fill cursors
+    s_cnt[2 * tid + 1] = 0;
+    const i64 base = s_base;
+    i64 *off = cell_off + (i64)g * (GR_CELLS + 1);
+    off[2 * tid] = base + excl;
+    off[2 * tid + 1] = base + excl + c0;
+    if (tid == 0) off[GR_CELLS] = base + s_total;
+    __syncthreads();
+    // ---- fill
+    for (int k = tid; k < P; k += GB_THREADS) {
+        const int4 b = bbox[cb + k];
+        if (b.z < b.x) continue;
+        const int cx0 = cell_of(b.x, s), cx1 = cell_of(b.z, s), cy0 = cell_of(b.y, s), cy1 = cell_of(b.w, s);
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int cx = cx0; cx <= cx1; cx++) {
+                const int cell = cy * GR_N + cx;
+                const i64 pos = base + s_off[cell] + atomicAdd(&s_cnt[cell], 1u);
+                if (pos < capacity) { entries[pos] = k; entry_bbox[pos] = b; }
+            }
+    }
 }
 
 struct GridRowArgs {
@@ -238,7 +282,7 @@ intersect_rows_grid_kernel(const GridRowArgs p)
 
     if (valid && ra != 0 && P > 0) {
         const int s = p.grp_shift[g];
-        const i64 *off = p.cell_off + (i64)g * GR_CELLS;
+        const i64 *off = p.cell_off + (i64)g * (GR_CELLS + 1);
         const i64 gbase = off[0];
         const int rcx0 = cell_of(rb.x, s), rcy0 = cell_of(rb.y, s);
         const int ncx = cell_of(rb.z, s) - rcx0 + 1, ncell = ncx * (cell_of(rb.w, s) - rcy0 + 1);
@@ -320,47 +364,23 @@ intersect_rows_grid_kernel(const GridRowArgs p)
 
 extern "C" int ampis_grid_cells(void) { return GR_CELLS; }
 
-extern "C" int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_begin,
-                                const int32_t *d_grp_col_count, int32_t n_groups, int32_t max_cols,
-                                int32_t *d_grp_shift, int64_t *d_cell_count, uint32_t *d_cell_fill, void *stream)
+extern "C" int ampis_grid_build(const int32_t *d_bbox, const int32_t *d_grp_col_begin,
+                                const int32_t *d_grp_col_count, int32_t n_groups, int32_t *d_grp_shift,
+                                int64_t *d_cell_off, int32_t *d_entries, int32_t *d_entry_bbox, int64_t capacity,
+                                uint64_t *d_cursor, void *stream)
 {
-    AMPIS_REQUIRE(n_groups >= 0 && max_cols >= 0, "negative size");
+    AMPIS_REQUIRE(n_groups >= 0 && capacity >= 0, "negative size");
     if (n_groups == 0) return AMPIS_OK;
-    AMPIS_REQUIRE(d_bbox && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_count && d_cell_fill,
+    AMPIS_REQUIRE(d_bbox && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_off && d_cursor,
                   "null pointer");
-    grid_setup_kernel<<<n_groups, 256, 0, as_stream(stream)>>>((const int4 *)d_bbox, d_grp_col_begin,
-                                                               d_grp_col_count, d_grp_shift, d_cell_count,
-                                                               d_cell_fill);
-    AMPIS_CHECK_LAUNCH("grid_setup_kernel");
-    if (max_cols == 0) return AMPIS_OK;
-    for (int32_t g0 = 0; g0 < n_groups; g0 += 65535) {             // gridDim.y limit
-        const dim3 grid((max_cols + 255) / 256, min(n_groups - g0, 65535));
-        grid_bin_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
-            (const int4 *)d_bbox, d_grp_col_begin + g0, d_grp_col_count + g0, d_grp_shift + g0,
-            d_cell_count + (i64)g0 * GR_CELLS, nullptr, nullptr, nullptr, nullptr, 0);
-        AMPIS_CHECK_LAUNCH("grid_bin_kernel<count>");
-    }
-    return AMPIS_OK;
-}
-
-extern "C" int ampis_grid_fill(const int32_t *d_bbox, const int32_t *d_grp_col_begin,
-                               const int32_t *d_grp_col_count, int32_t n_groups, int32_t max_cols,
-                               const int32_t *d_grp_shift, const int64_t *d_cell_off, uint32_t *d_cell_fill,
-                               int32_t *d_entries, int32_t *d_entry_bbox, int64_t capacity, void *stream)
-{
-    AMPIS_REQUIRE(n_groups >= 0 && max_cols >= 0 && capacity >= 0, "negative size");
-    if (n_groups == 0 || max_cols == 0) return AMPIS_OK;
-    AMPIS_REQUIRE(d_bbox && d_grp_col_begin && d_grp_col_count && d_grp_shift && d_cell_off && d_cell_fill &&
-                      d_entries && d_entry_bbox, "null pointer");
-    for (int32_t g0 = 0; g0 < n_groups; g0 += 65535) {
-        const dim3 grid((max_cols + 255) / 256, min(n_groups - g0, 65535));
-        // cell_off holds absolute entry positions, so only the per-group arrays are shifted
-        grid_bin_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(
-            (const int4 *)d_bbox, d_grp_col_begin + g0, d_grp_col_count + g0, d_grp_shift + g0, nullptr,
-            d_cell_off + (i64)g0 * GR_CELLS, d_cell_fill + (i64)g0 * GR_CELLS, d_entries, (int4 *)d_entry_bbox,
-            capacity);
-        AMPIS_CHECK_LAUNCH("grid_bin_kernel<fill>");
-    }
+    AMPIS_REQUIRE((d_entries && d_entry_bbox) || capacity == 0, "entries missing");
+    static_assert(GB_THREADS * 2 == GR_CELLS, "two cells per thread");
+    cudaError_t e = cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), as_stream(stream));
+    if (e != cudaSuccess) { ampis_set_error("cursor memset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+    grid_build_kernel<<<n_groups, GB_THREADS, 0, as_stream(stream)>>>(
+        (const int4 *)d_bbox, d_grp_col_begin, d_grp_col_count, d_grp_shift, d_cell_off, d_entries,
+        (int4 *)d_entry_bbox, capacity, (unsigned long long *)d_cursor);
+    AMPIS_CHECK_LAUNCH("grid_build_kernel");
     return AMPIS_OK;
 }
 

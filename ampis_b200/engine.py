@@ -396,19 +396,15 @@ ROWS_GRID_MIN_COLS = int(os.environ.get('AMPIS_ROWS_GRID_MIN_COLS', 384))
 
 class ColumnGrid(object):
     """Uniform 32 x 32 grid over every image of a batch with the column masks binned by bounding box
-    (the spatial index of ampis_intersect_rows_grid).  build() needs the measured boxes of `table`;
-    without a capacity the number of entries is read back (one sync) and the entry list sized exactly."""
+    (the spatial index of ampis_intersect_rows_grid), built by one kernel launch.  build() needs the measured boxes
+    of `table`; without a capacity a sizing launch is made first and the number of entries read back (one sync)."""
 
     def __init__(self, device, n_groups, capacity=None):
         self.device, self.n_groups = device, int(n_groups)
-        cells = N.lib().ampis_grid_cells() * max(self.n_groups, 1)
-        self.n_cells = cells
+        cells = N.lib().ampis_grid_cells()
         self.shift = torch.empty(max(self.n_groups, 1), dtype=torch.int32, device=device)
-        self.cell_count = torch.empty(cells, dtype=torch.int64, device=device)
-        self.cell_off = torch.empty(cells + 1, dtype=torch.int64, device=device)
-        self.cell_fill = torch.empty(cells, dtype=torch.int32, device=device)
-        self.tmp_bytes = N.lib().ampis_scan_tmp_bytes(cells)
-        self.tmp = torch.empty(max(self.tmp_bytes // 8, 1), dtype=torch.int64, device=device)
+        self.cell_off = torch.empty(max(self.n_groups, 1) * (cells + 1), dtype=torch.int64, device=device)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=device)
         self.entries = self.entry_bbox = None
         self.capacity = None
         if capacity is not None:
@@ -419,21 +415,21 @@ class ColumnGrid(object):
         self.entries = torch.empty(max(capacity, 1), dtype=torch.int32, device=self.device)
         self.entry_bbox = torch.empty(4 * max(capacity, 1), dtype=torch.int32, device=self.device)
 
+    def _launch(self, table, groups, capacity):
+        N.call('ampis_grid_build', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
+               groups.n_groups, _p(self.shift), _p(self.cell_off), _p(self.entries), _p(self.entry_bbox), capacity,
+               _p(self.cursor), _stream())
+
     def build(self, table, groups):
-        N.call('ampis_grid_count', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
-               groups.n_groups, groups.max_cols, _p(self.shift), _p(self.cell_count), _p(self.cell_fill), _stream())
-        N.call('ampis_exclusive_scan_i64', _p(self.cell_count), _p(self.cell_off), self.n_cells, _p(self.tmp),
-               self.tmp_bytes, _stream())
         if self.entries is None:
+            self._launch(table, groups, 0)          # sizing pass: counts only
             self._alloc(self.needed())
-        N.call('ampis_grid_fill', _p(table.bbox), _p(groups.grp_col_begin), _p(groups.grp_col_count),
-               groups.n_groups, groups.max_cols, _p(self.shift), _p(self.cell_off), _p(self.cell_fill),
-               _p(self.entries), _p(self.entry_bbox), self.capacity, _stream())
+        self._launch(table, groups, self.capacity)
         return self
 
     def needed(self):
         """Entries the last build() wanted (read-back; compare with .capacity)."""
-        return int(self.cell_off[self.n_cells].item())
+        return int(self.cursor.item())
 
 
 class SparseRows(object):

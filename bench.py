@@ -503,9 +503,9 @@ def main():
                    'parallelism': 'images sharded over %d GPU(s); one int64 all-reduce of TP/FP/FN%s per step' % (
                        world, ' + %d-bin area histogram' % cfg['area_bins'] if cfg.get('area_bins') else '')},
         'roofline': roofline_of(args, cfg, run, ms, kt, world),
-        # grid-pruned crop rows: + setup, count, 3 scan kernels, fill
+        # grid-pruned crop rows: + the grid build kernel
         'gpu_launches': int(args.steps * len(run.subs) * ((7 if args.unfused else 3) + (1 if args.kernel in ('mma', 'mma2') else 0) +
-                                                            (6 if getattr(run.pipes[0].grid, 'capacity', None) else 0) +
+                                                            (1 if getattr(run.pipes[0].grid, 'capacity', None) else 0) +
                                                             (1 if cfg.get('area_bins') else 0))),
         ('totals_tp_fp_fn_at_0.50' if cfg['mode'] == 0 else 'sat_matched_unmatched_satellited_particles+spp_hist'): final_totals[0].tolist(),
         'clocks': clocks, 'setup_s': {'synthesize+upload': run.t_gen},

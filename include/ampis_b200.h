@@ -180,24 +180,22 @@ int ampis_intersect_rows_crop(const void *d_bits, const int64_t *d_bits_off, con
 /* The crop rows kernel with the bbox pre-pruning (rleIou's bbIou pass, analyze.py:108,158) done through a
  * uniform grid instead of a scan of all G x P boxes -- for images with thousands of instances
  * (spheroidite, satellites vs 2,000 particles).  The column masks of every group are binned into
- * ampis_grid_cells() = 32 x 32 square cells of side 2^grp_shift[g] pixels:
- *   ampis_grid_count   d_grp_shift[g], d_cell_count i64[n_groups * cells] (+ clears d_cell_fill u32[same])
- *   ampis_exclusive_scan_i64(d_cell_count -> d_cell_off[n_groups * cells + 1]); d_cell_off[last] = entries needed
- *   ampis_grid_fill    d_entries i32[capacity]: column indices (inside the group) cell by cell, and
- *                      d_entry_bbox i32[4 * capacity]: their boxes (saves the rows kernel a dependent load)
- * ampis_intersect_rows_grid then gives the same per-row outputs (and dense rows, if asked: the first
- * imat_ints values of d_imat are zeroed by a memset node, the kernel patches the non-zero cells) as
- * ampis_intersect_rows_crop, bit for bit.  Eight lanes per row, four rows per warp.  Optional sparse output: the non-zero intersections as
- * (row, column-in-group, intersection) triplets in no particular order; *d_coo_count (zeroed by the
- * caller) counts them and may exceed coo_capacity, in which case the excess was dropped. */
+ * ampis_grid_cells() = 32 x 32 square cells of side 2^grp_shift[g] pixels by ampis_grid_build (one CTA per
+ * group: counts and their scan in shared memory, one atomicAdd on *d_cursor -- zeroed by the call -- per group):
+ *   d_grp_shift[g]                       log2 of the cell side (>= mean box side of the group's columns)
+ *   d_cell_off i64[n_groups * (cells+1)] absolute position of every cell's first entry (+ one end marker per group)
+ *   d_entries i32[capacity], d_entry_bbox i32[4 * capacity]   column index (inside the group) and box, cell by cell
+ * After the stream has completed *d_cursor = entries needed; beyond `capacity` nothing is written (call with
+ * capacity 0 to size the lists).  ampis_intersect_rows_grid then gives the same per-row outputs (and dense rows,
+ * if asked: the first imat_ints values of d_imat are zeroed by a memset node, the kernel patches the non-zero
+ * cells) as ampis_intersect_rows_crop, bit for bit.  Eight lanes per row, four rows per warp.  Optional sparse
+ * output: the non-zero intersections as (row, column-in-group, intersection) triplets in no particular order;
+ * *d_coo_count (zeroed by the caller) counts them and may exceed coo_capacity, in which case the excess was
+ * dropped. */
 int ampis_grid_cells(void);
-int ampis_grid_count(const int32_t *d_bbox, const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
-                     int32_t n_groups, int32_t max_cols, int32_t *d_grp_shift, int64_t *d_cell_count,
-                     uint32_t *d_cell_fill, void *stream);
-int ampis_grid_fill(const int32_t *d_bbox, const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
-                    int32_t n_groups, int32_t max_cols, const int32_t *d_grp_shift, const int64_t *d_cell_off,
-                    uint32_t *d_cell_fill, int32_t *d_entries, int32_t *d_entry_bbox, int64_t capacity,
-                    void *stream);
+int ampis_grid_build(const int32_t *d_bbox, const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
+                     int32_t n_groups, int32_t *d_grp_shift, int64_t *d_cell_off, int32_t *d_entries,
+                     int32_t *d_entry_bbox, int64_t capacity, uint64_t *d_cursor, void *stream);
 int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
                               const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_blk_grp,
                               const int32_t *d_blk_row0, int32_t n_blocks, const int32_t *d_grp_row_begin,
