@@ -87,6 +87,13 @@ def _piecewise_iou(a, b, interval=80):
     imax, jmax = len(a), len(b)
     if imax == 0 or jmax == 0:
         return np.zeros((imax, jmax))
+    if FUSED_CALL:
+        try:
+            r = engine.eval_image(a, b, engine.MODE_IOU, dense_iou=True)
+        except engine.N.AmpisNativeError:
+            r = None
+        if r is not None and not (min(imax, jmax) >= engine.MMA_MIN_SIDE and r.fill() >= engine.MMA_FILL_THRESHOLD):
+            return r.iou                  # crowded images go on to the tensor-core contraction, as in _image_rows
     table, groups, res = _rows_vs_cols(a, b, engine.MODE_IOU, dense=True)
     return engine.iou_matrix(table, res, groups, 0).cpu().numpy()
 

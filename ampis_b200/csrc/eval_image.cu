@@ -25,7 +25,8 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
                                      uint32_t h, uint32_t w, int32_t mode, int32_t grid_min_cols,
                                      void *d_ws, int64_t d_ws_bytes, void *h_ws, int64_t h_ws_bytes,
                                      int32_t *best_col, uint32_t *best_inter, double *best_score, uint32_t *area,
-                                     int32_t *bbox, uint32_t *span, int32_t *status, int64_t *need_bytes, void *stream)
+                                     int32_t *bbox, uint32_t *span, int32_t *status, double *iou_out, int64_t *need_bytes,
+                                     void *stream)
 {
     AMPIS_REQUIRE(n_rows >= 0 && n_cols >= 0, "negative size");
     AMPIS_REQUIRE(mode == AMPIS_MODE_IOU || mode == AMPIS_MODE_SAT, "bad mode");
@@ -60,6 +61,10 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
         g_shift = c.take(4); g_off = c.take(8 * ((int64_t)cells + 1)); g_ent = c.take(4 * grid_cap);
         g_entbb = c.take(16 * grid_cap);
     }
+    // optional dense output: int32 intersections and the float64 IoU matrix of _piecewise_iou (analyze.py:54-112)
+    const bool dense = iou_out && n_rows > 0 && n_cols > 0;
+    const int64_t gp = (int64_t)n_rows * n_cols;
+    const int64_t x_imat = dense ? c.take(4 * gp) : 0, x_iou = dense ? c.take(8 * gp) : 0, x_imoff = dense ? c.take(8) : 0;
     const int64_t arena0 = c.off;
     // arena: what is left, at least a window of 64 bytes per mask to start with
     if (h_ws_bytes < host_bytes || d_ws_bytes < arena0 + 64 * n + 4096) {
@@ -95,6 +100,10 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
                                  (uint32_t *)(D + o_span), (uint32_t *)(D + d_reg), (int64_t *)(D + d_bitsoff),
                                  (int32_t *)(D + o_status), D + arena0, arena_chunks, (uint64_t *)(D + o_cursor),
                                  (int32_t)(n_chars / n), stream));
+    if (dense) {
+        e = cudaMemsetAsync(D + x_imoff, 0, 8, st);                 // the image's matrix starts at offset 0
+        if (e != cudaSuccess) { ampis_set_error("imat offset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+    }
     if (n_rows > 0 && n_cols > 0) {
         if (use_grid) {
             STEP(ampis_grid_build((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
@@ -106,17 +115,25 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
                                            (const int32_t *)(D + u_grb), (const int32_t *)(D + u_grc),
                                            (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc),
                                            (const int32_t *)(D + g_shift), (const int64_t *)(D + g_off),
-                                           (const int32_t *)(D + g_ent), (const int32_t *)(D + g_entbb), grid_cap, nullptr, mode,
-                                           nullptr, 0, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter),
+                                           (const int32_t *)(D + g_ent), (const int32_t *)(D + g_entbb), grid_cap,
+                                           dense ? (const int64_t *)(D + x_imoff) : nullptr, mode,
+                                           dense ? (int32_t *)(D + x_imat) : nullptr, dense ? gp : 0, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter),
                                            (double *)(D + o_score), nullptr, nullptr, nullptr, 0, nullptr, stream));
         } else {
             STEP(ampis_intersect_rows_crop(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
                                            (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
                                            (const int32_t *)(D + u_blkgrp), (const int32_t *)(D + u_blkrow), nb,
                                            (const int32_t *)(D + u_grb), (const int32_t *)(D + u_grc),
-                                           (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), nullptr, mode, nullptr,
-                                           (int32_t *)(D + o_col), (uint32_t *)(D + o_inter), (double *)(D + o_score), stream));
+                                           (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc),
+                                           dense ? (const int64_t *)(D + x_imoff) : nullptr, mode,
+                                           dense ? (int32_t *)(D + x_imat) : nullptr, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter), (double *)(D + o_score), stream));
         }
+    }
+    if (dense) {
+        STEP(ampis_iou_matrix_f64((const int32_t *)(D + x_imat), (const uint32_t *)(D + o_area),
+                                  (const uint32_t *)(D + o_area) + n_rows, n_rows, n_cols, (double *)(D + x_iou), stream));
+        e = cudaMemcpyAsync(iou_out, D + x_iou, (size_t)(8 * gp), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { ampis_set_error("iou download: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     }
 #undef STEP
     e = cudaMemcpyAsync(H + dl0, D + dl0, (size_t)download_bytes, cudaMemcpyDeviceToHost, st);

@@ -223,7 +223,7 @@ def table_from_rle(masks, layout=None, paint=True):
 
 class ImageRows(object):
     """Result of eval_image(): per-row arg-max results and per-mask measurements of one image (numpy)."""
-    __slots__ = ('best_col', 'best_inter', 'best_score', 'area', 'bbox', 'span', 'n_rows', 'n_cols', 'hw')
+    __slots__ = ('best_col', 'best_inter', 'best_score', 'area', 'bbox', 'span', 'n_rows', 'n_cols', 'hw', 'iou')
 
     def fill(self):
         """Operand fill (see operand_fill) from the returned spans."""
@@ -236,7 +236,7 @@ _image_ws = {}          # device index -> [device workspace, pinned host workspa
 _image_ws_lock = threading.Lock()
 
 
-def eval_image(rows_rle, cols_rle, mode):
+def eval_image(rows_rle, cols_rle, mode, dense_iou=False):
     """One image, rows x columns, through ampis_eval_image_host: ONE library call stages the compressed strings,
     runs string decode -> fused measure + crop decode -> rows kernel and brings the per-row results back with one
     synchronisation (the drop-in matching functions call this once per image).  Raises ValueError when the masks
@@ -261,6 +261,7 @@ def eval_image(rows_rle, cols_rle, mode):
     r.bbox = np.empty((n, 4), np.int32)
     r.span = np.empty((n, 2), np.uint32)
     status = np.empty(n, np.int32)
+    r.iou = np.zeros((n_rows, n_cols)) if dense_iou else None       # float64 IoU matrix of _piecewise_iou
     if n == 0:
         return r
     need = C.c_int64(0)
@@ -274,7 +275,8 @@ def eval_image(rows_rle, cols_rle, mode):
             rc = lib.ampis_eval_image_host(blob, ptr(off), n_rows, n_cols, r.hw[0], r.hw[1], mode, ROWS_GRID_MIN_COLS,
                                            _p(d_ws), d_ws.numel(), _p(h_ws), h_ws.numel(), ptr(r.best_col),
                                            ptr(r.best_inter), ptr(r.best_score), ptr(r.area), ptr(r.bbox), ptr(r.span),
-                                           ptr(status), C.byref(need), _stream())
+                                           ptr(status), ptr(r.iou) if dense_iou and r.iou.size else None,
+                                           C.byref(need), _stream())
             if rc != N.ENOSPC:
                 break
             if need.value < 0:          # pinned host workspace too small

@@ -215,14 +215,16 @@ int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bits_off, con
  * decoded, measured and painted as bounding-box windows, intersected (all-columns scan below grid_min_cols
  * columns, grid-pruned from there on) and the results come back with one copy and ONE stream synchronisation:
  * per row best_col / best_inter / best_score as ampis_intersect_rows, per mask area, bbox, span and status
- * (AMPIS_ST_BAD_TOTAL marks malformed RLE).  Nothing is allocated: d_ws (256-byte aligned device memory) and
+ * (AMPIS_ST_BAD_TOTAL marks malformed RLE); iou_out, when not NULL, receives the full float64 n_rows x n_cols IoU
+ * matrix of analyze._piecewise_iou (analyze.py:54-112).  Nothing is allocated: d_ws (256-byte aligned device memory) and
  * h_ws are the caller's; when one is too small the call returns AMPIS_ENOSPC with *need_bytes = device bytes
  * wanted (> 0) or minus the host bytes wanted (< 0). */
 int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_off, int32_t n_rows, int32_t n_cols,
                           uint32_t h, uint32_t w, int32_t mode, int32_t grid_min_cols,
                           void *d_ws, int64_t d_ws_bytes, void *h_ws, int64_t h_ws_bytes,
                           int32_t *best_col, uint32_t *best_inter, double *best_score, uint32_t *area,
-                          int32_t *bbox, uint32_t *span, int32_t *status, int64_t *need_bytes, void *stream);
+                          int32_t *bbox, uint32_t *span, int32_t *status, double *iou_out, int64_t *need_bytes,
+                          void *stream);
 
 /* ---- dense intersection matrices on the tensor cores (tcgen05, int8 contraction) -----------
  * Same quantity as the dense output of ampis_intersect_rows -- I[r][c] = popcount(row AND col),
