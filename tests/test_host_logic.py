@@ -110,6 +110,31 @@ def test_group_bookkeeping_host_side():
     assert g.h_imat_off.tolist() == [0, 8, 8, 11] and g.imat_size == 11
 
 
+def test_rle_marshalling_host_side():
+    """Input handling of the RLE dict lists (pycocotools' _frString accepts bytes and str), size checks, the
+    staging upload helper and the operand-fill arithmetic of the one-call result -- no device needed."""
+    import torch
+    from ampis_b200 import analyze, engine
+    masks = [{'size': [6, 5], 'counts': b'02208'}, {'size': (6, 5), 'counts': '5d0'},
+             {'size': np.array([6, 5]), 'counts': bytearray(b'0n0')}]
+    strings, hs, ws = engine._rle_fields(masks)
+    assert strings == [b'02208', b'5d0', b'0n0'] and all(type(x) is bytes for x in strings)
+    assert hs.tolist() == [6, 6, 6] and ws.tolist() == [5, 5, 5]
+    with pytest.raises(TypeError):
+        engine._rle_fields([{'size': [6, 5], 'counts': [1, 2, 3]}])
+    analyze._check_same_size(masks[:2], masks[2:])
+    analyze._check_same_size([], [])
+    with pytest.raises(ValueError, match=r'different image sizes.*\(6, 5\) vs \(5, 6\)'):
+        analyze._check_same_size(masks, [{'size': [5, 6], 'counts': b'0n0'}])
+    a, b, c = engine._upload(torch.device('cpu'), np.arange(5, dtype=np.int64), np.zeros(0, np.int32),
+                             np.array([7, 8, 9], np.uint8))
+    assert a.tolist() == [0, 1, 2, 3, 4] and a.dtype == torch.int64 and b.numel() == 0 and c.tolist() == [7, 8, 9]
+    r = engine.ImageRows()
+    r.hw, r.area = (256, 256), np.zeros(4, np.uint32)                       # 512 slabs of 128 pixels per mask
+    r.span = np.array([[0, 512], [100, 356], [0, 0], [511, 512]], np.uint32)
+    assert r.fill() == (512 + 256 + 0 + 1) / (4 * 512)
+
+
 def test_match_bookkeeping_from_rows():
     from ampis_b200.analyze import _match_from_rows
     r = _match_from_rows(np.array([2, -1, 0, 2]), np.array([0.9, 0.0, 0.5, 0.6]), 4, 0.5)
