@@ -349,7 +349,7 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
 // Same steps: the group measures its mask (4 runs per lane and pass), lane 0 reserves arena space with its own
 // atomicAdd, the group paints the bounding-box window through its slice of the shared tile.
 template <int L>
-__global__ void __launch_bounds__(MP_WARPS * 32, 5)
+__global__ void __launch_bounds__(MP_WARPS * 32, 6)
 rle_measure_paint_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
                               const int *__restrict__ cnt_len, const u32 *__restrict__ hh,
                               const u32 *__restrict__ ww, int n, u32 *cum_g, u32 *__restrict__ area,
