@@ -516,6 +516,26 @@ def test_one_call_image_entry_equals_table_api(mods, monkeypatch):
                                                     'intersection_scores')) and a['match_pairs'].keys() == b['match_pairs'].keys()
 
 
+def test_integration_stub_from_the_docs_runs(mods):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer would paste into ampis/analyze.py) is executed
+    as it stands against the built library and gives the matcher's result on a golden image."""
+    import re
+    from ampis_b200 import build as bld
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, 'INTEGRATION.md')).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, re.S)
+    code = [b for b in blocks if 'ampis_eval_image_host' in b]
+    assert len(code) == 1
+    src = code[0].replace("ctypes.CDLL('libampis_b200.so')", "ctypes.CDLL(%r)" % bld.LIB)
+    ns = {}
+    exec(compile(src, 'INTEGRATION.md', 'exec'), ns)
+    _, gt, pr = U.powder_match_image(1)
+    got = ns['_piecewise_rle_match'](list(gt), list(pr), 0.5)
+    want = mods.analyze._piecewise_rle_match(gt, pr, 0.5)
+    for k in ('tp', 'fn', 'fp', 'iou'):
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
+
+
 def test_full_size_properties(mods):
     """BASELINE config sizes (C2 image count reduced): size-independent properties --
     span and full layouts agree bit for bit, I(gt,pred) == I(pred,gt)^T, area == popcount of the
