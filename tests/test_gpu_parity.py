@@ -536,6 +536,43 @@ def test_integration_stub_from_the_docs_runs(mods):
         assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
 
 
+def test_c_caller_of_the_abi(mods, tmp_path):
+    """A plain C program (tests/c_abi/eval_image_main.c: cudaMalloc / cudaHostAlloc, no Python, no PyTorch) links
+    libampis_b200.so, evaluates one golden image through ampis_eval_image_host -- growing its workspaces when told
+    AMPIS_ENOSPC -- and prints what the oracle computes."""
+    import subprocess
+    from ampis_b200 import build as bld
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'eval_image_main')
+    cc = subprocess.run(['gcc', '-O2', '-o', exe, os.path.join(root, 'tests', 'c_abi', 'eval_image_main.c'),
+                         '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include',
+                         '-L', os.path.dirname(bld.LIB), '-lampis_b200', '-L', '/usr/local/cuda/lib64', '-lcudart',
+                         '-Wl,-rpath,' + os.path.dirname(bld.LIB) + ',-rpath,/usr/local/cuda/lib64'],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    _, gt, pr = U.powder_match_image(2)
+    masks = list(gt) + list(pr)
+    off = np.zeros(len(masks) + 1, np.int64)
+    np.cumsum([len(m['counts']) for m in masks], out=off[1:])
+    h, w = masks[0]['size']
+    path = tmp_path / 'image.bin'
+    with open(path, 'wb') as f:
+        f.write(np.array([len(gt), len(pr), h, w, 0], np.int32).tobytes())
+        f.write(off.tobytes())
+        f.write(b''.join(m['counts'] for m in masks))
+    run = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stderr
+    rows = [l.split() for l in run.stdout.splitlines() if l.startswith('row')]
+    ms = [l.split() for l in run.stdout.splitlines() if l.startswith('mask')]
+    assert len(rows) == len(gt) and len(ms) == len(masks)
+    want = {}
+    mods.analyze._piecewise_rle_match(gt, pr, 0.5, _details=want)
+    assert [int(r[2]) for r in rows] == want['best_col'].tolist()
+    assert [int(r[3]) for r in rows] == want['best_inter'].tolist()
+    assert [float(r[4]) for r in rows] == want['best_iou'].tolist()
+    assert [int(m_[2]) for m_ in ms] == mods.rle.area(masks).tolist() and all(int(m_[7]) == 0 for m_ in ms)
+
+
 def test_full_size_properties(mods):
     """BASELINE config sizes (C2 image count reduced): size-independent properties --
     span and full layouts agree bit for bit, I(gt,pred) == I(pred,gt)^T, area == popcount of the
