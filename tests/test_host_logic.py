@@ -135,6 +135,46 @@ def test_rle_marshalling_host_side():
     assert r.fill() == (512 + 256 + 0 + 1) / (4 * 512)
 
 
+def test_grid_candidate_rule_sees_every_overlapping_pair_once():
+    """Model (plain numpy) of the candidate search of csrc/intersect_grid.cu: columns binned into 32 x 32 clamped
+    cells of side 2^shift, a row walks the cells of its box and takes a column only in the cell that holds the
+    top-left corner of the two boxes' overlap.  Property: every pair of overlapping boxes is taken exactly once,
+    no other pair ever -- for any shift, including boxes beyond the 32-cell extent (clamped) and huge boxes."""
+    rng = np.random.default_rng(7)
+    cell = lambda v, s: np.minimum(v >> s, 31)
+    for trial in range(60):
+        n_r, n_c = int(rng.integers(1, 40)), int(rng.integers(1, 60))
+        size = int(rng.choice([40, 300, 2048, 5000]))
+        def boxes(n):
+            x0, y0 = rng.integers(0, size, n), rng.integers(0, size, n)
+            big = rng.random(n) < 0.1
+            wd = np.where(big, rng.integers(1, size, n), rng.integers(1, max(size // 20, 2), n))
+            ht = np.where(big, rng.integers(1, size, n), rng.integers(1, max(size // 20, 2), n))
+            return np.stack([x0, y0, np.minimum(x0 + wd, size) , np.minimum(y0 + ht, size)], 1)      # x1, y1 inclusive
+        R, Cb = boxes(n_r), boxes(n_c)
+        ext = int(max(Cb[:, 2].max(), Cb[:, 3].max()))
+        mean = int(np.ceil((np.maximum(Cb[:, 2] - Cb[:, 0], Cb[:, 3] - Cb[:, 1]) + 1).mean()))
+        shift = max(max(0, ext.bit_length() - 5), (max(mean, 1) - 1).bit_length())
+        shift = int(rng.choice([shift, shift + 1, max(shift - 2, 0)]))          # the rule holds for any shift
+        cells = {}
+        for k, b in enumerate(Cb):
+            for cy in range(cell(b[1], shift), cell(b[3], shift) + 1):
+                for cx in range(cell(b[0], shift), cell(b[2], shift) + 1):
+                    cells.setdefault((cx, cy), []).append(k)
+        for r, a in enumerate(R):
+            taken = []
+            rcx0, rcy0 = cell(a[0], shift), cell(a[1], shift)
+            for cy in range(rcy0, cell(a[3], shift) + 1):
+                for cx in range(rcx0, cell(a[2], shift) + 1):
+                    for k in cells.get((cx, cy), []):
+                        b = Cb[k]
+                        if b[0] <= a[2] and b[2] >= a[0] and b[1] <= a[3] and b[3] >= a[1] and \
+                                max(rcx0, cell(b[0], shift)) == cx and max(rcy0, cell(b[1], shift)) == cy:
+                            taken.append(k)
+            want = [k for k, b in enumerate(Cb) if b[0] <= a[2] and b[2] >= a[0] and b[1] <= a[3] and b[3] >= a[1]]
+            assert sorted(taken) == want, (trial, r, shift)
+
+
 def test_match_bookkeeping_from_rows():
     from ampis_b200.analyze import _match_from_rows
     r = _match_from_rows(np.array([2, -1, 0, 2]), np.array([0.9, 0.0, 0.5, 0.6]), 4, 0.5)
