@@ -4,6 +4,7 @@ the kernels of libampis_b200.so.  PyTorch is used only for device memory, stream
 hand-written sm_100a kernels.  There is no CPU fallback anywhere in this module.
 """
 import ctypes as C
+import itertools
 import os
 import threading
 
@@ -168,7 +169,14 @@ def _rle_fields(masks):
                 strings[i] = bytes(c)
             else:
                 raise TypeError('RLE counts must be compressed bytes/str, got %s' % type(c))
-    hw = np.asarray([m['size'] for m in masks], np.int64).reshape(len(strings), -1)
+    n = len(strings)
+    try:                                    # [h, w] pairs, flattened without building n small arrays
+        hw = np.fromiter(itertools.chain.from_iterable(m['size'] for m in masks), np.int64)
+        if hw.size != 2 * n:
+            raise ValueError
+        hw = hw.reshape(n, 2)
+    except (ValueError, TypeError):         # sizes that are not plain pairs of ints
+        hw = np.asarray([m['size'] for m in masks], np.int64).reshape(n, -1)
     return strings, hw[:, 0], hw[:, 1]
 
 
