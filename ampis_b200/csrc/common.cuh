@@ -10,6 +10,10 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;
 
+// rows of a group one CTA of the rows kernels handles (blk_grp / blk_row0 lists are shared by all of them;
+// ampis_rows_per_block() reports it to the host)
+#define AMPIS_ROWS_PER_CTA 8
+
 #define AMPIS_CHUNK_BITS 128u   // one uint4 = 128 pixels of the column-major bit vector
 
 void ampis_set_error(const char *fmt, ...);

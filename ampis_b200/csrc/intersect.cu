@@ -25,7 +25,7 @@
 #include "common.cuh"
 #include "async.cuh"
 
-#define ROWS_PER_CTA 8
+#define ROWS_PER_CTA AMPIS_ROWS_PER_CTA
 #define COL_TILE 512
 #define CAND_LIST 64
 #define LONG_OVERLAP 128      // chunks (2 KB per operand) from which a candidate gets the whole warp

@@ -17,7 +17,7 @@
 #include "async.cuh"
 #include "crop_common.cuh"
 
-#define RC_ROWS 8
+#define RC_ROWS AMPIS_ROWS_PER_CTA
 #define RC_TILE 512
 #define RC_LIST 64
 #define RC_BIG 256          // overlap words from which a candidate gets the whole warp

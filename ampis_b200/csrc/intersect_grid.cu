@@ -27,7 +27,7 @@
 
 #define GR_N 32                 // cells per axis
 #define GR_CELLS (GR_N * GR_N)
-#define GR_ROWS 8               // rows per CTA (= ampis_rows_per_block())
+#define GR_ROWS AMPIS_ROWS_PER_CTA               // rows per CTA (= ampis_rows_per_block())
 #define GR_TILE 8               // lanes per row
 #define GR_THREADS (GR_ROWS * GR_TILE)
 #define GR_LIST 16              // candidates a tile collects before it intersects them
