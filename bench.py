@@ -384,6 +384,23 @@ def roofline_of(args, cfg, run, ms, kt, world):
             'kernel_share': {k: float(v) for k, v in zip(KERNELS, kt / kt.sum())}}
 
 
+def cropped_accounting(cfg, run, ms, args):
+    """SURVEY 8d's accounting for culled storage (prescribed for C4): bytes_img = 4 R_img + 2 sum(window bytes)
+    + 24 N_pairs + 8 (G + P) + 32 G, window bytes as this layout stores them (32-row bands of the box columns),
+    N_pairs = the non-zero intersections when the run produced the sparse list (a lower bound of the
+    bbox-overlapping pairs), else the dense 4 G P matrix."""
+    peak, peak_src = peaks()
+    n_img = args.images
+    per_image = cfg['n_rows'] + cfg['n_cols']
+    pairs_term = 24.0 * run.sparse_pairs / n_img if run.sparse_pairs is not None else 4.0 * cfg['n_rows'] * cfg['n_cols']
+    bytes_img = 4.0 * run.total_runs / n_img + 2.0 * run.stored_chunks * 16 / n_img + pairs_term + 8 * per_image + \
+        32 * cfg['n_rows']
+    gbs = bytes_img * n_img * args.steps / (ms / 1e3) / 1e9
+    return {'bytes_per_image': bytes_img, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+            'output': 'sparse triplets' if run.sparse_pairs is not None else 'dense G x P matrix',
+            'note': 'the culled step is bound by instruction issue / load latency, not by these bytes (DESIGN 8)'}
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -478,6 +495,9 @@ def main():
                 'intersection_kernel': 'grid' if getattr(crun.pipes[0].grid, 'capacity', None) else 'scan',
                 'note': 'same inputs and bit-identical results; only the bounding-box window of each mask is '
                         'stored (32-row bands of the box columns)'}
+        crop['cropped_accounting'] = cropped_accounting(cfg, crun, cms, args)
+        if crun.sparse_pairs is not None:
+            crop['nonzero_pairs_per_image'] = crun.sparse_pairs / args.images
         if not args.no_e2e:
             crop['e2e'] = run_e2e(args, crun.subs, dev, engine.LAYOUT_CROP, crun.arena, crun.rows_out,
                                   crun.thresholds, world, dist, sync, pipes=crun.pipes)
@@ -512,6 +532,8 @@ def main():
     }
     if run.sparse_pairs is not None:
         out['config']['nonzero_pairs_per_image'] = run.sparse_pairs / args.images
+    if layout == engine.LAYOUT_CROP:
+        out['cropped_accounting'] = cropped_accounting(cfg, run, ms, args)
     if e2e:
         out['e2e'] = e2e
     if span:
