@@ -245,7 +245,9 @@ _image_ws_lock = threading.Lock()
 
 
 def eval_image(rows_rle, cols_rle, mode, dense_iou=False):
-    """One image, rows x columns, through ampis_eval_image_host: ONE library call stages the compressed strings,
+    """One image, rows x columns, through ampis_eval_image_host -- the per-image work of the reference's
+    analyze.py:149-164 (G x ceil(P/80) RLE.iou calls + arg-max), analyze.py:315-321 (merge + area per match),
+    powder.py:80-86 (S x N RLE.merge + RLE.area) and, with dense_iou, analyze.py:54-112: ONE library call stages the compressed strings,
     runs string decode -> fused measure + crop decode -> rows kernel and brings the per-row results back with one
     synchronisation (the drop-in matching functions call this once per image).  Raises ValueError when the masks
     do not share one image size and on malformed RLE (like MaskTable.check())."""
@@ -300,8 +302,8 @@ def eval_image(rows_rle, cols_rle, mode, dense_iou=False):
 
 
 def measure_rle(masks):
-    """(area uint32[n], tight bbox int32[n, 4]) of a list of RLE dicts: rleArea and the box extract_boxes reads off
-    the decoded mask.  Masks of one image size go through the one-call entry point (no intersection is run); mixed
+    """(area uint32[n], tight bbox int32[n, 4]) of a list of RLE dicts: rleArea (structures.py:568,571;
+    powder.py:264) and the box extract_boxes (data_utils.py:229-239) reads off the decoded mask.  Masks of one image size go through the one-call entry point (no intersection is run); mixed
     sizes through the table API."""
     masks = list(masks)
     if masks:
