@@ -35,12 +35,17 @@ SIGNATURES = {
                                        _p, _p, _p]),
     'ampis_rle_measure_paint': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
                                           _i32, _p]),
+    'ampis_rle_measure_paint_flat': (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
+                                               _p, _i32, _p]),
     'ampis_intersect_rows_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p,
                                             _p, _p]),
     'ampis_grid_cells': (C.c_int, []),
     'ampis_grid_build': (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _p, _p]),
     'ampis_intersect_rows_grid': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64,
                                             _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
+    'ampis_intersect_rows_pairs': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p,
+                                             _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p,
+                                             _p]),
     'ampis_rle_decode_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     'ampis_mma_tile_rows': (C.c_int, []),
     'ampis_mma_tile_cols': (C.c_int, []),
@@ -78,6 +83,7 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 200       # ampis_version(): bumped whenever a signature of include/ampis_b200.h changes
 
 
 class AmpisNativeError(RuntimeError):
@@ -89,9 +95,15 @@ def lib():
     global _lib
     if _lib is None:
         path = _build.LIB
-        if not os.path.exists(path):
+        # (re)build when the library is missing or older than its sources -- unless nvcc is not there (a box that
+        # only received the prebuilt library): then a stale or missing library fails loudly below
+        nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+        if not os.path.exists(path) or (os.path.exists(nvcc) and _build.needs_build()):
             _build.build()
         l = C.CDLL(path)
+        if l.ampis_version() != ABI_VERSION:
+            raise AmpisNativeError('libampis_b200.so reports ABI %d, this package expects %d: rebuild with '
+                                   '`python -m ampis_b200.build --force`' % (l.ampis_version(), ABI_VERSION))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)     # AttributeError if the .so is stale / incomplete
             fn.restype = res

@@ -175,7 +175,7 @@ class Pipeline(object):
         self.kernel = kernel        # 'rows': bbox-culled AND+popc; 'mma': dense int8 tcgen05 contraction
         # crop layout: candidates through a uniform grid ('grid', or 'rows' with many columns per image)
         # instead of the scan of all columns ('scan'); the entry list is sized once from a dry run
-        self.grid, self.sparse = None, None
+        self.grid, self.sparse, self.pairs = None, None, None
         if layout == engine.LAYOUT_CROP and (kernel == 'grid' or sparse_capacity is not None or (
                 kernel == 'rows' and batch.groups.max_cols >= engine.ROWS_GRID_MIN_COLS)):
             probe = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
@@ -184,6 +184,11 @@ class Pipeline(object):
             self.grid = engine.ColumnGrid(dev, batch.groups.n_groups, capacity=need)
             if sparse_capacity is not None:
                 self.sparse = engine.SparseRows(dev, sparse_capacity)
+            if engine.ROWS_KERNEL == 'pairs':        # the pair list is sized once from a dry run, like the grid
+                probe.paint()
+                dry = engine.intersect_rows(probe, batch.groups, batch.mode, grid=self.grid)
+                self.pairs = engine.PairList(dev, batch.groups.n_rows, dry.pairs.needed())
+                del dry
         elif layout == engine.LAYOUT_CROP and kernel == 'scan':
             self.grid = 'scan'
         self.mma_sort = mma_sort    # tiles from spatially sorted masks (contracts fewer slabs on large frames)
@@ -225,7 +230,7 @@ class Pipeline(object):
                                  pair=self.kernel == 'mma2')
         else:
             engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows, grid=self.grid,
-                                  sparse=self.sparse)
+                                  sparse=self.sparse, pairs=self.pairs)
         if mark: mark(3)
         if self.batch.mode == engine.MODE_IOU:
             engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)

@@ -12,6 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libampis_b200.so')
+DIGEST = LIB + '.digest'
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
@@ -25,21 +26,55 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')) + glob.glob(os.path.join(CSRC, '*.cpp')))
 
 
+def source_digest():
+    """Digest of everything the library is compiled from (sources, headers, flags).  Content based, not mtime
+    based: a snapshot copied to another box keeps its contents but not necessarily its timestamps."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + \
+        [os.path.join(os.path.dirname(HERE), 'include', 'ampis_b200.h')]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """True when the library is missing or was compiled from other sources than the ones present (the digest of
+    the sources it was built from is kept beside it)."""
+    if not os.path.exists(LIB) or not os.path.exists(DIGEST):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + \
-        [os.path.join(os.path.dirname(HERE), 'include', 'ampis_b200.h'), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(DIGEST) as f:
+        return f.read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
+    """Compile when the library is missing or older than a source.  Safe when several processes (the ranks of
+    ampis_b200.distributed on a fresh checkout) arrive together: an exclusive file lock serialises them, the
+    compiler writes to a temporary file that is renamed into place, so nobody ever loads a half-written library."""
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + sources() + ['-lcudart']
-    subprocess.check_call(cmd)
+    import fcntl
+    with open(LIB + '.lock', 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another process built it while we waited
+                return LIB
+            nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+            tmp = '%s.tmp.%d' % (LIB, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp] + sources() + ['-lcudart']
+            try:
+                digest = source_digest()
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+                with open(DIGEST, 'w') as f:
+                    f.write(digest + '\n')
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

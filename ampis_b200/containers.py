@@ -189,15 +189,34 @@ except Exception:
         __repr__ = __str__
 
 
+#: exact (module, name) pairs a prediction pickle may reference besides detectron2's Instances: what numpy arrays,
+#: numpy scalars, paths and plain containers pickle to.  Nothing callable with side effects (no builtins.eval / exec /
+#: getattr / __import__, no numpy.* functions beyond the array reconstructors).
+_PICKLE_ALLOWED = frozenset([
+    ('numpy.core.multiarray', '_reconstruct'), ('numpy._core.multiarray', '_reconstruct'),
+    ('numpy.core.multiarray', 'scalar'), ('numpy._core.multiarray', 'scalar'),
+    ('numpy.core.numeric', '_frombuffer'), ('numpy._core.numeric', '_frombuffer'),
+    ('numpy', 'ndarray'), ('numpy', 'dtype'),
+    ('builtins', 'set'), ('builtins', 'frozenset'), ('builtins', 'slice'), ('builtins', 'complex'),
+    ('builtins', 'bytearray'), ('builtins', 'range'), ('builtins', 'list'), ('builtins', 'dict'),
+    ('builtins', 'tuple'), ('builtins', 'int'), ('builtins', 'float'), ('builtins', 'bool'), ('builtins', 'str'),
+    ('builtins', 'bytes'),
+    ('collections', 'OrderedDict'), ('collections', 'defaultdict'),
+    ('_codecs', 'encode'),
+    ('pathlib', 'PosixPath'), ('pathlib', 'WindowsPath'), ('pathlib', 'PurePosixPath'),
+    ('pathlib', 'PureWindowsPath'), ('pathlib', 'PurePath'), ('pathlib', 'Path'),
+])
+
+
 class _Unpickler(pickle.Unpickler):
-    """Loads prediction pickles written by the reference (data_utils.format_outputs output):
-    only numpy and a detectron2 ``Instances`` (mapped onto the class above) are allowed."""
+    """Loads prediction pickles written by the reference (data_utils.format_outputs output).  Only a detectron2
+    ``Instances`` (mapped onto the class above) and the exact names in _PICKLE_ALLOWED resolve; anything else --
+    in particular every other builtin and numpy function -- raises UnpicklingError."""
 
     def find_class(self, module, name):
-        if module.startswith('detectron2') and name == 'Instances':
+        if (module.startswith('detectron2') or module == __name__) and name == 'Instances':
             return Instances
-        if module.split('.')[0] == 'numpy' or module in ('builtins', 'collections', 'copyreg', '_codecs',
-                                                         'pathlib'):
+        if (module, name) in _PICKLE_ALLOWED:
             return super().find_class(module, name)
         raise pickle.UnpicklingError('refusing to load %s.%s' % (module, name))
 

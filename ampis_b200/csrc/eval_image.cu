@@ -51,27 +51,32 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
     const int64_t dl0 = c.off;
     const int64_t o_col = c.take(4 * (int64_t)n_rows), o_inter = c.take(4 * (int64_t)n_rows), o_score = c.take(8 * (int64_t)n_rows);
     const int64_t o_area = c.take(4 * n), o_bbox = c.take(16 * n), o_span = c.take(8 * n), o_status = c.take(4 * n), o_cursor = c.take(8);
-    const int64_t o_gridtot = c.take(8);
+    const int64_t o_gridtot = c.take(8), o_pairtot = c.take(8);
     const int64_t download_bytes = c.off - dl0;
     const int64_t host_bytes = c.off;
     const int64_t d_cnt = c.take(4 * n_chars), d_cum = c.take(4 * n_chars), d_cntlen = c.take(4 * n);
-    const int64_t d_reg = c.take(8 * n), d_bitsoff = c.take(8 * (n + 1));
-    int64_t g_shift = 0, g_off = 0, g_ent = 0, g_entbb = 0;
+    const int64_t d_reg = c.take(8 * n), d_bitsoff = c.take(8 * (n + 1)), d_list = c.take(4 * (n + 1));
+    int64_t g_shift = 0, g_off = 0, g_ent = 0, g_entbb = 0, p_off = 0, p_cnt = 0, p_grp = 0;
     if (use_grid) {
         g_shift = c.take(4); g_off = c.take(8 * ((int64_t)cells + 1)); g_ent = c.take(4 * grid_cap);
         g_entbb = c.take(16 * grid_cap);
+        p_off = c.take(8 * (int64_t)n_rows); p_cnt = c.take(4 * (int64_t)n_rows); p_grp = c.take(4 * (int64_t)n_rows);
     }
     // optional dense output: int32 intersections and the float64 IoU matrix of _piecewise_iou (analyze.py:54-112)
     const bool dense = iou_out && n_rows > 0 && n_cols > 0;
     const int64_t gp = (int64_t)n_rows * n_cols;
     const int64_t x_imat = dense ? c.take(4 * gp) : 0, x_iou = dense ? c.take(8 * gp) : 0, x_imoff = dense ? c.take(8) : 0;
-    const int64_t arena0 = c.off;
-    // arena: what is left, at least a window of 64 bytes per mask to start with
-    if (h_ws_bytes < host_bytes || d_ws_bytes < arena0 + 64 * n + 4096) {
-        *need_bytes = arena0 + 2048 * n + 65536;
+    const int64_t fixed0 = c.off;
+    // what is left: a quarter for the candidate-pair list of the join (44 bytes per pair), the rest for the arena
+    // (at least a window of 64 bytes per mask to start with)
+    if (h_ws_bytes < host_bytes || d_ws_bytes < fixed0 + 128 * n + 8192) {
+        *need_bytes = fixed0 + 4096 * n + 131072;
         if (h_ws_bytes < host_bytes) *need_bytes = -(host_bytes);      // negative: the HOST workspace is the short one
         return AMPIS_ENOSPC;
     }
+    const int64_t pair_cap = use_grid ? ((d_ws_bytes - fixed0) / 4 - 1024) / 44 : 0;
+    const int64_t p_ab = c.take(8 * pair_cap), p_desc = c.take(32 * pair_cap), p_inter = c.take(4 * pair_cap);
+    const int64_t arena0 = c.off;
     const int64_t arena_chunks = (d_ws_bytes - arena0) / 16;
     uint8_t *H = (uint8_t *)h_ws, *D = (uint8_t *)d_ws;
     cudaStream_t st = as_stream(stream);
@@ -94,12 +99,12 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
 #define STEP(call) do { rc = (call); if (rc != AMPIS_OK) return rc; } while (0)
     STEP(ampis_rle_string_decode(D + u_chars, (const int64_t *)(D + u_off), (int32_t)n, (uint32_t *)(D + d_cnt),
                                  (const int64_t *)(D + u_off), (int32_t *)(D + d_cntlen), stream));
-    STEP(ampis_rle_measure_paint((const uint32_t *)(D + d_cnt), (const int64_t *)(D + u_off), (const int32_t *)(D + d_cntlen),
-                                 (const uint32_t *)(D + u_h), (const uint32_t *)(D + u_w), (int32_t)n, AMPIS_LAYOUT_CROP,
-                                 (uint32_t *)(D + d_cum), (uint32_t *)(D + o_area), (int32_t *)(D + o_bbox),
-                                 (uint32_t *)(D + o_span), (uint32_t *)(D + d_reg), (int64_t *)(D + d_bitsoff),
-                                 (int32_t *)(D + o_status), D + arena0, arena_chunks, (uint64_t *)(D + o_cursor),
-                                 (int32_t)(n_chars / n), stream));
+    STEP(ampis_rle_measure_paint_flat((const uint32_t *)(D + d_cnt), (const int64_t *)(D + u_off), (const int32_t *)(D + d_cntlen),
+                                      (const uint32_t *)(D + u_h), (const uint32_t *)(D + u_w), (int32_t)n,
+                                      (uint32_t *)(D + d_cum), (uint32_t *)(D + o_area), (int32_t *)(D + o_bbox),
+                                      (uint32_t *)(D + o_span), (uint32_t *)(D + d_reg), (int64_t *)(D + d_bitsoff),
+                                      (int32_t *)(D + o_status), D + arena0, arena_chunks, (uint64_t *)(D + o_cursor),
+                                      (int32_t *)(D + d_list), (int32_t)(n_chars / n), stream));
     if (dense) {
         e = cudaMemsetAsync(D + x_imoff, 0, 8, st);                 // the image's matrix starts at offset 0
         if (e != cudaSuccess) { ampis_set_error("imat offset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
@@ -109,16 +114,20 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
             STEP(ampis_grid_build((const int32_t *)(D + o_bbox), (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc), 1,
                                   (int32_t *)(D + g_shift), (int64_t *)(D + g_off), (int32_t *)(D + g_ent),
                                   (int32_t *)(D + g_entbb), grid_cap, (uint64_t *)(D + o_gridtot), stream));
-            STEP(ampis_intersect_rows_grid(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
-                                           (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
-                                           (const int32_t *)(D + u_blkgrp), (const int32_t *)(D + u_blkrow), nb,
-                                           (const int32_t *)(D + u_grb), (const int32_t *)(D + u_grc),
-                                           (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc),
-                                           (const int32_t *)(D + g_shift), (const int64_t *)(D + g_off),
-                                           (const int32_t *)(D + g_ent), (const int32_t *)(D + g_entbb), grid_cap,
-                                           dense ? (const int64_t *)(D + x_imoff) : nullptr, mode,
-                                           dense ? (int32_t *)(D + x_imat) : nullptr, dense ? gp : 0, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter),
-                                           (double *)(D + o_score), nullptr, nullptr, nullptr, 0, nullptr, stream));
+            e = cudaMemsetAsync(D + p_grp, 0, (size_t)(4 * (int64_t)n_rows), st);          // every row belongs to group 0
+            if (e != cudaSuccess) { ampis_set_error("row groups: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
+            STEP(ampis_intersect_rows_pairs(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
+                                            (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
+                                            (const int32_t *)(D + p_grp), n_rows, (const int32_t *)(D + u_grb),
+                                            (const int32_t *)(D + u_gcb), (const int32_t *)(D + u_gcc),
+                                            (const int32_t *)(D + g_shift), (const int64_t *)(D + g_off),
+                                            (const int32_t *)(D + g_ent), (const int32_t *)(D + g_entbb), grid_cap,
+                                            (int32_t *)(D + p_ab), D + p_desc, (uint32_t *)(D + p_inter), pair_cap,
+                                            (int64_t *)(D + p_off), (int32_t *)(D + p_cnt), (uint64_t *)(D + o_pairtot),
+                                            dense ? (const int64_t *)(D + x_imoff) : nullptr, mode,
+                                            dense ? (int32_t *)(D + x_imat) : nullptr, dense ? gp : 0, (int32_t *)(D + o_col),
+                                            (uint32_t *)(D + o_inter), (double *)(D + o_score), nullptr, nullptr, nullptr,
+                                            0, nullptr, stream));
         } else {
             STEP(ampis_intersect_rows_crop(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
                                            (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),
@@ -142,8 +151,11 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
 
     // ---- did everything fit? ------------------------------------------------------------------------------------
     const uint64_t used = *(const uint64_t *)(H + o_cursor);
-    if ((int64_t)used > arena_chunks) {
-        *need_bytes = arena0 + 16 * (int64_t)used + 65536;
+    const int64_t pairs_found = use_grid && n_rows > 0 && n_cols > 0 ? *(const int64_t *)(H + o_pairtot) : 0;
+    if ((int64_t)used > arena_chunks || pairs_found > pair_cap) {
+        // the free part is split 1 : 3 between the pair list and the arena
+        const int64_t by_arena = (16 * (int64_t)used + 65536) * 4 / 3, by_pairs = (44 * pairs_found + 4096) * 4;
+        *need_bytes = fixed0 + (by_arena > by_pairs ? by_arena : by_pairs) + 65536;
         return AMPIS_ENOSPC;
     }
     if (use_grid && n_cols > 0 && *(const int64_t *)(H + o_gridtot) > grid_cap) {

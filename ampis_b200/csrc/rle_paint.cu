@@ -196,47 +196,59 @@ __device__ __forceinline__ void warp_paint_crop(const u32 *C, int m, u32 H, cons
     if (bb.z < bb.x) return;
     const u32 wy0 = (u32)bb.y >> 5, nwy = ((u32)bb.w >> 5) - wy0 + 1u;
     const u32 x_end = (u32)bb.z + 1u;
-    const u32 cols_per_tile = max(1u, tile_words / nwy);
-    const bool one_tile = (x_end - (u32)bb.x) <= cols_per_tile;
     const FastDiv byH = fastdiv_make(H);
-    for (u32 xa = (u32)bb.x; xa < x_end; xa += cols_per_tile) {
-        const u32 xb = min(xa + cols_per_tile, x_end);
-        const u32 tw = (xb - xa) * nwy;
-        for (u32 k = lane; k < tw; k += L) tile[k] = 0u;
-        __syncwarp(gm);
-        const u64 b0 = (u64)xa * H, b1 = (u64)xb * H;
-        int r0 = 0, r1 = m - 1;
-        if (!one_tile) {
-            r0 = upper_bound_u32(C, m, b0);          // run that owns bit b0
-            r1 = upper_bound_u32(C, m, b1 - 1);      // run that owns bit b1-1 (m if beyond the runs)
-        }
-        for (int r = (r0 | 1) + 2 * (int)lane; r <= r1 && r < m; r += 2 * L) {   // odd runs are the 1-runs
-            const u64 rs = (u64)C[r - 1], re = (u64)C[r];
-            u64 s = rs > b0 ? rs : b0;
-            const u64 e = re < b1 ? re : b1;
-            while (s < e) {
-                const u32 x = fastdiv((u32)s, byH);               // s < e <= a run end, which is a u32
-                const u64 cs = (u64)x * H;
-                // rows [ys,ye) of column x, clipped to the box rows (a well-formed mask never needs the clip;
-                // a malformed one -- flagged in status -- must not write outside its window)
-                const u32 ys = max((u32)(s - cs), (u32)bb.y), ye = min((u32)(min(e, cs + H) - cs), (u32)bb.w + 1u);
-                s = cs + H;
-                if (ye <= ys) continue;
-                u32 *col = tile + (x - xa) * nwy - wy0;
-                const u32 w0 = ys >> 5, w1 = (ye - 1) >> 5;
-                if (w0 == w1) {
-                    atomicOr(&col[w0], bit_range(ys & 31u, ((ye - 1) & 31u) + 1u));
-                } else {
-                    atomicOr(&col[w0], bit_range(ys & 31u, 32u));
-                    for (u32 w = w0 + 1; w < w1; w++) col[w] = 0xffffffffu;
-                    atomicOr(&col[w1], bit_range(0u, ((ye - 1) & 31u) + 1u));
+    // band slices: one slice holds all bands of the box unless the box is taller than 32 * tile_words rows (then a
+    // tile is a piece of ONE column and the window is assembled slice by slice)
+    for (u32 wa = 0; wa < nwy; wa += tile_words) {
+        const u32 nwb = min(tile_words, nwy - wa);
+        const bool whole = nwb == nwy;
+        const u32 y_lo = max((u32)bb.y, (wy0 + wa) << 5), y_hi = min((u32)bb.w + 1u, (wy0 + wa + nwb) << 5);
+        const u32 cols_per_tile = whole ? max(1u, tile_words / nwb) : 1u;
+        const bool one_tile = whole && (x_end - (u32)bb.x) <= cols_per_tile;
+        for (u32 xa = (u32)bb.x; xa < x_end; xa += cols_per_tile) {
+            const u32 xb = min(xa + cols_per_tile, x_end);
+            const u32 tw = (xb - xa) * nwb;
+            for (u32 k = lane; k < tw; k += L) tile[k] = 0u;
+            __syncwarp(gm);
+            const u64 b0 = (u64)xa * H, b1 = (u64)xb * H;
+            int r0 = 0, r1 = m - 1;
+            if (!one_tile) {
+                r0 = upper_bound_u32(C, m, b0);          // run that owns bit b0
+                r1 = upper_bound_u32(C, m, b1 - 1);      // run that owns bit b1-1 (m if beyond the runs)
+            }
+            for (int r = (r0 | 1) + 2 * (int)lane; r <= r1 && r < m; r += 2 * L) {   // odd runs are the 1-runs
+                const u64 rs = (u64)C[r - 1], re = (u64)C[r];
+                u64 s = rs > b0 ? rs : b0;
+                const u64 e = re < b1 ? re : b1;
+                while (s < e) {
+                    const u32 x = fastdiv((u32)s, byH);               // s < e <= a run end, which is a u32
+                    const u64 cs = (u64)x * H;
+                    // rows [ys,ye) of column x, clipped to the slice's rows of the box (a well-formed mask never
+                    // needs the box clip; a malformed one -- flagged in status -- must not write outside its window)
+                    const u32 ys = max((u32)(s - cs), y_lo), ye = min((u32)(min(e, cs + H) - cs), y_hi);
+                    s = cs + H;
+                    if (ye <= ys) continue;
+                    u32 *col = tile + (x - xa) * nwb - (wy0 + wa);
+                    const u32 w0 = ys >> 5, w1 = (ye - 1) >> 5;
+                    if (w0 == w1) {
+                        atomicOr(&col[w0], bit_range(ys & 31u, ((ye - 1) & 31u) + 1u));
+                    } else {
+                        atomicOr(&col[w0], bit_range(ys & 31u, 32u));
+                        for (u32 w = w0 + 1; w < w1; w++) col[w] = 0xffffffffu;
+                        atomicOr(&col[w1], bit_range(0u, ((ye - 1) & 31u) + 1u));
+                    }
                 }
             }
+            __syncwarp(gm);
+            if (whole) {
+                u32 *o = out + (xa - (u32)bb.x) * nwy;
+                for (u32 k = lane; k < tw; k += L) o[k] = tile[k];
+            } else {                                          // a piece of one column
+                u32 *o = out + (xa - (u32)bb.x) * nwy + wa;
+                for (u32 k = lane; k < tw; k += L) o[k] = tile[k];
+            }
+            __syncwarp(gm);
         }
-        __syncwarp(gm);
-        u32 *o = out + (xa - (u32)bb.x) * nwy;
-        for (u32 k = lane; k < tw; k += L) o[k] = tile[k];
-        __syncwarp(gm);
     }
 }
 
@@ -311,6 +323,8 @@ rle_measure_paint_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cn
             bits_off[i] = 0;
             reinterpret_cast<uint2 *>(span)[i] = make_uint2(0u, 0u);
             reinterpret_cast<uint2 *>(reg)[i] = make_uint2(0u, 0u);
+            // the crop rows kernels size their reads from the box, not from reg
+            if (KIND == 2) reinterpret_cast<int4 *>(bbox)[i] = make_int4(0, 0, -1, -1);
         }
         return;
     }
@@ -406,6 +420,7 @@ rle_measure_paint_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict
             bits_off[i] = 0;
             reinterpret_cast<uint2 *>(span)[i] = make_uint2(0u, 0u);
             reinterpret_cast<uint2 *>(reg)[i] = make_uint2(0u, 0u);
+            reinterpret_cast<int4 *>(bbox)[i] = make_int4(0, 0, -1, -1);    // rows kernels size their reads from it
         }
         return;
     }
@@ -489,6 +504,74 @@ extern "C" int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_c
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, layout, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off,
             d_status, (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
     AMPIS_CHECK_LAUNCH("rle_measure_paint_kernel");
+    return AMPIS_OK;
+}
+
+// Fallback of the flat decode kernel (rle_flat.cu): masks it left on a list -- too many runs or too large a window
+// for its per-warp budgets, or a frame of 2^31 pixels or more -- are measured and painted here, one warp per mask,
+// any size (run ends beyond the shared budget go through cum_g, the window is assembled tile by tile).  The list
+// length is only known on the device: list[0] = number of masks, list[1..] = mask ids; warps stride over it.
+__global__ void __launch_bounds__(MP_WARPS * 32, 5)
+rle_measure_paint_list_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off,
+                              const int *__restrict__ cnt_len, const u32 *__restrict__ hh,
+                              const u32 *__restrict__ ww, const int *__restrict__ list, u32 *cum_g,
+                              u32 *__restrict__ area, int *__restrict__ bbox, u32 *__restrict__ span,
+                              u32 *__restrict__ reg, i64 *__restrict__ bits_off, int *__restrict__ status,
+                              uint4 *__restrict__ bits, i64 capacity, unsigned long long *__restrict__ cursor)
+{
+    constexpr int CUM_CAP = MP_CUM_WORDS / MP_WARPS;
+    __shared__ __align__(16) u32 s_cum[MP_CUM_WORDS];
+    __shared__ __align__(16) u32 s_tile[MP_WARPS][MP_TILE * 4];
+    __shared__ uint2 s_span[MP_WARPS], s_reg[MP_WARPS];
+    __shared__ int4 s_bbox[MP_WARPS];
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const int count = list[0];
+    for (int q = blockIdx.x * MP_WARPS + (int)wid; q < count; q += gridDim.x * MP_WARPS) {
+        const int i = list[1 + q];
+        const int m = cnt_len[i];
+        const i64 base = cnt_off[i];
+        const u32 H = hh[i];
+        const u64 HW = (u64)H * ww[i];
+        __syncwarp();
+        const MaskMeasure ms = warp_measure(cnt + base, m, H, HW, s_cum + wid * CUM_CAP, CUM_CAP,
+                                            m > CUM_CAP ? cum_g + base : nullptr);
+        if (lane == 0)
+            store_measure(ms, H, HW, AMPIS_LAYOUT_CROP, i, area, bbox, span, reg, status, &s_span[wid], &s_reg[wid],
+                          &s_bbox[wid]);
+        __syncwarp();
+        const u32 sz = s_reg[wid].y - s_reg[wid].x;
+        unsigned long long o = 0;
+        if (lane == 0 && sz) o = atomicAdd(cursor, (unsigned long long)sz);
+        const i64 off = (i64)__shfl_sync(0xffffffffu, o, 0);
+        if (off + (i64)sz > capacity) {                      // arena exhausted: see rle_flat_crop_kernel
+            if (lane == 0) {
+                bits_off[i] = 0;
+                reinterpret_cast<int4 *>(bbox)[i] = make_int4(0, 0, -1, -1);
+                reinterpret_cast<uint2 *>(span)[i] = make_uint2(0u, 0u);
+                reinterpret_cast<uint2 *>(reg)[i] = make_uint2(0u, 0u);
+            }
+            continue;
+        }
+        if (lane == 0) bits_off[i] = off;
+        __threadfence_block();                               // run ends written to cum_g are read back below
+        const u32 *C = m > CUM_CAP ? cum_g + base : s_cum + wid * CUM_CAP;
+        warp_paint_crop(C, m, H, s_bbox[wid], s_tile[wid], MP_TILE * 4, reinterpret_cast<u32 *>(bits + off), lane);
+    }
+}
+
+int ampis_launch_measure_paint_list(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                                    const uint32_t *d_h, const uint32_t *d_w, const int32_t *d_list, int32_t max_n,
+                                    uint32_t *d_cum, uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span,
+                                    uint32_t *d_reg, int64_t *d_bits_off, int32_t *d_status, void *d_bits,
+                                    int64_t bits_capacity, uint64_t *d_cursor, cudaStream_t st)
+{
+    // the list is usually empty or short: a few waves of warps that stride over it
+    const int want = (max_n + MP_WARPS - 1) / MP_WARPS;
+    const int grid = want < 148 * 4 ? want : 148 * 4;
+    rle_measure_paint_list_kernel<<<grid, MP_WARPS * 32, 0, st>>>(
+        d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, d_list, d_cum, d_area, d_bbox, d_span, d_reg, d_bits_off, d_status,
+        (uint4 *)d_bits, bits_capacity, (unsigned long long *)d_cursor);
+    AMPIS_CHECK_LAUNCH("rle_measure_paint_list_kernel");
     return AMPIS_OK;
 }
 

@@ -58,6 +58,11 @@ def _dev(a, dtype, device):
 PAINT_RUNS_HINT = int(os.environ.get('AMPIS_PAINT_RUNS_HINT', -1))
 
 
+#: fused crop decode: 'flat' = a warp decodes several masks at once over their concatenated runs (rle_flat.cu);
+#: 'group' = 8 / 16 / 32 lanes per mask (rle_paint.cu, round 1) -- same results, kept for A/B measurements
+CROP_DECODE = os.environ.get('AMPIS_CROP_DECODE', 'flat')
+
+
 class MaskTable(object):
     """Structure-of-arrays table of n masks on the GPU (see include/ampis_b200.h)."""
 
@@ -76,6 +81,7 @@ class MaskTable(object):
         self.bits_off = torch.empty(n1 + 1, dtype=i64, device=device)
         self.cursor = torch.empty(1, dtype=i64, device=device)   # chunks the arena needed (fused path)
         self.fused = False
+        self.list = None        # scratch of the flat crop decode (masks left to its fallback kernel)
         self.bits = None
         self.bits_capacity = 0
 
@@ -112,10 +118,18 @@ class MaskTable(object):
         self.bits = arena
         self.bits_capacity = arena.numel() // 4
         self.fused = True
+        hint = PAINT_RUNS_HINT if PAINT_RUNS_HINT >= 0 else (self.cnt.numel() // max(self.n, 1))
+        if self.layout == LAYOUT_CROP and CROP_DECODE == 'flat':
+            if self.list is None:
+                self.list = torch.empty(self.n + 1, dtype=torch.int32, device=self.device)
+            N.call('ampis_rle_measure_paint_flat', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h),
+                   _p(self.w), self.n, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
+                   _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor),
+                   _p(self.list), hint, _stream())
+            return self
         N.call('ampis_rle_measure_paint', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h), _p(self.w),
                self.n, self.layout, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
-               _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor),
-               PAINT_RUNS_HINT if PAINT_RUNS_HINT >= 0 else (self.cnt.numel() // max(self.n, 1)), _stream())
+               _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor), hint, _stream())
         return self
 
     def relayout(self, layout):
@@ -444,6 +458,29 @@ class ColumnGrid(object):
         return int(self.cursor.item())
 
 
+#: grid-pruned crop rows: 'pairs' = spatial join in three flat passes (intersect_pairs.cu); 'grid' = one kernel,
+#: eight lanes per row (intersect_grid.cu, round 1) -- same results, kept for A/B measurements
+ROWS_KERNEL = os.environ.get('AMPIS_ROWS_KERNEL', 'pairs')
+
+
+class PairList(object):
+    """Candidate pairs of ampis_intersect_rows_pairs: (row mask, column mask) ids, their intersections, and the
+    range of every row.  `count` may exceed `capacity` (then the results are void and the list must grow)."""
+
+    def __init__(self, device, n_rows, capacity):
+        self.capacity = int(capacity)
+        c = max(self.capacity, 1)
+        self.ab = torch.empty(2 * c, dtype=torch.int32, device=device)
+        self.desc = torch.empty(8 * c, dtype=torch.int32, device=device)        # 32-byte overlap descriptors
+        self.inter = torch.empty(c, dtype=torch.int32, device=device)          # uint32 payload
+        self.row_off = torch.empty(max(n_rows, 1), dtype=torch.int64, device=device)
+        self.row_cnt = torch.empty(max(n_rows, 1), dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def needed(self):
+        return int(self.count.item())
+
+
 class SparseRows(object):
     """Sparse output of ampis_intersect_rows_grid: the non-zero intersections as (row, column-in-group,
     intersection) triplets, unordered; `count` may exceed `capacity` (the excess was dropped)."""
@@ -467,10 +504,12 @@ class SparseRows(object):
         return r[order], c[order], (self.inter[:n].long() & 0xffffffff)[order]
 
 
-def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None):
+def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=None):
     """Run the fused row kernel.  Returns device tensors (no sync).  Crop-layout tables with many
     columns per image (ROWS_GRID_MIN_COLS), or whenever a ColumnGrid / SparseRows is passed, go through
-    the grid-pruned kernel; grid='scan' forces the all-columns scan."""
+    the grid-pruned kernels; grid='scan' forces the all-columns scan.  The grid-pruned form is the three-pass
+    join (ROWS_KERNEL 'pairs'; `pairs` = a pre-sized PairList, else one is sized here with a read-back)
+    or the single rows kernel of round 1 ('grid')."""
     dev = table.device
     nr = max(groups.n_rows, 1)
     if out is None:
@@ -489,6 +528,29 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None):
         out.grid = grid
         if sparse is not None:
             sparse.count.zero_()
+        if ROWS_KERNEL == 'pairs':
+            own = pairs is None
+            if own:
+                pairs = PairList(dev, groups.n_rows, 8 * groups.n_rows + 4096)
+            while True:
+                N.call('ampis_intersect_rows_pairs', _p(table.bits), _p(table.bits_off), _p(table.bbox),
+                       _p(table.area), _p(groups.row_mask), _p(groups.row_grp), groups.n_rows,
+                       _p(groups.grp_row_begin), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(grid.shift),
+                       _p(grid.cell_off), _p(grid.entries), _p(grid.entry_bbox), grid.capacity, _p(pairs.ab),
+                       _p(pairs.desc), _p(pairs.inter), pairs.capacity, _p(pairs.row_off), _p(pairs.row_cnt), _p(pairs.count),
+                       _p(groups.imat_off), mode, _p(out.imat),
+                       groups.imat_size if groups.imat_off is not None and out.imat is not None else 0,
+                       _p(out.best_col), _p(out.best_inter), _p(out.best_score),
+                       _p(sparse.row) if sparse else None, _p(sparse.col) if sparse else None,
+                       _p(sparse.inter) if sparse else None, sparse.capacity if sparse else 0,
+                       _p(sparse.count) if sparse else None, _stream())
+                if not own or pairs.needed() <= pairs.capacity:
+                    break
+                pairs = PairList(dev, groups.n_rows, pairs.needed())         # crowded images: grow and repeat
+                if sparse is not None:
+                    sparse.count.zero_()
+            out.pairs = pairs
+            return out
         N.call('ampis_intersect_rows_grid', _p(table.bits), _p(table.bits_off), _p(table.bbox), _p(table.area),
                _p(groups.row_mask), _p(groups.blk_grp), _p(groups.blk_row0), groups.n_blocks,
                _p(groups.grp_row_begin), _p(groups.grp_row_count), _p(groups.grp_col_begin),

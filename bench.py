@@ -445,7 +445,10 @@ def main():
         by_imat = max(1, int(4e9 // (4 * cfg['n_rows'] * cfg['n_cols'])))          # dense matrices <= 4 GB per launch
         if args.sparse and lay == engine.LAYOUT_CROP:
             by_imat = args.images
-        return min(args.images, 250, by_imat)
+        # culled layouts: the arena is small, so all images of the step go out in ONE launch of each kernel (bounded by
+        # 4 GB of dense matrices) -- at 91 or 250 images per launch the short kernels of this step were mostly ramp and
+        # tail (profiles/kernels_r02.md: 2.69 / 1.83 / 1.45 ms per 1,000 C2 images at 91 / 250 / 1,000 per launch)
+        return min(args.images, by_imat)
 
     sampler = ClockSampler(local) if rank == 0 else None       # samples cover warm-up + timed steps
     wall0 = time.time()
@@ -624,7 +627,8 @@ def run_e2e(args, subs, dev, layout, arena, rows_out, thresholds, world, dist, s
                 rows = engine.intersect_mma(t, b.groups, b.mode, out=rows_out, sort=args.mma_sort, pair=args.kernel == 'mma2')
             else:
                 rows = engine.intersect_rows(t, b.groups, b.mode, out=rows_out, grid=pipes[i].grid if pipes else None,
-                                             sparse=pipes[i].sparse if pipes else None)
+                                             sparse=pipes[i].sparse if pipes else None,
+                                             pairs=pipes[i].pairs if pipes else None)
             if b.mode == engine.MODE_IOU:
                 counts, _ = engine.match_counts(rows, b.groups, thresholds, totals=totals)
             else:       # satellites: per-image (matched, unmatched, satellited particles, particles) + global histogram

@@ -122,6 +122,18 @@ int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off, con
                             uint32_t *d_reg, int64_t *d_bits_off, int32_t *d_status, void *d_bits,
                             int64_t bits_capacity, uint64_t *d_cursor, int32_t runs_hint, void *stream);
 
+/* AMPIS_LAYOUT_CROP form of ampis_rle_measure_paint, third generation ("flat"): a warp decodes several masks at
+ * once with its lanes spread over their concatenated (0-run, 1-run) pairs -- one segmented scan per 32 pairs, one
+ * record-forming lane per mask, one arena reservation and one contiguous copy-out per warp (csrc/rle_flat.cu).
+ * Same outputs as ampis_rle_measure_paint(layout = AMPIS_LAYOUT_CROP), bit for bit; arena order differs.
+ * d_list: int32[n + 1] scratch; masks outside the per-warp budgets (more than 512 runs, window larger than 2 KB,
+ * frame of 2^31 pixels or more) are listed there and worked off by a second launch (a warp per mask, any size). */
+int ampis_rle_measure_paint_flat(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                                 const uint32_t *d_h, const uint32_t *d_w, int32_t n, uint32_t *d_cum,
+                                 uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span, uint32_t *d_reg,
+                                 int64_t *d_bits_off, int32_t *d_status, void *d_bits, int64_t bits_capacity,
+                                 uint64_t *d_cursor, int32_t *d_list, int32_t runs_hint, void *stream);
+
 /* bits -> bool[n][h][w] row-major bytes (RLE.decode(...).astype(bool).transpose(2,0,1),
  * structures.py:752,765).  All n masks must share (h,w). d_mask_ids selects masks. */
 int ampis_unpack_bool_nrc(const void *d_bits, const int64_t *d_bits_off, const uint32_t *d_reg,
@@ -207,6 +219,28 @@ int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bits_off, con
                               int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                               int32_t *d_coo_row, int32_t *d_coo_col, uint32_t *d_coo_inter,
                               int64_t coo_capacity, uint64_t *d_coo_count, void *stream);
+
+/* The grid-pruned crop rows as a spatial JOIN in three flat passes (csrc/intersect_pairs.cu), same outputs as
+ * ampis_intersect_rows_grid bit for bit (same grid from ampis_grid_build):
+ *   1. one thread per row walks the grid cells of its box and appends the (row mask, column mask) pairs whose
+ *      boxes overlap -- rleIou's bbIou pre-pass (analyze.py:108,158) -- to d_pair_ab (int32[2 * pair_capacity],
+ *      8-byte aligned) and the geometry of the overlap of their windows to d_pair_desc (32 bytes per pair,
+ *      16-byte aligned); the pairs of row r are d_row_pair_cnt[r] consecutive entries from d_row_pair_off[r];
+ *   2. eight lanes per pair: d_pair_inter[q] = popcount(A & B) over the overlap of the two windows;
+ *   3. one thread per row: score and first arg-max over its pairs, dense cells / sparse triplets.
+ * d_row_grp[r] = group of row r.  *d_pair_count (zeroed by the call) = pairs found; when it exceeds pair_capacity
+ * nothing useful was computed and the caller retries with a larger list. */
+int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
+                               const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_row_grp,
+                               int32_t n_rows, const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
+                               const int32_t *d_grp_col_count, const int32_t *d_grp_shift,
+                               const int64_t *d_cell_off, const int32_t *d_entries, const int32_t *d_entry_bbox,
+                               int64_t grid_capacity, int32_t *d_pair_ab, void *d_pair_desc,
+                               uint32_t *d_pair_inter, int64_t pair_capacity, int64_t *d_row_pair_off, int32_t *d_row_pair_cnt,
+                               uint64_t *d_pair_count, const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
+                               int64_t imat_ints, int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
+                               int32_t *d_coo_row, int32_t *d_coo_col, uint32_t *d_coo_inter, int64_t coo_capacity,
+                               uint64_t *d_coo_count, void *stream);
 
 /* ---- one image, one call (host entry point) ---------------------------------------------------------
  * The per-image work of analyze.py:149-164 (rle_instance_matcher / det_seg_scores: G x ceil(P/80) RLE.iou calls +

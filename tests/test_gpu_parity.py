@@ -402,11 +402,13 @@ def test_crop_layout_equals_span_layout(mods, cfg, over, n_img):
     ('c2_powder_batch', dict(h=512, w=512, n_rows=40, n_cols=40, median_diam=150.0), 2),   # large overlaps: warp-wide phase
     ('dense_overlap', dict(h=512, w=512, n_rows=64, n_cols=64, median_diam=220.0), 2),     # ... more than a warp parks
 ])
-def test_grid_pruned_rows_equal_scanned_rows(mods, cfg, over, n_img):
-    """Crop rows kernel with the box pre-pruning through the uniform grid == the kernel that tests every
-    column's box, bit for bit (dense matrix, arg-max, scores, counts); its sparse output is exactly the
-    set of non-zero cells of the dense matrix."""
+@pytest.mark.parametrize('rows_kernel', ['pairs', 'grid'])
+def test_grid_pruned_rows_equal_scanned_rows(mods, cfg, over, n_img, rows_kernel, monkeypatch):
+    """Crop rows with the box pre-pruning through the uniform grid -- as the three-pass join ('pairs') and as the
+    single rows kernel of round 1 ('grid') -- == the kernel that tests every column's box, bit for bit (dense
+    matrix, arg-max, scores, counts); the sparse output is exactly the set of non-zero cells of the dense matrix."""
     B, E, torch = mods.batch, mods.engine, mods.torch
+    monkeypatch.setattr(E, 'ROWS_KERNEL', rows_kernel)
     host = B.synth(dict(B.CONFIGS[cfg], **over), n_img, 4242)
     dev = B.DeviceBatch(host, dense=True)
     a = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, kernel='scan')
@@ -434,6 +436,15 @@ def test_grid_pruned_rows_equal_scanned_rows(mods, cfg, over, n_img):
     assert torch.equal(pipe.rows.best_col[:dev2.groups.n_rows], a.rows.best_col[:dev2.groups.n_rows])
     assert int(pipe.sparse.count.item()) == len(wr)
     assert pipe.grid.needed() == pipe.grid.capacity
+    if rows_kernel == 'pairs':
+        # the pair list holds every pair with overlapping boxes (at least the non-zero ones), sized exactly by the dry run
+        assert pipe.pairs.needed() == pipe.pairs.capacity >= len(wr)
+        # a list that is too small is detected, not overrun
+        short = E.PairList('cuda', dev2.groups.n_rows, max(pipe.pairs.capacity // 3, 1))
+        t = E.MaskTable(pipe.table.device, host.n_masks, dev2.cnt, dev2.cnt_off, dev2.cnt_len, dev2.h, dev2.w,
+                        E.LAYOUT_CROP).measure_paint(arena)
+        E.intersect_rows(t, dev2.groups, dev2.mode, grid=pipe.grid, pairs=short)
+        assert short.needed() == pipe.pairs.capacity > short.capacity
 
 
 def test_sparse_iou_equals_nonzeros_of_the_dense_matrix(mods):
@@ -470,14 +481,86 @@ def test_crop_decode_lane_groups_agree(mods, cfg, over, n_img, monkeypatch):
     dev = B.DeviceBatch(host, dense=True)
     ref = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, fused=False, kernel='scan')
     arena = torch.empty(4 * B.arena_chunks_needed(dev, E.LAYOUT_CROP), dtype=torch.int32, device='cuda')
-    for hint in (0, 30, 100):                       # warp per mask, 8 lanes, 16 lanes
+    # group decode: warp per mask, 8 lanes, 16 lanes; flat decode: 4, 16, 10, 3, 1 masks per warp
+    for decode, hint in [('group', 0), ('group', 30), ('group', 100), ('flat', 0), ('flat', 2), ('flat', 30),
+                         ('flat', 100), ('flat', 400)]:
+        monkeypatch.setattr(E, 'CROP_DECODE', decode)
         monkeypatch.setattr(E, 'PAINT_RUNS_HINT', hint)
         got = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, arena=arena, kernel='scan')
         n = host.n_masks
-        assert torch.equal(got.table.area[:n], ref.table.area[:n]) and torch.equal(got.table.bbox[:4 * n], ref.table.bbox[:4 * n])
-        assert torch.equal(got.table.status[:n], ref.table.status[:n])
-        assert torch.equal(got.rows.imat, ref.rows.imat), hint
-        assert torch.equal(got.rows.best_col, ref.rows.best_col) and torch.equal(got.counts, ref.counts)
+        tag = (decode, hint)
+        assert torch.equal(got.table.area[:n], ref.table.area[:n]) and torch.equal(got.table.bbox[:4 * n], ref.table.bbox[:4 * n]), tag
+        assert torch.equal(got.table.status[:n], ref.table.status[:n]), tag
+        assert torch.equal(got.table.span[:2 * n], ref.table.span[:2 * n]) and torch.equal(got.table.reg[:2 * n], ref.table.reg[:2 * n]), tag
+        assert int(got.table.cursor.item()) == int(ref.table.bits_off[n].item()), tag      # same arena need
+        assert torch.equal(got.rows.imat, ref.rows.imat), tag
+        assert torch.equal(got.rows.best_col, ref.rows.best_col) and torch.equal(got.counts, ref.counts), tag
+
+
+def _csr_table(mods, masks_bool, layout):
+    """bool[n,h,w] -> (device MaskTable inputs) through the oracle's encoder."""
+    E, rle, torch = mods.engine, mods.rle, mods.torch
+    n, h, w = masks_bool.shape
+    cnts = [rle.counts_from_string(rle.encode(np.asfortranarray(m.astype(np.uint8)))['counts']) for m in masks_bool]
+    lens = np.array([len(c) for c in cnts], np.int32)
+    off = np.zeros(n, np.int64)
+    off[1:] = np.cumsum(lens[:-1])
+    dev = 'cuda'
+    cnt = torch.from_numpy(np.concatenate(cnts).astype(np.uint32).view(np.int32)).to(dev)
+    return E.MaskTable(torch.device('cuda', torch.cuda.current_device()), n, cnt, torch.from_numpy(off).to(dev),
+                       torch.from_numpy(lens).to(dev), torch.full((n,), h, dtype=torch.int32, device=dev),
+                       torch.full((n,), w, dtype=torch.int32, device=dev), layout)
+
+
+@pytest.mark.parametrize('h,w', [(8200, 24), (16500, 12), (40, 3000)])
+def test_crop_decode_of_tall_wide_and_busy_masks(mods, h, w, monkeypatch):
+    """Frames taller than the shared-memory tile of the crop painter (a box of more than 128 / 256 / 512 32-row
+    bands used to overflow the tile: ADVICE r1), masks with thousands of runs, full frames and empty masks next to
+    small blobs: every fused crop decode (flat with its fallback list, 8 / 16 / 32 lanes per mask) and the unfused
+    painter give the measurements and the all-pairs intersections of a dense numpy formulation."""
+    B, E, torch = mods.batch, mods.engine, mods.torch
+    rng = np.random.default_rng(h * 7 + w)
+    n = 14
+    m = np.zeros((n, h, w), bool)
+    m[0, :, 2:4] = True                                   # full-height thin mask
+    m[1, 1:h - 1, w // 2] = True                          # almost full height, one column
+    m[2, ::2, : min(w, 40)] = True                        # thousands of short runs
+    m[3] = True                                           # the whole frame
+    m[5, h // 2: h // 2 + 9, 1:8] = True                  # small blobs around the tall ones
+    m[6, 0:5, 0:3] = True
+    m[7, h - 4:, w - 3:] = True
+    m[8] = rng.random((h, w)) < 0.3                       # noise: runs everywhere
+    m[9, 5: h - 5: 3, 1] = True
+    m[10, h // 3: h // 3 + 40, : w // 2] = True
+    m[11, :, w - 1] = True
+    m[12, 100: h - 100, 0: w: 5] = True
+    t_ref = _csr_table(mods, m, E.LAYOUT_CROP).measure().paint().check()
+    groups = E.Groups(t_ref.device, np.arange(n), np.zeros(n, np.int64), [0], [n], [0], [n], dense=True)
+    ref = E.intersect_rows(t_ref, groups, E.MODE_IOU, grid='scan')
+    flat = m.reshape(n, -1).astype(np.int64)
+    want_I = flat @ flat.T
+    assert np.array_equal(ref.imat.cpu().numpy()[:n * n].reshape(n, n), want_I)
+    assert np.array_equal(t_ref.areas_np(), m.sum(axis=(1, 2)))
+    need = int(t_ref.bits_off[n].item())
+    for decode, hint in [('flat', 0), ('flat', 30), ('flat', 5000), ('group', 0), ('group', 30), ('group', 100)]:
+        monkeypatch.setattr(E, 'CROP_DECODE', decode)
+        monkeypatch.setattr(E, 'PAINT_RUNS_HINT', hint)
+        t = _csr_table(mods, m, E.LAYOUT_CROP)
+        arena = torch.empty(4 * need, dtype=torch.int32, device='cuda')
+        t.measure_paint(arena).check()
+        got = E.intersect_rows(t, groups, E.MODE_IOU, grid='scan')
+        tag = (decode, hint)
+        assert torch.equal(t.area[:n], t_ref.area[:n]) and torch.equal(t.bbox[:4 * n], t_ref.bbox[:4 * n]), tag
+        assert int(t.cursor.item()) == need, tag
+        assert np.array_equal(got.imat.cpu().numpy()[:n * n].reshape(n, n), want_I), tag
+        # arena exhausted: no kernel may touch memory beyond it, the masks that did not fit are left empty
+        small = torch.empty(4 * max(need // 3, 1), dtype=torch.int32, device='cuda')
+        t2 = _csr_table(mods, m, E.LAYOUT_CROP)
+        t2.measure_paint(small)
+        with pytest.raises(mods.engine.N.AmpisNativeError, match='arena too small'):
+            t2.check()
+        E.intersect_rows(t2, groups, E.MODE_IOU, grid='scan')
+        torch.cuda.synchronize()
 
 
 def test_one_call_image_entry_equals_table_api(mods, monkeypatch):
@@ -1031,7 +1114,10 @@ def test_randomised_batches_all_layouts_and_kernels_vs_dense_numpy(mods, seed):
                     arena = torch.empty(4 * max(B.arena_chunks_needed(dev, layout), 1), dtype=torch.int32, device='cuda')
                 kernels = ('rows', 'grid') if layout == E.LAYOUT_CROP else ('rows', 'mma')
                 for kernel in kernels:
+                    # fused crop decode: the flat kernel (default) and the lane-group kernels of round 1 in turn
+                    E.CROP_DECODE = 'group' if (fused and layout == E.LAYOUT_CROP and kernel == 'grid') else 'flat'
                     r = B.eval_step(dev, layout=layout, check=True, arena=arena, kernel=kernel)
+                    E.CROP_DECODE = 'flat'
                     I = r.rows.imat.cpu().numpy()[:n_img * G * Pn].reshape(n_img, G, Pn)
                     tag = (trial, h, w, G, Pn, layout, fused, kernel)
                     assert np.array_equal(I, want_I), tag
@@ -1113,3 +1199,84 @@ def test_det_seg_scores_batch_equals_per_image_calls(mods):
     assert A.det_seg_scores_batch([], []) == []
     with pytest.raises(ZeroDivisionError):
         A.det_seg_scores_batch([images[0][0], mods.structures.RLEMasks([])], [images[0][1], mods.structures.RLEMasks([])])
+
+
+def _dicts(mods, host, g=0):
+    rows, cols = host.image_masks(g)
+    mk = lambda cs: [{'size': [host.h, host.w], 'counts': mods.rle.string_from_counts(c)} for c in cs]
+    return mk(rows), mk(cols)
+
+
+@pytest.mark.parametrize('decode,rows_kernel', [('flat', 'pairs'), ('group', 'grid'), ('flat', 'grid')])
+def test_native_size_c4_image_vs_oracle(mods, decode, rows_kernel, monkeypatch):
+    """BASELINE.json configs[3] at its NATIVE size -- one 2048 x 2048 frame, 5,000 x 5,000 small instances --
+    through the drop-in functions against the oracle (one rleIou call over all 25 M pairs, the reference's matcher
+    rules on its matrix, rleMerge on the matched pairs): det_seg_scores at three thresholds, the sparse IoU list
+    against the non-zero cells of the oracle's matrix, areas and equivalent diameters.  Crop windows of 13-px blobs,
+    the grid at 5,000 columns, the join and both decode kernels are exactly what VERDICT r1 asked to see here."""
+    A, B, E, S, rle = mods.analyze, mods.batch, mods.engine, mods.structures, mods.rle
+    monkeypatch.setattr(E, 'CROP_DECODE', decode)
+    monkeypatch.setattr(E, 'ROWS_KERNEL', rows_kernel)
+    host = B.synth('c4_spheroidite', 1, 4004)
+    assert (host.h, host.w, host.n_rows, host.n_cols) == (2048, 2048, 5000, 5000)
+    gt, pr = _dicts(mods, host)
+    iou = U.iou_matrix_one_shot(rle, gt, pr)
+    for th in (0.5, 0.75, 0.9):
+        want = U.det_seg_scores_one_shot(rle, gt, pr, th, iou=iou)
+        got = A.det_seg_scores(gt, pr, th)
+        assert want.keys() == got.keys()
+        for k in want:
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), (th, k)
+        assert len(want['det_tp']) > 1000
+    # through the table API as bench.py drives it (crop layout, sparse triplets)
+    dev = B.DeviceBatch(host, dense=False)
+    sp = E.SparseRows('cuda', 64 * host.n_rows)
+    res = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, kernel='grid', sparse=sp)
+    r, c, v = (x.cpu().numpy() for x in sp.triplets())
+    wr, wc = np.nonzero(iou)
+    assert np.array_equal(r, wr) and np.array_equal(c, wc)
+    a_g, a_p = rle.area(gt).astype(np.int64), rle.area(pr).astype(np.int64)
+    assert np.array_equal(v / (a_g[r] + a_p[c] - v), iou[wr, wc])
+    m = U.match_from_iou(iou, 0.5)
+    assert res.counts.cpu().numpy()[0, 0].tolist() == [len(m['tp']), len(m['fp']), len(m['fn'])]
+    if decode == 'flat' and rows_kernel == 'pairs':
+        sp2 = A.sparse_iou(gt, pr)
+        assert np.array_equal(sp2['row'], wr) and np.array_equal(sp2['col'], wc) and np.array_equal(sp2['iou'], iou[wr, wc])
+        assert np.array_equal(S.mask_areas(gt), rle.area(gt))
+        d_eq = np.sqrt(4 * rle.area(pr).astype(np.float64) / np.pi)
+        keep = np.nonzero(rle.area(pr))[0][:600]                     # regionprops rows exist for non-empty masks
+        iset = S.InstanceSet()
+        iset.instances = S.Instances((host.h, host.w), masks=S.RLEMasks([pr[i] for i in keep]),
+                                     class_idx=np.zeros(len(keep), int))
+        df = iset.compute_rprops(keys=['area', 'equivalent_diameter'], return_df=True)
+        got_d = np.array([float(np.asarray(x).ravel()[0]) for x in df['equivalent_diameter']])
+        assert np.allclose(got_d, d_eq[keep], rtol=1e-6, atol=0)        # north_star: 1e-6 relative on derived floats
+        assert np.array_equal(np.array([int(np.asarray(x).ravel()[0]) for x in df['area']]), rle.area(pr)[keep])
+
+
+@pytest.mark.parametrize('decode,rows_kernel', [('flat', 'pairs'), ('group', 'grid')])
+def test_native_size_c3_image_vs_oracle(mods, decode, rows_kernel, monkeypatch):
+    """BASELINE.json configs[2] at its NATIVE size -- 200 satellites x 2,000 particles in a 2048 x 2048 frame --
+    _rle_satellite_match and satellite_measurements against the oracle (intersections by rleMerge wherever rleIou is
+    non-zero, then the reference's per-satellite arg-max over all particles)."""
+    B, E, P, rle = mods.batch, mods.engine, mods.powder, mods.rle
+    monkeypatch.setattr(E, 'CROP_DECODE', decode)
+    monkeypatch.setattr(E, 'ROWS_KERNEL', rows_kernel)
+    host = B.synth('c3_satellites', 2, 3003)
+    assert (host.h, host.w, host.n_rows, host.n_cols) == (2048, 2048, 200, 2000)
+    for g in range(2):
+        sat, part = _dicts(mods, host, g)
+        want = U.satellite_match_one_shot(rle, part, sat, 0.5)
+        got = P._rle_satellite_match(part, sat, 0.5)
+        for k in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched', 'intersection_scores'):
+            assert np.array_equal(got[k], want[k]), (g, k)
+        assert {a: list(b) for a, b in got['match_pairs'].items()} == {a: list(b) for a, b in want['match_pairs'].items()}
+        assert 100 < len(want['satellite_matches']) < 200
+    # the batch step on the same two frames: per-image counts
+    dev = B.DeviceBatch(host, dense=False)
+    res = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True)
+    for g in range(2):
+        sat, part = _dicts(mods, host, g)
+        want = U.satellite_match_one_shot(rle, part, sat, 0.5)
+        assert res.counts.cpu().numpy()[g].tolist() == [len(want['satellite_matches']), len(want['satellites_unmatched']),
+                                                        len(want['match_pairs']), host.n_cols]

@@ -250,3 +250,27 @@ def test_bench_reference_arm_prints_one_json_line():
     assert 'workload' in d['config'] and 'model' not in d['config']
     r = subprocess.run(cmd, env=dict(env, RANK='1', WORLD_SIZE='2'), capture_output=True, text=True, timeout=100)
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_prediction_pickles_only_resolve_allowlisted_names():
+    """containers.load_pickle: numpy arrays / scalars, plain containers and detectron2's Instances load; any other
+    global -- builtins.eval, os.system, a numpy function -- is refused (the old filter let every builtin
+    and every numpy.* name through)."""
+    import io
+    import os
+    import pickle
+    from ampis_b200.containers import Instances, _Unpickler
+    x = {'a': np.arange(5, dtype=np.float32), 'b': np.float64(3.0), 'c': [np.int64(3)], 'd': (1, 2), 's': {1, 2},
+         'i': Instances((4, 4), scores=np.ones(2))}
+    y = _Unpickler(io.BytesIO(pickle.dumps(x))).load()
+    assert np.array_equal(y['a'], x['a']) and y['b'] == 3.0 and y['s'] == {1, 2} and len(y['i']) == 2
+
+    class Evil(object):
+        def __init__(self, fn, arg):
+            self.fn, self.arg = fn, arg
+
+        def __reduce__(self):
+            return (self.fn, (self.arg,))
+    for fn, arg in ((eval, '1+1'), (os.system, 'true'), (getattr, 'x'), (np.load, 'nothing.npy'), (__import__, 'os')):
+        with pytest.raises(pickle.UnpicklingError, match='refusing to load'):
+            _Unpickler(io.BytesIO(pickle.dumps(Evil(fn, arg)))).load()

@@ -280,3 +280,51 @@ def test_edge_distance_and_class_maps_known_answers():
     masks = R.seg_perf_masks(ge, pe, np.array([[0, 0]]), 'reduced')
     assert [int(rle.area(m)) for m in masks] == [12, 4, 4, 0]     # TP, FN, FP, overlap classes
     assert R.merge_boxes([2, 6, 2, 6], [2, 6, 3, 7]).tolist() == [2, 6, 2, 7]
+
+
+def test_one_shot_oracle_forms_equal_the_literal_loops():
+    """tests/_util.py's one-shot forms (one rleIou call over all pairs + merges on overlapping pairs only), which the
+    native-size GPU tests use as the checker, against the literal restatement of the reference's loops
+    (oracle/ampis_ref.py) on the shipped powder fixtures and on random masks with empty, tied and full-frame cases."""
+    for k in (0, 2):
+        _, gt, pr = U.powder_match_image(k)
+        iou = U.iou_matrix_one_shot(rle, gt, pr)
+        assert np.array_equal(iou, R.piecewise_iou(gt, pr))
+        for th in (0.5, 0.75, 0.95):
+            want, got = R.det_seg_scores(gt, pr, th), U.det_seg_scores_one_shot(rle, gt, pr, th, iou=iou)
+            assert want.keys() == got.keys()
+            for key in want:
+                assert np.array_equal(np.asarray(want[key]), np.asarray(got[key])), (k, th, key)
+    s, part, sat = U.powder_satellite_image(1)
+    want, got = R.rle_satellite_match(part, sat, 0.5), U.satellite_match_one_shot(rle, part, sat, 0.5)
+    for key in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched', 'intersection_scores'):
+        assert np.array_equal(want[key], got[key]), key
+    assert {k_: list(v) for k_, v in want['match_pairs'].items()} == {k_: list(v) for k_, v in got['match_pairs'].items()}
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        h, w = int(rng.integers(3, 60)), int(rng.integers(3, 60))
+        m = U.rand_masks(rng, 22, h, w, p_empty=0.2)
+        m[3] = m[4]                                    # exact ties: the first arg-max must win
+        m[15] = m[16] = m[4]
+        m[7] = True
+        enc = [rle.encode(np.asfortranarray(x.astype(np.uint8))) for x in m]
+        gt, pr = enc[:9], enc[9:]
+        for th in (0.0, 0.3, 0.5):
+            try:
+                want = R.det_seg_scores(gt, pr, th)
+            except ZeroDivisionError:
+                with pytest.raises(ZeroDivisionError):
+                    U.det_seg_scores_one_shot(rle, gt, pr, th)
+                continue
+            got = U.det_seg_scores_one_shot(rle, gt, pr, th)
+            for key in want:
+                assert np.array_equal(np.asarray(want[key]), np.asarray(got[key]), equal_nan=True), (trial, th, key)
+        try:
+            want = R.rle_satellite_match(pr, gt, 0.4)
+        except IndexError:
+            with pytest.raises(IndexError):
+                U.satellite_match_one_shot(rle, pr, gt, 0.4)
+            continue
+        got = U.satellite_match_one_shot(rle, pr, gt, 0.4)
+        for key in ('satellite_matches', 'satellites_unmatched', 'particles_unmatched', 'intersection_scores'):
+            assert np.array_equal(want[key], got[key]), (trial, key)
