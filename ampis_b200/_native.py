@@ -52,6 +52,8 @@ SIGNATURES = {
     'ampis_intersect_tcgen05': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     'ampis_eval_image_host': (C.c_int, [_p, _p, _i32, _i32, _u32, _u32, _i32, _i32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p,
                                         _p, _p, _p, _p, _p]),
+    'ampis_eval_images_host': (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _f64, _p, _i64, _p, _i64, _p, _p, _p, _p, _p,
+                                         _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     'ampis_mma_pair_tile_rows': (C.c_int, []),
     'ampis_mma_pair_tile_cols': (C.c_int, []),
     'ampis_intersect_tcgen05_pair': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p,
@@ -78,11 +80,16 @@ SIGNATURES = {
                                        _p, _p]),
     'ampis_poly_to_rle': (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p]),
     'ampis_polygon2mask': (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
+}
+
+#: libampis_synth.so (bench / test data generator, include/ampis_synth.h) -- a separate library on purpose
+SYNTH_SIGNATURES = {
     'ampis_synth_batch': (_i64, [_u64, _i32, _u32, _u32, _i32, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64,
                                  _f64, _f64, _i32, _p, _i64, _p, _p]),
 }
 
 _lib = None
+_synth = None
 ABI_VERSION = 200       # ampis_version(): bumped whenever a signature of include/ampis_b200.h changes
 
 
@@ -110,6 +117,19 @@ def lib():
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def synth_lib():
+    """Load (building if necessary) libampis_synth.so, the synthetic-data generator.  Never touches libampis_b200.so."""
+    global _synth
+    if _synth is None:
+        l = C.CDLL(_build.build_synth())
+        for name, (res, args) in SYNTH_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _synth = l
+    return _synth
 
 
 def check(rc, what=''):

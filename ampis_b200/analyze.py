@@ -42,15 +42,18 @@ def _check_same_size(*mask_lists):
                          % (tuple(a[0].tolist()), tuple(a[bad[0]].tolist())))
 
 
-def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False):
-    """One image: rows x cols through the fused kernel. Returns host arrays + device handles."""
+def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False, crowded=None):
+    """One image: rows x cols through the table API, kernel by kernel. Returns host arrays + device handles.
+    crowded: True when the caller already knows the image belongs to the tensor-core contraction (the one-call
+    entry flagged it); None = decide here from the operand fill."""
     _check_same_size(rows_rle, cols_rle)
     # measured as bounding-box windows (the smallest storage, the fastest culled walk) ...
     table = engine.table_from_rle(list(rows_rle) + list(cols_rle), layout=engine.MATCH_LAYOUT, paint=False)
     # ... unless the image is crowded (operand fill above the measured crossover): then linear spans and the
     # tensor-core contraction.  The results are identical either way.
-    crowded = min(len(rows_rle), len(cols_rle)) >= engine.MMA_MIN_SIDE and \
-        engine.operand_fill(table) >= engine.MMA_FILL_THRESHOLD
+    if crowded is None:
+        crowded = min(len(rows_rle), len(cols_rle)) >= engine.MMA_MIN_SIDE and \
+            engine.operand_fill(table) >= engine.MMA_FILL_THRESHOLD
     if crowded and table.layout == engine.LAYOUT_CROP:
         table.relayout(engine.LAYOUT_SPAN)
     table.paint()
@@ -63,20 +66,35 @@ def _rows_vs_cols(rows_rle, cols_rle, mode, dense=False):
 FUSED_CALL = os.environ.get('AMPIS_FUSED_CALL', '1') != '0'
 
 
+def _grid_capacity_error(e):
+    """True for the one library error the table API is the answer to: boxes registered in far more grid cells than
+    the one-call entries provide for.  Everything else (CUDA failures, exhausted retries) must surface."""
+    return 'grid entry list too small' in str(e)
+
+
 def _image_rows(rows_rle, cols_rle, mode):
     """Per-row arg-max results of one image as host arrays: (best_col int64, best_score float64, best_inter int64,
-    areas uint32 of rows then columns).  Normally ONE call into the library (ampis_eval_image_host: bounding-box
-    windows, culled AND+popc); an image that turns out to be crowded (operand fill above the measured crossover,
-    known from the spans the call returns) is evaluated again through the table API with the tensor-core
-    contraction, which is where the time goes on such images.  Identical results either way."""
+    areas uint32 of rows then columns).  Normally ONE call into the library (ampis_eval_images_host: bounding-box
+    windows, candidate-pair join, culled AND+popc).  A crowded image -- candidate pairs above
+    engine.CROWD_PAIR_FRACTION of all pairs, decided on the device right after the join, before any intersection is
+    computed -- comes back flagged and goes through the table API with the tensor-core contraction instead, which is
+    where the time goes on such images.  Identical results either way.  The last result is cached on the identity of
+    the string objects, so a loop over IoU thresholds evaluates the image once."""
     G = len(rows_rle)
     if FUSED_CALL:
+        crowd = engine.CROWD_PAIR_FRACTION if min(G, len(cols_rle)) >= engine.MMA_MIN_SIDE else -1.0
         try:
-            r = engine.eval_image(rows_rle, cols_rle, mode)
-        except engine.N.AmpisNativeError:
-            r = None                      # e.g. boxes spread over very many grid cells: the table API sizes things exactly
-        if r is not None and not (min(G, len(cols_rle)) >= engine.MMA_MIN_SIDE and r.fill() >= engine.MMA_FILL_THRESHOLD):
-            return r.best_col.astype(np.int64), r.best_score, r.best_inter.astype(np.int64), r.area
+            r = engine.eval_images([rows_rle], [cols_rle], mode, crowd_frac=crowd, cache=True)
+        except engine.N.AmpisNativeError as e:
+            if not _grid_capacity_error(e):
+                raise
+            r = None                      # the table API sizes the grid exactly
+        if r is not None and not r.crowded:             # copies: the cached arrays stay untouched
+            return r.best_col.astype(np.int64), r.best_score.copy(), r.best_inter.astype(np.int64), r.area.copy()
+        if r is not None:
+            table, groups, res = _rows_vs_cols(rows_rle, cols_rle, mode, crowded=True)
+            return (res.best_col[:G].cpu().numpy().astype(np.int64), res.best_score[:G].cpu().numpy(),
+                    res.best_inter[:G].cpu().numpy().view(np.uint32).astype(np.int64), table.areas_np())
     table, groups, res = _rows_vs_cols(rows_rle, cols_rle, mode)
     return (res.best_col[:G].cpu().numpy().astype(np.int64), res.best_score[:G].cpu().numpy(),
             res.best_inter[:G].cpu().numpy().view(np.uint32).astype(np.int64), table.areas_np())
@@ -90,7 +108,9 @@ def _piecewise_iou(a, b, interval=80):
     if FUSED_CALL:
         try:
             r = engine.eval_image(a, b, engine.MODE_IOU, dense_iou=True)
-        except engine.N.AmpisNativeError:
+        except engine.N.AmpisNativeError as e:
+            if not _grid_capacity_error(e):
+                raise
             r = None
         if r is not None and not (min(imax, jmax) >= engine.MMA_MIN_SIDE and r.fill() >= engine.MMA_FILL_THRESHOLD):
             return r.iou                  # crowded images go on to the tensor-core contraction, as in _image_rows
@@ -211,36 +231,87 @@ def _scores_from_rows(G, P, best_col, best_iou, best_inter, areas_gt, areas_pred
 
 def det_seg_scores_batch(gt_list, pred_list, iou_thresh=0.5, size=None):
     """``det_seg_scores`` for many images at once -- not in the reference API, which scores one image
-    per Python call (Colab cell 44 loops over the dataset).  All images go through ONE mask table and
-    ONE launch of each kernel; the result is the list of per-image dicts the loop would have produced,
-    key for key and bit for bit.  Images with no ground truth or no predictions raise ZeroDivisionError
-    like the per-image function."""
+    per Python call (Colab cell 44 loops over the dataset: ``[det_seg_scores(g, p) for g, p in zip(gt, pred)]``).
+    All images go through ONE library call (engine.eval_images -> ampis_eval_images_host: the strings are picked up
+    where Python keeps them, one upload, one launch of each kernel, one download) and the bookkeeping of
+    analyze.py:300-339 is done for all images at once on flat arrays; the result is the list of per-image dicts the
+    loop would have produced, key for key and bit for bit.  Images with no ground truth or no predictions raise
+    ZeroDivisionError like the per-image function."""
     assert len(gt_list) == len(pred_list)
     gts = [masks_to_rle(g, size) for g in gt_list]
     prs = [masks_to_rle(p, size) for p in pred_list]
-    for g, p in zip(gts, prs):
-        _check_same_size(g, p)
     n_img = len(gts)
     if n_img == 0:
         return []
-    flat = [m for g, p in zip(gts, prs) for m in list(g) + list(p)]
-    Gs, Ps = [len(g) for g in gts], [len(p) for p in prs]
-    if not flat:
+    if sum(map(len, gts)) + sum(map(len, prs)) == 0:
         raise ZeroDivisionError('division by zero')
-    table = engine.table_from_rle(flat, layout=engine.MATCH_LAYOUT)
-    groups = engine.Groups.interleaved(table.device, Gs, Ps)
-    res = engine.intersect_rows(table, groups, engine.MODE_IOU)
-    n_rows = groups.n_rows
-    best_col = res.best_col[:n_rows].cpu().numpy().astype(np.int64)
-    best_iou = res.best_score[:n_rows].cpu().numpy()
-    best_inter = res.best_inter[:n_rows].cpu().numpy().view(np.uint32).astype(np.int64)
-    areas = table.areas_np()
-    out, r0, m0 = [], 0, 0
-    for G, P in zip(Gs, Ps):
-        out.append(_scores_from_rows(G, P, best_col[r0:r0 + G], best_iou[r0:r0 + G], best_inter[r0:r0 + G],
-                                     areas[m0:m0 + G], areas[m0 + G:m0 + G + P], iou_thresh))
-        r0 += G
-        m0 += G + P
+    # the crowd gate only matters when some image is large enough for the contraction to pay off
+    big = max(min(len(g), len(p)) for g, p in zip(gts, prs)) >= engine.MMA_MIN_SIDE
+    try:
+        r = engine.eval_images(gts, prs, engine.MODE_IOU, crowd_frac=engine.CROWD_PAIR_FRACTION if big else -1.0)
+    except engine.N.AmpisNativeError as e:
+        if not _grid_capacity_error(e):
+            raise
+        r = None
+    if r is None or r.crowded:             # crowded batch: image by image (each picks its kernel)
+        return [det_seg_scores(g, p, iou_thresh) for g, p in zip(gts, prs)]
+    return _scores_from_rows_batch(r, iou_thresh)
+
+
+def _scores_from_rows_batch(r, iou_thresh):
+    """analyze.py:166-179 + 300-339 for all images of an engine.ImagesRows at once: every array is formed over the
+    concatenated rows / predictions and cut into per-image views at the end (the per-image Python work is a dozen
+    slices)."""
+    n_img = len(r.n_rows)
+    G, P = r.n_rows.astype(np.int64), r.n_cols.astype(np.int64)
+    row_off, mask_off = r.row_off, r.mask_off
+    pred_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(P, out=pred_off[1:])
+    img_of_row = np.repeat(np.arange(n_img), G)
+    img_of_pred = np.repeat(np.arange(n_img), P)
+    best_col = r.best_col.astype(np.int64)
+    matched = r.best_score > iou_thresh
+    gt_local = np.arange(len(matched), dtype=np.int64) - row_off[img_of_row]
+    m_img = img_of_row[matched]
+    m_gt, m_pr = gt_local[matched], best_col[matched]
+    n_tp = np.bincount(m_img, minlength=n_img)
+    pm = np.zeros(int(pred_off[-1]), bool)
+    pm[pred_off[m_img] + m_pr] = True
+    fp_glob = np.nonzero(~pm)[0]
+    fp_local = (fp_glob - pred_off[img_of_pred[fp_glob]]).astype(int)
+    n_fp = P - np.bincount(img_of_pred[pm], minlength=n_img)
+    fn_glob = np.nonzero(~matched)[0]
+    fn_local = gt_local[fn_glob].astype(int)
+    n_fn = G - n_tp
+    bad = np.nonzero((n_tp + n_fp == 0) | (n_tp + n_fn == 0))[0]
+    if len(bad):
+        raise ZeroDivisionError('division by zero')      # image %d has no ground truth or no predictions
+    tp = np.stack([m_gt, m_pr], axis=1).astype(int)
+    inter = r.best_inter[matched].astype(np.int64)
+    a_gt = r.area[mask_off[m_img] + m_gt].astype(np.int64)
+    a_pr = r.area[mask_off[m_img] + G[m_img] + m_pr].astype(np.int64)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        seg_p = inter / (inter + (a_pr - inter))
+        seg_r = inter / (inter + (a_gt - inter))
+    seg_fn, seg_fp = a_gt - inter, a_pr - inter
+    iou = r.best_score[matched]
+    t_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(n_tp, out=t_off[1:])
+    fp_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(n_fp, out=fp_off[1:])
+    fn_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(n_fn, out=fn_off[1:])
+    empty_tp = np.asarray([], int)
+    out = []
+    for g in range(n_img):
+        a, b = int(t_off[g]), int(t_off[g + 1])
+        ntp, nfp, nfn = b - a, int(n_fp[g]), int(n_fn[g])
+        out.append({'det_precision': ntp / (ntp + nfp), 'det_recall': ntp / (ntp + nfn),
+                    'seg_precision': seg_p[a:b], 'seg_recall': seg_r[a:b],
+                    'det_tp': tp[a:b] if ntp else empty_tp,
+                    'det_fn': fn_local[int(fn_off[g]):int(fn_off[g + 1])],
+                    'det_fp': fp_local[int(fp_off[g]):int(fp_off[g + 1])],
+                    'seg_tp': inter[a:b], 'seg_fn': seg_fn[a:b], 'seg_fp': seg_fp[a:b], 'det_tp_iou': iou[a:b]})
     return out
 
 

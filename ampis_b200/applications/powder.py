@@ -110,7 +110,8 @@ _PSD_X = {'d_eq': ('Equivalent diameter', ', {}'), 'area': ('Mask area', '- ${}^
 _PSD_Y = {'cvf': 'cumulative volume fraction', 'counts': 'counts (cumulative)'}
 
 
-def psd(particles, xvals='d_eq', yvals='cvf', c=None, distance='length', ax=None, plot=True, return_results=False):
+def psd(particles, xvals='d_eq', yvals='cvf', c=None, distance='length', ax=None, plot=True, return_results=False,
+        _areas_of=None):
     """Cumulative particle size distribution (reference powder.py:288-461).
 
     Areas come from the GPU measurement pass; they are scaled to length units by *c* (a number, one
@@ -119,7 +120,11 @@ def psd(particles, xvals='d_eq', yvals='cvf', c=None, distance='length', ax=None
     ``d_eq = 2 sqrt(A / pi)`` when ``xvals='d_eq'``, weighted by the sphere volume
     ``4/3 pi^(-1/2) A^(3/2)`` when ``yvals='cvf'``, accumulated and normalised to end at 1.  The same
     arguments raise the same ``ValueError``s as the reference.  Nothing is drawn unless an axis is
-    passed (matplotlib is not a dependency); ``return_results=True`` returns the curve and labels."""
+    passed (matplotlib is not a dependency); ``return_results=True`` returns the curve and labels.
+    ``_areas_of`` (internal): replaces the per-image area measurement -- ``distributed.psd_sharded`` passes the
+    sharded, all-gathered form, everything after it is this very code on every rank."""
+    if _areas_of is None:
+        _areas_of = lambda items: [mask_areas(item) for item in items]
     xkey, ykey, how = xvals.lower(), yvals.lower(), distance.lower()
     units = ''
     if type(c) == tuple:
@@ -128,7 +133,7 @@ def psd(particles, xvals='d_eq', yvals='cvf', c=None, distance='length', ax=None
         particles = [particles]
     if type(particles[0]) == PowderSatelliteImage:
         particles = [item.particles for item in particles]
-    per_image = [mask_areas(item) for item in particles]          # the reference's list branch is dead (quirk B.6)
+    per_image = _areas_of(particles)                              # the reference's list branch is dead (quirk B.6)
 
     if how == 'length':
         if c is None:
@@ -143,7 +148,7 @@ def psd(particles, xvals='d_eq', yvals='cvf', c=None, distance='length', ax=None
             raise ValueError('c (or c[0] if passed as tuple) must be a list, array, int, or float')
     elif how == 'pixels':
         units = 'px'
-        per_image = mask_areas(particles)                            # recomputed, as in the reference (powder.py:410)
+        per_image = _areas_of(particles)                             # recomputed, as in the reference (powder.py:410)
     else:
         raise ValueError('distance must be "length" or "pixels"')
     areas = np.concatenate(per_image, axis=0) if type(per_image[0]) in (list, np.ndarray) else per_image
@@ -181,6 +186,35 @@ _SUMMARY_ROWS = (('n_images', 'number of images'),
                  ('mspp', 'median number of satellites per\nsatellited particle             '))
 
 
+def _satellite_summary(per_particle, n_images, n_particles_unmatched, n_satellites_unmatched, n_particle_instances,
+                       n_satellite_instances):
+    """The dataset-level numbers of powder.py:525-562 from the satellites-per-satellited-particle list and four
+    sums (shared by satellite_measurements and distributed.satellite_measurements_sharded, which gathers exactly
+    these quantities from all ranks)."""
+    per_particle = np.asarray(per_particle)
+    out = {'n_images': n_images}
+    satellited = len(per_particle)
+    out['n_particles'] = satellited + n_particles_unmatched
+    out['n_satellites'] = sum(per_particle)
+    out['n_satellites_unmatched'] = n_satellites_unmatched
+    out['n_satellited_particels'] = satellited
+    out['sat_frac'] = satellited / out['n_particles']
+    out['mspp'] = np.median(per_particle)
+    values, freq = np.unique(per_particle, return_counts=True)
+    # consistency with the instance lists themselves (the reference asserts the same three sums)
+    assert freq.sum() == satellited
+    assert out['n_particles'] == n_particle_instances
+    assert out['n_satellites'] + out['n_satellites_unmatched'] == n_satellite_instances
+    out['unique_satellites_per_particle'] = values
+    out['counts_satellites_per_particle'] = freq.cumsum() / freq.sum()
+    return out
+
+
+def _print_summary(out):
+    for key, label in _SUMMARY_ROWS:
+        print('{:35}\t{}'.format(label, out[key]))
+
+
 def satellite_measurements(psi, print_summary=True, output_dict=False):
     """Satellite content of a set of images (reference powder.py:463-569): totals, the fraction of
     particles that carry satellites, the median number of satellites per satellited particle and
@@ -194,24 +228,13 @@ def satellite_measurements(psi, print_summary=True, output_dict=False):
     found = [im.matches for im in images]
 
     per_particle = np.asarray([len(sats) for m in found for sats in m['match_pairs'].values()])
-    out = {'n_images': len(images)}
-    satellited = sum(len(m['match_pairs']) for m in found)
-    out['n_particles'] = satellited + sum(len(m['particles_unmatched']) for m in found)
-    out['n_satellites'] = sum(per_particle)
-    out['n_satellites_unmatched'] = sum(len(m['satellites_unmatched']) for m in found)
-    out['n_satellited_particels'] = satellited
-    out['sat_frac'] = satellited / out['n_particles']
-    out['mspp'] = np.median(per_particle)
-    values, freq = np.unique(per_particle, return_counts=True)
-    # consistency with the instance lists themselves (the reference asserts the same three sums)
-    assert freq.sum() == satellited
-    assert out['n_particles'] == sum(len(im.particles.instances) for im in images)
-    assert out['n_satellites'] + out['n_satellites_unmatched'] == sum(len(im.satellites.instances) for im in images)
-    out['unique_satellites_per_particle'] = values
-    out['counts_satellites_per_particle'] = freq.cumsum() / freq.sum()
+    out = _satellite_summary(per_particle, len(images),
+                             sum(len(m['particles_unmatched']) for m in found),
+                             sum(len(m['satellites_unmatched']) for m in found),
+                             sum(len(im.particles.instances) for im in images),
+                             sum(len(im.satellites.instances) for im in images))
 
     if print_summary:
-        for key, label in _SUMMARY_ROWS:
-            print('{:35}\t{}'.format(label, out[key]))
+        _print_summary(out)
     if output_dict:
         return out

@@ -69,9 +69,18 @@ class HostCSR(object):
     def total_runs(self):
         return int(self.cnt_len.sum())
 
+    def slice(self, i0, i1):
+        """Images [i0, i1) as a HostCSR of their own (run counts copied out, offsets rebased)."""
+        a, b = i0 * self.per_image, i1 * self.per_image
+        off, ln = self.cnt_off[a:b], self.cnt_len[a:b]
+        if b <= a:
+            return HostCSR(self.cfg, 0, np.zeros(0, np.uint32), off.copy(), ln.copy())
+        lo, hi = int(off.min()), int((off + ln).max())
+        return HostCSR(self.cfg, i1 - i0, self.cnt[lo:hi].copy(), off - lo, ln.copy())
+
 
 def synth(cfg, n_images, seed, jitter_px=2.0, scale_sigma=0.05, drop_frac=0.08, empty_frac=0.01, n_threads=None):
-    """Generate a synthetic batch on the host (csrc/synth.cpp).  In satellite configs the primaries
+    """Generate a synthetic batch on the host (synth/synth.cpp -> libampis_synth.so, bench / test data only).  In satellite configs the primaries
     are the particles (columns) and the secondaries the satellites (rows); the generator emits
     primaries first, so the masks are re-ordered to rows-first here."""
     if isinstance(cfg, str):
@@ -87,7 +96,7 @@ def synth(cfg, n_images, seed, jitter_px=2.0, scale_sigma=0.05, drop_frac=0.08, 
     cnt_len = np.zeros(max(n, 1), np.int32)
     while True:
         cnt = np.empty(cap, np.uint32)
-        r = N.lib().ampis_synth_batch(int(seed), n_images, cfg['h'], cfg['w'], n_gt, n_sec, kind,
+        r = N.synth_lib().ampis_synth_batch(int(seed), n_images, cfg['h'], cfg['w'], n_gt, n_sec, kind,
                                       float(cfg['median_diam']), float(cfg['sigma_ln']), float(cfg['max_aspect']),
                                       float(cfg['sec_median_diam']), float(jitter_px), float(scale_sigma),
                                       float(drop_frac), float(empty_frac), int(n_threads),

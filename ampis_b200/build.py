@@ -78,6 +78,63 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _build_host_lib(src, out, cmd_head, extra_digest=''):
+    """Compile one host-only source into `out` when missing or built from other contents (digest beside it);
+    locked and renamed into place like build()."""
+    import fcntl
+    import hashlib
+    with open(src, 'rb') as f:
+        digest = hashlib.sha256(f.read() + extra_digest.encode()).hexdigest()
+    dpath = out + '.digest'
+    fresh = lambda: os.path.exists(out) and os.path.exists(dpath) and open(dpath).read().strip() == digest
+    if fresh():
+        return out
+    with open(out + '.lock', 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if fresh():
+                return out
+            tmp = '%s.tmp.%d' % (out, os.getpid())
+            try:
+                subprocess.check_call(cmd_head + ['-o', tmp, src])
+                os.replace(tmp, out)
+                with open(dpath, 'w') as f:
+                    f.write(digest + '\n')
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return out
+
+
+SYNTH_SRC = os.path.join(HERE, 'synth', 'synth.cpp')
+SYNTH = os.path.join(HERE, 'libampis_synth.so')
+
+
+def build_synth():
+    """libampis_synth.so: the synthetic micrograph generator (bench / test data only; plain g++, no CUDA)."""
+    return _build_host_lib(SYNTH_SRC, SYNTH, [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-shared', '-fPIC',
+                                              '-Wall', '-pthread'])
+
+
+MARSHAL_SRC = os.path.join(HERE, 'cext', 'pymarshal.c')
+MARSHAL = os.path.join(HERE, '_pymarshal.so')
+
+
+def build_marshal(force=False):
+    """Compile the CPython extension ampis_b200._pymarshal (host marshaller, plain C, gcc) in-tree."""
+    import sysconfig
+    if force and os.path.exists(MARSHAL + '.digest'):
+        os.unlink(MARSHAL + '.digest')
+    return _build_host_lib(MARSHAL_SRC, MARSHAL, [os.environ.get('CC', 'gcc'), '-O2', '-shared', '-fPIC', '-Wall', '-I',
+                                                  sysconfig.get_paths()['include']], extra_digest=sys.version)
+
+
 if __name__ == '__main__':
     build(force='--force' in sys.argv, verbose='-v' in sys.argv)
+    build_marshal(force='--force' in sys.argv)
+    build_synth()
     print(LIB)
+    print(MARSHAL)
+    print(SYNTH)

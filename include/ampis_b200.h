@@ -260,6 +260,35 @@ int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_off, int32_t 
                           int32_t *bbox, uint32_t *span, int32_t *status, double *iou_out, int64_t *need_bytes,
                           void *stream);
 
+/* ---- many images, one call (host entry point) -------------------------------------------------------
+ * The loop a user of the reference writes around det_seg_scores / _rle_satellite_match (Colab cell 44 ->
+ * analyze.py:226-339; cell 62 -> powder.py:138 -> powder.py:28-112), i.e. per image analyze.py:149-164 or
+ * powder.py:80-86, for n_images images in ONE call from HOST string descriptors: str_ptr[k] / str_len[k] = address
+ * and length of the k-th compressed RLE string, image after image, rows (ground truth / satellites) of an image
+ * before its columns (predictions / particles); n_rows[g], n_cols[g], h[g], w[g] per image.  The strings are
+ * gathered into h_ws (pinned), uploaded with one copy, decoded (rleFrString), measured and painted as windows (flat
+ * decode), the columns binned into per-image grids, candidate pairs joined, intersected and reduced to per-row
+ * results; one download, ONE stream synchronisation.  Outputs: best_col / best_inter / best_score for all rows
+ * (concatenated in image order; best_col counts inside the image), area / bbox / span / status for all masks.
+ * *pairs_found = candidate pairs (overlapping boxes).  crowd_frac in [0, 1): when the candidate pairs exceed that
+ * fraction of all row x column pairs the AND+popc pass is skipped ON THE DEVICE and *crowded = 1 is returned (the
+ * per-row outputs are void; measurements are valid) -- such batches belong to ampis_intersect_tcgen05; pass a
+ * negative value to disable.  flags & AMPIS_STRINGS_CONTIGUOUS: the caller's strings already lie back to back
+ * starting at str_ptr[0] (e.g. a blob in pinned memory): they are uploaded from where they are, nothing is gathered.
+ * bbox and span may be NULL (not downloaded).  n_thresh > 0 (AMPIS_MODE_IOU): TP / FP / FN of the matcher
+ * (analyze.py:166-174) at every IoU threshold, grp_counts int32[n_images][n_thresh][3] and totals int64[n_thresh][3],
+ * counted on the device (ampis_match_counts) before the download.  Batches of more than 16,384 masks form their per-mask bookkeeping
+ * on the device (expand_images_kernel + offset scan), so the host work per call is O(n_images) plus the gather.
+ * Workspaces and AMPIS_ENOSPC protocol as ampis_eval_image_host. */
+#define AMPIS_STRINGS_CONTIGUOUS 1   /* flags: the strings lie back to back from str_ptr[0] (only that pointer is read) */
+int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32_t *str_len, int32_t n_images,
+                           const int32_t *n_rows, const int32_t *n_cols, const uint32_t *h, const uint32_t *w,
+                           int32_t mode, int32_t flags, double crowd_frac, void *d_ws, int64_t d_ws_bytes, void *h_ws,
+                           int64_t h_ws_bytes, int32_t *best_col, uint32_t *best_inter, double *best_score,
+                           uint32_t *area, int32_t *bbox, uint32_t *span, int32_t *status,
+                           const double *thresholds, int32_t n_thresh, int32_t *grp_counts, int64_t *totals,
+                           int64_t *pairs_found, int32_t *crowded, int64_t *need_bytes, void *stream);
+
 /* ---- dense intersection matrices on the tensor cores (tcgen05, int8 contraction) -----------
  * Same quantity as the dense output of ampis_intersect_rows -- I[r][c] = popcount(row AND col),
  * what rleIou's run walk accumulates per pair (analyze.py:108,158; powder.py:82) -- computed for
@@ -440,18 +469,6 @@ int ampis_poly_to_rle(const double *d_xy, const int64_t *d_xy_off, const uint32_
  * of all polygons (the same layout as ampis_poly_to_rle).  d_out: u8[n][h][w], zeroed here. */
 int ampis_polygon2mask(const double *d_xy, const int64_t *d_xy_off, int32_t n, int32_t h, int32_t w,
                        uint8_t *d_out, void *stream);
-
-/* ---- synthetic micrograph generator (bench / test data only; HOST code, host buffers) ----
- * Deterministic powder-like images: per image n_gt primary blobs followed by n_sec secondary
- * masks (kind 0: predictions of the primaries -- jitter, scale, drop_frac dropped and replaced
- * by spurious blobs, shuffled; kind 1: satellites, 85 % on primary rims).  Writes the run
- * counts of all n_images*(n_gt+n_sec) masks (image-major, primaries first) as CSR.
- * Returns the number of counts written; if cnt_capacity is too small returns -(needed). */
-int64_t ampis_synth_batch(uint64_t seed, int32_t n_images, uint32_t h, uint32_t w, int32_t n_gt,
-                          int32_t n_sec, int32_t kind, double median_diam, double sigma_ln,
-                          double max_aspect, double sec_median_diam, double jitter_px,
-                          double scale_sigma, double drop_frac, double empty_frac, int32_t n_threads,
-                          uint32_t *cnt, int64_t cnt_capacity, int64_t *cnt_off, int32_t *cnt_len);
 
 #ifdef __cplusplus
 }

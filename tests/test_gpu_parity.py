@@ -1047,8 +1047,8 @@ def test_public_api_takes_the_tensor_core_path_on_crowded_images(mods, monkeypat
     assert np.array_equal(A._piecewise_iou(gt, pr), R.piecewise_iou(gt, pr)) and used == ['mma', 'mma']
     _, g2, p2 = U.powder_match_image(0)
     calls = []
-    real_eval = E.eval_image
-    monkeypatch.setattr(E, 'eval_image', lambda *a: (calls.append(1), real_eval(*a))[1])
+    real_eval = E.eval_images
+    monkeypatch.setattr(E, 'eval_images', lambda *a, **k: (calls.append(1), real_eval(*a, **k))[1])
     n_before = len(used)
     one_call = A.rle_instance_matcher(g2, p2)                  # ordinary image: ONE library call, no table API
     assert calls == [1] and len(used) == n_before
@@ -1217,21 +1217,25 @@ def test_native_size_c4_image_vs_oracle(mods, decode, rows_kernel, monkeypatch):
     A, B, E, S, rle = mods.analyze, mods.batch, mods.engine, mods.structures, mods.rle
     monkeypatch.setattr(E, 'CROP_DECODE', decode)
     monkeypatch.setattr(E, 'ROWS_KERNEL', rows_kernel)
+    if (decode, rows_kernel) != ('flat', 'pairs'):       # the one-call entries always run flat + pairs: the other
+        monkeypatch.setattr(A, 'FUSED_CALL', False)      # kernels are reached through the table API
     host = B.synth('c4_spheroidite', 1, 4004)
     assert (host.h, host.w, host.n_rows, host.n_cols) == (2048, 2048, 5000, 5000)
     gt, pr = _dicts(mods, host)
     iou = U.iou_matrix_one_shot(rle, gt, pr)
-    for th in (0.5, 0.75, 0.9):
+    for th in (0.1, 0.5, 0.75):
         want = U.det_seg_scores_one_shot(rle, gt, pr, th, iou=iou)
         got = A.det_seg_scores(gt, pr, th)
         assert want.keys() == got.keys()
         for k in want:
             assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), (th, k)
-        assert len(want['det_tp']) > 1000
+    # 13-px blobs displaced by N(0, 2 px): most pairs overlap, few reach IoU 0.5
+    assert len(U.match_from_iou(iou, 0.1)['tp']) > 2000 and len(U.match_from_iou(iou, 0.5)['tp']) > 50
     # through the table API as bench.py drives it (crop layout, sparse triplets)
     dev = B.DeviceBatch(host, dense=False)
     sp = E.SparseRows('cuda', 64 * host.n_rows)
-    res = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, kernel='grid', sparse=sp)
+    arena = mods.torch.empty(4 * B.arena_chunks_needed(dev, E.LAYOUT_CROP), dtype=mods.torch.int32, device='cuda')
+    res = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, kernel='grid', sparse=sp, arena=arena)   # fused decode
     r, c, v = (x.cpu().numpy() for x in sp.triplets())
     wr, wc = np.nonzero(iou)
     assert np.array_equal(r, wr) and np.array_equal(c, wc)
@@ -1262,6 +1266,8 @@ def test_native_size_c3_image_vs_oracle(mods, decode, rows_kernel, monkeypatch):
     B, E, P, rle = mods.batch, mods.engine, mods.powder, mods.rle
     monkeypatch.setattr(E, 'CROP_DECODE', decode)
     monkeypatch.setattr(E, 'ROWS_KERNEL', rows_kernel)
+    if (decode, rows_kernel) != ('flat', 'pairs'):
+        monkeypatch.setattr(mods.analyze, 'FUSED_CALL', False)
     host = B.synth('c3_satellites', 2, 3003)
     assert (host.h, host.w, host.n_rows, host.n_cols) == (2048, 2048, 200, 2000)
     for g in range(2):
@@ -1274,9 +1280,88 @@ def test_native_size_c3_image_vs_oracle(mods, decode, rows_kernel, monkeypatch):
         assert 100 < len(want['satellite_matches']) < 200
     # the batch step on the same two frames: per-image counts
     dev = B.DeviceBatch(host, dense=False)
-    res = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True)
+    arena = mods.torch.empty(4 * B.arena_chunks_needed(dev, E.LAYOUT_CROP), dtype=mods.torch.int32, device='cuda')
+    res = B.eval_step(dev, layout=E.LAYOUT_CROP, check=True, arena=arena)
     for g in range(2):
         sat, part = _dicts(mods, host, g)
         want = U.satellite_match_one_shot(rle, part, sat, 0.5)
         assert res.counts.cpu().numpy()[g].tolist() == [len(want['satellite_matches']), len(want['satellites_unmatched']),
                                                         len(want['match_pairs']), host.n_cols]
+
+
+def test_many_images_one_call_entry(mods, monkeypatch):
+    """engine.eval_images (ampis_eval_images_host: string descriptors from the C marshaller, one upload, one launch
+    of each kernel, one download for ALL images) == the per-image entry image by image: mixed image sizes and
+    instance counts in one call, empty images, str / bytearray counts, both modes; the result cache; the crowd gate."""
+    A, B, E, P, rle = mods.analyze, mods.batch, mods.engine, mods.powder, mods.rle
+    imgs = []
+    for k, (cfg, over) in enumerate([('c1_powder_example', {}), ('c2_powder_batch', {}),
+                                     ('c4_spheroidite', dict(n_rows=900, n_cols=1100, h=1024, w=1024)),
+                                     ('c2_powder_batch', dict(h=70, w=45, n_rows=9, n_cols=11, median_diam=30.0)),
+                                     ('c3_satellites', dict(h=1024, w=1024, n_cols=700))]):
+        host = B.synth(dict(B.CONFIGS[cfg], **over), 1, 900 + k)
+        imgs.append(_dicts(mods, host))
+    imgs.insert(2, ([], imgs[0][1][:5]))                        # no rows
+    imgs.insert(4, (imgs[0][0][:7], []))                        # no columns
+    imgs[3] = ([dict(m, counts=m['counts'].decode('ascii')) for m in imgs[3][0]],            # str counts
+               [dict(m, counts=bytearray(m['counts']), size=tuple(m['size'])) for m in imgs[3][1]])
+    for mode in (E.MODE_IOU, E.MODE_SAT):
+        r = E.eval_images([x[0] for x in imgs], [x[1] for x in imgs], mode)
+        assert not r.crowded and r.pairs_found > 0
+        for g, (rows, cols) in enumerate(imgs):
+            one = E.eval_image(rows, cols, mode)
+            r0, r1, m0, m1 = int(r.row_off[g]), int(r.row_off[g + 1]), int(r.mask_off[g]), int(r.mask_off[g + 1])
+            assert np.array_equal(r.area[m0:m1], one.area) and np.array_equal(r.bbox[m0:m1], one.bbox), (mode, g)
+            assert np.array_equal(r.span[m0:m1], one.span), (mode, g)
+            if len(rows) and len(cols):
+                assert np.array_equal(r.best_col[r0:r1], one.best_col), (mode, g)
+                assert np.array_equal(r.best_inter[r0:r1], one.best_inter), (mode, g)
+                assert np.array_equal(r.best_score[r0:r1], one.best_score, equal_nan=True), (mode, g)
+                assert abs(r.fill(g) - one.fill()) < 1e-12
+    # errors: mixed sizes inside an image, malformed RLE, wrong types
+    with pytest.raises(ValueError, match='different image sizes'):
+        E.eval_images([imgs[0][0]], [imgs[1][1]], E.MODE_IOU)
+    bad = [{'size': [45, 37], 'counts': rle.string_from_counts(np.array([3, 5000, 7, 900], np.uint32))}]
+    with pytest.raises(ValueError, match='malformed RLE'):
+        E.eval_images([bad, imgs[0][0]], [bad, imgs[0][1]], E.MODE_IOU)
+    with pytest.raises(TypeError):
+        E.eval_images([[{'size': [4, 4], 'counts': 7}]], [[]], E.MODE_IOU)
+    # the cache: same string objects -> no second evaluation; new objects with the same content -> evaluated again
+    calls = []
+    real = E.N.lib().ampis_eval_images_host
+    gt, pr = imgs[0]
+    first = A.det_seg_scores(gt, pr, 0.5)
+
+    class Spy(object):
+        def __getattr__(self, name):
+            if name == 'ampis_eval_images_host':
+                return lambda *a: (calls.append(1), real(*a))[1]
+            return getattr(E.N._lib, name)
+    lib = E.N.lib()
+    monkeypatch.setattr(E.N, 'lib', lambda: Spy())
+    for th in (0.5, 0.6, 0.7, 0.95):
+        res = A.det_seg_scores(gt, pr, th)
+    assert calls == [] and all(np.array_equal(np.asarray(res[k]), np.asarray(mods.R.det_seg_scores(gt, pr, 0.95)[k])) for k in res)
+    gt2 = [dict(m, counts=bytes(bytearray(m['counts']))) for m in gt]           # equal content, other objects
+    again = A.det_seg_scores(gt2, pr, 0.5)
+    assert calls == [1] and all(np.array_equal(np.asarray(again[k]), np.asarray(first[k])) for k in first)
+    gt2[0] = dict(gt2[0], counts=gt2[1]['counts'])                                # content changed in place
+    changed = A.det_seg_scores(gt2, pr, 0.5)
+    assert calls == [1, 1]
+    want = mods.R.det_seg_scores(gt2, pr, 0.5)
+    assert all(np.array_equal(np.asarray(changed[k]), np.asarray(want[k])) for k in want)
+    monkeypatch.setattr(E.N, 'lib', lambda: lib)
+    # the crowd gate: a crowded image comes back flagged without its intersections having been computed
+    host = B.synth(dict(B.CONFIGS['dense_overlap'], h=128, w=128, n_rows=70, n_cols=90, median_diam=70.0), 1, 5)
+    cg, cp = _dicts(mods, host)
+    r = E.eval_images([cg], [cp], E.MODE_IOU, crowd_frac=E.CROWD_PAIR_FRACTION)
+    assert r.crowded and r.pairs_found > E.CROWD_PAIR_FRACTION * 70 * 90
+    full = E.eval_images([cg], [cp], E.MODE_IOU)                                   # gate off: the culled walk does it all
+    one = E.eval_image(cg, cp, E.MODE_IOU)
+    assert not full.crowded and np.array_equal(full.best_col, one.best_col) and np.array_equal(full.best_score, one.best_score)
+    assert np.array_equal(r.area, one.area)                                        # measurements are valid either way
+    # batch scoring on a mix that contains a crowded image: still the per-image dicts
+    res = A.det_seg_scores_batch([gt, cg], [pr, cp], 0.5)
+    for got, (a_, b_) in zip(res, [(gt, pr), (cg, cp)]):
+        want = mods.R.det_seg_scores(a_, b_, 0.5)
+        assert all(np.array_equal(np.asarray(got[k]), np.asarray(want[k])) for k in want)
