@@ -58,6 +58,8 @@ SIGNATURES = {
     'ampis_mma_pair_tile_cols': (C.c_int, []),
     'ampis_intersect_tcgen05_pair': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p,
                                                _p]),
+    'ampis_tma_tile': (C.c_int, []),
+    'ampis_intersect_tma': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     'ampis_rows_from_imat': (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p]),
     'ampis_iou_matrix_f64': (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p]),
     'ampis_match_counts': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p]),

@@ -17,6 +17,13 @@ from . import engine
 
 COCO_THRESHOLDS = np.arange(0.5, 1.0, 0.05)     # IoU 0.50:0.05:0.95
 
+#: Pipeline: zero the dense matrices of the join on a side stream while the decode kernel runs ('1': fill kernel, '2':
+#: device-to-device copies from a block of zeros).  Measured on C2 (profiles/experiments_r02.md): no gain -- the fill
+#: kernel takes the SMs it needs from the decode (1.331 vs 1.333 ms per step), the copy engines are slower than the
+#: fill (1.505 ms) -- so the default stays in line ('0').
+ZERO_AHEAD = os.environ.get('AMPIS_ZERO_AHEAD', '0') != '0'
+ZERO_BY_COPY = os.environ.get('AMPIS_ZERO_AHEAD', '0') == '2' 
+
 #: synthetic workloads named after BASELINE.json's configs (DESIGN.md "Synthetic data")
 CONFIGS = {
     # C1: one 1024x768 powder image, ~300 GT x ~300 predictions
@@ -185,6 +192,7 @@ class Pipeline(object):
         # crop layout: candidates through a uniform grid ('grid', or 'rows' with many columns per image)
         # instead of the scan of all columns ('scan'); the entry list is sized once from a dry run
         self.grid, self.sparse, self.pairs = None, None, None
+        self.zero_stream = self.zero_done = self.zero_block = None
         if layout == engine.LAYOUT_CROP and (kernel == 'grid' or sparse_capacity is not None or (
                 kernel == 'rows' and batch.groups.max_cols >= engine.ROWS_GRID_MIN_COLS)):
             probe = engine.MaskTable(dev, batch.host.n_masks, batch.cnt, batch.cnt_off, batch.cnt_len, batch.h,
@@ -225,6 +233,29 @@ class Pipeline(object):
     def launch(self, mark=None):
         """Enqueue the kernels on the current stream; `mark(i)` is called between kernel groups."""
         t = self.table
+        g = self.batch.groups
+        # dense matrices of the join: zeroed on a side stream while the decode kernel (instruction bound, a few % of
+        # HBM) runs on the main one -- the rows only patch the non-zero cells afterwards
+        zero_ahead = self.pairs is not None and g.imat_off is not None and self.rows.imat is not None and \
+            engine.ROWS_KERNEL == 'pairs' and ZERO_AHEAD
+        if zero_ahead:
+            main = torch.cuda.current_stream()
+            if self.zero_stream is None:
+                self.zero_stream, self.zero_done = torch.cuda.Stream(device=self.batch.device), torch.cuda.Event()
+            self.zero_stream.wait_stream(main)          # whoever used the matrices before is done
+            with torch.cuda.stream(self.zero_stream):
+                if ZERO_BY_COPY:
+                    # device-to-device copies from a block of zeros: work for the copy engines, which idle during the
+                    # decode, instead of a fill kernel that competes with it for the SMs
+                    if self.zero_block is None:
+                        self.zero_block = torch.zeros(16 << 20, dtype=torch.int32, device=self.batch.device)
+                    zb = self.zero_block.numel()
+                    for o in range(0, g.imat_size, zb):
+                        k = min(zb, g.imat_size - o)
+                        self.rows.imat[o:o + k].copy_(self.zero_block[:k], non_blocking=True)
+                else:
+                    self.rows.imat[:g.imat_size].zero_()
+                self.zero_done.record()
         if mark: mark(0)
         if self.fused:
             if mark: mark(1)
@@ -239,7 +270,7 @@ class Pipeline(object):
                                  pair=self.kernel == 'mma2')
         else:
             engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows, grid=self.grid,
-                                  sparse=self.sparse, pairs=self.pairs)
+                                  sparse=self.sparse, pairs=self.pairs, zeroed=self.zero_done if zero_ahead else None)
         if mark: mark(3)
         if self.batch.mode == engine.MODE_IOU:
             engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)

@@ -61,8 +61,13 @@ static PyObject *gather(PyObject *self, PyObject *args)
         if (!inner) goto done;
         const Py_ssize_t n = PySequence_Fast_GET_SIZE(inner);
         const Py_ssize_t k0 = k;
+        PyObject **items = PySequence_Fast_ITEMS(inner);
         for (Py_ssize_t i = 0; i < n; i++, k++) {
-            PyObject *m = PySequence_Fast_GET_ITEM(inner, i);
+            PyObject *m = items[i];
+            /* the walk is a chain of cache misses (dict -> its table -> the bytes object / the size list); ask for
+             * the objects a few masks ahead so that the misses of neighbouring masks overlap */
+            if (i + 8 < n) __builtin_prefetch(items[i + 8]);
+            if (i + 4 < n && PyDict_Check(items[i + 4])) __builtin_prefetch(((PyDictObject *)items[i + 4])->ma_keys);
             if (k >= cap) { PyErr_SetString(PyExc_ValueError, "gather: more masks than capacity"); Py_DECREF(inner); goto done; }
             if (!PyDict_Check(m)) {
                 PyErr_Format(PyExc_TypeError, "RLE masks must be dicts with 'size' and 'counts', got %s", Py_TYPE(m)->tp_name);

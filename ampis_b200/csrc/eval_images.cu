@@ -83,6 +83,16 @@ expand_images_kernel(const int *__restrict__ n_rows, const int *__restrict__ n_c
 
 #define EI_HOST_FILL_MAX 16384          // up to this many masks the host fills the per-mask arrays itself
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister)?  Such buffers are DMA targets themselves: large batches
+// skip the staging copy for them
+static bool is_pinned(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32_t *str_len, int32_t n_images,
                                       const int32_t *n_rows, const int32_t *n_cols, const uint32_t *h,
                                       const uint32_t *w, int32_t mode, int32_t flags, double crowd_frac,
@@ -136,7 +146,6 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
     Carve c;
     const int64_t u_chars = contiguous ? 0 : c.take(n_chars);
     const int64_t u_off = on_device ? 0 : c.take(8 * (n + 1));
-    const int64_t u_len = on_device ? c.take(4 * n) : 0;
     const int64_t u_h = on_device ? 0 : c.take(4 * n), u_w = on_device ? 0 : c.take(4 * n);
     const int64_t u_rowmask = on_device ? 0 : c.take(4 * R), u_rowgrp = on_device ? 0 : c.take(4 * R);
     const int64_t u_grb = on_device ? 0 : c.take(4 * NI), u_grc = on_device ? 0 : c.take(4 * NI),
@@ -145,17 +154,25 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
     const int64_t i_nr = on_device ? c.take(4 * NI) : 0, i_nc = on_device ? c.take(4 * NI) : 0,
                   i_h = on_device ? c.take(4 * NI) : 0, i_w = on_device ? c.take(4 * NI) : 0,
                   i_moff = on_device ? c.take(8 * NI) : 0, i_roff = on_device ? c.take(8 * NI) : 0;
-    const int64_t upload_bytes = c.off;
-    // download: the per-row results and the areas first, the optional per-mask arrays last
+    // the string lengths last: when the caller keeps them in pinned memory they are uploaded from where they are
+    const bool len_direct = on_device && is_pinned(str_len);
+    const int64_t staged_upload = c.off;
+    const int64_t u_len = on_device ? c.take(4 * n) : 0;
+    const int64_t upload_bytes = len_direct ? staged_upload : c.off;
+    // download: counters and counts first (always through the staging buffer), then the per-row results and the
+    // per-mask arrays -- straight into the caller's arrays when those are pinned, else through the staging buffer too
     const int64_t dl0 = c.off;
-    const int64_t o_col = c.take(4 * R), o_inter = c.take(4 * R), o_score = c.take(8 * R);
-    const int64_t o_area = c.take(4 * n), o_status = c.take(4 * n);
     const int64_t o_counts = c.take(12 * (int64_t)n_thresh * NI), o_totals = c.take(24 * (int64_t)n_thresh);
     const int64_t o_cursor = c.take(8), o_gridtot = c.take(8), o_pairtot = c.take(8), o_pairfound = c.take(8),
                   o_crowd = c.take(8);
+    const int64_t dl_small = c.off - dl0;
+    const int64_t o_col = c.take(4 * R), o_inter = c.take(4 * R), o_score = c.take(8 * R);
+    const int64_t o_area = c.take(4 * n), o_status = c.take(4 * n);
     const int64_t dl_short = c.off - dl0;
     const int64_t o_bbox = c.take(16 * n), o_span = c.take(8 * n);
-    const int64_t download_bytes = (bbox || span) ? c.off - dl0 : dl_short;
+    const bool out_direct = n > EI_HOST_FILL_MAX && is_pinned(best_col) && is_pinned(best_inter) && is_pinned(best_score) &&
+                            is_pinned(area) && is_pinned(status) && (!bbox || is_pinned(bbox)) && (!span || is_pinned(span));
+    const int64_t download_bytes = out_direct ? dl_small : ((bbox || span) ? c.off - dl0 : dl_short);
     const int64_t host_bytes = dl0 + download_bytes;
     // device only
     const int64_t x_chars = contiguous ? c.take(n_chars) : u_chars;
@@ -188,7 +205,7 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
     // ---- fill the upload block ------------------------------------------------------------------------------------
     if (n_thresh) memcpy(H + u_th, thresholds, (size_t)(8 * n_thresh));
     if (on_device) {
-        memcpy(H + u_len, str_len, (size_t)(4 * n));
+        if (!len_direct) memcpy(H + u_len, str_len, (size_t)(4 * n));
         memcpy(H + i_nr, n_rows, (size_t)(4 * NI));
         memcpy(H + i_nc, n_cols, (size_t)(4 * NI));
         memcpy(H + i_h, h, (size_t)(4 * NI));
@@ -230,6 +247,8 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
         po[n] = pos;
     }
     e = cudaMemcpyAsync(D, H, (size_t)upload_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && len_direct)
+        e = cudaMemcpyAsync(D + u_len, str_len, (size_t)(4 * n), cudaMemcpyHostToDevice, st);
     // strings that already lie back to back (ideally in pinned memory) are uploaded from where they are
     if (e == cudaSuccess && contiguous && n_chars)
         e = cudaMemcpyAsync(D + x_chars, str_ptr[0], (size_t)n_chars, cudaMemcpyHostToDevice, st);
@@ -289,7 +308,17 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
         }
     }
 #undef STEP
+    const bool have_rows = R > 0 && all_pairs > 0;
     e = cudaMemcpyAsync(H + dl0, D + dl0, (size_t)download_bytes, cudaMemcpyDeviceToHost, st);
+    if (out_direct) {
+#define DL(dst, off, bytes) if (e == cudaSuccess && (bytes) > 0) e = cudaMemcpyAsync(dst, D + (off), (size_t)(bytes), cudaMemcpyDeviceToHost, st)
+        if (have_rows) { DL(best_col, o_col, 4 * R); DL(best_inter, o_inter, 4 * R); DL(best_score, o_score, 8 * R); }
+        DL(area, o_area, 4 * n);
+        DL(status, o_status, 4 * n);
+        if (bbox) DL(bbox, o_bbox, 16 * n);
+        if (span) DL(span, o_span, 8 * n);
+#undef DL
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { ampis_set_error("download: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
 
@@ -307,10 +336,12 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
         ampis_set_error("grid entry list too small (%lld entries)", (long long)*(const int64_t *)(H + o_gridtot));
         return AMPIS_EINVAL;          // boxes spread over far more cells than 16 per mask: use the table API
     }
-    if (R > 0 && all_pairs > 0) {
-        memcpy(best_col, H + o_col, (size_t)(4 * R));
-        memcpy(best_inter, H + o_inter, (size_t)(4 * R));
-        memcpy(best_score, H + o_score, (size_t)(8 * R));
+    if (have_rows) {
+        if (!out_direct) {
+            memcpy(best_col, H + o_col, (size_t)(4 * R));
+            memcpy(best_inter, H + o_inter, (size_t)(4 * R));
+            memcpy(best_score, H + o_score, (size_t)(8 * R));
+        }
     } else {
         for (int64_t r = 0; r < R; r++) { best_col[r] = -1; best_inter[r] = 0; best_score[r] = 0.0; }
     }
@@ -326,9 +357,11 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
                 totals[3 * t + 2] += n_rows[g];
             }
     }
-    memcpy(area, H + o_area, (size_t)(4 * n));
-    memcpy(status, H + o_status, (size_t)(4 * n));
-    if (bbox) memcpy(bbox, H + o_bbox, (size_t)(16 * n));
-    if (span) memcpy(span, H + o_span, (size_t)(8 * n));
+    if (!out_direct) {
+        memcpy(area, H + o_area, (size_t)(4 * n));
+        memcpy(status, H + o_status, (size_t)(4 * n));
+        if (bbox) memcpy(bbox, H + o_bbox, (size_t)(16 * n));
+        if (span) memcpy(span, H + o_span, (size_t)(8 * n));
+    }
     return AMPIS_OK;
 }

@@ -290,12 +290,13 @@ rle_flat_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_of
     }
 }
 
-// masks per warp for a typical number of runs per mask: fill ~2/3 of the pair budget
+// masks per warp for a typical number of runs per mask: fill ~4/5 of the pair budget (a warp whose masks exceed
+// it simply works in two rounds)
 static int flat_masks_per_warp(int runs_hint)
 {
     if (runs_hint <= 0) return 4;
     const int pairs = runs_hint / 2 + 1;
-    int k = (FL_PAIR_CAP * 2 / 3) / pairs;
+    int k = (FL_PAIR_CAP * 4 / 5) / pairs;
     if (k < 1) k = 1;
     if (k > FL_KMAX) k = FL_KMAX;
     return k;

@@ -380,16 +380,20 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
     lists[1::2] = cols_lists
     got, mixed = marshal().gather(lists, ptr, ln, hw)
     assert got == n
-    # one size per image: the first mask of each image speaks for it; rows and columns must agree
+    # one size per image: the first mask of each image speaks for it.  The marshaller has checked every list on its
+    # own (mixed = first list holding two sizes); what is left is rows against columns of the same image
     first = np.minimum(r.mask_off[:-1], max(n - 1, 0))
     r.hw = np.where(((r.n_rows + r.n_cols) > 0)[:, None], hw[first], 0).astype(np.int64)
     if n:
-        img_of = np.repeat(np.arange(n_img), r.n_rows.astype(np.int64) + r.n_cols)
-        bad = np.nonzero((hw[:n] != r.hw[img_of]).any(axis=1))[0] if mixed >= 0 or n_img else []
-        if len(bad):
-            k = int(bad[0])
+        first_col = np.minimum(r.mask_off[:-1] + r.n_rows, n - 1)
+        both = (r.n_rows > 0) & (r.n_cols > 0)
+        clash = np.nonzero(both & (hw[first_col] != hw[first]).any(axis=1))[0]
+        if mixed >= 0 or len(clash):
+            g = min(([mixed // 2] if mixed >= 0 else []) + [int(c) for c in clash[:1]])
+            m0, m1 = int(r.mask_off[g]), int(r.mask_off[g + 1])
+            k = m0 + int(np.nonzero((hw[m0:m1] != hw[m0]).any(axis=1))[0][0])
             raise ValueError('masks of different image sizes cannot be compared (%s vs %s)'
-                             % (tuple(int(v) for v in r.hw[img_of[k]]), tuple(int(v) for v in hw[k])))
+                             % (tuple(int(v) for v in hw[m0]), tuple(int(v) for v in hw[k])))
     key = None
     if cache:
         key = (mode, float(crowd_frac), ptr[:n].tobytes(), ln[:n].tobytes(), hw[:n].tobytes(), r.n_rows.tobytes())
@@ -493,16 +497,20 @@ class Groups(object):
             self.imat_off = _dev(off[:-1], torch.int64, device)
 
     def mma_tiles(self, pair=False):
-        """Tile list of the tensor-core contraction (ampis_intersect_tcgen05[_pair]): every group's dense
-        matrix cut into tiles of the kernel's size (128 x 256, or 256 x 256 for CTA pairs); built once, cached."""
+        """Tile list of the dense kernels: every group's dense matrix cut into tiles of the kernel's size -- 128 x 256
+        (tcgen05 contraction, ampis_intersect_tcgen05), 256 x 256 (CTA pairs, pair=True) or the square tile of the
+        TMA-staged AND+popc kernel (pair='tma'); built once, cached."""
         cache = getattr(self, '_mma', None)
         if cache is None:
             cache = self._mma = {}
         if pair not in cache:
-            assert self.imat_off is not None, 'the tensor-core path writes dense matrices: Groups(dense=True)'
+            assert self.imat_off is not None, 'the dense kernels write dense matrices: Groups(dense=True)'
             lib = N.lib()
-            tm, tn = (lib.ampis_mma_pair_tile_rows(), lib.ampis_mma_pair_tile_cols()) if pair else \
-                (lib.ampis_mma_tile_rows(), lib.ampis_mma_tile_cols())
+            if pair == 'tma':
+                tm = tn = lib.ampis_tma_tile()
+            else:
+                tm, tn = (lib.ampis_mma_pair_tile_rows(), lib.ampis_mma_pair_tile_cols()) if pair else \
+                    (lib.ampis_mma_tile_rows(), lib.ampis_mma_tile_cols())
             grp, m0, n0 = [], [], []
             for g in range(self.n_groups):
                 G, P = int(self.h_row_count[g]), int(self.h_col_count[g])
@@ -628,12 +636,13 @@ class SparseRows(object):
         return r[order], c[order], (self.inter[:n].long() & 0xffffffff)[order]
 
 
-def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=None):
+def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=None, zeroed=None):
     """Run the fused row kernel.  Returns device tensors (no sync).  Crop-layout tables with many
     columns per image (ROWS_GRID_MIN_COLS), or whenever a ColumnGrid / SparseRows is passed, go through
     the grid-pruned kernels; grid='scan' forces the all-columns scan.  The grid-pruned form is the three-pass
     join (ROWS_KERNEL 'pairs'; `pairs` = a pre-sized PairList, else one is sized here with a read-back)
-    or the single rows kernel of round 1 ('grid')."""
+    or the single rows kernel of round 1 ('grid').  zeroed: a CUDA event after which the dense matrices are known to
+    be all zeros (the caller cleared them on another stream); the join then waits for it instead of clearing them."""
     dev = table.device
     nr = max(groups.n_rows, 1)
     if out is None:
@@ -656,6 +665,8 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=
             own = pairs is None
             if own:
                 pairs = PairList(dev, groups.n_rows, 8 * groups.n_rows + 4096)
+            if zeroed is not None:
+                torch.cuda.current_stream().wait_event(zeroed)
             while True:
                 N.call('ampis_intersect_rows_pairs', _p(table.bits), _p(table.bits_off), _p(table.bbox),
                        _p(table.area), _p(groups.row_mask), _p(groups.row_grp), groups.n_rows,
@@ -663,7 +674,7 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=
                        _p(grid.cell_off), _p(grid.entries), _p(grid.entry_bbox), grid.capacity, _p(pairs.ab),
                        _p(pairs.desc), _p(pairs.inter), pairs.capacity, _p(pairs.row_off), _p(pairs.row_cnt), _p(pairs.count),
                        _p(groups.imat_off), mode, _p(out.imat),
-                       groups.imat_size if groups.imat_off is not None and out.imat is not None else 0,
+                       groups.imat_size if groups.imat_off is not None and out.imat is not None and zeroed is None else 0,
                        _p(out.best_col), _p(out.best_inter), _p(out.best_score),
                        _p(sparse.row) if sparse else None, _p(sparse.col) if sparse else None,
                        _p(sparse.inter) if sparse else None, sparse.capacity if sparse else 0,
@@ -766,6 +777,35 @@ def intersect_mma(table, groups, mode, out=None, sort=True, pair=None):
            _p(groups.grp_row_begin),
            _p(groups.grp_row_count), _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off),
            _p(out.imat), _stream())
+    N.call('ampis_rows_from_imat', _p(out.imat), _p(groups.imat_off), _p(table.area), _p(groups.row_mask),
+           _p(groups.row_grp), groups.n_rows, _p(groups.grp_row_begin), _p(groups.grp_col_begin),
+           _p(groups.grp_col_count), mode, _p(out.best_col), _p(out.best_inter), _p(out.best_score), _stream())
+    return out
+
+
+def intersect_tma(table, groups, mode, out=None):
+    """Dense intersection matrices by the TMA-staged shared-memory tiled AND+popc kernel (ampis_intersect_tma), then
+    the per-row arg-max from the matrices.  Same RowResult as intersect_rows() / intersect_mma(), bit for bit.  Needs
+    a FULL-layout table painted by the unfused path (frames stored regularly, which is what a tensor map describes)
+    whose masks all share one frame size.  A measurement kernel (profiles/crossover_r02.md), not a product path."""
+    dev = table.device
+    assert table.layout == LAYOUT_FULL and not table.fused, 'regular full frames: MaskTable(..., LAYOUT_FULL).measure().paint()'
+    nr = max(groups.n_rows, 1)
+    n_tiles, tile_grp, tile_m0, tile_n0 = groups.mma_tiles('tma')
+    if out is None:
+        out = RowResult(torch.empty(nr, dtype=torch.int32, device=dev),
+                        torch.empty(nr, dtype=torch.int32, device=dev),
+                        torch.empty(nr, dtype=torch.float64, device=dev),
+                        torch.empty(max(groups.imat_size, 1), dtype=torch.int32, device=dev))
+    assert out.imat is not None
+    frame_chunks = getattr(table, '_frame_chunks', None)
+    if frame_chunks is None:            # one frame size for the whole table (read back once)
+        hw = (table.h[:table.n].to(torch.int64) * table.w[:table.n].to(torch.int64))
+        assert table.n and bool((hw == hw[0]).all().item()), 'all masks must share one frame size'
+        frame_chunks = table._frame_chunks = (int(hw[0].item()) + 127) // 128
+    N.call('ampis_intersect_tma', _p(table.bits), frame_chunks, table.n, _p(table.span), _p(groups.row_mask),
+           _p(tile_grp), _p(tile_m0), _p(tile_n0), n_tiles, _p(groups.grp_row_begin), _p(groups.grp_row_count),
+           _p(groups.grp_col_begin), _p(groups.grp_col_count), _p(groups.imat_off), _p(out.imat), _stream())
     N.call('ampis_rows_from_imat', _p(out.imat), _p(groups.imat_off), _p(table.area), _p(groups.row_mask),
            _p(groups.row_grp), groups.n_rows, _p(groups.grp_row_begin), _p(groups.grp_col_begin),
            _p(groups.grp_col_count), mode, _p(out.best_col), _p(out.best_inter), _p(out.best_score), _stream())

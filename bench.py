@@ -564,7 +564,6 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
     counts back on the host.  Two host threads with a stream and workspaces each keep two calls in flight, so the
     upload of one chunk overlaps the evaluation of the other."""
     import torch
-    from concurrent.futures import ThreadPoolExecutor
     from ampis_b200 import batch
     from ampis_b200 import _native as N
     lib = N.lib()
@@ -576,36 +575,38 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
             part = hst.slice(s0, min(s0 + args.e2e_chunk, hst.n_images))
             blob, ln = strings_of(batch.DeviceBatch(part, dev))
             ni = part.n_images
-            ch = {'blob': torch.from_numpy(blob).pin_memory(), 'len': ln, 'n_images': ni,
+            pin = lambda a: torch.from_numpy(a).pin_memory().numpy()          # page-locked arrays: DMA endpoints
+            ch = {'blob': torch.from_numpy(blob).pin_memory(), 'len': pin(ln), 'n_images': ni,
                   'n_rows': np.full(ni, part.n_rows, np.int32), 'n_cols': np.full(ni, part.n_cols, np.int32),
                   'h': np.full(ni, part.h, np.uint32), 'w': np.full(ni, part.w, np.uint32)}
             R, n = ni * part.n_rows, part.n_masks
-            ch.update(best_col=np.empty(R, np.int32), best_inter=np.empty(R, np.uint32), best_score=np.empty(R),
-                      area=np.empty(n, np.uint32), status=np.empty(n, np.int32),
-                      counts=np.zeros((ni, max(len(thr), 1), 3), np.int32),
-                      totals=np.zeros((max(len(thr), 1), 3), np.int64))
+            # two sets of outputs: the calls of consecutive steps may be in flight together
+            ch['out'] = [dict(best_col=pin(np.empty(R, np.int32)), best_inter=pin(np.empty(R, np.uint32)),
+                              best_score=pin(np.empty(R)), area=pin(np.empty(n, np.uint32)),
+                              status=pin(np.empty(n, np.int32)), counts=np.zeros((ni, max(len(thr), 1), 3), np.int32),
+                              totals=np.zeros((max(len(thr), 1), 3), np.int64)) for _ in range(2)]
             ch['ptr'] = (C.c_void_p * 1)(ch['blob'].data_ptr())
             ch['h2d'] = int(blob.nbytes + 4 * n + 32 * ni + 8 * len(thr))
             ch['d2h'] = int(16 * R + 8 * n + 12 * len(thr) * ni + 24 * len(thr))
             chunks.append(ch)
-    n_workers = 2
+    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '3'))
     workers = [{'stream': torch.cuda.Stream(device=dev),
                 'd_ws': torch.empty(1 << 24, dtype=torch.uint8, device=dev),
                 'h_ws': torch.empty(1 << 22, dtype=torch.uint8, pin_memory=True)} for _ in range(n_workers)]
     pa = lambda a: a.ctypes.data_as(C.c_void_p)
 
-    def one(ch, wk):
+    def one(ch, wk, o):
         need, found, crowded = C.c_int64(0), C.c_int64(0), C.c_int32(0)
         for _ in range(8):
             rc = lib.ampis_eval_images_host(ch['ptr'], pa(ch['len']), ch['n_images'], pa(ch['n_rows']), pa(ch['n_cols']),
                                             pa(ch['h']), pa(ch['w']), mode, 1, -1.0,
                                             C.c_void_p(wk['d_ws'].data_ptr()), wk['d_ws'].numel(),
                                             C.c_void_p(wk['h_ws'].data_ptr()), wk['h_ws'].numel(),
-                                            pa(ch['best_col']), pa(ch['best_inter']), pa(ch['best_score']),
-                                            pa(ch['area']), None, None, pa(ch['status']),
+                                            pa(o['best_col']), pa(o['best_inter']), pa(o['best_score']),
+                                            pa(o['area']), None, None, pa(o['status']),
                                             pa(thr) if len(thr) else None, len(thr),
-                                            pa(ch['counts']) if len(thr) else None,
-                                            pa(ch['totals']) if len(thr) else None, C.byref(found), C.byref(crowded),
+                                            pa(o['counts']) if len(thr) else None,
+                                            pa(o['totals']) if len(thr) else None, C.byref(found), C.byref(crowded),
                                             C.byref(need), C.c_void_p(wk['stream'].cuda_stream))
             if rc != N.ENOSPC:
                 break
@@ -617,31 +618,69 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
                 wk['d_ws'] = torch.empty(int(need.value * 5 // 4), dtype=torch.uint8, device=dev)
         N.check(rc, 'ampis_eval_images_host')
 
-    def work(w):
-        torch.cuda.set_device(dev)
-        for i in range(w, len(chunks), n_workers):
-            one(chunks[i], workers[w])
+    # Every worker owns a stream, its workspaces and a queue of calls; a step is the calls of all its chunks.  The
+    # steps are PIPELINED: the calls of step i+1 are already queued while step i is being evaluated, so its upload
+    # overlaps that evaluation (as a data loader prefetches the next batch); the main thread collects the totals of a
+    # step as soon as its calls have returned (and all-reduces them when N > 1).
+    import queue
+    jobs = queue.Queue()                      # one queue: whichever worker is free takes the next call
 
-    pool = ThreadPoolExecutor(n_workers)
+    def worker(w):
+        torch.cuda.set_device(dev)
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            ch, o, done = job
+            try:
+                one(ch, workers[w], o)
+                assert not o['status'].any()
+                done.put(o['totals'].copy())
+            except Exception as ex:          # surface in the main thread
+                done.put(ex)
+
+    threads = [threading.Thread(target=worker, args=(w,), daemon=True) for w in range(n_workers)]
+    for t_ in threads:
+        t_.start()
     red = torch.zeros(max(3 * len(thr), 4), dtype=torch.int64, device=dev)
 
-    def step():
-        list(pool.map(work, range(n_workers)))
-        tot = sum(ch['totals'] for ch in chunks)
+    parity = [0]
+
+    def submit():
+        done = queue.Queue()
+        for ch in chunks:
+            jobs.put((ch, ch['out'][parity[0]], done))
+        parity[0] ^= 1
+        return done
+
+    def collect(done):
+        tot = 0
+        for _ in chunks:
+            r = done.get()
+            if isinstance(r, Exception):
+                raise r
+            tot = tot + r
         if world > 1:           # the same exchange as the device-resident step
             red[:tot.size] = torch.from_numpy(np.ascontiguousarray(tot).reshape(-1)).to(dev)
             dist.all_reduce(red)
             return red.cpu().numpy()[:tot.size].reshape(tot.shape)
         return tot
 
-    for _ in range(max(args.warmup, 3)):       # also sizes the workspaces
-        tot = step()
+    def run_steps(k):
+        pending = [submit()]
+        tot = None
+        for i in range(k):
+            if i + 1 < k:
+                pending.append(submit())         # one step ahead
+            tot = collect(pending.pop(0))
+        return tot
+
+    run_steps(max(args.warmup, 3))             # also sizes the workspaces
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        tot = step()
+    tot = run_steps(args.steps)
     e1.record()
     sync()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -649,14 +688,18 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    pool.shutdown()
-    assert all(not c_['status'].any() for c_ in chunks)
+    for _ in threads:
+        jobs.put(None)
+    for t_ in threads:
+        t_.join()
     n_img = sum(c_['n_images'] for c_ in chunks)
     pairs = world * n_img * cfg['n_rows'] * cfg['n_cols']
     return {'value': pairs * args.steps / (ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': sum(c_['h2d'] for c_ in chunks),
             'd2h_bytes_per_step': sum(c_['d2h'] for c_ in chunks), 'ms_per_step': ms / args.steps,
             'images_per_s': world * n_img * args.steps / (ms / 1e3), 'wall_ms_per_step': wall_ms / args.steps,
             'calls_per_step': len(chunks), 'images_per_call': args.e2e_chunk, 'calls_in_flight': n_workers,
+            'pipelining': 'the calls of step i+1 are queued while step i is evaluated (its upload overlaps that '
+                          'evaluation); the totals of every step are read on the host before the step counts as done',
             'entry': 'ampis_eval_images_host (C ABI, include/ampis_b200.h): strings back to back in pinned host memory '
                      '(AMPIS_STRINGS_CONTIGUOUS), one upload / one download / one synchronisation per call; host '
                      'read of the totals every step'}, (tot if len(thr) else None)

@@ -279,6 +279,8 @@ int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_off, int32_t 
  * (analyze.py:166-174) at every IoU threshold, grp_counts int32[n_images][n_thresh][3] and totals int64[n_thresh][3],
  * counted on the device (ampis_match_counts) before the download.  Batches of more than 16,384 masks form their per-mask bookkeeping
  * on the device (expand_images_kernel + offset scan), so the host work per call is O(n_images) plus the gather.
+ * For such batches, str_len and the output arrays are used as DMA endpoints directly when they are page-locked
+ * (cudaHostAlloc / cudaHostRegister): no staging copy on either side.
  * Workspaces and AMPIS_ENOSPC protocol as ampis_eval_image_host. */
 #define AMPIS_STRINGS_CONTIGUOUS 1   /* flags: the strings lie back to back from str_ptr[0] (only that pointer is read) */
 int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32_t *str_len, int32_t n_images,
@@ -327,6 +329,20 @@ int ampis_intersect_tcgen05_pair(const void *d_bits, const int64_t *d_bits_off, 
                             int32_t n_tiles, const int32_t *d_grp_row_begin, const int32_t *d_grp_row_count,
                             const int32_t *d_grp_col_begin, const int32_t *d_grp_col_count,
                             const int64_t *d_grp_imat_off, int32_t *d_imat, void *stream);
+
+/* The same dense matrices by the TMA-staged, shared-memory tiled AND+popc kernel north_star names (no tensor cores,
+ * no pruning beyond the K range a tile's spans share): operands are FULL-layout frames stored REGULARLY -- mask i
+ * at d_bits + i * frame_chunks uint4, i.e. the arena of ampis_rle_measure + scan + ampis_rle_decode_packed -- and are
+ * described to the TMA unit by one 2-D tensor map (cuTensorMapEncodeTiled, 128-byte swizzle); every CTA computes an
+ * ampis_tma_tile() x ampis_tma_tile() tile through a 4-stage cp.async.bulk.tensor / mbarrier ring.  The rows of a
+ * group must be consecutive masks (row_mask[r0 + k] = row_mask[r0] + k).  Built to be measured against the culled
+ * kernels and the tensor-core contraction (profiles/crossover_r02.md): it is bound by the POPC pipe. */
+int ampis_tma_tile(void);
+int ampis_intersect_tma(const void *d_bits, int64_t frame_chunks, int32_t n_masks, const uint32_t *d_span,
+                        const int32_t *d_row_mask, const int32_t *d_tile_grp, const int32_t *d_tile_m0,
+                        const int32_t *d_tile_n0, int32_t n_tiles, const int32_t *d_grp_row_begin,
+                        const int32_t *d_grp_row_count, const int32_t *d_grp_col_begin,
+                        const int32_t *d_grp_col_count, const int64_t *d_grp_imat_off, int32_t *d_imat, void *stream);
 
 /* Per-row results (same outputs and tie rules as ampis_intersect_rows) from dense matrices:
  * row_grp[r] = group of row r. */

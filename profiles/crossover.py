@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Culled AND+popc rows kernel vs dense tcgen05 contraction as a function of crowding.
+"""Culled AND+popc rows kernels vs dense tcgen05 contraction vs TMA-staged tiled AND+popc as a function of crowding.
 
     python profiles/crossover.py > gpurun_out/crossover.json      (on the B200)
 
@@ -38,7 +38,20 @@ def main():
                       (np.maximum(r[..., 1], c[..., 1]) <= np.minimum(r[..., 3], c[..., 3]))).mean())
         res = {}
         ref = None
-        for name, fn in (('rows', engine.intersect_rows), ('mma', engine.intersect_mma)):
+        # the TMA-staged shared-memory tiled AND+popc kernel reads regular full frames: its own table
+        tf = engine.MaskTable(dev, host.n_masks, db.cnt, db.cnt_off, db.cnt_len, db.h, db.w, engine.LAYOUT_FULL)
+        tf.measure().paint().check()
+        tc = engine.MaskTable(dev, host.n_masks, db.cnt, db.cnt_off, db.cnt_len, db.h, db.w, engine.LAYOUT_CROP)
+        tc.measure().paint().check()
+        grid = engine.ColumnGrid(dev, db.groups.n_groups).build(tc, db.groups)
+        pairs_list = engine.intersect_rows(tc, db.groups, db.mode, grid=grid).pairs
+        runs = (('rows', lambda out=None: engine.intersect_rows(t, db.groups, db.mode, out=out)),
+                ('mma', lambda out=None: engine.intersect_mma(t, db.groups, db.mode, out=out)),
+                ('tma', lambda out=None: engine.intersect_tma(tf, db.groups, db.mode, out=out)),
+                ('crop', lambda out=None: engine.intersect_rows(tc, db.groups, db.mode, out=out, grid=grid,
+                                                                pairs=pairs_list)))
+        for name, fn_ in runs:
+            fn = lambda t_, g_, m_, out=None, fn_=fn_: fn_(out)
             o = fn(t, db.groups, db.mode)
             for _ in range(3):
                 fn(t, db.groups, db.mode, out=o)
@@ -56,7 +69,9 @@ def main():
                 assert torch.equal(ref, o.imat), 'kernels disagree'
         pairs = n_img * n * n
         out.append({'frame': frame, 'instances': n, 'median_diam': diam, 'images': n_img, 'fill': fill, 'cand': cand,
-                    'rows_ms': res['rows'], 'mma_ms': res['mma'], 'rows_gpairs_s': pairs / res['rows'] / 1e6,
+                    'rows_ms': res['rows'], 'mma_ms': res['mma'], 'tma_ms': res['tma'], 'crop_join_ms': res['crop'],
+                    'tma_gwordpairs_s': pairs * (frame * frame / 32.0) / res['tma'] / 1e6,
+                    'rows_gpairs_s': pairs / res['rows'] / 1e6,
                     'mma_gpairs_s': pairs / res['mma'] / 1e6,
                     'mma_tops': 2.0 * pairs * frame * frame / res['mma'] / 1e9,
                     'choose_kernel': engine.choose_kernel(t, db.groups)})

@@ -731,6 +731,12 @@ def test_tensor_core_contraction_equals_culled_popc(mods, cfg, over, n_img, layo
     assert torch.equal(a.best_col, m.best_col) and torch.equal(a.best_inter, m.best_inter)
     sa, sm = a.best_score.cpu().numpy(), m.best_score.cpu().numpy()
     assert np.array_equal(sa, sm, equal_nan=True)
+    if layout == 'full':                             # TMA-staged shared-memory tiled AND+popc (64 x 64 tiles, tensor map)
+        tm = E.intersect_tma(t, dev.groups, dev.mode)
+        torch.cuda.synchronize()
+        assert torch.equal(a.imat, tm.imat), 'TMA tiled kernel'
+        assert torch.equal(a.best_col, tm.best_col) and torch.equal(a.best_inter, tm.best_inter)
+        assert np.array_equal(sa, tm.best_score.cpu().numpy(), equal_nan=True)
     rows, cols = host.image_masks(0)
     er, ec = _counts_to_rle(rle, rows, host.h, host.w), _counts_to_rle(rle, cols, host.h, host.w)
     imat = m.imat.cpu().numpy()[:host.n_rows * host.n_cols].reshape(host.n_rows, host.n_cols)
