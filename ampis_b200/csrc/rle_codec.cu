@@ -34,12 +34,13 @@ extern "C" int ampis_sm_count(void)
 // varint stream (5 payload bits per character, bit 0x20 = "more", bit 0x10 of the last character =
 // sign) with a second-order delta: count m > 2 is stored relative to count m-2.
 //   1. a ballot of the "last character of a number" flags splits the 32 characters into numbers;
-//   2. every character contributes payload << 5*(its position inside its number); the last lane of
-//      a number ORs the contributions of up to 6 lanes below it (a number that matters has at most
-//      7 characters: only the low 32 bits of the sum are kept, exactly what the reference's
-//      (uint) cast of its long keeps);
-//   3. numbers are compacted to the low lanes (__fns) and the delta is undone by a stride-2 warp
-//      scan (two interleaved chains; count 0 belongs to no chain: count 2 is stored absolute);
+//   2. every character contributes payload << 5*(its position inside its number) (nothing beyond the 7th
+//      character: only the low 32 bits are kept, exactly what the reference's (uint) cast of its long
+//      keeps); the contributions of a number fill disjoint bit ranges, so its value is a SUM over its
+//      lanes = a difference of two warp prefix sums (exact modulo 2^32);
+//   3. numbers are compacted to the low lanes through shared memory (slot = rank of the end flag) and the
+//      delta is undone by a stride-2 warp scan (two interleaved chains; count 0 belongs to no chain:
+//      count 2 is stored absolute);
 //   4. a number cut by the 32-character boundary carries its partial value into the next step.
 // Reads and writes are coalesced; the previous thread-per-mask version spent its time in
 // 32-way divergent byte loads.
@@ -47,9 +48,10 @@ __global__ void __launch_bounds__(256)
 rle_string_decode_kernel(const uint8_t *__restrict__ chars, const i64 *__restrict__ chr_off, int n,
                          u32 *__restrict__ cnt, const i64 *__restrict__ cnt_off, int *__restrict__ cnt_len)
 {
+    __shared__ u32 s_x[8][32];            // numbers of a step, compacted (one row per warp)
     const int i = (int)((blockIdx.x * (u32)blockDim.x + threadIdx.x) >> 5);
     if (i >= n) return;
-    const u32 lane = lane_id();
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1u;
     const uint8_t *s = chars + chr_off[i];
     const i64 len = chr_off[i + 1] - chr_off[i];
@@ -65,26 +67,32 @@ rle_string_decode_kernel(const uint8_t *__restrict__ chars, const i64 *__restric
         const bool end = valid && (!(c & 0x20u) || pos == len - 1);
         const u32 e_mask = __ballot_sync(0xffffffffu, end);
         const u32 below = e_mask & lt;
-        const u32 k_in = lane - (below ? 32u - (u32)__clz(below) : 0u);      // characters of my number below me, this step
-        const u32 k = k_in + (below ? 0u : carry_k);                         // my position inside my number
+        const u32 first = below ? 32u - (u32)__clz(below) : 0u;             // first lane of my number in this step
+        const u32 k = lane - first + (below ? 0u : carry_k);                // my position inside my number
         const u32 contrib = (valid && k < 7u) ? (c & 0x1fu) << (5u * k) : 0u;
-        u32 x = contrib;
+        // the characters of a number fill disjoint bit ranges, so OR-ing them is adding them, and a sum over lanes
+        // first..me is a difference of two prefix sums (exact modulo 2^32, which is all the reference keeps)
+        u32 P = contrib;
 #pragma unroll
-        for (u32 d = 1; d <= 6; d++) {
-            const u32 t = __shfl_up_sync(0xffffffffu, contrib, d);
-            if (d <= k_in) x |= t;
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, P, d);
+            if (lane >= d) P += t;
         }
+        const u32 before = __shfl_sync(0xffffffffu, P, (first + 31u) & 31u);      // P[first - 1]
+        u32 x = P - (first ? before : 0u);
         if (!below) x |= carry_x;
         if (end && !(c & 0x20u) && (c & 0x10u)) {
             const u32 sh = 5u * (k + 1u);
             if (sh < 32u) x |= 0xffffffffu << sh;
         }
         const u32 nn = __popc(e_mask);
-        // number t of this step sits in the lane of the (t+1)-th end flag
-        const u32 src = __fns(e_mask, 0, lane + 1);
-        const u32 xv = __shfl_sync(0xffffffffu, x, src & 31u);
+        // number t of this step: written to slot t by the lane that ends it, read back by lane t
+        if (end) s_x[wid][__popc(below)] = x;
+        __syncwarp();
         const u32 m = m_base + lane;
         const bool have = lane < nn;
+        const u32 xv = have ? s_x[wid][lane] : 0u;
+        __syncwarp();
         u32 y = (have && m != 0) ? xv : 0u;
 #pragma unroll
         for (u32 d = 2; d < 32; d <<= 1) {
@@ -104,8 +112,9 @@ rle_string_decode_kernel(const uint8_t *__restrict__ chars, const i64 *__restric
         m_base += nn;
         // characters above the last end flag start a number that finishes in a later step
         const int last_end = e_mask ? 31 - __clz(e_mask) : -1;
-        const u32 tail = __reduce_or_sync(0xffffffffu, (int)lane > last_end ? contrib : 0u);
-        carry_x = (e_mask ? 0u : carry_x) | tail;
+        const u32 total = __shfl_sync(0xffffffffu, P, 31);
+        const u32 upto = last_end >= 0 ? __shfl_sync(0xffffffffu, P, last_end) : 0u;
+        carry_x = (e_mask ? 0u : carry_x) | (total - upto);
         carry_k = (e_mask ? 0u : carry_k) + (u32)(31 - last_end);
     }
     if (lane == 0) cnt_len[i] = (int)m_base;

@@ -549,7 +549,7 @@ class RowResult(object):
 #: uniform grid over the image (ampis_intersect_rows_grid) instead of scanning every column's box
 #: (measured: C2, 500 columns per image, rows kernel 1.25 -> 1.00 ms per 1,000 images; C4, 5,000 columns, 2.4 ->
 #: 0.25 ms per 40 images; below a few hundred columns the six small launches that build the grid cost more)
-ROWS_GRID_MIN_COLS = int(os.environ.get('AMPIS_ROWS_GRID_MIN_COLS', 384))
+ROWS_GRID_MIN_COLS = int(os.environ.get('AMPIS_ROWS_GRID_MIN_COLS', 64))
 
 
 class ColumnGrid(object):

@@ -152,6 +152,14 @@ class ClockSampler(object):
         return out
 
 
+def cpu_seconds_per_task(cfg_name, cfg):
+    """Seconds one (image, threshold) task of the reference port takes on one core (measured), used to bound the
+    CPU samples: G x ceil(P / 80) rleIou calls that re-parse 81 strings each grow with G x P."""
+    if cfg['mode'] != 0:
+        return 2.5
+    return max(0.05, 0.75 * (cfg['n_rows'] * cfg['n_cols']) / 250000.0)
+
+
 def workload_config(args, cfg, images_per_gpu):
     """The `config` object -- the WORKLOAD, identical (keys and values) in both arms; how an arm runs it is in `run`."""
     sat = cfg['mode'] != 0
@@ -215,7 +223,7 @@ def reference_arm(args):
     cores = args.cpu_threads or (os.cpu_count() or 1)
     cfg = batch.CONFIGS[args.config]
     thresholds = list(batch.COCO_THRESHOLDS) if cfg['mode'] == 0 else [0.5]
-    per_task = 0.75 if cfg['mode'] == 0 else 2.5        # seconds per (image, threshold) on one core, measured
+    per_task = cpu_seconds_per_task(args.config, cfg)
     budget = min(8.0, 200.0 / max(args.steps + args.warmup, 1))
     n_img = args.cpu_images or max(1, int(cores * budget / (per_task * len(thresholds))))
     host, images = cpu_images(args.config, n_img, 777)
@@ -589,7 +597,7 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
             ch['h2d'] = int(blob.nbytes + 4 * n + 32 * ni + 8 * len(thr))
             ch['d2h'] = int(16 * R + 8 * n + 12 * len(thr) * ni + 24 * len(thr))
             chunks.append(ch)
-    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '3'))
+    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '4'))
     workers = [{'stream': torch.cuda.Stream(device=dev),
                 'd_ws': torch.empty(1 << 24, dtype=torch.uint8, device=dev),
                 'h_ws': torch.empty(1 << 22, dtype=torch.uint8, pin_memory=True)} for _ in range(n_workers)]
@@ -944,7 +952,7 @@ def cpu_baseline(args):
     from ampis_b200 import batch
     cfg = batch.CONFIGS[args.config]
     n_thr = len(batch.COCO_THRESHOLDS) if cfg['mode'] == 0 else 1
-    per_task = 0.75 if cfg['mode'] == 0 else 2.5
+    per_task = cpu_seconds_per_task(args.config, cfg)
     env = dict(os.environ, RANK='0', WORLD_SIZE='1', CUDA_VISIBLE_DEVICES='')
     try:
         os.sched_setaffinity(0, range(cores))        # the CPU arm may use every core again
@@ -965,7 +973,9 @@ def cpu_baseline(args):
         return cb
 
     allc = arm(args.cpu_images or max(1, int(cores * 15.0 / (per_task * n_thr))), 0)
-    one = arm(1, 1)
+    # the single-thread figure on one image; where even that takes minutes (C4: 25 M pairs per image) it is skipped
+    one = arm(1, 1) if per_task * n_thr <= 60.0 else {'value': None, 'images_per_s': None, 'cores': 1,
+                                                        'sample': 'skipped: one image takes ~%d s on one core' % (per_task * n_thr)}
     out = dict(allc)
     out['all_cores'] = {k: allc.get(k) for k in ('value', 'images_per_s', 'cores', 'sample')}
     out['single_thread'] = {k: one.get(k) for k in ('value', 'images_per_s', 'cores', 'sample')}
