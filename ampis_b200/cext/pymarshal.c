@@ -31,14 +31,17 @@ static int get_dim(PyObject *o, long *out)
     return 0;
 }
 
-/* gather(list_of_mask_lists, ptr_u64, len_i32, hw_i32) -> (n_masks, first_mixed_size_list or -1)
+/* gather(list_of_mask_lists, ptr_u64, len_i32, hw_i32[, keep]) -> (n_masks, first_mixed_size_list or -1)
  * ptr_u64[k], len_i32[k]: address and length of the k-th mask's compressed counts (masks of list 0, then list 1, ...)
  * hw_i32[2 k], hw_i32[2 k + 1]: its image size.  str counts are accepted (their cached UTF-8 form is used).
- * The second result is the index of the first inner list whose masks do not all share one size. */
+ * The second result is the index of the first inner list whose masks do not all share one size.
+ * keep: optional list; every counts object is appended to it (references that keep the strings alive). */
 static PyObject *gather(PyObject *self, PyObject *args)
 {
-    PyObject *lists, *o_ptr, *o_len, *o_hw;
-    if (!PyArg_ParseTuple(args, "OOOO", &lists, &o_ptr, &o_len, &o_hw)) return NULL;
+    PyObject *lists, *o_ptr, *o_len, *o_hw, *keep = NULL;
+    if (!PyArg_ParseTuple(args, "OOOO|O", &lists, &o_ptr, &o_len, &o_hw, &keep)) return NULL;
+    if (keep == Py_None) keep = NULL;
+    if (keep && !PyList_Check(keep)) { PyErr_SetString(PyExc_TypeError, "gather: keep must be a list"); return NULL; }
     Py_buffer b_ptr, b_len, b_hw;
     if (PyObject_GetBuffer(o_ptr, &b_ptr, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) return NULL;
     if (PyObject_GetBuffer(o_len, &b_len, PyBUF_WRITABLE | PyBUF_C_CONTIGUOUS) < 0) { PyBuffer_Release(&b_ptr); return NULL; }
@@ -94,6 +97,8 @@ static PyObject *gather(PyObject *self, PyObject *args)
                 PyErr_Format(PyExc_TypeError, "RLE counts must be compressed bytes/str, got %s", Py_TYPE(c)->tp_name);
                 Py_DECREF(inner); goto done;
             }
+            /* the caller's cache keeps the string objects alive: their addresses are its key */
+            if (keep && PyList_Append(keep, c) < 0) { Py_DECREF(inner); goto done; }
             long hh, ww;
             if (PyList_CheckExact(sz) && PyList_GET_SIZE(sz) >= 2) {
                 if (get_dim(PyList_GET_ITEM(sz, 0), &hh) < 0 || get_dim(PyList_GET_ITEM(sz, 1), &ww) < 0) { Py_DECREF(inner); goto done; }
@@ -126,7 +131,7 @@ done:
 }
 
 static PyMethodDef methods[] = {
-    {"gather", gather, METH_VARARGS, "gather(list_of_mask_lists, ptr_u64, len_i32, hw_i32) -> (n_masks, first_mixed_list)"},
+    {"gather", gather, METH_VARARGS, "gather(list_of_mask_lists, ptr_u64, len_i32, hw_i32[, keep]) -> (n_masks, first_mixed_list)"},
     {NULL, NULL, 0, NULL}
 };
 

@@ -119,14 +119,14 @@ rle_flat_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_of
 
         // ---- pass over the pairs: run end positions by a segmented scan, statistics of the 1-runs
         u32 carry = 0;
+        int j = 0;                                   // my mask: the last one that starts at or before my pair; only grows
         for (u32 f0 = 0; f0 < T; f0 += 32) {
             const u32 f = f0 + lane;
             const bool ok = f < T;
-            int j = 0;
             u32 p = 0, z = 0, o = 0, H = 1, rcp = 0, HW = 0;
             int len = 0;
             if (ok) {
-                for (int q = 1; q < nb; q++) j += f >= S.pb[q];        // my mask: the last one that starts at or before f
+                while (j + 1 < nb && f >= S.pb[j + 1]) j++;
                 S.mid[f] = (uint8_t)j;
                 p = f - S.pb[j];
                 len = S.len[a + j];

@@ -258,6 +258,16 @@ _image_ws = {}          # device index -> [device workspace, pinned host workspa
 _image_ws_lock = threading.Lock()
 
 
+def _workspaces(device):
+    """[device workspace, pinned host workspace] of the one-call entries on `device` (created once, grown on demand;
+    call with _image_ws_lock held)."""
+    ws = _image_ws.get(device.index)
+    if ws is None:
+        ws = _image_ws[device.index] = [torch.empty(1 << 22, dtype=torch.uint8, device=device),
+                                        torch.empty(1 << 20, dtype=torch.uint8, pin_memory=True)]
+    return ws
+
+
 def eval_image(rows_rle, cols_rle, mode, dense_iou=False):
     """One image, rows x columns, through ampis_eval_image_host -- the per-image work of the reference's
     analyze.py:149-164 (G x ceil(P/80) RLE.iou calls + arg-max), analyze.py:315-321 (merge + area per match),
@@ -292,8 +302,7 @@ def eval_image(rows_rle, cols_rle, mode, dense_iou=False):
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     lib = N.lib()
     with _image_ws_lock:
-        ws_pair = _image_ws.setdefault(device.index, [torch.empty(1 << 22, dtype=torch.uint8, device=device),
-                                                      torch.empty(1 << 20, dtype=torch.uint8, pin_memory=True)])
+        ws_pair = _workspaces(device)
         for _ in range(8):
             d_ws, h_ws = ws_pair
             rc = lib.ampis_eval_image_host(blob, ptr(off), n_rows, n_cols, r.hw[0], r.hw[1], mode, ROWS_GRID_MIN_COLS,
@@ -378,7 +387,8 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
     lists = [None] * (2 * n_img)
     lists[0::2] = rows_lists
     lists[1::2] = cols_lists
-    got, mixed = marshal().gather(lists, ptr, ln, hw)
+    refs = [] if cache else None            # the string objects themselves: their addresses are the cache key
+    got, mixed = marshal().gather(lists, ptr, ln, hw, refs)
     assert got == n
     # one size per image: the first mask of each image speaks for it.  The marshaller has checked every list on its
     # own (mixed = first list holding two sizes); what is left is rows against columns of the same image
@@ -410,12 +420,11 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
     r.pairs_found, r.crowded = 0, False
     if n:
         need, found, crowded = C.c_int64(0), C.c_int64(0), C.c_int32(0)
-        pa = lambda a: a.ctypes.data_as(C.c_void_p)
+        pa = lambda a: a.__array_interface__['data'][0]          # plain address (argtypes say c_void_p); cheaper than .ctypes
         h32, w32 = np.ascontiguousarray(r.hw[:, 0].astype(np.uint32)), np.ascontiguousarray(r.hw[:, 1].astype(np.uint32))
         lib = N.lib()
         with _image_ws_lock:
-            ws_pair = _image_ws.setdefault(device.index, [torch.empty(1 << 22, dtype=torch.uint8, device=device),
-                                                          torch.empty(1 << 20, dtype=torch.uint8, pin_memory=True)])
+            ws_pair = _workspaces(device)
             for _ in range(8):
                 d_ws, h_ws = ws_pair
                 rc = lib.ampis_eval_images_host(pa(ptr), pa(ln), n_img, pa(r.n_rows), pa(r.n_cols), pa(h32), pa(w32),
@@ -439,7 +448,7 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
                              % np.nonzero(r.status)[0][:8].tolist())
     if cache:
         # the references keep every string object alive, so an address in the key cannot be recycled while the entry lives
-        _images_cache[mode] = (key, [[m['counts'] for m in x] for x in lists], r)
+        _images_cache[mode] = (key, refs, r)
     return r
 
 
