@@ -147,7 +147,12 @@ def _satellite_rows(part_lists, sat_lists, thresh):
     n = len(part_lists)
     if n == 0 or sum(map(len, part_lists)) + sum(map(len, sat_lists)) == 0:
         return np.zeros((n, 4), np.int64), [np.zeros(0, np.int64) for _ in range(n)]
-    r = engine.eval_images(sat_lists, part_lists, engine.MODE_SAT)
+    return _satellite_counts_from_rows(engine.eval_images(sat_lists, part_lists, engine.MODE_SAT), thresh)
+
+
+def _satellite_counts_from_rows(r, thresh):
+    """powder.py:85-103 on the flat per-row output of engine.eval_images (rows = satellites, columns = particles)."""
+    n = len(r.n_rows)
     S, Np = r.n_rows.astype(np.int64), r.n_cols.astype(np.int64)
     img_of_row = np.repeat(np.arange(n), S)
     part_off = np.zeros(n + 1, np.int64)

@@ -654,6 +654,47 @@ def test_c_caller_of_the_abi(mods, tmp_path):
     assert [int(r[3]) for r in rows] == want['best_inter'].tolist()
     assert [float(r[4]) for r in rows] == want['best_iou'].tolist()
     assert [int(m_[2]) for m_ in ms] == mods.rle.area(masks).tolist() and all(int(m_[7]) == 0 for m_ in ms)
+    # ---- the many-image entry from C: three golden images of different instance counts in ONE call, strings passed
+    # as one contiguous blob and as one descriptor per string; per-row results, areas and TP/FP/FN at two thresholds
+    exe2 = str(tmp_path / 'eval_images_main')
+    cc = subprocess.run(['gcc', '-O2', '-o', exe2, os.path.join(root, 'tests', 'c_abi', 'eval_images_main.c'),
+                         '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include',
+                         '-L', os.path.dirname(bld.LIB), '-lampis_b200', '-L', '/usr/local/cuda/lib64', '-lcudart',
+                         '-Wl,-rpath,' + os.path.dirname(bld.LIB) + ',-rpath,/usr/local/cuda/lib64'],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    imgs = [U.powder_match_image(k)[1:] for k in (0, 2, 4)]
+    allm = [m for g_, p_ in imgs for m in list(g_) + list(p_)]
+    path2 = tmp_path / 'images.bin'
+    with open(path2, 'wb') as f:
+        f.write(np.array([len(imgs)], np.int32).tobytes())
+        f.write(np.array([len(g_) for g_, _ in imgs], np.int32).tobytes())
+        f.write(np.array([len(p_) for _, p_ in imgs], np.int32).tobytes())
+        f.write(np.array([g_[0]['size'][0] for g_, _ in imgs], np.int32).tobytes())
+        f.write(np.array([g_[0]['size'][1] for g_, _ in imgs], np.int32).tobytes())
+        f.write(np.array([len(m['counts']) for m in allm], np.int32).tobytes())
+        f.write(b''.join(m['counts'] for m in allm))
+    for extra in ([], ['scattered']):
+        run = subprocess.run([exe2, str(path2)] + extra, capture_output=True, text=True, timeout=120)
+        assert run.returncode == 0, run.stderr
+        rows = [l.split() for l in run.stdout.splitlines() if l.startswith('row')]
+        cnt = [[int(v) for v in l.split()[2:]] for l in run.stdout.splitlines() if l.startswith('counts')]
+        tot = [l.split() for l in run.stdout.splitlines() if l.startswith('totals')][0]
+        r0, want_tot = 0, np.zeros(6, np.int64)
+        for (g_, p_), c_ in zip(imgs, cnt):
+            want = {}
+            mods.analyze._piecewise_rle_match(g_, p_, 0.5, _details=want)
+            assert [int(r[2]) for r in rows[r0:r0 + len(g_)]] == want['best_col'].tolist()
+            assert [float(r[4]) for r in rows[r0:r0 + len(g_)]] == want['best_iou'].tolist()
+            r0 += len(g_)
+            ref = []
+            for th in (0.5, 0.75):
+                m_ = mods.R.piecewise_rle_match(g_, p_, th)
+                ref += [len(m_['tp']), len(m_['fp']), len(m_['fn'])]
+            assert c_ == ref
+            want_tot += np.array(ref)
+        assert [int(v) for v in tot[1:7]] == want_tot.tolist() and tot[-1] == '0'
+        assert [int(l.split()[2]) for l in run.stdout.splitlines() if l.startswith('mask')] == mods.rle.area(allm).tolist()
 
 
 def test_full_size_properties(mods):

@@ -274,3 +274,87 @@ def test_prediction_pickles_only_resolve_allowlisted_names():
     for fn, arg in ((eval, '1+1'), (os.system, 'true'), (getattr, 'x'), (np.load, 'nothing.npy'), (__import__, 'os')):
         with pytest.raises(pickle.UnpicklingError, match='refusing to load'):
             _Unpickler(io.BytesIO(pickle.dumps(Evil(fn, arg)))).load()
+
+
+def _rows_from_oracle(gts, prs, mode):
+    """An engine.ImagesRows filled by the ORACLE (what ampis_eval_images_host returns, computed on the CPU), so that
+    the host-side bookkeeping over it can be tested without a GPU."""
+    from ampis_b200 import engine
+    from oracle import cocomask as rle
+    r = engine.ImagesRows()
+    n_img = len(gts)
+    r.n_rows = np.array([len(g) for g in gts], np.int32)
+    r.n_cols = np.array([len(p) for p in prs], np.int32)
+    r.row_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(r.n_rows, out=r.row_off[1:])
+    r.mask_off = np.zeros(n_img + 1, np.int64)
+    np.cumsum(r.n_rows.astype(np.int64) + r.n_cols, out=r.mask_off[1:])
+    best_col, best_inter, best_score, area = [], [], [], []
+    for g, p in zip(gts, prs):
+        a_g, a_p = rle.area(g).astype(np.int64), rle.area(p).astype(np.int64)
+        inter = np.array([[int(rle.merge_area(x, y, intersect=True)) for y in p] for x in g], np.int64).reshape(len(g), len(p))
+        with np.errstate(invalid='ignore', divide='ignore'):
+            score = np.where(inter > 0, inter / (a_g[:, None] + a_p[None, :] - inter), 0.0) if mode == 0 else \
+                inter / a_g[:, None].astype(np.float64)
+        if mode == 0:
+            bc = np.where(score.max(axis=1) > 0, score.argmax(axis=1), -1)
+            bs = score.max(axis=1)
+        else:
+            bc = inter.argmax(axis=1)               # first maximum of the intersections, as the kernel
+            with np.errstate(invalid='ignore', divide='ignore'):
+                bs = inter[np.arange(len(g)), bc] / a_g.astype(np.float64)
+        best_col.append(bc)
+        best_score.append(bs)
+        best_inter.append(np.where(bc >= 0, inter[np.arange(len(g)), np.maximum(bc, 0)], 0))
+        area += [a_g, a_p]
+    r.best_col = np.concatenate(best_col).astype(np.int32)
+    r.best_score = np.concatenate(best_score).astype(np.float64)
+    r.best_inter = np.concatenate(best_inter).astype(np.uint32)
+    r.area = np.concatenate(area).astype(np.uint32)
+    return r
+
+
+def test_batch_bookkeeping_equals_the_reference_loops():
+    """The vectorised host bookkeeping of round 2 -- analyze._scores_from_rows_batch (det_seg_scores_batch),
+    distributed._counts_from_rows (evaluate_sharded) and distributed._satellite_counts_from_rows
+    (satellite_measurements_sharded) -- against the oracle's literal loops, image by image, with the per-row
+    results supplied by the oracle instead of the GPU: ties, empty masks, images of different sizes."""
+    from ampis_b200 import analyze, distributed
+    from oracle import ampis_ref as R
+    from oracle import cocomask as rle
+    from tests import _util as U
+    rng = np.random.default_rng(11)
+    gts, prs = [], []
+    for k in range(5):
+        h, w = int(rng.integers(20, 60)), int(rng.integers(20, 60))
+        m = U.rand_masks(rng, 9 + k + 7, h, w, p_empty=0.15)
+        m[2] = m[9 + k]                                       # exact match
+        m[9 + k + 1] = m[9 + k + 2] = m[3]                    # two identical predictions: the first one wins
+        enc = [rle.encode(np.asfortranarray(x.astype(np.uint8))) for x in m]
+        gts.append(enc[:9 + k])
+        prs.append(enc[9 + k:])
+    r = _rows_from_oracle(gts, prs, 0)
+    for th in (0.0, 0.5, 0.8):
+        got = analyze._scores_from_rows_batch(r, th)
+        for g, p, res in zip(gts, prs, got):
+            want = R.det_seg_scores(g, p, th)
+            assert list(res) == list(want)
+            for key in want:
+                assert np.array_equal(np.asarray(res[key]), np.asarray(want[key]), equal_nan=True), (th, key)
+                assert np.asarray(res[key]).dtype == np.asarray(want[key]).dtype, key
+    ths = [0.3, 0.5, 0.75]
+    counts = distributed._counts_from_rows(r, ths)
+    for i, (g, p) in enumerate(zip(gts, prs)):
+        for t, th in enumerate(ths):
+            m = R.piecewise_rle_match(g, p, th)
+            assert counts[i, t].tolist() == [len(m['tp']), len(m['fp']), len(m['fn'])]
+    rs = _rows_from_oracle(gts, prs, 1)                       # "satellites" = gts, "particles" = prs
+    sc, per = distributed._satellite_counts_from_rows(rs, 0.3)
+    for i, (g, p) in enumerate(zip(gts, prs)):
+        try:
+            m = R.rle_satellite_match(p, g, 0.3)
+            nm, pairs = len(m['satellite_matches']), m['match_pairs']
+        except IndexError:
+            nm, pairs = 0, {}
+        assert sc[i].tolist() == [nm, len(g) - nm, len(pairs), len(p)]
+        assert per[i].tolist() == [len(pairs[k]) for k in sorted(pairs)]
