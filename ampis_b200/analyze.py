@@ -303,14 +303,15 @@ def _scores_from_rows_batch(r, iou_thresh):
     np.cumsum(n_fn, out=fn_off[1:])
     empty_tp = np.asarray([], int)
     out = []
+    t_cut, fp_cut, fn_cut = t_off.tolist(), fp_off.tolist(), fn_off.tolist()      # Python ints: cheap in the loop
     for g in range(n_img):
-        a, b = int(t_off[g]), int(t_off[g + 1])
-        ntp, nfp, nfn = b - a, int(n_fp[g]), int(n_fn[g])
+        a, b = t_cut[g], t_cut[g + 1]
+        ntp, nfp, nfn = b - a, fp_cut[g + 1] - fp_cut[g], fn_cut[g + 1] - fn_cut[g]
         out.append({'det_precision': ntp / (ntp + nfp), 'det_recall': ntp / (ntp + nfn),
                     'seg_precision': seg_p[a:b], 'seg_recall': seg_r[a:b],
                     'det_tp': tp[a:b] if ntp else empty_tp,
-                    'det_fn': fn_local[int(fn_off[g]):int(fn_off[g + 1])],
-                    'det_fp': fp_local[int(fp_off[g]):int(fp_off[g + 1])],
+                    'det_fn': fn_local[fn_cut[g]:fn_cut[g + 1]],
+                    'det_fp': fp_local[fp_cut[g]:fp_cut[g + 1]],
                     'seg_tp': inter[a:b], 'seg_fn': seg_fn[a:b], 'seg_fp': seg_fp[a:b], 'det_tp_iou': iou[a:b]})
     return out
 

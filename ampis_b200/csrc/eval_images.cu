@@ -319,7 +319,22 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
         if (span) DL(span, o_span, 8 * n);
 #undef DL
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+        if (on_device) {
+            // a large batch takes milliseconds: wait on a BLOCKING event instead of spinning in cudaStreamSynchronize,
+            // so that the cores stay free for the other calls in flight (several host threads per GPU, several ranks
+            // per host: profiles/scaling_r02.md)
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+            if (e == cudaSuccess) {
+                e = cudaEventRecord(ev, st);
+                if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+                cudaEventDestroy(ev);
+            }
+        } else {
+            e = cudaStreamSynchronize(st);
+        }
+    }
     if (e != cudaSuccess) { ampis_set_error("download: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
 
     // ---- did everything fit? -------------------------------------------------------------------------------------
