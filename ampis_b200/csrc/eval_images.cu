@@ -320,10 +320,10 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
 #undef DL
     }
     if (e == cudaSuccess) {
-        if (on_device) {
-            // a large batch takes milliseconds: wait on a BLOCKING event instead of spinning in cudaStreamSynchronize,
-            // so that the cores stay free for the other calls in flight (several host threads per GPU, several ranks
-            // per host: profiles/scaling_r02.md)
+        if (flags & AMPIS_WAIT_BLOCKING) {
+            // wait on a BLOCKING event instead of spinning in cudaStreamSynchronize: the cores stay free for the other
+            // calls in flight (several host threads per GPU, several ranks per host) at the price of a slower wake-up
+            // (one rank alone: 2.75 vs 2.25 ms per C2 step, profiles/scaling_r02.md)
             cudaEvent_t ev;
             e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
             if (e == cudaSuccess) {

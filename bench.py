@@ -598,6 +598,8 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
             ch['d2h'] = int(16 * R + 8 * n + 12 * len(thr) * ni + 24 * len(thr))
             chunks.append(ch)
     n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '4'))
+    # AMPIS_STRINGS_CONTIGUOUS (1) [+ AMPIS_WAIT_BLOCKING (2): measured per box, profiles/scaling_r02.md]
+    call_flags = 1 | (2 if os.environ.get('AMPIS_E2E_BLOCKING', '0') == '1' else 0)
     workers = [{'stream': torch.cuda.Stream(device=dev),
                 'd_ws': torch.empty(1 << 24, dtype=torch.uint8, device=dev),
                 'h_ws': torch.empty(1 << 22, dtype=torch.uint8, pin_memory=True)} for _ in range(n_workers)]
@@ -607,7 +609,7 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
         need, found, crowded = C.c_int64(0), C.c_int64(0), C.c_int32(0)
         for _ in range(8):
             rc = lib.ampis_eval_images_host(ch['ptr'], pa(ch['len']), ch['n_images'], pa(ch['n_rows']), pa(ch['n_cols']),
-                                            pa(ch['h']), pa(ch['w']), mode, 1, -1.0,
+                                            pa(ch['h']), pa(ch['w']), mode, call_flags, -1.0,
                                             C.c_void_p(wk['d_ws'].data_ptr()), wk['d_ws'].numel(),
                                             C.c_void_p(wk['h_ws'].data_ptr()), wk['h_ws'].numel(),
                                             pa(o['best_col']), pa(o['best_inter']), pa(o['best_score']),

@@ -283,6 +283,7 @@ int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_off, int32_t 
  * (cudaHostAlloc / cudaHostRegister): no staging copy on either side.
  * Workspaces and AMPIS_ENOSPC protocol as ampis_eval_image_host. */
 #define AMPIS_STRINGS_CONTIGUOUS 1   /* flags: the strings lie back to back from str_ptr[0] (only that pointer is read) */
+#define AMPIS_WAIT_BLOCKING      2   /* flags: wait for the results on a blocking event instead of spinning */
 int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32_t *str_len, int32_t n_images,
                            const int32_t *n_rows, const int32_t *n_cols, const uint32_t *h, const uint32_t *w,
                            int32_t mode, int32_t flags, double crowd_frac, void *d_ws, int64_t d_ws_bytes, void *h_ws,

@@ -37,7 +37,7 @@ int main(int argc, char **argv)
         if (h_ws) cudaFreeHost(h_ws);
         if (cudaMalloc(&d_ws, (size_t)d_bytes) != cudaSuccess) return 3;
         if (cudaHostAlloc(&h_ws, (size_t)h_bytes, cudaHostAllocDefault) != cudaSuccess) return 3;
-        rc = ampis_eval_image_host(chars, off, n_rows, n_cols, (uint32_t)hdr[2], (uint32_t)hdr[3], hdr[4], 384,
+        rc = ampis_eval_image_host(chars, off, n_rows, n_cols, (uint32_t)hdr[2], (uint32_t)hdr[3], hdr[4], 64,
                                    d_ws, d_bytes, h_ws, h_bytes, best_col, best_inter, best_score, area, bbox, span,
                                    status, NULL, &need, NULL /* default stream */);
     }
