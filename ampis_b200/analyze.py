@@ -16,7 +16,7 @@ import torch
 
 from . import engine
 from .containers import Instances
-from .structures import InstanceSet, RLEMasks, masks_to_rle, masks_to_bitmask_array  # noqa: F401
+from .structures import InstanceSet, RLEMasks, masks_to_rle, masks_to_bitmask_array  # noqa: F401 (re-exported like ampis.analyze)
 
 
 def align_instance_sets(a, b):
