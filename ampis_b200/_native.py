@@ -45,7 +45,7 @@ SIGNATURES = {
                                             _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     'ampis_intersect_rows_pairs': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p,
                                              _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p,
-                                             _p]),
+                                             _p, _p]),
     'ampis_rle_decode_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     'ampis_mma_tile_rows': (C.c_int, []),
     'ampis_mma_tile_cols': (C.c_int, []),

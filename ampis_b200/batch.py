@@ -22,6 +22,8 @@ COCO_THRESHOLDS = np.arange(0.5, 1.0, 0.05)     # IoU 0.50:0.05:0.95
 #: kernel takes the SMs it needs from the decode (1.331 vs 1.333 ms per step), the copy engines are slower than the
 #: fill (1.505 ms) -- so the default stays in line ('0').
 ZERO_AHEAD = os.environ.get('AMPIS_ZERO_AHEAD', '0') != '0'
+#: Pipeline: zero the dense matrices on a side stream BESIDE the join's first two passes (load-latency bound)
+ZERO_BESIDE_JOIN = os.environ.get('AMPIS_ZERO_BESIDE_JOIN', '1') != '0'
 ZERO_BY_COPY = os.environ.get('AMPIS_ZERO_AHEAD', '0') == '2' 
 
 #: synthetic workloads named after BASELINE.json's configs (DESIGN.md "Synthetic data")
@@ -269,8 +271,14 @@ class Pipeline(object):
             engine.intersect_mma(t, self.batch.groups, self.batch.mode, out=self.rows, sort=self.mma_sort,
                                  pair=self.kernel == 'mma2')
         else:
+            side = None
+            if ZERO_BESIDE_JOIN and not zero_ahead and self.pairs is not None and g.imat_off is not None:
+                if self.zero_stream is None:
+                    self.zero_stream = torch.cuda.Stream(device=self.batch.device)
+                side = self.zero_stream
             engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows, grid=self.grid,
-                                  sparse=self.sparse, pairs=self.pairs, zeroed=self.zero_done if zero_ahead else None)
+                                  sparse=self.sparse, pairs=self.pairs, zeroed=self.zero_done if zero_ahead else None,
+                                  zero_stream=side)
         if mark: mark(3)
         if self.batch.mode == engine.MODE_IOU:
             engine.match_counts(self.rows, self.batch.groups, self.th, totals=self.totals, counts=self.counts)

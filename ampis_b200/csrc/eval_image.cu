@@ -127,7 +127,7 @@ extern "C" int ampis_eval_image_host(const uint8_t *chars, const int64_t *chr_of
                                             dense ? (const int64_t *)(D + x_imoff) : nullptr, mode,
                                             dense ? (int32_t *)(D + x_imat) : nullptr, dense ? gp : 0, (int32_t *)(D + o_col),
                                             (uint32_t *)(D + o_inter), (double *)(D + o_score), nullptr, nullptr, nullptr,
-                                            0, nullptr, stream));
+                                            0, nullptr, nullptr, stream));
         } else {
             STEP(ampis_intersect_rows_crop(D + arena0, (const int64_t *)(D + d_bitsoff), (const int32_t *)(D + o_bbox),
                                            (const uint32_t *)(D + o_area), (const int32_t *)(D + u_rowmask),

@@ -47,7 +47,7 @@ extern "C" int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_b
                                           int32_t *d_imat, int64_t imat_ints, int32_t *d_best_col,
                                           uint32_t *d_best_inter, double *d_best_score, int32_t *d_coo_row,
                                           int32_t *d_coo_col, uint32_t *d_coo_inter, int64_t coo_capacity,
-                                          uint64_t *d_coo_count, void *stream);
+                                          uint64_t *d_coo_count, void *zero_stream, void *stream);
 
 // Per-mask bookkeeping of a large batch formed ON THE DEVICE from the per-image arrays (a host loop over a million
 // masks costs more than the GPU needs for the whole evaluation): one CTA per image writes the image size of each of
@@ -294,7 +294,7 @@ extern "C" int ampis_eval_images_host(const uint8_t *const *str_ptr, const int32
                                         (int32_t *)(D + p_ab), D + p_desc, (uint32_t *)(D + p_inter), cap,
                                         (int64_t *)(D + p_off), (int32_t *)(D + p_cnt), (uint64_t *)(D + o_pairtot),
                                         nullptr, mode, nullptr, 0, (int32_t *)(D + o_col), (uint32_t *)(D + o_inter),
-                                        (double *)(D + o_score), nullptr, nullptr, nullptr, 0, nullptr, stream));
+                                        (double *)(D + o_score), nullptr, nullptr, nullptr, 0, nullptr, nullptr, stream));
         crowd_gate_kernel<<<1, 1, 0, st>>>((unsigned long long *)(D + o_pairtot), (unsigned long long *)(D + o_pairfound),
                                            limit, (int *)(D + o_crowd));
         AMPIS_CHECK_LAUNCH("crowd_gate_kernel");

@@ -296,7 +296,7 @@ extern "C" int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_b
                                           int64_t imat_ints, int32_t *d_best_col, uint32_t *d_best_inter,
                                           double *d_best_score, int32_t *d_coo_row, int32_t *d_coo_col,
                                           uint32_t *d_coo_inter, int64_t coo_capacity, uint64_t *d_coo_count,
-                                          void *stream)
+                                          void *zero_stream, void *stream)
 {
     AMPIS_REQUIRE(n_rows >= 0 && pair_capacity >= 0 && grid_capacity >= 0 && imat_ints >= 0, "negative size");
     AMPIS_REQUIRE(mode == AMPIS_MODE_IOU || mode == AMPIS_MODE_SAT, "bad mode");
@@ -310,10 +310,25 @@ extern "C" int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_b
                   "pair list must be 8-byte aligned, pair descriptors 16-byte aligned");
     AMPIS_REQUIRE(!d_coo_count || (d_coo_row && d_coo_col && d_coo_inter && coo_capacity >= 0) || coo_capacity == 0,
                   "sparse output arrays missing");
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = as_stream(stream), zs = as_stream(zero_stream);
     cudaError_t e = cudaMemsetAsync(d_pair_count, 0, sizeof(uint64_t), st);
-    if (e == cudaSuccess && d_imat && d_grp_imat_off && imat_ints > 0)      // dense rows: zeros first, rows patch their cells
+    // dense rows: zeros first, the row pass patches the non-zero cells.  With a zero_stream the fill runs beside the
+    // join and the AND+popc pass (both bound by load latency, not by bandwidth) and the row pass waits for it
+    const bool dense = d_imat && d_grp_imat_off && imat_ints > 0;
+    const bool side = dense && zero_stream && zs != st;
+    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (e == cudaSuccess && side) {
+        if (!ev_fork) {
+            e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ev_fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(zs, ev_fork, 0);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_imat, 0, (size_t)imat_ints * 4, zs);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_join, zs);
+    } else if (e == cudaSuccess && dense) {
         e = cudaMemsetAsync(d_imat, 0, (size_t)imat_ints * 4, st);
+    }
     if (e != cudaSuccess) { ampis_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     PairJoinArgs j;
     j.bits_off = d_bits_off; j.pair_desc = (PairDesc *)d_pair_desc;
@@ -334,6 +349,10 @@ extern "C" int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_b
                                                               d_pair_inter, (const unsigned long long *)d_pair_count,
                                                               pair_capacity);
         AMPIS_CHECK_LAUNCH("pair_intersect_kernel");
+    }
+    if (side) {
+        e = cudaStreamWaitEvent(st, ev_join, 0);
+        if (e != cudaSuccess) { ampis_set_error("cudaStreamWaitEvent: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
     }
     PairRowArgs a;
     a.area = d_area; a.row_mask = d_row_mask; a.row_grp = d_row_grp; a.n_rows = n_rows;

@@ -645,13 +645,14 @@ class SparseRows(object):
         return r[order], c[order], (self.inter[:n].long() & 0xffffffff)[order]
 
 
-def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=None, zeroed=None):
+def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=None, zeroed=None, zero_stream=None):
     """Run the fused row kernel.  Returns device tensors (no sync).  Crop-layout tables with many
     columns per image (ROWS_GRID_MIN_COLS), or whenever a ColumnGrid / SparseRows is passed, go through
     the grid-pruned kernels; grid='scan' forces the all-columns scan.  The grid-pruned form is the three-pass
     join (ROWS_KERNEL 'pairs'; `pairs` = a pre-sized PairList, else one is sized here with a read-back)
     or the single rows kernel of round 1 ('grid').  zeroed: a CUDA event after which the dense matrices are known to
-    be all zeros (the caller cleared them on another stream); the join then waits for it instead of clearing them."""
+    be all zeros (the caller cleared them on another stream); the join then waits for it instead of clearing them.
+    zero_stream: a torch stream on which the join zeroes the dense matrices itself while its first two passes run."""
     dev = table.device
     nr = max(groups.n_rows, 1)
     if out is None:
@@ -687,7 +688,8 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=
                        _p(out.best_col), _p(out.best_inter), _p(out.best_score),
                        _p(sparse.row) if sparse else None, _p(sparse.col) if sparse else None,
                        _p(sparse.inter) if sparse else None, sparse.capacity if sparse else 0,
-                       _p(sparse.count) if sparse else None, _stream())
+                       _p(sparse.count) if sparse else None,
+                       C.c_void_p(zero_stream.cuda_stream) if zero_stream is not None else None, _stream())
                 if not own or pairs.needed() <= pairs.capacity:
                     break
                 pairs = PairList(dev, groups.n_rows, pairs.needed())         # crowded images: grow and repeat

@@ -229,7 +229,9 @@ int ampis_intersect_rows_grid(const void *d_bits, const int64_t *d_bits_off, con
  *   2. eight lanes per pair: d_pair_inter[q] = popcount(A & B) over the overlap of the two windows;
  *   3. one thread per row: score and first arg-max over its pairs, dense cells / sparse triplets.
  * d_row_grp[r] = group of row r.  *d_pair_count (zeroed by the call) = pairs found; when it exceeds pair_capacity
- * nothing useful was computed and the caller retries with a larger list. */
+ * nothing useful was computed and the caller retries with a larger list.  zero_stream (may be NULL): a second
+ * stream on which the dense matrices are zeroed while passes 1 and 2 run on `stream` (fork / join by events inside
+ * the call); NULL = zeroed in line. */
 int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_bits_off, const int32_t *d_bbox,
                                const uint32_t *d_area, const int32_t *d_row_mask, const int32_t *d_row_grp,
                                int32_t n_rows, const int32_t *d_grp_row_begin, const int32_t *d_grp_col_begin,
@@ -240,7 +242,7 @@ int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_bits_off, co
                                uint64_t *d_pair_count, const int64_t *d_grp_imat_off, int32_t mode, int32_t *d_imat,
                                int64_t imat_ints, int32_t *d_best_col, uint32_t *d_best_inter, double *d_best_score,
                                int32_t *d_coo_row, int32_t *d_coo_col, uint32_t *d_coo_inter, int64_t coo_capacity,
-                               uint64_t *d_coo_count, void *stream);
+                               uint64_t *d_coo_count, void *zero_stream, void *stream);
 
 /* ---- one image, one call (host entry point) ---------------------------------------------------------
  * The per-image work of analyze.py:149-164 (rle_instance_matcher / det_seg_scores: G x ceil(P/80) RLE.iou calls +

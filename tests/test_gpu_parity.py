@@ -512,10 +512,11 @@ def _csr_table(mods, masks_bool, layout):
                        torch.full((n,), w, dtype=torch.int32, device=dev), layout)
 
 
-@pytest.mark.parametrize('h,w', [(8200, 24), (16500, 12), (40, 3000)])
+@pytest.mark.parametrize('h,w', [(8200, 24), (16500, 12), (40, 3000), (65536, 6), (70000, 6)])
 def test_crop_decode_of_tall_wide_and_busy_masks(mods, h, w, monkeypatch):
     """Frames taller than the shared-memory tile of the crop painter (a box of more than 128 / 256 / 512 32-row
-    bands used to overflow the tile: ADVICE r1), masks with thousands of runs, full frames and empty masks next to
+    bands used to overflow the tile: ADVICE r1; the flat decode keeps rows in 16 bits and hands frames of more than
+    65,536 rows to its fallback kernel), masks with thousands of runs, full frames and empty masks next to
     small blobs: every fused crop decode (flat with its fallback list, 8 / 16 / 32 lanes per mask) and the unfused
     painter give the measurements and the all-pairs intersections of a dense numpy formulation."""
     B, E, torch = mods.batch, mods.engine, mods.torch
