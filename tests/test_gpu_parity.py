@@ -74,6 +74,45 @@ def test_string_codec_and_measure_on_fixtures(mods):
         assert s == [x['counts'] for x in masks]
 
 
+def test_string_decode_of_long_numbers_and_any_alignment(mods):
+    """rleFrString on the GPU (four characters per lane, 128 per step) against the oracle on strings the fixtures do
+    not hold: numbers of one to ten characters (only the first seven reach the low 32 bits), counts up to 2^28 with
+    negative deltas, strings of 0 to ~1,000 characters (several steps, carries of an unfinished number and of both
+    delta chains), laid back to back so that they start at every byte alignment."""
+    E, rle, torch = mods.engine, mods.rle, mods.torch
+    rng = np.random.default_rng(77)
+    strings = []
+    for t in range(1500):
+        if t % 2 == 0:
+            m = int(rng.integers(0, 260))
+            mag = int(rng.choice([4, 40, 1000, 70000, 2 ** 22, 2 ** 28]))
+            strings.append(rle.string_from_counts(rng.integers(0, mag, m, dtype=np.int64).astype(np.uint32)))
+        else:
+            out = bytearray()
+            for _ in range(int(rng.integers(0, 120))):
+                k = int(rng.integers(1, 11))
+                out += bytes((48 + (int(rng.integers(0, 32)) | 0x20)) for _ in range(k - 1))
+                out += bytes([48 + int(rng.integers(0, 32))])
+            strings.append(bytes(out))
+    n = len(strings)
+    lens = np.array([len(x) for x in strings], np.int64)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    blob = np.frombuffer(b''.join(strings), np.uint8)
+    for lead in range(4):                                  # every alignment of the first string, too
+        d_chars = torch.from_numpy(np.concatenate([np.zeros(lead, np.uint8), blob])).cuda()
+        d_off = torch.from_numpy(off + lead).cuda()
+        cnt = torch.full((int(off[-1]) + lead + 1,), -1, dtype=torch.int32, device='cuda')
+        cnt_len = torch.empty(n, dtype=torch.int32, device='cuda')
+        E.N.call('ampis_rle_string_decode', E._p(d_chars), E._p(d_off), n, E._p(cnt), E._p(d_off), E._p(cnt_len),
+                 E._stream())
+        got, ln = cnt.cpu().numpy().view(np.uint32), cnt_len.cpu().numpy()
+        for i in range(n):
+            want = rle.counts_from_string(strings[i]) if len(strings[i]) else np.zeros(0, np.uint32)
+            assert ln[i] == len(want), (lead, i)
+            assert np.array_equal(got[off[i] + lead: off[i] + lead + ln[i]], want), (lead, i)
+
+
 def test_structures_measurements(mods):
     S, R = mods.structures, mods.R
     from ampis_b200.containers import Instances
