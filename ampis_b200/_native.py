@@ -37,6 +37,8 @@ SIGNATURES = {
                                           _i32, _p]),
     'ampis_rle_measure_paint_flat': (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
                                                _p, _i32, _p]),
+    'ampis_rle_measure_paint_flat_zero': (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64,
+                                                    _p, _p, _i32, _p, _i64, _p]),
     'ampis_intersect_rows_crop': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p,
                                             _p, _p]),
     'ampis_grid_cells': (C.c_int, []),

@@ -24,6 +24,9 @@ COCO_THRESHOLDS = np.arange(0.5, 1.0, 0.05)     # IoU 0.50:0.05:0.95
 ZERO_AHEAD = os.environ.get('AMPIS_ZERO_AHEAD', '0') != '0'
 #: Pipeline: zero the dense matrices on a side stream BESIDE the join's first two passes (load-latency bound)
 ZERO_BESIDE_JOIN = os.environ.get('AMPIS_ZERO_BESIDE_JOIN', '1') != '0'
+# dense matrices cleared by the decode kernel itself, a share per group of masks (it is bound by instruction issue and
+# leaves HBM idle): profiles/experiments_r02.md
+ZERO_WITH_DECODE = os.environ.get('AMPIS_ZERO_WITH_DECODE', '1') != '0'
 ZERO_BY_COPY = os.environ.get('AMPIS_ZERO_AHEAD', '0') == '2' 
 
 #: synthetic workloads named after BASELINE.json's configs (DESIGN.md "Synthetic data")
@@ -259,9 +262,14 @@ class Pipeline(object):
                     self.rows.imat[:g.imat_size].zero_()
                 self.zero_done.record()
         if mark: mark(0)
+        zeroed = self.zero_done if zero_ahead else None
         if self.fused:
             if mark: mark(1)
-            t.measure_paint(self.arena)
+            with_decode = ZERO_WITH_DECODE and not zero_ahead and self.pairs is not None and g.imat_off is not None \
+                and self.rows.imat is not None and engine.ROWS_KERNEL == 'pairs' and self.kernel not in ('mma', 'mma2')
+            t.measure_paint(self.arena, zero=self.rows.imat[:g.imat_size] if with_decode else None)
+            if with_decode and t.zeroed:
+                zeroed = True
         else:
             t.measure()
             if mark: mark(1)
@@ -272,12 +280,12 @@ class Pipeline(object):
                                  pair=self.kernel == 'mma2')
         else:
             side = None
-            if ZERO_BESIDE_JOIN and not zero_ahead and self.pairs is not None and g.imat_off is not None:
+            if ZERO_BESIDE_JOIN and zeroed is None and self.pairs is not None and g.imat_off is not None:
                 if self.zero_stream is None:
                     self.zero_stream = torch.cuda.Stream(device=self.batch.device)
                 side = self.zero_stream
             engine.intersect_rows(t, self.batch.groups, self.batch.mode, out=self.rows, grid=self.grid,
-                                  sparse=self.sparse, pairs=self.pairs, zeroed=self.zero_done if zero_ahead else None,
+                                  sparse=self.sparse, pairs=self.pairs, zeroed=zeroed,
                                   zero_stream=side)
         if mark: mark(3)
         if self.batch.mode == engine.MODE_IOU:

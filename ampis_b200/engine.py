@@ -82,6 +82,7 @@ class MaskTable(object):
         self.cursor = torch.empty(1, dtype=i64, device=device)   # chunks the arena needed (fused path)
         self.fused = False
         self.list = None        # scratch of the flat crop decode (masks left to its fallback kernel)
+        self.zeroed = False     # the last measure_paint also cleared the buffer it was handed
         self.bits = None
         self.bits_capacity = 0
 
@@ -111,10 +112,13 @@ class MaskTable(object):
                    _p(self.reg), _p(self.bits_off), self.n, _p(self.bits), self.bits_capacity, _stream())
         return self
 
-    def measure_paint(self, arena):
+    def measure_paint(self, arena, zero=None):
         """Fused single-launch form of measure() + paint(arena): arena space is handed out by an
         atomic cursor, so the arena must be supplied (size it with a previous measure() or
-        generously) and overflow is detected afterwards by check()."""
+        generously) and overflow is detected afterwards by check().  zero: a device tensor the launch also clears
+        (the dense matrices of the rows that follow; flat crop decode only -- returns with self.zeroed set when the
+        kernel took the job, else the caller clears it)."""
+        self.zeroed = False
         self.bits = arena
         self.bits_capacity = arena.numel() // 4
         self.fused = True
@@ -122,6 +126,13 @@ class MaskTable(object):
         if self.layout == LAYOUT_CROP and CROP_DECODE == 'flat':
             if self.list is None:
                 self.list = torch.empty(self.n + 1, dtype=torch.int32, device=self.device)
+            if zero is not None and zero.numel() and zero.data_ptr() % 16 == 0:
+                N.call('ampis_rle_measure_paint_flat_zero', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len),
+                       _p(self.h), _p(self.w), self.n, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span),
+                       _p(self.reg), _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity,
+                       _p(self.cursor), _p(self.list), hint, _p(zero), zero.numel() * zero.element_size(), _stream())
+                self.zeroed = True
+                return self
             N.call('ampis_rle_measure_paint_flat', _p(self.cnt), _p(self.cnt_off), _p(self.cnt_len), _p(self.h),
                    _p(self.w), self.n, _p(self.cum), _p(self.area), _p(self.bbox), _p(self.span), _p(self.reg),
                    _p(self.bits_off), _p(self.status), _p(self.bits), self.bits_capacity, _p(self.cursor),
@@ -650,8 +661,8 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=
     columns per image (ROWS_GRID_MIN_COLS), or whenever a ColumnGrid / SparseRows is passed, go through
     the grid-pruned kernels; grid='scan' forces the all-columns scan.  The grid-pruned form is the three-pass
     join (ROWS_KERNEL 'pairs'; `pairs` = a pre-sized PairList, else one is sized here with a read-back)
-    or the single rows kernel of round 1 ('grid').  zeroed: a CUDA event after which the dense matrices are known to
-    be all zeros (the caller cleared them on another stream); the join then waits for it instead of clearing them.
+    or the single rows kernel of round 1 ('grid').  zeroed: True = the dense matrices are all zeros already on this stream (MaskTable.measure_paint(zero=...)), or a
+    CUDA event after which they are (the caller cleared them on another stream); the join then does not clear them.
     zero_stream: a torch stream on which the join zeroes the dense matrices itself while its first two passes run."""
     dev = table.device
     nr = max(groups.n_rows, 1)
@@ -675,7 +686,7 @@ def intersect_rows(table, groups, mode, out=None, grid=None, sparse=None, pairs=
             own = pairs is None
             if own:
                 pairs = PairList(dev, groups.n_rows, 8 * groups.n_rows + 4096)
-            if zeroed is not None:
+            if zeroed is not None and zeroed is not True:
                 torch.cuda.current_stream().wait_event(zeroed)
             while True:
                 N.call('ampis_intersect_rows_pairs', _p(table.bits), _p(table.bits_off), _p(table.bbox),

@@ -127,12 +127,23 @@ int ampis_rle_measure_paint(const uint32_t *d_cnt, const int64_t *d_cnt_off, con
  * record-forming lane per mask, one arena reservation and one contiguous copy-out per warp (csrc/rle_flat.cu).
  * Same outputs as ampis_rle_measure_paint(layout = AMPIS_LAYOUT_CROP), bit for bit; arena order differs.
  * d_list: int32[n + 1] scratch; masks outside the per-warp budgets (more than 512 runs, window larger than 2 KB,
- * frame of 2^31 pixels or more) are listed there and worked off by a second launch (a warp per mask, any size). */
+ * frame of 2^31 pixels or more or taller than 65,536 rows) are listed there and worked off by a second launch (a warp per mask, any size). */
 int ampis_rle_measure_paint_flat(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
                                  const uint32_t *d_h, const uint32_t *d_w, int32_t n, uint32_t *d_cum,
                                  uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span, uint32_t *d_reg,
                                  int64_t *d_bits_off, int32_t *d_status, void *d_bits, int64_t bits_capacity,
                                  uint64_t *d_cursor, int32_t *d_list, int32_t runs_hint, void *stream);
+
+/* The same launch with a side job: the kernel also ZEROES d_zero[0 .. zero_bytes) (16-byte aligned; NULL = nothing), a
+ * share per group of masks.  The decode is bound by instruction issue and leaves HBM idle, so the dense matrices the
+ * row pass will patch (analyze.py:149-158: one G x P matrix per image, 1 GB per 1,000 C2 images) are cleared here for
+ * ~1 % more instructions instead of by a separate fill.  Pass imat_ints = 0 to ampis_intersect_rows_pairs afterwards. */
+int ampis_rle_measure_paint_flat_zero(const uint32_t *d_cnt, const int64_t *d_cnt_off, const int32_t *d_cnt_len,
+                                      const uint32_t *d_h, const uint32_t *d_w, int32_t n, uint32_t *d_cum,
+                                      uint32_t *d_area, int32_t *d_bbox, uint32_t *d_span, uint32_t *d_reg,
+                                      int64_t *d_bits_off, int32_t *d_status, void *d_bits, int64_t bits_capacity,
+                                      uint64_t *d_cursor, int32_t *d_list, int32_t runs_hint, void *d_zero,
+                                      int64_t zero_bytes, void *stream);
 
 /* bits -> bool[n][h][w] row-major bytes (RLE.decode(...).astype(bool).transpose(2,0,1),
  * structures.py:752,765).  All n masks must share (h,w). d_mask_ids selects masks. */
