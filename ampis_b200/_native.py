@@ -94,7 +94,7 @@ SYNTH_SIGNATURES = {
 
 _lib = None
 _synth = None
-ABI_VERSION = 200       # ampis_version(): bumped whenever a signature of include/ampis_b200.h changes
+ABI_VERSION = 201       # ampis_version(): bumped whenever a signature of include/ampis_b200.h changes
 
 
 class AmpisNativeError(RuntimeError):

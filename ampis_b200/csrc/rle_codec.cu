@@ -17,7 +17,7 @@ void ampis_set_error(const char *fmt, ...)
 }
 
 extern "C" const char *ampis_last_error(void) { return g_err; }
-extern "C" int ampis_version(void) { return 200; }
+extern "C" int ampis_version(void) { return 201; }
 
 extern "C" int ampis_sm_count(void)
 {

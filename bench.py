@@ -72,7 +72,8 @@ def parse():
     ap.add_argument('--span-sub', type=int, default=0, help='images per launch group of the secondary runs')
     ap.add_argument('--unfused', action='store_true', help='separate measure / scan / paint launches')
     ap.add_argument('--no-span', action='store_true', help='skip the secondary layouts')
-    ap.add_argument('--e2e-chunk', type=int, default=250, help='images per C-ABI call of the e2e leg')
+    ap.add_argument('--e2e-chunk', type=int, default=0,
+                    help='images per C-ABI call of the e2e leg (0 = about 250,000 masks per call, equal calls)')
     ap.add_argument('--api-images', type=int, default=200, help='images per call of the e2e_api leg')
     ap.add_argument('--cpu-images', type=int, default=0)
     ap.add_argument('--cpu-threads', type=int, default=0, help='reference arm: worker processes (0 = all cores)')
@@ -438,6 +439,11 @@ def roofline_of(args, run, ms, kt, steps):
     # per-kernel algorithmic bytes: decode = 4R in + stored bytes out; intersection = every stored mask read once +
     # the intersections out (full layout: stored = N * B_m, SURVEY 8d's canonical per-kernel figure)
     alg = {'paint': 4.0 * run.total_runs + stored, 'rows': stored + out_bytes}
+    # the flat decode kernel also clears the dense matrices (a share per group of masks): those bytes are written by
+    # it, not by the rows, which then only patch the non-zero cells
+    zero_in_decode = bool(dense_out and getattr(run.pipes[0].table, 'zeroed', False))
+    if zero_in_decode:
+        alg = {'paint': 4.0 * run.total_runs + stored + out_bytes, 'rows': float(stored)}
     canonical_img = 4.0 * run.total_runs / n_img + 2 * per_image * B_m + 4 * pairs_img + 8 * per_image + 32 * cfg['n_rows']
     own_img = 4.0 * run.total_runs / n_img + 2.0 * stored / n_img + out_bytes / n_img + 8 * per_image + 32 * cfg['n_rows']
     dom = 'paint' if kt[1] >= kt[2] else 'rows'
@@ -483,12 +489,13 @@ def roofline_of(args, run, ms, kt, steps):
             'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
             'traffic_detail': traffic_detail, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': alg[dom] / launches, 'launch_ms': dur_ms,
+            'dense_matrices_cleared_by': ('decode kernel' if zero_in_decode else 'rows (fill)') if dense_out else None,
             'bound_note': {'full': 'pure write stream of full frames: HBM-bound; the measured peak is a COPY (half reads, '
                                    'half writes), a write-only stream sustains slightly more, hence frac a little above 1',
                            'span': 'culled storage: the kernels are bound by instruction issue / load latency, not by '
                                    'these bytes',
                            'crop': 'culled storage: the decode kernel is bound by instruction issue (ncu: issue slots '
-                                   '~72 % busy, DRAM a few %), the join by load latency -- these are the bytes the kernel '
+                                   '~72 % busy, DRAM 35 % of peak with the dense matrices it clears), the join by load latency -- these are the bytes the kernel '
                                    'MUST move; the fraction says how far from bandwidth-bound it is '
                                    '(profiles/kernels_r02.md)'}[lay],
             'step': step, 'canonical': canonical, 'kernel_share': share}
@@ -580,8 +587,16 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
     thr = np.ascontiguousarray(batch.COCO_THRESHOLDS.astype(np.float64)) if mode == 0 else np.zeros(0)
     chunks = []
     for hst in hosts:
-        for s0 in range(0, hst.n_images, args.e2e_chunk):
-            part = hst.slice(s0, min(s0 + args.e2e_chunk, hst.n_images))
+        # calls of ~250,000 masks but at least 80 images, all of the same size.  Measured (images per call / calls in
+        # flight -> ms per step): C2 125/4 6.6, 250/4 1.88, 250/6 1.80, 334/4 1.90, 500/3 1.94, 1000/2 2.31;
+        # C4 (10,000 masks per image, 160 images) 23/2 3.84, 80/3 1.98, 160/2 2.27; C3 100/3 0.94, 200/2 1.05
+        e2e_chunk = args.e2e_chunk
+        if e2e_chunk <= 0:
+            want = max(80, 250000 // max(hst.per_image, 1))
+            n_calls = max(1, -(-hst.n_images // want))
+            e2e_chunk = max(1, -(-hst.n_images // n_calls))
+        for s0 in range(0, hst.n_images, e2e_chunk):
+            part = hst.slice(s0, min(s0 + e2e_chunk, hst.n_images))
             blob, ln = strings_of(batch.DeviceBatch(part, dev))
             ni = part.n_images
             pin = lambda a: torch.from_numpy(a).pin_memory().numpy()          # page-locked arrays: DMA endpoints
@@ -598,7 +613,10 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
             ch['h2d'] = int(blob.nbytes + 4 * n + 32 * ni + 8 * len(thr))
             ch['d2h'] = int(16 * R + 8 * n + 12 * len(thr) * ni + 24 * len(thr))
             chunks.append(ch)
-    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '6'))      # measured 4 / 6 / 8: 1.88 / 1.82 / 6.1 ms per step
+    # calls in flight: three quarters of the calls of two steps (the main thread queues one step ahead).  Measured on
+    # C2 (4 calls per step): 4 / 6 / 8 workers = 1.88 / 1.82 / 6.1 ms per step -- with a worker for every queued call
+    # the kernels of step i+1 share the GPU with those of step i, whose totals the main thread is waiting for
+    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '0')) or max(2, min(6, (3 * 2 * len(chunks)) // 4))
     # AMPIS_STRINGS_CONTIGUOUS (1) [+ AMPIS_WAIT_BLOCKING (2): measured per box, profiles/scaling_r02.md]
     call_flags = 1 | (2 if os.environ.get('AMPIS_E2E_BLOCKING', '0') == '1' else 0)
     workers = [{'stream': torch.cuda.Stream(device=dev),
@@ -708,7 +726,7 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
     return {'value': pairs * args.steps / (ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': sum(c_['h2d'] for c_ in chunks),
             'd2h_bytes_per_step': sum(c_['d2h'] for c_ in chunks), 'ms_per_step': ms / args.steps,
             'images_per_s': world * n_img * args.steps / (ms / 1e3), 'wall_ms_per_step': wall_ms / args.steps,
-            'calls_per_step': len(chunks), 'images_per_call': args.e2e_chunk, 'calls_in_flight': n_workers,
+            'calls_per_step': len(chunks), 'images_per_call': max(c_['n_images'] for c_ in chunks), 'calls_in_flight': n_workers,
             'pipelining': 'the calls of step i+1 are queued while step i is evaluated (its upload overlaps that '
                           'evaluation); the totals of every step are read on the host before the step counts as done',
             'entry': 'ampis_eval_images_host (C ABI, include/ampis_b200.h): strings back to back in pinned host memory '

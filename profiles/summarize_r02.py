@@ -113,15 +113,15 @@ def main():
         for r in rows:
             k = r['Kernel Name'].split('(')[0].replace('void ', '')
             agg.setdefault(k, []).append(float(r['Metric Value']) / 1e3)
-        step = ('rle_flat_crop_kernel', 'rle_measure_paint_list_kernel', 'grid_build_kernel', 'pairs_from_grid_kernel',
+        step = ('rle_flat_crop_kernel', 'rle_flat_crop_kernel<1>', 'rle_flat_crop_kernel<0>', 'rle_measure_paint_list_kernel', 'grid_build_kernel', 'pairs_from_grid_kernel',
                 'pair_intersect_kernel', 'rows_from_pairs_kernel<0>', 'match_counts_kernel')
         tot = sum(sum(v) for k, v in agg.items() if k in step)
         md = ['# ncu launch list, round 2 (%s): crop layout, 1,000 C2 images per launch' % tag, '',
               '`ncu --metrics gpu__time_duration.sum --clock-control none -c 300 python bench.py --steps 2 --warmup 3 '
-              '--no-e2e --no-cpu --no-span --no-c5 --no-check`', '',
+              '--no-graph --no-e2e --no-cpu --no-span --no-c5 --no-check`', '',
               'Per-launch times under ncu are cold-cache and serialised: compare SHARES with `roofline.kernel_share` of '
-              'the bench line (paint = flat decode + list kernel; rows = grid build + the three join kernels + the '
-              'memset of the dense matrices, which ncu does not list; counts = match_counts).', '',
+              'the bench line (paint = flat decode, which also clears the dense matrices, + list kernel; rows = grid build + the '
+              'three join kernels; counts = match_counts).', '',
               '| kernel | launches | mean us | total us | share of the step kernels |', '|---|---|---|---|---|']
         for k, v in sorted(agg.items(), key=lambda x: -sum(x[1])):
             md.append('| `%s` | %d | %.1f | %.1f | %s |' % (k, len(v), sum(v) / len(v), sum(v),
