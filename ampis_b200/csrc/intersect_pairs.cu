@@ -12,10 +12,13 @@
 //       column masks, built by grid_build_kernel), tests the boxes stored with the entries -- rleIou's bbIou
 //       pre-pass -- and appends the candidate pairs (row mask id, column mask id).  The pairs of a row are contiguous:
 //       counts are scanned over the warp and the warp reserves its range with one atomicAdd.
-//   pair_intersect_kernel    eight lanes per candidate pair (four pairs per warp, grid-stride): popcount(A & B) over
-//       the overlap of the two bounding-box windows; pairs with large overlaps get the whole warp.
+//   pair_intersect_flat_kernel   a warp per eight consecutive pairs, lanes over their concatenated overlap columns:
+//       popcount(A & B) per column, per-pair sums by a segmented warp scan.  (pair_intersect_kernel, eight lanes per
+//       pair and the whole warp for large overlaps, is the first form of the pass: AMPIS_PI_FLAT=0.)
 //   rows_from_pairs_kernel   one thread per row: IoU / overlap score of its pairs, first arg-max (ties broken on the
 //       column index, so the order of a row's pairs does not matter), dense matrix cells and sparse triplets.
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 #define PJ_GR_N 32                       // cells per axis of the column grid (= GR_N of intersect_grid.cu)
@@ -223,6 +226,110 @@ pair_intersect_kernel(const u32 *__restrict__ words, const PairDesc *__restrict_
     }
 }
 
+// The same pass FLAT: a warp takes eight consecutive pairs and spreads its lanes over their concatenated overlap columns
+// (a column of more than four bands is several items), so every lane has a column whatever the sizes of the eight
+// overlaps are, and the per-pair sums are one segmented warp scan per 32 items.  With eight lanes per pair the four
+// pairs of a warp ran in lockstep to the trip count of the largest, 2/3 of the lanes busy on average.
+#define PF_PAIRS 8
+#define PF_WORDS 4u
+
+struct __align__(16) PfWarp {
+    uint4 lo[PF_PAIRS], hi[PF_PAIRS];       // the descriptors of the batch
+    u32 start[PF_PAIRS + 1];                // first item of every pair
+    u32 nsub[PF_PAIRS];                     // items per overlap column
+    u32 acc[PF_PAIRS];
+};
+
+// U = passes of 32 items a warp has in flight (their loads are issued before the first popcount)
+template <int U>
+__global__ void __launch_bounds__(256, 6)
+pair_intersect_flat_kernel(const u32 *__restrict__ words, const PairDesc *__restrict__ pair_desc,
+                           u32 *__restrict__ pair_inter, const unsigned long long *__restrict__ pair_count,
+                           i64 pair_capacity)
+{
+    __shared__ PfWarp s_w[8];
+    PfWarp &S = s_w[threadIdx.x >> 5];
+    const u32 lane = lane_id();
+    const i64 n = (i64)*pair_count;
+    if (n > pair_capacity) return;          // the list overflowed (rows without room wrote nothing): the caller retries
+    const i64 stride = (i64)gridDim.x * (blockDim.x >> 5) * PF_PAIRS;
+    for (i64 q0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PF_PAIRS; q0 < n; q0 += stride) {
+        u32 items = 0;
+        if (lane < PF_PAIRS) {
+            uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+            u32 ns = 1u;
+            if (q0 + lane < n) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(pair_desc + q0 + lane);
+                lo = __ldg(src);
+                hi = __ldg(src + 1);
+                ns = max((hi.z + PF_WORDS - 1u) / PF_WORDS, 1u);
+                items = hi.z ? hi.w * ns : 0u;
+            }
+            S.lo[lane] = lo; S.hi[lane] = hi; S.nsub[lane] = ns; S.acc[lane] = 0u;
+        }
+        u32 incl = items;
+#pragma unroll
+        for (int d = 1; d < PF_PAIRS; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        if (lane < PF_PAIRS) S.start[lane] = incl - items;
+        if (lane == PF_PAIRS - 1) S.start[PF_PAIRS] = incl;
+        __syncwarp();
+        const u32 T = S.start[PF_PAIRS];
+        const u32 s1 = S.start[1], s2 = S.start[2], s3 = S.start[3], s4 = S.start[4], s5 = S.start[5], s6 = S.start[6],
+                  s7 = S.start[7];
+        for (u32 c0 = 0; c0 < T; c0 += 32 * U) {
+            u32 v[U], j[U], it[U], x0[U], x1[U], wa[U], wb[U];
+            const u32 *pa[U], *pb[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const u32 c = c0 + 32u * u + lane;
+                ok[u] = c < T;
+                v[u] = 0u; j[u] = 0u; it[u] = 0u; x0[u] = 0u; x1[u] = 0u; wa[u] = 0u; wb[u] = 0u;
+                pa[u] = pb[u] = words;
+                if (ok[u]) {
+                    j[u] = (u32)(c >= s1) + (u32)(c >= s2) + (u32)(c >= s3) + (u32)(c >= s4) + (u32)(c >= s5) +
+                           (u32)(c >= s6) + (u32)(c >= s7);
+                    it[u] = c - S.start[j[u]];
+                    const uint4 lo = S.lo[j[u]], hi = S.hi[j[u]];
+                    const u32 ns = S.nsub[j[u]];
+                    u32 dx = it[u], w0 = 0u, w1 = hi.z;
+                    if (ns > 1u) {
+                        dx = it[u] / ns;
+                        w0 = (it[u] - dx * ns) * PF_WORDS;
+                        w1 = min(hi.z, w0 + PF_WORDS);
+                    }
+                    pa[u] = words + (i64)(((u64)lo.y << 32) | lo.x) + (i64)dx * hi.x + w0;
+                    pb[u] = words + (i64)(((u64)lo.w << 32) | lo.z) + (i64)dx * hi.y + w0;
+                    wa[u] = w0; wb[u] = w1;
+                    // the first two bands of the column (most overlaps have one or two): all loads of all passes in flight
+                    x0[u] = __ldg(pa[u]) & __ldg(pb[u]);
+                    if (w0 + 1u < w1) x1[u] = __ldg(pa[u] + 1) & __ldg(pb[u] + 1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                v[u] = __popc(x0[u]) + __popc(x1[u]);
+                for (u32 w = wa[u] + 2u; w < wb[u]; w++) v[u] += __popc(__ldg(pa[u] + (w - wa[u])) & __ldg(pb[u] + (w - wa[u])));
+                // sums per pair: the lanes of a pair are contiguous
+                const u32 reach = ok[u] ? min(lane, it[u]) : 0u;
+#pragma unroll
+                for (u32 d = 1; d < 32; d <<= 1) {
+                    const u32 t = __shfl_up_sync(0xffffffffu, v[u], d);
+                    if (d <= reach) v[u] += t;
+                }
+                const u32 c = c0 + 32u * u + lane;
+                if (ok[u] && (lane == 31u || c + 1u == S.start[j[u] + 1])) atomicAdd(&S.acc[j[u]], v[u]);
+            }
+        }
+        __syncwarp();
+        if (lane < PF_PAIRS && q0 + lane < n) pair_inter[q0 + lane] = S.acc[lane];
+        __syncwarp();
+    }
+}
+
 struct PairRowArgs {
     const u32 *area;
     const int *row_mask, *row_grp;
@@ -345,7 +452,19 @@ extern "C" int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_b
         i64 want = (pair_capacity + 31) / 32;                      // 8 warps x 4 pairs per CTA and trip
         const i64 cap = 148 * 8 * 8;
         if (want > cap) want = cap;
-        pair_intersect_kernel<<<(unsigned)want, 256, 0, st>>>((const u32 *)d_bits, (const PairDesc *)d_pair_desc,
+        // AMPIS_PI_FLAT: 1 (default) = lanes over the concatenated columns of eight pairs, 2 = the same with two passes in
+        // flight, 0 = eight lanes per pair (profiles/experiments_r02.md: 0.395 / 0.387 / 0.383 ms of rows per C2 step)
+        static const int flat = [] { const char *v = getenv("AMPIS_PI_FLAT"); return v ? atoi(v) : 1; }();
+        if (flat == 1)
+            pair_intersect_flat_kernel<1><<<(unsigned)std::min<i64>((pair_capacity + 63) / 64, cap), 256, 0, st>>>(
+                (const u32 *)d_bits, (const PairDesc *)d_pair_desc, d_pair_inter, (const unsigned long long *)d_pair_count,
+                pair_capacity);
+        else if (flat == 2)
+            pair_intersect_flat_kernel<2><<<(unsigned)std::min<i64>((pair_capacity + 63) / 64, cap), 256, 0, st>>>(
+                (const u32 *)d_bits, (const PairDesc *)d_pair_desc, d_pair_inter, (const unsigned long long *)d_pair_count,
+                pair_capacity);
+        else
+            pair_intersect_kernel<<<(unsigned)want, 256, 0, st>>>((const u32 *)d_bits, (const PairDesc *)d_pair_desc,
                                                               d_pair_inter, (const unsigned long long *)d_pair_count,
                                                               pair_capacity);
         AMPIS_CHECK_LAUNCH("pair_intersect_kernel");

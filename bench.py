@@ -616,7 +616,10 @@ def run_e2e_cabi(args, hosts, dev, cfg, world, dist, sync):
     # calls in flight: three quarters of the calls of two steps (the main thread queues one step ahead).  Measured on
     # C2 (4 calls per step): 4 / 6 / 8 workers = 1.88 / 1.82 / 6.1 ms per step -- with a worker for every queued call
     # the kernels of step i+1 share the GPU with those of step i, whose totals the main thread is waiting for
-    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '0')) or max(2, min(6, (3 * 2 * len(chunks)) // 4))
+    # ... and never more spinning threads than this rank's share of the host cores (8 ranks on a 32-core host: 3;
+    # with 6 each the 8-rank step took 5.54 ms instead of 5.0, profiles/scaling_r02.md)
+    n_workers = int(os.environ.get('AMPIS_E2E_WORKERS', '0')) or \
+        max(2, min(6, (3 * 2 * len(chunks)) // 4, (os.cpu_count() or 8) // max(world, 1) - 1))
     # AMPIS_STRINGS_CONTIGUOUS (1) [+ AMPIS_WAIT_BLOCKING (2): measured per box, profiles/scaling_r02.md]
     call_flags = 1 | (2 if os.environ.get('AMPIS_E2E_BLOCKING', '0') == '1' else 0)
     workers = [{'stream': torch.cuda.Stream(device=dev),
