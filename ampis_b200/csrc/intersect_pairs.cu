@@ -253,7 +253,11 @@ pair_intersect_flat_kernel(const u32 *__restrict__ words, const PairDesc *__rest
     const i64 n = (i64)*pair_count;
     if (n > pair_capacity) return;          // the list overflowed (rows without room wrote nothing): the caller retries
     const i64 stride = (i64)gridDim.x * (blockDim.x >> 5) * PF_PAIRS;
-    for (i64 q0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PF_PAIRS; q0 < n; q0 += stride) {
+    // batches are taken from the END of the list: the windows of the last images were written last by the decode and
+    // are the ones still in L2
+    const i64 n_batches = (n + PF_PAIRS - 1) / PF_PAIRS;
+    for (i64 bi = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bi < n_batches; bi += stride / PF_PAIRS) {
+        const i64 q0 = (n_batches - 1 - bi) * PF_PAIRS;
         u32 items = 0;
         if (lane < PF_PAIRS) {
             uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);

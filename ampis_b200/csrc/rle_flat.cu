@@ -116,7 +116,8 @@ rle_flat_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_of
         // group replace a separate 1 GB fill per 1,000 C2 images
         if (ZERO) {
             const u32 z0 = (u32)gw * zero_per_group, z1 = min(z0 + zero_per_group, zero_chunks);     // no overflow: see the launch
-            for (u32 k = z0 + lane; k < z1; k += 32) zero[k] = make_uint4(0u, 0u, 0u, 0u);
+            // streaming stores: the zeros must not push the windows written below out of L2 (the join reads them next)
+            for (u32 k = z0 + lane; k < z1; k += 32) __stcs(zero + k, make_uint4(0u, 0u, 0u, 0u));
         }
 
         // ---- the warp's masks: one lane each
@@ -170,8 +171,8 @@ rle_flat_crop_kernel(const u32 *__restrict__ cnt, const i64 *__restrict__ cnt_of
                     const uint4 g = S.geo[a + j];
                     H = g.x; rcp = g.y; HW = g.z;
                     const u32 *c = S.src[a + j] + 2 * p;
-                    z = min(__ldg(c), FL_SAT);
-                    if ((int)(2 * p + 1) < (int)g.w) o = min(__ldg(c + 1), FL_SAT);
+                    z = min(__ldcs(c), FL_SAT);                        // read once: evict first
+                    if ((int)(2 * p + 1) < (int)g.w) o = min(__ldcs(c + 1), FL_SAT);
                 }
                 u32 end = sat_add(z, o), osum = o;
                 const u32 reach = ok ? min(lane, p) : 0u;            // lanes below me that belong to my mask
