@@ -92,11 +92,12 @@ def main():
                                                          'images_per_launch': n_img, 'source': 'profiles/kernels_r02.md'}
         if n_img == 1000:
             rows_k = [r for r in rows if r['kernel'].split('<')[0] in ('grid_build_kernel', 'pairs_from_grid_kernel',
-                                                                      'pair_intersect_kernel', 'rows_from_pairs_kernel')]
+                                                                      'pair_intersect_kernel', 'pair_intersect_flat_kernel',
+                                                                      'rows_from_pairs_kernel')]
             tot = sum(r.get('DRAM read MB', 0) + r.get('DRAM write MB', 0) for r in rows_k)
             traffic['c2_powder_batch/crop/rows'] = {'bytes_per_image': tot * 1e6 / n_img, 'bytes_per_launch': tot * 1e6,
-                                                    'images_per_launch': n_img, 'source': 'profiles/kernels_r02.md (four join '
-                                                    'kernels; the memset of the dense matrices is not a kernel)'}
+                                                    'images_per_launch': n_img, 'source': 'profiles/kernels_r02.md (grid build + the '
+                                                    'three join kernels; the dense matrices are cleared by the decode kernel)'}
         md.append('')
     open(os.path.join(PROF, 'kernels_r02.md'), 'w').write('\n'.join(md) + '\n')
     json.dump(traffic, open(os.path.join(PROF, 'traffic.json'), 'w'), indent=1, sort_keys=True)
@@ -113,8 +114,9 @@ def main():
         for r in rows:
             k = r['Kernel Name'].split('(')[0].replace('void ', '')
             agg.setdefault(k, []).append(float(r['Metric Value']) / 1e3)
-        step = ('rle_flat_crop_kernel', 'rle_flat_crop_kernel<1>', 'rle_flat_crop_kernel<0>', 'rle_measure_paint_list_kernel', 'grid_build_kernel', 'pairs_from_grid_kernel',
-                'pair_intersect_kernel', 'rows_from_pairs_kernel<0>', 'match_counts_kernel')
+        step_prefixes = ('rle_flat_crop_kernel', 'rle_measure_paint_list_kernel', 'grid_build_kernel', 'pairs_from_grid_kernel',
+                         'pair_intersect', 'rows_from_pairs_kernel', 'match_counts_kernel')
+        step = tuple(k for k in agg if k.startswith(step_prefixes))
         tot = sum(sum(v) for k, v in agg.items() if k in step)
         md = ['# ncu launch list, round 2 (%s): crop layout, 1,000 C2 images per launch' % tag, '',
               '`ncu --metrics gpu__time_duration.sum --clock-control none -c 300 python bench.py --steps 2 --warmup 3 '
