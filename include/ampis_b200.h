@@ -65,7 +65,9 @@ int         ampis_sm_count(void);
  * structures.py:467,568,571,752,761).  d_chars holds the n compressed strings back
  * to back, d_chr_off[n+1] their byte offsets.  Counts of mask i are written at
  * d_cnt + d_cnt_off[i] (a string of L bytes yields at most L counts, so
- * cnt_off = chr_off is always large enough); d_cnt_len[i] receives the run count. */
+ * cnt_off = chr_off is always large enough); d_cnt_len[i] receives the run count.
+ * The kernel reads d_chars as aligned 32-bit words (only words that hold a character of a string): the allocation
+ * behind d_chars must cover whole words, as every cudaMalloc / torch allocation does.  One thread per string. */
 int ampis_rle_string_decode(const uint8_t *d_chars, const int64_t *d_chr_off, int32_t n,
                             uint32_t *d_cnt, const int64_t *d_cnt_off, int32_t *d_cnt_len,
                             void *stream);
