@@ -551,6 +551,46 @@ def _csr_table(mods, masks_bool, layout):
                        torch.full((n,), w, dtype=torch.int32, device=dev), layout)
 
 
+def test_flat_decode_clears_the_buffer_it_is_handed(mods, monkeypatch):
+    """MaskTable.measure_paint(arena, zero=buf): the flat crop decode also clears buf (the dense matrices of the rows
+    that follow), whatever its length -- whole 16-byte chunks by the kernel, a tail by a memset, nothing beyond it --
+    and decodes exactly what it decodes without the side job."""
+    E, torch = mods.engine, mods.torch
+    monkeypatch.setattr(E, 'CROP_DECODE', 'flat')
+    rng = np.random.default_rng(3)
+    n, h, w = 37, 90, 70
+    m = np.zeros((n, h, w), bool)
+    for k in range(n):
+        y, x, r = rng.integers(5, h - 5), rng.integers(5, w - 5), rng.integers(2, 14)
+        yy, xx = np.ogrid[:h, :w]
+        m[k] = (yy - y) ** 2 + (xx - x) ** 2 <= r * r
+    ref = _csr_table(mods, m, E.LAYOUT_CROP)
+    arena = torch.empty(1 << 16, dtype=torch.int32, device='cuda')
+    ref.measure_paint(arena).check()
+    assert not ref.zeroed
+    want_bits = arena[:4 * int(ref.cursor.item())].clone()
+    for ints in (1, 3, 4, 5, 1027, 40000, 1 << 20):
+        buf = torch.full((ints + 8,), 7, dtype=torch.int32, device='cuda')
+        t = _csr_table(mods, m, E.LAYOUT_CROP)
+        arena2 = torch.empty(1 << 16, dtype=torch.int32, device='cuda')
+        t.measure_paint(arena2, zero=buf[4:4 + ints])            # 16-byte aligned start, any length
+        t.check()
+        assert t.zeroed
+        assert bool((buf[4:4 + ints] == 0).all()) and bool((buf[:4] == 7).all()) and bool((buf[4 + ints:] == 7).all()), ints
+        assert torch.equal(t.area[:n], ref.area[:n]) and torch.equal(t.bbox[:4 * n], ref.bbox[:4 * n])
+        assert int(t.cursor.item()) == int(ref.cursor.item())
+        # same windows (the arena order may differ between launches: compare through the offsets)
+        for k in range(n):
+            a0, b0 = int(ref.bits_off[k].item()) * 4, int(t.bits_off[k].item()) * 4
+            nw = int(ref.reg[2 * k + 1].item()) * 4
+            assert torch.equal(want_bits[a0:a0 + nw], arena2[b0:b0 + nw]), (ints, k)
+    # an unaligned buffer is declined: the caller clears it
+    t = _csr_table(mods, m, E.LAYOUT_CROP)
+    buf = torch.full((64,), 7, dtype=torch.int32, device='cuda')
+    t.measure_paint(torch.empty(1 << 16, dtype=torch.int32, device='cuda'), zero=buf[1:33])
+    assert not t.zeroed and bool((buf == 7).all())
+
+
 @pytest.mark.parametrize('h,w', [(8200, 24), (16500, 12), (40, 3000), (65536, 6), (70000, 6)])
 def test_crop_decode_of_tall_wide_and_busy_masks(mods, h, w, monkeypatch):
     """Frames taller than the shared-memory tile of the crop painter (a box of more than 128 / 256 / 512 32-row
