@@ -75,8 +75,8 @@ def test_string_codec_and_measure_on_fixtures(mods):
 
 
 def test_string_decode_of_long_numbers_and_any_alignment(mods):
-    """rleFrString on the GPU (four characters per lane, 128 per step) against the oracle on strings the fixtures do
-    not hold: numbers of one to ten characters (only the first seven reach the low 32 bits), counts up to 2^28 with
+    """rleFrString on the GPU (both kernels: a warp per mask for small batches, a thread per mask for large ones)
+    against the oracle on strings the fixtures do not hold: numbers of one to ten characters (only the first seven reach the low 32 bits), counts up to 2^28 with
     negative deltas, strings of 0 to ~1,000 characters (several steps, carries of an unfinished number and of both
     delta chains), laid back to back so that they start at every byte alignment."""
     E, rle, torch = mods.engine, mods.rle, mods.torch
@@ -94,12 +94,20 @@ def test_string_decode_of_long_numbers_and_any_alignment(mods):
                 out += bytes((48 + (int(rng.integers(0, 32)) | 0x20)) for _ in range(k - 1))
                 out += bytes([48 + int(rng.integers(0, 32))])
             strings.append(bytes(out))
+    want_of = [rle.counts_from_string(x) if len(x) else np.zeros(0, np.uint32) for x in strings]
+    # 1,500 strings go through the warp-per-mask kernel (small batches), 18,000 through the thread-per-mask one
+    for reps in (1, 12):
+        _check_string_decode(mods, strings * reps, want_of * reps, leads=range(4) if reps == 1 else (0, 3))
+
+
+def _check_string_decode(mods, strings, want_of, leads):
+    E, torch = mods.engine, mods.torch
     n = len(strings)
     lens = np.array([len(x) for x in strings], np.int64)
     off = np.zeros(n + 1, np.int64)
     np.cumsum(lens, out=off[1:])
     blob = np.frombuffer(b''.join(strings), np.uint8)
-    for lead in range(4):                                  # every alignment of the first string, too
+    for lead in leads:                                     # every alignment of the first string, too
         d_chars = torch.from_numpy(np.concatenate([np.zeros(lead, np.uint8), blob])).cuda()
         d_off = torch.from_numpy(off + lead).cuda()
         cnt = torch.full((int(off[-1]) + lead + 1,), -1, dtype=torch.int32, device='cuda')
@@ -108,7 +116,7 @@ def test_string_decode_of_long_numbers_and_any_alignment(mods):
                  E._stream())
         got, ln = cnt.cpu().numpy().view(np.uint32), cnt_len.cpu().numpy()
         for i in range(n):
-            want = rle.counts_from_string(strings[i]) if len(strings[i]) else np.zeros(0, np.uint32)
+            want = want_of[i]
             assert ln[i] == len(want), (lead, i)
             assert np.array_equal(got[off[i] + lead: off[i] + lead + ln[i]], want), (lead, i)
 
