@@ -152,6 +152,104 @@ pairs_from_grid_kernel(const PairJoinArgs p)
     }
 }
 
+// The same pass with EIGHT lanes per row (four rows per warp): the lanes test the entries of the row's cells eight at
+// a time, so a row's walk is a few load latencies instead of one per entry, and the descriptors of its candidates are
+// formed by different lanes at once.  (A row's pairs come out in no particular order: the row pass breaks ties on the
+// column index.)
+#define PJ8_ROWS (PJ_THREADS / 8)
+#define PJ8_KEEP 2
+
+template <class F>
+__device__ __forceinline__ void pj_walk8(const PairJoinArgs &p, int g, const int4 rb, u32 t, F emit)
+{
+    const int s = p.grp_shift[g];
+    const i64 *off = p.cell_off + (i64)g * (PJ_GR_CELLS + 1);
+    const int cx0 = pj_cell_of(rb.x, s), cx1 = pj_cell_of(rb.z, s), cy0 = pj_cell_of(rb.y, s), cy1 = pj_cell_of(rb.w, s);
+    for (int cy = cy0; cy <= cy1; cy++) {
+        const i64 e0 = off[cy * PJ_GR_N + cx0], e1 = min(off[cy * PJ_GR_N + cx1 + 1], p.grid_capacity);
+        for (i64 e = e0 + t; e < e1; e += 8) {
+            const int4 b = __ldg(p.entry_bbox + e);
+            if (b.x > rb.z || b.z < rb.x || b.y > rb.w || b.w < rb.y) continue;
+            if (max(cy0, pj_cell_of(b.y, s)) != cy) continue;          // taken once: see pj_walk
+            const int bx = max(cx0, pj_cell_of(b.x, s));
+            if (e < off[cy * PJ_GR_N + bx] || e >= off[cy * PJ_GR_N + bx + 1]) continue;
+            emit(__ldg(p.entries + e), b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PJ_THREADS)
+pairs_from_grid8_kernel(const PairJoinArgs p)
+{
+    const u32 lane = lane_id(), t = lane & 7u, tile = lane >> 3;
+    const int r = blockIdx.x * PJ8_ROWS + (int)(threadIdx.x >> 3);
+    const bool valid = r < p.n_rows;
+    int g = 0, rm = 0, cb = 0;
+    int4 rb = make_int4(0, 0, -1, -1);
+    bool active = false;
+    if (valid) {
+        rm = p.row_mask[r];
+        g = p.row_grp[r];
+        rb = p.bbox[rm];
+        cb = p.grp_col_begin[g];
+        active = rb.z >= rb.x && p.area[rm] != 0u && p.grp_col_count[g] > 0;
+    }
+    int cnt = 0, k0 = 0, k1 = 0;                      // my candidates of the row (the first two kept)
+    if (active)
+        pj_walk8(p, g, rb, t, [&](int k, const int4) {
+            if (cnt == 0) k0 = k;
+            else if (cnt == 1) k1 = k;
+            cnt++;
+        });
+    u32 incl = (u32)cnt;                              // prefix over the lanes of the row
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl, d, 8);
+        if ((int)t >= d) incl += v;
+    }
+    const u32 row_cnt = __shfl_sync(0xffffffffu, incl, 7, 8);
+    // the warp's pairs are one contiguous range, row after row
+    const u32 c0 = __shfl_sync(0xffffffffu, row_cnt, 0), c1 = __shfl_sync(0xffffffffu, row_cnt, 8),
+              c2 = __shfl_sync(0xffffffffu, row_cnt, 16), c3 = __shfl_sync(0xffffffffu, row_cnt, 24);
+    const u32 total = c0 + c1 + c2 + c3;
+    const u32 before = (tile > 0u ? c0 : 0u) + (tile > 1u ? c1 : 0u) + (tile > 2u ? c2 : 0u);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(p.pair_count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!valid) return;
+    const i64 first = (i64)base + before;
+    const bool room = first + row_cnt <= p.pair_capacity;      // otherwise the caller retries with a larger list
+    if (t == 0u) {
+        p.row_pair_off[r] = first;
+        p.row_pair_cnt[r] = room ? (int)row_cnt : 0;
+    }
+    if (!room || cnt == 0) return;
+    const i64 mine = first + (incl - (u32)cnt);
+    const i64 a_base = p.bits_off[rm] * 4;
+    auto put = [&](i64 q, int k, const int4 cbx) {
+        const int cm = cb + k;
+        p.pair_ab[q] = make_int2(rm, cm);
+        const u32 xa = (u32)max(rb.x, cbx.x), xb = (u32)min(rb.z, cbx.z);
+        const u32 rw0 = (u32)rb.y >> 5, rw1 = (u32)rb.w >> 5, cw0 = (u32)cbx.y >> 5, cw1 = (u32)cbx.w >> 5;
+        const u32 wa = max(rw0, cw0), wb = min(rw1, cw1);
+        PairDesc d;
+        d.rn = rw1 - rw0 + 1u;
+        d.cn = cw1 - cw0 + 1u;
+        d.nw = wb - wa + 1u;
+        d.ncols = xb - xa + 1u;
+        d.a_word = a_base + (i64)(xa - (u32)rb.x) * d.rn + (wa - rw0);
+        d.b_word = __ldg(p.bits_off + cm) * 4 + (i64)(xa - (u32)cbx.x) * d.cn + (wa - cw0);
+        p.pair_desc[q] = d;
+    };
+    if (cnt <= PJ8_KEEP) {
+        put(mine, k0, __ldg(p.bbox + cb + k0));
+        if (cnt == 2) put(mine + 1, k1, __ldg(p.bbox + cb + k1));
+    } else {
+        int w = 0;
+        pj_walk8(p, g, rb, t, [&](int k, const int4 b) { put(mine + w, k, b); w++; });
+    }
+}
+
 // popcount(A & B) over an overlap of ncols columns x nw bands, by `n_lanes` lanes (lane index t): lanes take
 // columns (and walk the few bands of a column) unless the overlap is taller than wide in words, then they take bands
 __device__ __forceinline__ u32 desc_popc(const u32 *__restrict__ words, const PairDesc &d, u32 t, u32 n_lanes)
@@ -449,7 +547,16 @@ extern "C" int ampis_intersect_rows_pairs(const void *d_bits, const int64_t *d_b
     j.grid_capacity = grid_capacity; j.pair_ab = (int2 *)d_pair_ab; j.pair_capacity = pair_capacity;
     j.row_pair_off = d_row_pair_off; j.row_pair_cnt = d_row_pair_cnt; j.pair_count = (unsigned long long *)d_pair_count;
     const unsigned row_blocks = (unsigned)((n_rows + PJ_THREADS - 1) / PJ_THREADS);
-    pairs_from_grid_kernel<<<row_blocks, PJ_THREADS, 0, st>>>(j);
+    // Lanes per row in the candidate walk.  A thread per row (default) is the cheaper form in instructions: C2 with
+    // 500,000 rows per launch 0.385 against 0.418 ms of rows with eight lanes.  Eight lanes per row (AMPIS_PJ_LANES=8)
+    // make the shorter chain of dependent loads: device-resident C3 (40,000 rows) 0.114 -> 0.087 ms -- but end to end,
+    // with several calls in flight, the same C3 step went from 0.95 to 1.16 ms (eight times the threads compete with
+    // the other calls' kernels), so it is not chosen automatically.
+    static const int pj_lanes = [] { const char *v = getenv("AMPIS_PJ_LANES"); return v ? atoi(v) : 1; }();
+    if (pj_lanes == 8)
+        pairs_from_grid8_kernel<<<(unsigned)((n_rows + PJ8_ROWS - 1) / PJ8_ROWS), PJ_THREADS, 0, st>>>(j);
+    else
+        pairs_from_grid_kernel<<<row_blocks, PJ_THREADS, 0, st>>>(j);
     AMPIS_CHECK_LAUNCH("pairs_from_grid_kernel");
     if (pair_capacity > 0) {
         // the number of pairs is only known on the device: a grid that covers the capacity, at most ~8 waves
