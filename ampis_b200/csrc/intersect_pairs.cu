@@ -469,21 +469,35 @@ rows_from_pairs_kernel(const PairRowArgs p)
     double best_s = 0.0;
     u32 best_i = 0;
     int best_c = MODE == AMPIS_MODE_IOU ? -1 : (P > 0 ? 0 : -1);
-    for (int i = 0; i < cnt; i++) {
-        const u32 inter = __ldg(p.pair_inter + first + i);
-        if (!inter) continue;
-        const int cm = __ldg(p.pair_ab + first + i).y;
-        const int k = cm - cb;
-        if (irow) irow[k] = (int)inter;
-        if (p.coo_count) {
-            const unsigned long long pos = atomicAdd(p.coo_count, 1ull);
-            if ((i64)pos < p.coo_capacity) { p.coo_row[pos] = r; p.coo_col[pos] = k; p.coo_inter[pos] = inter; }
+    // four pairs at a time: their intersections, column ids and column areas are requested before any is looked at
+    // (the loop was one dependent chain of three loads per pair)
+    for (int i0 = 0; i0 < cnt; i0 += 4) {
+        u32 in4[4], ca4[4];
+        int cm4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool on = i0 + u < cnt;
+            in4[u] = on ? __ldg(p.pair_inter + first + i0 + u) : 0u;
+            cm4[u] = on ? __ldg(p.pair_ab + first + i0 + u).y : cb;
         }
-        if (MODE == AMPIS_MODE_IOU) {
-            const double s = (double)inter / (double)(ra + __ldg(p.area + cm) - inter);
-            if (s > best_s || (s == best_s && (unsigned)k < (unsigned)best_c)) { best_s = s; best_i = inter; best_c = k; }
-        } else {
-            if (inter > best_i || (inter == best_i && (unsigned)k < (unsigned)best_c)) { best_i = inter; best_c = k; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) ca4[u] = (MODE == AMPIS_MODE_IOU && in4[u]) ? __ldg(p.area + cm4[u]) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const u32 inter = in4[u];
+            if (!inter) continue;
+            const int k = cm4[u] - cb;
+            if (irow) irow[k] = (int)inter;
+            if (p.coo_count) {
+                const unsigned long long pos = atomicAdd(p.coo_count, 1ull);
+                if ((i64)pos < p.coo_capacity) { p.coo_row[pos] = r; p.coo_col[pos] = k; p.coo_inter[pos] = inter; }
+            }
+            if (MODE == AMPIS_MODE_IOU) {
+                const double s = (double)inter / (double)(ra + ca4[u] - inter);
+                if (s > best_s || (s == best_s && (unsigned)k < (unsigned)best_c)) { best_s = s; best_i = inter; best_c = k; }
+            } else {
+                if (inter > best_i || (inter == best_i && (unsigned)k < (unsigned)best_c)) { best_i = inter; best_c = k; }
+            }
         }
     }
     if (MODE == AMPIS_MODE_SAT) best_s = (double)best_i / (double)ra;   // 0/0 = NaN like numpy
