@@ -18,6 +18,12 @@ static PyObject *s_counts, *s_size;
 static int get_dim(PyObject *o, long *out)
 {
     long v;
+#if PY_VERSION_HEX >= 0x030c0000
+    if (PyLong_CheckExact(o) && PyUnstable_Long_IsCompact((const PyLongObject *)o)) {      /* one digit: no call */
+        *out = (long)PyUnstable_Long_CompactValue((const PyLongObject *)o);
+        return 0;
+    }
+#endif
     if (PyLong_Check(o)) {
         v = PyLong_AsLong(o);
     } else {
@@ -53,6 +59,8 @@ static PyObject *gather(PyObject *self, PyObject *args)
     const Py_ssize_t cap = b_ptr.len / 8;
     PyObject *outer = NULL, *result = NULL;
     Py_ssize_t k = 0, mixed = -1;
+    PyObject *last_sz = NULL, *last_i0 = NULL, *last_i1 = NULL;      /* borrowed, only compared */
+    long last_h = 0, last_w = 0, items_h = 0, items_w = 0;
     if (b_len.len / 4 < cap || b_hw.len / 8 < cap) {
         PyErr_SetString(PyExc_ValueError, "gather: output arrays of different capacity");
         goto done;
@@ -100,8 +108,16 @@ static PyObject *gather(PyObject *self, PyObject *args)
             /* the caller's cache keeps the string objects alive: their addresses are its key */
             if (keep && PyList_Append(keep, c) < 0) { Py_DECREF(inner); goto done; }
             long hh, ww;
-            if (PyList_CheckExact(sz) && PyList_GET_SIZE(sz) >= 2) {
-                if (get_dim(PyList_GET_ITEM(sz, 0), &hh) < 0 || get_dim(PyList_GET_ITEM(sz, 1), &ww) < 0) { Py_DECREF(inner); goto done; }
+            if (sz == last_sz) {                          /* the same size object as the mask before: parsed already */
+                hh = last_h; ww = last_w;
+            } else if (PyList_CheckExact(sz) && PyList_GET_SIZE(sz) >= 2) {
+                PyObject *i0 = PyList_GET_ITEM(sz, 0), *i1 = PyList_GET_ITEM(sz, 1);
+                if (i0 == last_i0 && i1 == last_i1) {     /* [h, w] built from the same two int objects: same values */
+                    hh = items_h; ww = items_w;
+                } else {
+                    if (get_dim(i0, &hh) < 0 || get_dim(i1, &ww) < 0) { Py_DECREF(inner); goto done; }
+                    last_i0 = i0; last_i1 = i1; items_h = hh; items_w = ww;
+                }
             } else {
                 PyObject *f = PySequence_Fast(sz, "RLE 'size' must be a pair [h, w]");
                 if (!f) { Py_DECREF(inner); goto done; }
@@ -117,6 +133,7 @@ static PyObject *gather(PyObject *self, PyObject *args)
                 PyErr_SetString(PyExc_ValueError, "RLE 'size' out of range");
                 Py_DECREF(inner); goto done;
             }
+            last_sz = sz; last_h = hh; last_w = ww;
             hw[2 * k] = (int32_t)hh;
             hw[2 * k + 1] = (int32_t)ww;
             if (mixed < 0 && k > k0 && (hw[2 * k] != hw[2 * k0] || hw[2 * k + 1] != hw[2 * k0 + 1])) mixed = li;

@@ -751,8 +751,9 @@ def run_e2e_api(args, host, cfg, world, dist, sync, dev):
     off = np.zeros(len(ln) + 1, np.int64)
     np.cumsum(ln, out=off[1:])
     raw = blob.tobytes()
-    size = [part.h, part.w]
-    masks = [{'size': size, 'counts': raw[off[i]:off[i + 1]]} for i in range(len(ln))]
+    # every dict with its own size list and its own int objects, as pycocotools' encode / a json file hand them out
+    hs, ws = np.full(len(ln), part.h), np.full(len(ln), part.w)
+    masks = [{'size': [int(hs[i]), int(ws[i])], 'counts': raw[off[i]:off[i + 1]]} for i in range(len(ln))]
     per = part.per_image
     rows = [masks[g * per:g * per + part.n_rows] for g in range(n_img)]
     cols = [masks[g * per + part.n_rows:(g + 1) * per] for g in range(n_img)]

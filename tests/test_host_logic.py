@@ -135,6 +135,67 @@ def test_rle_marshalling_host_side():
     assert r.fill() == (512 + 256 + 0 + 1) / (4 * 512)
 
 
+def test_c_marshaller_walks_the_dict_lists():
+    """ampis_b200/cext/pymarshal.c (CPython C API, no device): address and length of every compressed string and the
+    image size of every mask, for all the container shapes the reference API is handed -- bytes / str / bytearray
+    counts; a size list per dict, ONE list shared by all dicts, lists built from the same two int objects (the three
+    fast paths), tuples and numpy integers (the generic path) -- plus the first list whose masks differ in size, the
+    references that keep the strings alive for the result cache, and the errors."""
+    import ctypes
+    from ampis_b200 import engine
+    m = engine.marshal()
+    rng = np.random.default_rng(11)
+
+    def walk(lists, keep=None, cap=None):
+        n = sum(len(x) for x in lists)
+        cap = n if cap is None else cap
+        ptr, ln, hw = np.zeros(max(cap, 1), np.uint64), np.zeros(max(cap, 1), np.int32), np.zeros((max(cap, 1), 2), np.int32)
+        k, mixed = m.gather(lists, ptr, ln, hw) if keep is None else m.gather(lists, ptr, ln, hw, keep)
+        assert k == n
+        got = [ctypes.string_at(int(ptr[i]), int(ln[i])) for i in range(n)]
+        return got, hw[:n].tolist(), mixed
+
+    def counts(i):
+        return bytes(rng.integers(48, 112, 3 + i % 9, dtype=np.uint8))
+
+    shared, h, w = [37, 41], 37, 41
+    big = 100000                                            # not a cached small int: every int(...) is a new object
+    for size_of in (lambda i: [37, 41], lambda i: shared, lambda i: [h, w], lambda i: (37, 41),
+                    lambda i: np.array([37, 41]), lambda i: [np.int32(37), np.int64(41)],
+                    lambda i: [int(str(big)), int(str(big + 1))]):
+        lists = [[{'size': size_of(i), 'counts': counts(i)} for i in range(n)] for n in (3, 0, 5, 1)]
+        got, hw, mixed = walk(lists)
+        want_hw = list(size_of(0)) if not isinstance(size_of(0), np.ndarray) else size_of(0).tolist()
+        assert got == [d['counts'] for l in lists for d in l] and mixed == -1
+        assert hw == [[int(want_hw[0]), int(want_hw[1])]] * 9
+    # str and bytearray counts; the kept references
+    lists = [[{'size': [5, 6], 'counts': 'abc0'}, {'size': [5, 6], 'counts': bytearray(b'0n0')}, {'size': [5, 6], 'counts': b'5d0'}]]
+    keep = []
+    got, hw, mixed = walk(lists, keep)
+    assert got == [b'abc0', b'0n0', b'5d0'] and len(keep) == 3 and keep[0] is lists[0][0]['counts']
+    # sizes: the first list whose masks differ (each way the fast paths could hide it)
+    a, b = [7, 9], [7, 9]
+    for odd in ([9, 7], (7, 10), [7, 9, 3][:2][::-1]):
+        lists = [[{'size': a, 'counts': b'0'}, {'size': b, 'counts': b'1'}],
+                 [{'size': a, 'counts': b'2'}, {'size': odd, 'counts': b'3'}, {'size': a, 'counts': b'4'}],
+                 [{'size': odd, 'counts': b'5'}]]
+        got, hw, mixed = walk(lists)
+        assert mixed == 1 and hw[3] == [int(odd[0]), int(odd[1])] and hw[4] == [7, 9] and hw[5] == hw[3]
+    # a generic-path size between two fast-path ones must not leave stale cached values behind
+    i0, i1 = 300, 400
+    lists = [[{'size': [i0, i1], 'counts': b'0'}, {'size': (500, 600), 'counts': b'1'}, {'size': [i0, i1], 'counts': b'2'}]]
+    assert walk(lists)[1] == [[300, 400], [500, 600], [300, 400]]
+    # errors
+    for bad, exc in (([[{'size': [1, 2]}]], KeyError), ([[{'counts': b'0'}]], KeyError), ([[[1, 2]]], TypeError),
+                     ([[{'size': [1, 2], 'counts': [1, 2]}]], TypeError), ([[{'size': [1], 'counts': b'0'}]], ValueError),
+                     ([[{'size': [-1, 2], 'counts': b'0'}]], ValueError), ([[{'size': ['a', 2], 'counts': b'0'}]], TypeError),
+                     ([3], TypeError)):
+        with pytest.raises(exc):
+            walk(bad, cap=4)
+    with pytest.raises(ValueError, match='more masks than capacity'):
+        walk([[{'size': [1, 2], 'counts': b'0'}] * 3], cap=2)
+
+
 def test_grid_candidate_rule_sees_every_overlapping_pair_once():
     """Model (plain numpy) of the candidate search of csrc/intersect_grid.cu: columns binned into 32 x 32 clamped
     cells of side 2^shift, a row walks the cells of its box and takes a column only in the cell that holds the
