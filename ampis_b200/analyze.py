@@ -267,34 +267,37 @@ def _scores_from_rows_batch(r, iou_thresh):
     row_off, mask_off = r.row_off, r.mask_off
     pred_off = np.zeros(n_img + 1, np.int64)
     np.cumsum(P, out=pred_off[1:])
-    img_of_row = np.repeat(np.arange(n_img), G)
-    img_of_pred = np.repeat(np.arange(n_img), P)
-    best_col = r.best_col.astype(np.int64)
     matched = r.best_score > iou_thresh
-    gt_local = np.arange(len(matched), dtype=np.int64) - row_off[img_of_row]
-    m_img = img_of_row[matched]
-    m_gt, m_pr = gt_local[matched], best_col[matched]
-    n_tp = np.bincount(m_img, minlength=n_img)
-    pm = np.zeros(int(pred_off[-1]), bool)
-    pm[pred_off[m_img] + m_pr] = True
-    fp_glob = np.nonzero(~pm)[0]
-    fp_local = (fp_glob - pred_off[img_of_pred[fp_glob]]).astype(int)
-    n_fp = P - np.bincount(img_of_pred[pm], minlength=n_img)
-    fn_glob = np.nonzero(~matched)[0]
-    fn_local = gt_local[fn_glob].astype(int)
+    # index arrays once, then gathers (a boolean mask costs a pass over all rows every time it is applied); rows and
+    # predictions are grouped by image, so "image of item k" is a repeat of the per-image counts
+    images = np.arange(n_img)
+    before = np.zeros(len(matched) + 1, np.int64)            # matched rows before each row
+    np.cumsum(matched, out=before[1:])
+    n_tp = before[row_off[1:]] - before[row_off[:-1]]
     n_fn = G - n_tp
+    mi = np.flatnonzero(matched)
+    m_img = np.repeat(images, n_tp)
+    m_gt = mi - np.repeat(row_off[:-1], n_tp)
+    m_pr = r.best_col[mi].astype(np.int64)
+    pm = np.zeros(int(pred_off[-1]) + 1, np.int64)           # 1 at every matched prediction (+ a sentinel slot)
+    pm[pred_off[m_img] + m_pr] = 1
+    used_before = np.zeros(len(pm) + 1, np.int64)            # matched predictions before each prediction
+    np.cumsum(pm, out=used_before[1:])
+    n_fp = P - (used_before[pred_off[1:]] - used_before[pred_off[:-1]])
+    fp_local = (np.flatnonzero(pm[:-1] == 0) - np.repeat(pred_off[:-1], n_fp)).astype(int)
+    fn_local = (np.flatnonzero(~matched) - np.repeat(row_off[:-1], n_fn)).astype(int)
     bad = np.nonzero((n_tp + n_fp == 0) | (n_tp + n_fn == 0))[0]
     if len(bad):
         raise ZeroDivisionError('division by zero')      # image %d has no ground truth or no predictions
     tp = np.stack([m_gt, m_pr], axis=1).astype(int)
-    inter = r.best_inter[matched].astype(np.int64)
+    inter = r.best_inter[mi].astype(np.int64)
     a_gt = r.area[mask_off[m_img] + m_gt].astype(np.int64)
     a_pr = r.area[mask_off[m_img] + G[m_img] + m_pr].astype(np.int64)
-    with np.errstate(invalid='ignore', divide='ignore'):
-        seg_p = inter / (inter + (a_pr - inter))
-        seg_r = inter / (inter + (a_gt - inter))
     seg_fn, seg_fp = a_gt - inter, a_pr - inter
-    iou = r.best_score[matched]
+    with np.errstate(invalid='ignore', divide='ignore'):
+        seg_p = inter / a_pr          # TP / (TP + FP) with FP = area(pred) - TP: the integer sum is the area
+        seg_r = inter / a_gt
+    iou = r.best_score[mi]
     t_off = np.zeros(n_img + 1, np.int64)
     np.cumsum(n_tp, out=t_off[1:])
     fp_off = np.zeros(n_img + 1, np.int64)
