@@ -153,15 +153,27 @@ def sparse_iou(a, b, size=None):
 def _match_from_rows(best_col, best_iou, n_pred, iou_thresh):
     """The bookkeeping of analyze.py:166-179 on the per-GT (arg-max, max IoU) arrays."""
     matched = best_iou > iou_thresh
-    gt_idx = np.nonzero(matched)[0]
-    tp = np.stack([gt_idx, best_col[matched]], axis=1).astype(int) if len(gt_idx) else np.asarray([], int)
-    pred_matched = np.zeros(n_pred, bool)
+    gt_idx = np.flatnonzero(matched)
     if len(gt_idx):
-        pred_matched[best_col[matched]] = True
-    return {'tp': tp,
-            'fn': np.nonzero(~matched)[0].astype(int),
-            'fp': np.nonzero(~pred_matched)[0].astype(int),
-            'iou': best_iou[matched]}
+        cols = best_col[gt_idx]
+        tp = np.empty((len(gt_idx), 2), int)
+        tp[:, 0] = gt_idx
+        tp[:, 1] = cols
+        pred_matched = np.zeros(n_pred, bool)
+        pred_matched[cols] = True
+        fp = np.flatnonzero(~pred_matched)
+    else:
+        tp = np.asarray([], int)
+        fp = np.arange(n_pred)
+    return {'tp': tp, 'fn': np.flatnonzero(~matched), 'fp': fp, 'iou': best_iou[gt_idx]}
+
+
+def _rows_of_image(gt, pred):
+    """(best_col, best_iou, best_inter, areas) of one image; the conventions of analyze.py:115-181 for empty sides."""
+    G = len(gt)
+    if G == 0 or len(pred) == 0:
+        return np.full(G, -1, np.int64), np.zeros(G), np.zeros(G, np.int64), None
+    return _image_rows(gt, pred, engine.MODE_IOU)
 
 
 def _piecewise_rle_match(gt, pred, iou_thresh=0.5, interval=80, _details=None):
@@ -170,17 +182,10 @@ def _piecewise_rle_match(gt, pred, iou_thresh=0.5, interval=80, _details=None):
     For each ground-truth mask the prediction with the highest IoU is taken (first one on ties,
     only IoUs strictly above 0 count); it is a match when that IoU is strictly above
     *iou_thresh*.  Several ground-truth masks may match the same prediction."""
-    G, P = len(gt), len(pred)
-    if G == 0 or P == 0:
-        best_col = np.full(G, -1, np.int64)
-        best_iou = np.zeros(G)
-        best_inter = np.zeros(G, np.int64)
-        areas = None
-    else:
-        best_col, best_iou, best_inter, areas = _image_rows(gt, pred, engine.MODE_IOU)
+    best_col, best_iou, best_inter, areas = _rows_of_image(gt, pred)
     if _details is not None:
         _details.update(best_col=best_col, best_iou=best_iou, best_inter=best_inter, areas=areas)
-    return _match_from_rows(best_col, best_iou, P, iou_thresh)
+    return _match_from_rows(best_col, best_iou, len(pred), iou_thresh)
 
 
 def rle_instance_matcher(gt, pred, iou_thresh=0.5, size=None):
@@ -201,11 +206,9 @@ def det_seg_scores(gt, pred, iou_thresh=0.5, size=None):
     intersection of every matched pair is a by-product of the row kernel, so there is no second pass
     of merges.  Raises ZeroDivisionError like the reference when TP+FP or TP+FN is zero."""
     gtmasks, predmasks = masks_to_rle(gt, size), masks_to_rle(pred, size)
-    rows = {}
-    _piecewise_rle_match(gtmasks, predmasks, iou_thresh, _details=rows)
     G, P = len(gtmasks), len(predmasks)
-    areas = rows['areas']
-    return _scores_from_rows(G, P, rows['best_col'], rows['best_iou'], rows['best_inter'],
+    best_col, best_iou, best_inter, areas = _rows_of_image(gtmasks, predmasks)     # the matching is done once, below
+    return _scores_from_rows(G, P, best_col, best_iou, best_inter,
                              None if areas is None else areas[:G], None if areas is None else areas[G:], iou_thresh)
 
 
@@ -222,8 +225,8 @@ def _scores_from_rows(G, P, best_col, best_iou, best_inter, areas_gt, areas_pred
     else:
         inter = a_gt = a_pr = np.array([], np.int64)
     with np.errstate(invalid='ignore', divide='ignore'):
-        out['seg_precision'] = inter / (inter + (a_pr - inter))
-        out['seg_recall'] = inter / (inter + (a_gt - inter))
+        out['seg_precision'] = inter / a_pr       # TP / (TP + FP) with FP = area(pred) - TP: the integer sum is the area
+        out['seg_recall'] = inter / a_gt
     out.update(det_tp=tp, det_fn=det['fn'], det_fp=det['fp'], seg_tp=inter, seg_fn=a_gt - inter, seg_fp=a_pr - inter,
                det_tp_iou=det['iou'])
     return out

@@ -369,6 +369,15 @@ def marshal():
 #: fifth of all pairs have overlapping boxes)
 CROWD_PAIR_FRACTION = 0.2
 
+def _addr(a):
+    """Address of a numpy array's data: 0.7 us through the buffer protocol against 2.8 us for a.ctypes.data /
+    __array_interface__ -- a single-image call passes thirteen arrays."""
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError, BufferError):          # empty, read-only or non-contiguous
+        return a.ctypes.data
+
+
 _images_cache = {}      # mode -> (key, references that keep the strings alive, result)
 
 
@@ -385,16 +394,23 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
     n_img = len(rows_lists)
     assert len(cols_lists) == n_img
     r = ImagesRows()
-    r.n_rows = np.fromiter(map(len, rows_lists), np.int32, n_img)
-    r.n_cols = np.fromiter(map(len, cols_lists), np.int32, n_img)
-    r.row_off = np.zeros(n_img + 1, np.int64)
-    np.cumsum(r.n_rows, out=r.row_off[1:])
-    r.mask_off = np.zeros(n_img + 1, np.int64)
-    np.cumsum(r.n_rows.astype(np.int64) + r.n_cols, out=r.mask_off[1:])
-    n, R = int(r.mask_off[-1]), int(r.row_off[-1])
-    ptr = np.empty(max(n, 1), np.uint64)
-    ln = np.empty(max(n, 1), np.int32)
-    hw = np.empty((max(n, 1), 2), np.int32)
+    if n_img == 1:
+        # one image per call (det_seg_scores, _rle_satellite_match, mask_areas): the bookkeeping in plain Python -- a
+        # dozen numpy calls on one-element arrays cost more than the GPU needs for the image
+        G1, P1 = len(rows_lists[0]), len(cols_lists[0])
+        n, R = G1 + P1, G1
+        r.n_rows, r.n_cols = np.array([G1], np.int32), np.array([P1], np.int32)
+        r.row_off, r.mask_off = np.array([0, G1], np.int64), np.array([0, n], np.int64)
+    else:
+        r.n_rows = np.fromiter(map(len, rows_lists), np.int32, n_img)
+        r.n_cols = np.fromiter(map(len, cols_lists), np.int32, n_img)
+        r.row_off = np.zeros(n_img + 1, np.int64)
+        np.cumsum(r.n_rows, out=r.row_off[1:])
+        r.mask_off = np.zeros(n_img + 1, np.int64)
+        np.cumsum(r.n_rows.astype(np.int64) + r.n_cols, out=r.mask_off[1:])
+        n, R = int(r.mask_off[-1]), int(r.row_off[-1])
+    n1 = max(n, 1)
+    ptr, ln, hw = np.empty(n1, np.uint64), np.empty(n1, np.int32), np.empty((n1, 2), np.int32)
     lists = [None] * (2 * n_img)
     lists[0::2] = rows_lists
     lists[1::2] = cols_lists
@@ -403,18 +419,21 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
     assert got == n
     # one size per image: the first mask of each image speaks for it.  The marshaller has checked every list on its
     # own (mixed = first list holding two sizes); what is left is rows against columns of the same image
-    first = np.minimum(r.mask_off[:-1], max(n - 1, 0))
-    r.hw = np.where(((r.n_rows + r.n_cols) > 0)[:, None], hw[first], 0).astype(np.int64)
-    if n:
-        first_col = np.minimum(r.mask_off[:-1] + r.n_rows, n - 1)
-        both = (r.n_rows > 0) & (r.n_cols > 0)
-        clash = np.nonzero(both & (hw[first_col] != hw[first]).any(axis=1))[0]
-        if mixed >= 0 or len(clash):
-            g = min(([mixed // 2] if mixed >= 0 else []) + [int(c) for c in clash[:1]])
-            m0, m1 = int(r.mask_off[g]), int(r.mask_off[g + 1])
-            k = m0 + int(np.nonzero((hw[m0:m1] != hw[m0]).any(axis=1))[0][0])
-            raise ValueError('masks of different image sizes cannot be compared (%s vs %s)'
-                             % (tuple(int(v) for v in hw[m0]), tuple(int(v) for v in hw[k])))
+    if n_img == 1 and mixed < 0 and (G1 == 0 or P1 == 0 or (hw[0, 0] == hw[G1, 0] and hw[0, 1] == hw[G1, 1])):
+        r.hw = np.array([[int(hw[0, 0]), int(hw[0, 1])] if n else [0, 0]], np.int64)
+    else:
+        first = np.minimum(r.mask_off[:-1], max(n - 1, 0))
+        r.hw = np.where(((r.n_rows + r.n_cols) > 0)[:, None], hw[first], 0).astype(np.int64)
+        if n:
+            first_col = np.minimum(r.mask_off[:-1] + r.n_rows, n - 1)
+            both = (r.n_rows > 0) & (r.n_cols > 0)
+            clash = np.nonzero(both & (hw[first_col] != hw[first]).any(axis=1))[0]
+            if mixed >= 0 or len(clash):
+                g = min(([mixed // 2] if mixed >= 0 else []) + [int(c) for c in clash[:1]])
+                m0, m1 = int(r.mask_off[g]), int(r.mask_off[g + 1])
+                k = m0 + int(np.nonzero((hw[m0:m1] != hw[m0]).any(axis=1))[0][0])
+                raise ValueError('masks of different image sizes cannot be compared (%s vs %s)'
+                                 % (tuple(int(v) for v in hw[m0]), tuple(int(v) for v in hw[k])))
     key = None
     if cache:
         key = (mode, float(crowd_frac), ptr[:n].tobytes(), ln[:n].tobytes(), hw[:n].tobytes(), r.n_rows.tobytes())
@@ -431,7 +450,7 @@ def eval_images(rows_lists, cols_lists, mode, crowd_frac=-1.0, cache=False):
     r.pairs_found, r.crowded = 0, False
     if n:
         need, found, crowded = C.c_int64(0), C.c_int64(0), C.c_int32(0)
-        pa = lambda a: a.__array_interface__['data'][0]          # plain address (argtypes say c_void_p); cheaper than .ctypes
+        pa = _addr                                               # plain address (argtypes say c_void_p)
         h32, w32 = np.ascontiguousarray(r.hw[:, 0].astype(np.uint32)), np.ascontiguousarray(r.hw[:, 1].astype(np.uint32))
         lib = N.lib()
         with _image_ws_lock:

@@ -196,6 +196,76 @@ def test_c_marshaller_walks_the_dict_lists():
         walk([[{'size': [1, 2], 'counts': b'0'}] * 3], cap=2)
 
 
+def test_eval_images_wrapper_hands_the_library_the_right_arrays(monkeypatch):
+    """engine.eval_images without a device: the library call is replaced by a stand-in that READS its inputs and WRITES
+    its outputs through the raw addresses it is given, exactly as libampis_b200.so would.  Checks the marshalled string
+    addresses / lengths, the per-image counts and sizes, that every output array comes back filled (addresses of
+    empty and non-empty arrays alike), and the per-image bookkeeping of det_seg_scores on top -- for one image (the
+    plain-Python fast path) and for several."""
+    import ctypes as C
+    import torch
+    from ampis_b200 import analyze, engine
+    rng = np.random.default_rng(0)
+    seen = {}
+
+    def mk(n, size=(768, 1024)):
+        return [{'size': list(size), 'counts': bytes(rng.integers(48, 112, int(rng.integers(60, 110)), dtype=np.uint8))}
+                for _ in range(n)]
+
+    def arr(addr, n, ct):
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(ct)), shape=(max(n, 1),))[:n]
+
+    class StandIn(object):
+        def ampis_eval_images_host(self, ptr, ln, n_img, n_rows, n_cols, h32, w32, mode, flags, crowd, d_ws, d_n, h_ws,
+                                   h_n, best_col, best_inter, best_score, area, bbox, span, status, thr, n_thr, counts,
+                                   totals, found, crowded, need, stream):
+            G, P = arr(n_rows, n_img, C.c_int32).copy(), arr(n_cols, n_img, C.c_int32).copy()
+            n, R = int((G + P).sum()), int(G.sum())
+            p_, l_ = arr(ptr, n, C.c_uint64), arr(ln, n, C.c_int32)
+            seen.update(strings=[C.string_at(int(p_[i]), int(l_[i])) for i in range(n)], G=G.tolist(), P=P.tolist(),
+                        hw=(arr(h32, n_img, C.c_uint32).tolist(), arr(w32, n_img, C.c_uint32).tolist()))
+            bc, bs, bi = arr(best_col, R, C.c_int32), arr(best_score, R, C.c_double), arr(best_inter, R, C.c_uint32)
+            r0 = 0
+            for g in range(n_img):
+                for k in range(G[g]):
+                    bc[r0 + k] = k % P[g] if P[g] else -1
+                    bs[r0 + k] = 0.9 if (k % 3 and P[g]) else 0.0
+                    bi[r0 + k] = 7
+                r0 += G[g]
+            arr(area, n, C.c_uint32)[:] = 11
+            arr(status, n, C.c_int32)[:] = 0
+            arr(bbox, 4 * n, C.c_int32)[:] = 1
+            arr(span, 2 * n, C.c_uint32)[:] = 2
+            return 0
+
+    ws = [torch.empty(1 << 16, dtype=torch.uint8), torch.empty(1 << 16, dtype=torch.uint8)]
+    monkeypatch.setattr(engine, 'require_cuda', lambda: torch.device('cpu'))
+    monkeypatch.setattr(engine, '_workspaces', lambda device: ws)
+    monkeypatch.setattr(engine, '_stream', lambda: None)
+    monkeypatch.setattr(engine.N, 'lib', lambda: StandIn())
+    for G, P in ((5, 7), (1, 1), (0, 3), (4, 0), (300, 300)):
+        gt, pr = mk(G), mk(P)
+        r = engine.eval_images([gt], [pr], engine.MODE_IOU)
+        assert seen['strings'] == [m['counts'] for m in gt + pr] and seen['G'] == [G] and seen['P'] == [P]
+        assert seen['hw'] == ([768], [1024]) and r.hw.tolist() == [[768, 1024]]
+        assert (r.area == 11).all() and (r.status == 0).all() and len(r.best_col) == G and len(r.area) == G + P
+        if G and P:
+            assert r.best_col.tolist() == [k % P for k in range(G)] and (r.bbox == 1).all() and (r.span == 2).all()
+            d = analyze.det_seg_scores(gt, pr, 0.5)
+            assert len(d['det_tp']) == sum(1 for k in range(G) if k % 3) and (d['seg_tp'] == 7).all()
+            if len(d['det_tp']):
+                assert d['det_tp'][:, 0].tolist() == [k for k in range(G) if k % 3]
+    gts, prs = [mk(3), mk(0), mk(2)], [mk(2), mk(4), mk(5, (64, 48))]
+    with pytest.raises(ValueError, match=r'different image sizes.*\(768, 1024\) vs \(64, 48\)'):
+        engine.eval_images(gts, prs, engine.MODE_IOU)
+    prs[2] = mk(5)
+    r = engine.eval_images(gts, prs, engine.MODE_IOU)
+    assert seen['strings'] == [m['counts'] for g, p in zip(gts, prs) for m in g + p]
+    assert seen['G'] == [3, 0, 2] and seen['P'] == [2, 4, 5] and r.row_off.tolist() == [0, 3, 3, 5]
+    with pytest.raises(ValueError, match='different image sizes'):
+        engine.eval_images([mk(2) + mk(1, (5, 6))], [mk(2)], engine.MODE_IOU)
+
+
 def test_grid_candidate_rule_sees_every_overlapping_pair_once():
     """Model (plain numpy) of the candidate search of csrc/intersect_grid.cu: columns binned into 32 x 32 clamped
     cells of side 2^shift, a row walks the cells of its box and takes a column only in the cell that holds the
