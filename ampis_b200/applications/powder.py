@@ -27,11 +27,12 @@ def _rle_satellite_match(particles, satellites, match_thresh=0.5):
     if S and Np == 0:
         raise ValueError('attempt to get argmax of an empty sequence')
     if S:
-        for m in list(particles) + list(satellites):
-            if list(m['size']) != list(particles[0]['size']):
-                raise ValueError('particle and satellite masks must share one image size')
-        best, score, _, _ = analyze._image_rows(satellites, particles, engine.MODE_SAT)   # NaN score for zero-area
-                                                                                         # satellites, as numpy's 0/0
+        try:        # the marshaller checks every mask's size on its way (a Python loop over them cost half the call)
+            best, score, _, _ = analyze._image_rows(satellites, particles, engine.MODE_SAT)   # NaN score for zero-area
+        except ValueError as e:                                                               # satellites, as numpy's 0/0
+            if 'different image sizes' in str(e):
+                raise ValueError('particle and satellite masks must share one image size') from e
+            raise
     else:
         best, score = np.zeros(0, np.int64), np.zeros(0)
     with np.errstate(invalid='ignore'):
