@@ -264,6 +264,14 @@ def test_eval_images_wrapper_hands_the_library_the_right_arrays(monkeypatch):
     assert seen['G'] == [3, 0, 2] and seen['P'] == [2, 4, 5] and r.row_off.tolist() == [0, 3, 3, 5]
     with pytest.raises(ValueError, match='different image sizes'):
         engine.eval_images([mk(2) + mk(1, (5, 6))], [mk(2)], engine.MODE_IOU)
+    # powder's satellite matcher leaves the size check to the marshaller and keeps its own message
+    from ampis_b200.applications import powder
+    with pytest.raises(ValueError, match='particle and satellite masks must share one image size'):
+        powder._rle_satellite_match(mk(4), mk(2) + mk(1, (5, 6)))
+    with pytest.raises(ValueError, match='particle and satellite masks must share one image size'):
+        powder._rle_satellite_match(mk(4, (5, 6)), mk(3))
+    out = powder._rle_satellite_match(mk(4), mk(6))          # the stand-in scores 0.9 for rows 1, 2, 4, 5
+    assert out['satellite_matches'].tolist() == [[1, 1], [2, 2], [4, 0], [5, 1]] and out['satellites_unmatched'].tolist() == [0, 3]
 
 
 def test_grid_candidate_rule_sees_every_overlapping_pair_once():
