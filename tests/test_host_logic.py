@@ -274,6 +274,107 @@ def test_eval_images_wrapper_hands_the_library_the_right_arrays(monkeypatch):
     assert out['satellite_matches'].tolist() == [[1, 1], [2, 2], [4, 0], [5, 1]] and out['satellites_unmatched'].tolist() == [0, 3]
 
 
+def test_model_of_the_warp_string_decoder_equals_the_oracle():
+    """Lane-by-lane model (plain Python) of rle_string_decode_warp_kernel (csrc/rle_codec.cu): four characters per lane
+    read as aligned words, numbers that end inside a lane, the start of a lane's first number from the nearest lower
+    lane with a number end and the two lanes after it (sd_incoming), compaction, the two delta chains and the carries
+    between steps of 128 characters -- against the oracle's rleFrString on valid encodings and on arbitrary numbers of
+    1 to 10 characters, at every byte alignment.  The GPU test of the same name runs the kernel itself."""
+    from oracle import cocomask as rle
+    M32 = 0xffffffff
+    shl = lambda x, sft: (x << sft) & M32 if sft < 32 else 0
+
+    def incoming(E, L, pk, cx, ck):
+        below = E if L >= 32 else (E & ((1 << L) - 1))
+        pe = below.bit_length() - 1 if below else -1
+        g0, g1, g2 = pk[max(pe, 0)], pk[min(pe + 1, 31)], pk[min(pe + 2, 31)]
+        pv, pl = (g0 & 0xffffff, g0 >> 24) if pe >= 0 else (cx, ck)
+        if pe + 1 < L:
+            pv |= shl(g1 & 0xffffff, 5 * pl); pl += g1 >> 24
+        if pe + 2 < L:
+            pv |= shl(g2 & 0xffffff, 5 * pl); pl += g2 >> 24
+        if pe + 3 < L:
+            pl = 8
+        return pv, min(pl, 8)
+
+    def decode(buf, start, ln):
+        a, out, m_base, cx, ck, ce, co, p0 = start & 3, {}, 0, 0, 0, 0, 0, 0
+        while p0 < ln:
+            nloc, v, hk, hs, pk = [0] * 32, [[0] * 4 for _ in range(32)], [0] * 32, [False] * 32, [0] * 32
+            for lane in range(32):
+                rem = ln - (p0 + 4 * lane)
+                nv = 0 if rem <= 0 else min(rem, 4)
+                lastb = nv - 1 if 1 <= rem <= 4 else 8
+                byts = 0
+                if nv:
+                    wi = (start - a) + 4 * ((p0 >> 2) + lane)
+                    w0 = int.from_bytes(buf[wi:wi + 4].ljust(4, b'\0'), 'little')
+                    w1 = int.from_bytes(buf[wi + 4:wi + 8].ljust(4, b'\0'), 'little') if a + nv > 4 else 0
+                    byts = ((w1 << 32 | w0) >> (8 * a)) & M32
+                cur = curk = 0
+                for b in range(nv):
+                    c = (((byts >> (8 * b)) & 0xff) - 48) & M32
+                    cur |= (c & 0x1f) << (5 * curk); curk += 1
+                    if not (c & 0x20) or b == lastb:
+                        sign = (not (c & 0x20)) and bool(c & 0x10)
+                        x = cur
+                        if nloc[lane] == 0:
+                            hk[lane], hs[lane] = curk, sign
+                        elif sign:
+                            x |= (M32 << (5 * curk)) & M32
+                        v[lane][nloc[lane]] = x; nloc[lane] += 1; cur = curk = 0
+                pk[lane] = cur | (curk << 24)
+            E = sum(1 << l for l in range(32) if nloc[l])
+            S, slot = [0] * 132, 0
+            for lane in range(32):
+                pv, pl = incoming(E, lane, pk, cx, ck)
+                if nloc[lane]:
+                    v[lane][0] = pv | shl(v[lane][0], 5 * pl)
+                    if hs[lane]:
+                        v[lane][0] |= shl(M32, 5 * (pl + hk[lane]))
+                S[slot:slot + nloc[lane]] = v[lane][:nloc[lane]]
+                slot += nloc[lane]
+            nn, odd = slot, m_base & 1
+            ys = [[(S[4 * l + q] if 4 * l + q < nn and m_base + 4 * l + q != 0 else 0) for q in range(4)] for l in range(32)]
+            A, B = [(y[0] + y[2]) & M32 for y in ys], [(y[1] + y[3]) & M32 for y in ys]
+            SA, SB = np.cumsum(A) & M32, np.cumsum(B) & M32
+            cA, cB = (co, ce) if odd else (ce, co)
+            for l in range(32):
+                y = ys[l]
+                w0 = (int(SA[l]) - A[l] + y[0] + cA) & M32; w1 = (int(SB[l]) - B[l] + y[1] + cB) & M32
+                w = [w0, w1, (w0 + y[2]) & M32, (w1 + y[3]) & M32]
+                for q in range(4):
+                    if 4 * l + q < nn:
+                        out[m_base + 4 * l + q] = S[4 * l + q] if m_base + 4 * l + q == 0 else w[q]
+            if p0 + 128 < ln:
+                nA, nB = (cA + int(SA[31])) & M32, (cB + int(SB[31])) & M32
+                ce, co = (nB, nA) if odd else (nA, nB)
+                cx, ck = incoming(E, 32, pk, cx, ck)
+            m_base += nn
+            p0 += 128
+        return np.array([out[k] for k in range(m_base)], np.uint32)
+
+    rng = np.random.default_rng(5)
+    for t in range(160):
+        strs = []
+        for _ in range(3):
+            if rng.random() < 0.5:
+                m, mag = int(rng.integers(0, 200)), int(rng.choice([4, 40, 1000, 70000, 2 ** 22, 2 ** 28]))
+                strs.append(rle.string_from_counts(rng.integers(0, mag, m, dtype=np.int64).astype(np.uint32)))
+            else:
+                o = bytearray()
+                for _ in range(int(rng.integers(0, 90))):
+                    k = int(rng.integers(1, 11))
+                    o += bytes((48 + (int(rng.integers(0, 32)) | 0x20)) for _ in range(k - 1)) + bytes([48 + int(rng.integers(0, 32))])
+                strs.append(bytes(o))
+        blob = b'x' * int(rng.integers(0, 4)) + b''.join(strs)
+        off = len(blob) - sum(len(x) for x in strs)
+        for x in strs:
+            want = rle.counts_from_string(x) if len(x) else np.zeros(0, np.uint32)
+            assert np.array_equal(decode(blob, off, len(x)), want), (t, len(x))
+            off += len(x)
+
+
 def test_grid_candidate_rule_sees_every_overlapping_pair_once():
     """Model (plain numpy) of the candidate search of csrc/intersect_grid.cu: columns binned into 32 x 32 clamped
     cells of side 2^shift, a row walks the cells of its box and takes a column only in the cell that holds the
