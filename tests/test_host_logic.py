@@ -375,6 +375,125 @@ def test_model_of_the_warp_string_decoder_equals_the_oracle():
             off += len(x)
 
 
+def test_model_of_the_flat_decode_pass_equals_the_oracle():
+    """Lane-by-lane model (numpy) of the measure pass of rle_flat_crop_kernel (csrc/rle_flat.cu): the masks of a warp laid
+    end to end as (0-run, 1-run) pairs, 32 pairs per pass; run ends and 1-pixel counts by segmented inclusive scans
+    (a lane reaches min(lane, pair index in its mask) lanes down, the carry of lane 31 continues a mask into the next
+    pass); first / last 1-pixel from two ballots; row ranges as 16-bit halves (min row | 0xffff - max row) under a
+    per-half minimum; the segment's last lane adds to its mask; the painter's record per pair (column, first row,
+    last row), or start | flag and length for runs that cross a column boundary.  Against area and tight box of the
+    oracle's decoded mask, and the records against the mask itself."""
+    from oracle import cocomask as rle
+    rng = np.random.default_rng(9)
+    SAT, SPAN = 0x7fffffff, 0x80000000
+
+    def model(cnts, H, W):
+        """cnts: list of uint32 run-count arrays (masks of one warp round) -> per-mask stats, per-pair records"""
+        npairs = [(len(c) + 1) >> 1 for c in cnts]
+        pb = np.concatenate([[0], np.cumsum(npairs)]).astype(np.int64)
+        T, K = int(pb[-1]), len(cnts)
+        area, first, last = np.zeros(K, np.int64), np.full(K, 0xffffffff, np.int64), np.zeros(K, np.int64)
+        ymin, ymaxi, total = np.full(K, 0xffffffff, np.int64), np.full(K, 0xffffffff, np.int64), np.zeros(K, np.int64)
+        rec, carry = [None] * T, 0
+        for f0 in range(0, T, 32):
+            lanes = np.arange(32)
+            f = f0 + lanes
+            ok = f < T
+            j = np.searchsorted(pb, np.minimum(f, T - 1), side='right') - 1
+            p = np.where(ok, f - pb[j], 0)
+            z, o = np.zeros(32, np.int64), np.zeros(32, np.int64)
+            for l in lanes[ok]:
+                c = cnts[j[l]]
+                z[l] = min(int(c[2 * p[l]]), SAT)
+                o[l] = min(int(c[2 * p[l] + 1]), SAT) if 2 * p[l] + 1 < len(c) else 0
+            end, osum = np.minimum(z + o, SAT), o.copy()
+            reach = np.where(ok, np.minimum(lanes, p), 0)
+            d = 1
+            while d < 32:
+                te, to = np.concatenate([np.zeros(d, np.int64), end[:-d]]), np.concatenate([np.zeros(d, np.int64), osum[:-d]])
+                sel = d <= reach
+                end, osum = np.where(sel, np.minimum(end + te, SAT), end), np.where(sel, osum + to, osum)
+                d <<= 1
+            end = np.where(ok & (p > lanes), np.minimum(end + carry, SAT), end)
+            carry = int(end[31])
+            inb = ok & (end <= H * W)
+            good = inb & (o > 0)
+            start = end - o
+            ypk = np.full(32, 0xffffffff, np.int64)
+            for l in lanes[ok]:
+                if not good[l]:
+                    rec[f[l]] = (0, 0x0000ffff)
+                    continue
+                x = int(start[l]) // H
+                ys = int(start[l]) - x * H
+                yl = ys + int(o[l]) - 1
+                if yl >= H:
+                    rec[f[l]] = (int(start[l]) | SPAN, int(o[l])); ypk[l] = (0xffff - (H - 1)) << 16
+                else:
+                    rec[f[l]] = (x, ys | (yl << 16)); ypk[l] = ys | ((0xffff - yl) << 16)
+            d = 1
+            while d < 32:
+                t = np.concatenate([np.full(d, 0xffffffff, np.int64), ypk[:-d]])
+                lo, hi = np.minimum(ypk & 0xffff, t & 0xffff), np.minimum(ypk >> 16, t >> 16)
+                ypk = np.where(d <= reach, lo | (hi << 16), ypk)
+                d <<= 1
+            gm = sum(1 << int(l) for l in lanes[good])
+            im = sum(1 << int(l) for l in lanes[inb])
+            for l in lanes[ok]:
+                seg_end = f[l] + 1 == pb[j[l] + 1]
+                if not (seg_end or l == 31):
+                    continue
+                seg = ((2 << int(l)) - 1) & (0xffffffff << int(l - reach[l])) & 0xffffffff
+                gs, i_s = gm & seg, im & seg
+                if gs:
+                    fl, ll, li = (gs & -gs).bit_length() - 1, gs.bit_length() - 1, i_s.bit_length() - 1
+                    area[j[l]] += osum[li]
+                    first[j[l]], last[j[l]] = min(first[j[l]], start[fl]), max(last[j[l]], end[ll])
+                    ymin[j[l]], ymaxi[j[l]] = min(ymin[j[l]], ypk[l] & 0xffff), min(ymaxi[j[l]], ypk[l] >> 16)
+                if seg_end:
+                    total[j[l]] = end[l]
+        return area, first, last, ymin, 0xffff - ymaxi, total, rec, pb
+
+    done = 0
+    for trial in range(40):
+        H, W = int(rng.integers(3, 90)), int(rng.integers(3, 90))
+        K = int(rng.integers(1, 7))
+        masks = np.zeros((K, H, W), bool)
+        for k in range(K):
+            kind = rng.integers(0, 5)
+            if kind == 0:
+                continue                                                    # empty mask
+            if kind == 1:
+                masks[k] = rng.random((H, W)) < rng.random()              # noise: many runs, runs across columns
+            elif kind == 2:
+                masks[k, :, int(rng.integers(0, W)):] = True                # whole columns: one long run
+            else:
+                y, x, r = rng.integers(0, H), rng.integers(0, W), rng.integers(1, 12)
+                yy, xx = np.ogrid[:H, :W]
+                masks[k] = (yy - y) ** 2 + (xx - x) ** 2 <= r * r
+        cnts = [rle.counts_from_string(rle.encode(np.asfortranarray(m.astype(np.uint8)))['counts']).astype(np.int64) for m in masks]
+        if sum((len(c) + 1) >> 1 for c in cnts) > 256:                      # the kernel would split the round
+            continue
+        done += 1
+        area, first, last, ymin, ymax, total, rec, pb = model(cnts, H, W)
+        for k in range(K):
+            m = masks[k]
+            assert area[k] == m.sum() and total[k] == H * W, (trial, k)
+            painted = np.zeros((W, H), bool)                                # column-major frame
+            for fidx in range(int(pb[k]), int(pb[k + 1])):
+                x, y = rec[fidx]
+                if x & SPAN:
+                    painted.reshape(-1)[(x & ~SPAN):(x & ~SPAN) + y] = True
+                elif (y & 0xffff) <= (y >> 16):
+                    painted[x, (y & 0xffff):(y >> 16) + 1] = True
+            assert np.array_equal(painted.T, m), (trial, k)
+            if m.any():
+                ys_, xs_ = np.nonzero(m)
+                assert first[k] // H == xs_.min() and (last[k] - 1) // H == xs_.max(), (trial, k)
+                assert (ymin[k], ymax[k]) == (ys_.min(), ys_.max()), (trial, k)
+    assert done >= 12
+
+
 def test_grid_candidate_rule_sees_every_overlapping_pair_once():
     """Model (plain numpy) of the candidate search of csrc/intersect_grid.cu: columns binned into 32 x 32 clamped
     cells of side 2^shift, a row walks the cells of its box and takes a column only in the cell that holds the
