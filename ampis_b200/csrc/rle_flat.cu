@@ -359,13 +359,14 @@ extern "C" int ampis_rle_measure_paint_flat_zero(const uint32_t *d_cnt, const in
     AMPIS_REQUIRE(!d_zero || ((uintptr_t)d_zero & 15u) == 0, "buffer to zero must be 16-byte aligned");
     cudaError_t e = cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_list, 0, sizeof(int32_t), st);
-    // the kernel zeroes whole 16-byte chunks (at most 2^32 - 2^24 of them); what is left is cleared here
-    const int64_t zero_chunks = d_zero ? std::min<int64_t>(zero_bytes / 16, 0xff000000ll) : 0;
+    const int K = flat_masks_per_warp(runs_hint);
+    const int64_t warps = ((int64_t)n + K - 1) / K;
+    // the kernel zeroes whole 16-byte chunks with 32-bit indices: at most 2^32 - 2^24 of them over at most 2^24 groups
+    // (84 million masks per launch), so that group x share stays below 2^32; what is left is cleared here
+    const int64_t zero_chunks = (d_zero && warps <= (1 << 24)) ? std::min<int64_t>(zero_bytes / 16, 0xff000000ll) : 0;
     if (e == cudaSuccess && d_zero && zero_bytes > zero_chunks * 16)
         e = cudaMemsetAsync((char *)d_zero + zero_chunks * 16, 0, (size_t)(zero_bytes - zero_chunks * 16), st);
     if (e != cudaSuccess) { ampis_set_error("cursor memset: %s", cudaGetErrorString(e)); return AMPIS_ECUDA; }
-    const int K = flat_masks_per_warp(runs_hint);
-    const int64_t warps = ((int64_t)n + K - 1) / K;
     static thread_local int wave = 0;                 // one wave of CTAs; every warp strides over the groups
     if (!wave) {
         int dev = 0, sms = 0;
@@ -377,8 +378,7 @@ extern "C" int ampis_rle_measure_paint_flat_zero(const uint32_t *d_cnt, const in
     }
     const unsigned grid = (unsigned)std::min<int64_t>((warps + FL_WARPS - 1) / FL_WARPS, wave);
     if (zero_chunks > 0) {
-        // 32-bit chunk indices in the kernel: groups x share stays below 2^32 because the kernel takes at most
-        // 2^32 - 2^24 chunks (64 GB) and a share is a ceiling over >= 1 group
+        // (groups - 1) x share < chunks + groups <= 2^32
         const uint32_t per = (uint32_t)((zero_chunks + warps - 1) / warps);
         rle_flat_crop_kernel<true><<<grid, FL_WARPS * 32, 0, st>>>(
             d_cnt, d_cnt_off, d_cnt_len, d_h, d_w, n, K, d_area, d_bbox, d_span, d_reg, d_bits_off, d_status,
